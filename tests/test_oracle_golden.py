@@ -1,0 +1,95 @@
+"""CPU: pins the C oracle (oracle/nlspn_oracle.c) against the golden vectors that the
+UNMODIFIED reference produced (oracle/gen_golden.py).  Tolerances: the referee is the
+reference's fp32 run; the oracle restates the same fp32 arithmetic, differing only in
+summation order / libm tanh, so forward agrees to a few ulp of the depth scale."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+PATHS = golden_names("path_") + golden_names("fullmodel_")
+
+
+def _meta(g):
+    return dict(K=int(g["meta_K"]), T=int(g["meta_T"]), affinity=str(g["meta_affinity"]),
+                preserve=bool(int(g["meta_preserve"])), use_conf=bool(int(g["meta_use_conf"])),
+                always_clip=bool(int(g.get("meta_always_clip", 0))), gamma=float(g["meta_gamma"]))
+
+
+def _fwd(oracle, g, dtype=np.float32):
+    m = _meta(g)
+    conf = g["in_confidence"].astype(dtype) if m["use_conf"] else None
+    return oracle.nlspn_forward(g["in_feat_init"].astype(dtype), g["in_guidance"].astype(dtype), conf,
+                                g["in_feat_fix"].astype(dtype), m["gamma"], m["K"], m["T"],
+                                m["affinity"], m["preserve"], m["always_clip"]), m
+
+
+@pytest.mark.parametrize("name", PATHS)
+def test_forward_matches_reference(oracle, name):
+    g = load_golden(name)
+    out, m = _fwd(oracle, g)
+    # offsets are copies: exact
+    assert np.array_equal(out["offset"], g["out_offset"])
+    # centre pair identically zero (nlspnmodel.py:256)
+    ref = (m["K"] ** 2 - 1) // 2
+    assert not out["offset"][:, 2 * ref:2 * ref + 2].any()
+    np.testing.assert_allclose(out["aff"], g["out_aff"], rtol=0, atol=2e-6)
+    if m["use_conf"]:
+        assert np.array_equal(out["confidence"], g["out_conf_fixed"])
+    scale = max(1.0, float(np.abs(g["out_list_feat"]).max()))
+    # north-star bound: 1e-4 m absolute on the stable sets; relative 1e-5 on the signed set
+    tol = 1e-4 if "signed" not in name and "clip" not in name else 1e-5 * scale
+    err = np.abs(out["list_feat"] - g["out_list_feat"]).max()
+    assert err <= tol, (name, err)
+    assert np.abs(out["feat_result"] - g["out_feat_result"]).max() <= tol
+    # fixed pixels hold the sparse depth exactly after every iteration (nlspnmodel.py:357)
+    if m["preserve"]:
+        fix = g["in_feat_fix"] > 0
+        for t in range(m["T"]):
+            assert np.array_equal(out["list_feat"][t][fix], g["in_feat_fix"][fix])
+
+
+@pytest.mark.parametrize("name", [n for n in PATHS if "fullmodel" not in n and "clip" not in n])
+def test_backward_matches_reference_autograd(oracle, name):
+    g = load_golden(name)
+    out, m = _fwd(oracle, g)
+    conf = g["in_confidence"] if m["use_conf"] else None
+    gi, gg, gc, ggam = oracle.nlspn_backward(g["in_feat_init"], g["in_guidance"], conf, g["in_feat_fix"],
+                                             m["gamma"], m["K"], out, g["out_g_list"], m["affinity"],
+                                             m["preserve"])
+
+    def rel(a, b):
+        return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+    N = m["K"] ** 2 - 1
+    assert rel(gi, g["out_g_feat_init"]) < 1e-4
+    assert rel(gg[:, 2 * N:], g["out_g_guidance"][:, 2 * N:]) < 2e-4          # raw affinities
+    if m["use_conf"]:
+        assert rel(gc, g["out_g_confidence"]) < 1e-4
+    if "out_g_gamma" in g:
+        assert abs(ggam - float(g["out_g_gamma"])) <= 2e-4 * max(abs(float(g["out_g_gamma"])), 1e-6)
+    # offset gradients: piecewise-constant derivative, a floor() flip changes single entries
+    # completely -- require the bulk to agree and bound the outlier fraction.
+    d = np.abs(gg[:, :2 * N] - g["out_g_guidance"][:, :2 * N])
+    s = np.abs(g["out_g_guidance"][:, :2 * N]).max()
+    assert (d > 1e-4 * s).mean() < 1e-3, (name, (d > 1e-4 * s).mean())
+
+
+def test_fp64_oracle_close_to_fp32_reference(oracle):
+    g = load_golden("path_stable_k3_t18")
+    out, m = _fwd(oracle, g, np.float64)
+    assert np.abs(out["list_feat"] - g["out_list_feat"]).max() < 1e-3
+
+
+@pytest.mark.parametrize("name", golden_names("dcn_"))
+def test_dcn_step_matches_reference_function(oracle, name):
+    g = load_golden(name)
+    y = oracle.dcn_step_fwd(g["in_x"], g["in_off"], g["in_msk"], g["in_w"].reshape(-1), g["in_b"])
+    np.testing.assert_allclose(y, g["out_y"], rtol=0, atol=2e-5)
+    gx, goff, gmsk, gw, gb = oracle.dcn_step_bwd(g["in_x"], g["in_off"], g["in_msk"], g["in_gout"],
+                                                 g["in_w"].reshape(-1))
+    np.testing.assert_allclose(gx, g["out_gx"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(gmsk, g["out_gmsk"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(goff, g["out_goff"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(gw.reshape(-1), g["out_gw"].reshape(-1), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(gb, g["out_gb"], rtol=1e-4, atol=1e-4)
