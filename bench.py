@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- NLSPN propagation throughput on B200 (metric of BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch shard: fused prologue + T propagation
+iterations (forward) and the fused reverse replay (backward), K=3, T=18 on KITTI 352x1216 frames
+(the shape BASELINE.json's metric is quoted on), B frames per GPU (weak scaling: batch shards,
+no collective on the data path -- SURVEY 8e).
+
+metric  Gpix*iter/s = (GPUs * B * H * W * T) / seconds, forward+backward.
+value   device-timed (CUDA events, max over ranks), inputs resident in HBM.
+e2e     same metric through the public module with PINNED HOST inputs: H2D of the step's
+        inputs and D2H of the step's loss inside the timed region.
+roofline  dominant kernel = the backward iteration kernel; achieved = algorithmic bytes per
+        launch (36N+36 B/px) / average launch duration from CUDA events around
+        the backward phase of every timed step; peak = MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline  the reference path restated over torchvision.ops.deform_conv2d (north_star's CPU
+        stand-in; oracle/torchvision_port.py, pinned against the unmodified reference), one image
+        per host thread, on a bounded sample of the same workload.  Rank 0, N=1 only.
+--impl reference  times that CPU implementation alone (rank 0), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "nlspn_propagation_fwd_bwd_gpix_iter_per_s"
+UNIT = "Gpix*iter/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="kitti", choices=["kitti", "nyu"])
+    p.add_argument("--batch", type=int, default=None, help="frames per GPU (default: kitti 8, nyu 12)")
+    p.add_argument("--kernel", type=int, default=3)
+    p.add_argument("--iters", type=int, default=18)
+    p.add_argument("--mode", default="fwdbwd", choices=["fwdbwd", "fwd"])
+    p.add_argument("--smooth-offsets", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-images", type=int, default=None, help="images in the CPU sample")
+    return p.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return json.load(f), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def alg_bytes(K, T, mode):
+    """Algorithmic bytes per pixel*iteration (fork semantics, fp32)."""
+    N = K * K - 1
+    fwd = 12 * N + 20 + (24 * N + 28) / T
+    bwd = 36 * N + 36 + (28 * N + 12) / T
+    return fwd if mode == "fwd" else fwd + bwd
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons during the timed region (pynvml, else nvidia-smi)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        n = self._nvml
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self._nvml is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_run(args, H, W, md, n_images, steps, warmup):
+    """Times oracle/torchvision_port.py (the reference path over torchvision) on host cores."""
+    import torch
+    from nlspn_eccv20_b200.synth import make_inputs
+    from oracle import torchvision_port as TP
+    cores = os.cpu_count() or 1
+    workers = min(cores, n_images)
+    K, T = args.kernel, args.iters
+    gamma = 0.5 * (K * K - 1)
+    kw = dict(num_sample=500) if args.workload == "nyu" else dict(density=0.05)
+    images = []
+    for i in range(n_images):
+        d = make_inputs(1, H, W, K, max_depth=md, seed=7240 + i, **kw)
+        images.append(d)
+    backward = args.mode == "fwdbwd"
+    times = []
+    for s in range(warmup + steps):
+        dt = TP.time_batch_parallel(images, gamma, K, T, backward=backward, workers=workers)
+        if s >= warmup:
+            times.append(dt)
+    torch.set_num_threads(cores)
+    best = min(times)
+    mean = sum(times) / len(times)
+    pix_iter = n_images * H * W * T
+    return dict(value=pix_iter / mean / 1e9, best=pix_iter / best / 1e9, seconds=mean, cores=workers,
+                host_cores=cores, n_images=n_images)
+
+
+def main():
+    args = parse()
+    import torch
+    from nlspn_eccv20_b200.synth import SHAPES
+    H, W, md = SHAPES[args.workload]
+    K, T = args.kernel, args.iters
+    B = args.batch if args.batch is not None else (8 if args.workload == "kitti" else 12)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "%s_%dx%d_B%d_per_gpu_K%d_T%d_%s" % (args.workload, H, W, B, K, T, args.mode),
+              "frames_per_gpu": B, "height": H, "width": W, "prop_kernel": K, "prop_time": T,
+              "affinity": "TGASS", "conf_prop": True, "preserve_input": True,
+              "offsets": "smooth" if args.smooth_offsets else "iid N(0,2^2) px",
+              "sharding": "batch shard per GPU, no collective on the data path",
+              "l2": "inputs exceed L2 (guidance alone is %.0f MB per GPU)" % (B * 3 * (K * K - 1) * H * W * 4 / 1e6)}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        n_img = args.cpu_images or min(os.cpu_count() or 1, 8)
+        r = cpu_reference_run(args, H, W, md, n_img, max(1, args.steps), max(0, args.warmup))
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                 "sample": "%d full %dx%d frames per step, one frame per host thread "
+                                           "(torchvision deform_conv2d stand-in, fwd%s), %d host cores"
+                                           % (r["n_images"], H, W, "+bwd" if args.mode == "fwdbwd" else "",
+                                              r["host_cores"])},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm (GPU)
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from nlspn_eccv20_b200 import NLSPN, _lib
+    from nlspn_eccv20_b200.synth import workload
+    lib = _lib.load()
+
+    host = workload(args.workload, B, K, seed=7240 + rank, smooth_offsets=args.smooth_offsets, pin=True)
+    names = ["feat_init", "guidance", "confidence", "feat_fix"]
+    dev_in = {k: host[k].to(dev) for k in names}
+    gt = host["gt"].to(dev)
+    mod = NLSPN(prop_kernel=K, prop_time=T).to(dev)
+    train = args.mode == "fwdbwd"
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(inp, rec=None):
+        fi, gd, cf = inp["feat_init"], inp["guidance"], inp["confidence"]
+        if train:
+            fi, gd, cf = (t.detach().requires_grad_(True) for t in (fi, gd, cf))
+            mod.aff_scale_const.grad = None
+        e0, e1, e2 = (ev(), ev(), ev()) if rec is not None else (None, None, None)
+        if rec is not None:
+            e0.record()
+        with torch.set_grad_enabled(train):
+            feat_result, list_feat, offset, aff, _ = mod(fi, gd, cf, inp["feat_fix"])
+            pred = torch.clamp(feat_result, min=0)
+            loss = (pred - gt).abs().sum()      # L1 surrogate of the reference loss (l1loss.py:27-42)
+        if rec is not None:
+            e1.record()
+        if train:
+            loss.backward()
+        if rec is not None:
+            e2.record()
+            rec.append((e0, e1, e2))
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(dev_in)
+    sync_all()
+
+    # ---- device-resident timing
+    sampler = ClockSampler(local)
+    sampler.start()
+    rec = []
+    n0 = lib.nlspn_launch_count()
+    t_start, t_end = ev(), ev()
+    t_start.record()
+    for _ in range(args.steps):
+        step(dev_in, rec)
+    t_end.record()
+    sync_all()
+    launches = lib.nlspn_launch_count() - n0
+    clocks = sampler.stop()
+    total_ms = t_start.elapsed_time(t_end)
+    fwd_ms = sum(a.elapsed_time(b) for a, b, _ in rec) / len(rec)
+    bwd_ms = sum(b.elapsed_time(c) for _, b, c in rec) / len(rec)
+
+    # ---- end to end: pinned host inputs -> H2D -> module -> D2H of the loss, every step
+    h2d = sum(host[k].numel() * 4 for k in names)
+    for _ in range(min(2, args.warmup)):
+        float(step({k: host[k].to(dev, non_blocking=True) for k in names}))
+    sync_all()
+    e_start, e_end = ev(), ev()
+    e_start.record()
+    for _ in range(args.steps):
+        inp = {k: host[k].to(dev, non_blocking=True) for k in names}
+        loss_host = float(step(inp))           # D2H of the result + sync
+    e_end.record()
+    sync_all()
+    e2e_ms = e_start.elapsed_time(e_end)
+
+    tms = torch.tensor([total_ms, e2e_ms, fwd_ms, bwd_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, fwd_ms, bwd_ms = (float(x) for x in tms.tolist())
+
+    pix_iter_step = world * B * H * W * T
+    value = pix_iter_step * args.steps / (total_ms * 1e-3) / 1e9
+    e2e_val = pix_iter_step * args.steps / (e2e_ms * 1e-3) / 1e9
+    peaks, peak_kind = measured_peaks()
+    N = K * K - 1
+    if train:
+        kern, kb, kms = "iter_bwd_kernel", (36 * N + 36), bwd_ms / T
+    else:
+        kern, kb, kms = "iter_fwd_kernel", (12 * N + 20), fwd_ms / T
+    achieved = kb * B * H * W / (kms * 1e-3) / 1e9
+    step_gbs = alg_bytes(K, T, args.mode) * (pix_iter_step / world) * args.steps / (total_ms * 1e-3) / 1e9
+    line = {"metric": METRIC if train else "nlspn_propagation_fwd_gpix_iter_per_s", "value": value,
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "phases_ms": {"forward": fwd_ms, "backward": bwd_ms,
+                          "forward_gpix_iter_per_s": pix_iter_step / world / (fwd_ms * 1e-3) / 1e9},
+            "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
+                         "alg_bytes_per_launch": kb * B * H * W,
+                         "launch_ms": kms,
+                         "note": "launch duration = CUDA-event time of the phase / T (includes the "
+                                 "fused final kernel and memsets: conservative)"},
+            "roofline_step": {"alg_bytes_per_pix_iter": alg_bytes(K, T, args.mode), "achieved": step_gbs,
+                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": step_gbs / peaks["hbm_gbs"]}}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_img = args.cpu_images or min(os.cpu_count() or 1, 8)
+        r = cpu_reference_run(args, H, W, md, n_img, 1, 0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "sample": "%d full %dx%d frames, one per host thread, fwd%s, torchvision "
+                                          "deform_conv2d stand-in (oracle/torchvision_port.py), %d host cores, %.1f s"
+                                          % (r["n_images"], H, W, "+bwd" if train else "", r["host_cores"], r["seconds"])}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,153 @@
+/*
+ * nlspn_b200.h -- C ABI of the B200-native NLSPN propagation library (libnlspn_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of XJTUXYC/NLSPN_ECCV20: the iterative
+ * non-local spatial propagation.  Reference paths below are relative to the reference
+ * repository root.  Every entry point
+ *   - takes plain device pointers (fp32, NCHW, contiguous) and sizes; no torch types,
+ *   - allocates nothing: outputs and workspace are caller-owned (size: *_workspace_bytes),
+ *   - only enqueues work on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) and never synchronises, unless documented (the *_host entry),
+ *   - returns 0 on success, a NEGATIVE nlspn_status on a validation error (nothing was
+ *     enqueued), or a POSITIVE cudaError_t if the CUDA runtime refused a launch;
+ *     nlspn_last_error() returns a thread-local message for the last non-zero return.
+ * The library keeps no global mutable state apart from per-device attributes that are
+ * queried once (SM count, L2 size) under a mutex; calls are re-entrant.
+ *
+ * Tensor vocabulary (K = prop_kernel, KK = K*K, N = KK-1 neighbours, T = prop_time):
+ *   feat_init   [B,1,H,W]    initial depth                 (pred_init, nlspnmodel.py:297)
+ *   guidance    [B,3N,H,W]   2N offset channels (pair n = channels 2n:dh, 2n+1:dw) followed
+ *                            by N raw affinities            (off_aff, nlspnmodel.py:301-305)
+ *   confidence  [B,1,H,W]    raw confidence or NULL         (nlspnmodel.py:313)
+ *   feat_fix    [B,1,H,W]    sparse depth or NULL           (dep, nlspnmodel.py:273)
+ *   offset      [B,2KK,H,W]  offsets after the zero centre pair was inserted (nlspnmodel.py:252-259)
+ *   aff         [B,KK,H,W]   normalised affinities incl. the centre weight    (nlspnmodel.py:179-201,261-269)
+ *   conf_fixed  [B,1,H,W]    (1-m)*confidence + m, m = [feat_fix>0]          (nlspnmodel.py:328-334)
+ *   list_feat   [T,B,1,H,W]  state after every iteration    (list_pred, nlspnmodel.py:363)
+ *   src         [S,B,1,H,W]  the planes the gather read: src[t] = x_t * conf_fixed (x_0 = blended
+ *                            feat_init).  S = T keeps all of them for backward; S = 2 ping-pongs
+ *                            (inference); without confidence src[0] only (S = 1) -- later
+ *                            iterations gather list_feat directly.
+ */
+#ifndef NLSPN_B200_H
+#define NLSPN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLSPN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NLSPN_API __attribute__((visibility("default")))
+#else
+#define NLSPN_API
+#endif
+
+/* negative return codes */
+enum nlspn_status {
+    NLSPN_OK = 0,
+    NLSPN_ERR_NULL = -1,        /* a required pointer is NULL                                  */
+    NLSPN_ERR_SHAPE = -2,       /* B/H/W/T <= 0 or sizes overflow int32 indexing               */
+    NLSPN_ERR_KERNEL = -3,      /* prop_kernel not one of 3, 5, 7                              */
+    NLSPN_ERR_DOMAIN = -4,      /* DCN call outside the supported domain (see nlspn_dcn_*)     */
+    NLSPN_ERR_WORKSPACE = -5,   /* workspace too small or misaligned                           */
+    NLSPN_ERR_AFFINITY = -6,    /* unknown affinity mode                                       */
+    NLSPN_ERR_ALIGN = -7        /* a tensor pointer is not 16-byte aligned                     */
+};
+
+/* affinity normalisation modes, nlspnmodel.py:93-104,179-197 */
+enum nlspn_affinity { NLSPN_AFF_AS = 0, NLSPN_AFF_ASS = 1, NLSPN_AFF_TC = 2, NLSPN_AFF_TGASS = 3 };
+
+/* flags */
+#define NLSPN_FLAG_PRESERVE_INPUT 1u /* args.preserve_input, nlspnmodel.py:328,341-344,355-357 (needs feat_fix) */
+#define NLSPN_FLAG_ALWAYS_CLIP    2u /* args.always_clip,    nlspnmodel.py:346-348,359-361                       */
+
+NLSPN_API int nlspn_abi_version(void);
+NLSPN_API const char *nlspn_last_error(void);
+
+/* Number of kernels this library has launched in this process so far (monotonic; used by
+ * bench.py to report gpu_launches). */
+NLSPN_API unsigned long long nlspn_launch_count(void);
+
+/* Device facts the host side sizes its shards with: SM count and L2 bytes of `device`. */
+NLSPN_API int nlspn_device_info(int device, int *sm_count, int *l2_bytes);
+
+/* ---- fused prologue ------------------------------------------------------------------
+ * Replaces _off_insert + _affinity_normalization + _aff_insert + the mask/confidence fix-up
+ * + the first input-preserving blend + the first confidence pre-multiply
+ * (nlspnmodel.py:323-325,328-334,341-351: ~20 elementwise kernels in the reference).
+ * Writes offset, aff, conf_fixed (if confidence != NULL) and src0 = x_0 * conf_fixed where
+ * x_0 = blend(feat_init) (clamped at 0 under ALWAYS_CLIP). */
+NLSPN_API int nlspn_prologue_fwd(const float *guidance, const float *confidence, const float *feat_init,
+                       const float *feat_fix, float gamma, int affinity, unsigned flags,
+                       int B, int H, int W, int K,
+                       float *offset, float *aff, float *conf_fixed, float *src0, void *stream);
+
+/* ---- T propagation iterations ---------------------------------------------------------
+ * Replaces the loop nlspnmodel.py:340-363, i.e. T x { x*c ; ModulatedDeformConvFunction
+ * (modulated_deform_conv_func.py:17-36 -> modulated_deform_conv_cuda.cu:19-121 ->
+ * modulated_deform_im2col_cuda.cuh:127-194) ; blend ; [clamp] ; append }.
+ * `src` must already hold plane 0 (from nlspn_prologue_fwd).  S as described above. */
+NLSPN_API int nlspn_propagate_fwd(const float *offset, const float *aff, const float *conf_fixed,
+                        const float *feat_fix, unsigned flags, int B, int H, int W, int K, int T,
+                        float *src, int S, float *list_feat, void *stream);
+
+/* ---- backward of prologue + loop ------------------------------------------------------
+ * Replaces T x ModulatedDeformConvFunction.backward (modulated_deform_conv_func.py:38-56 ->
+ * modulated_deform_conv_cuda.cu:124-280 -> cuh:196-328), autograd's elementwise backward of
+ * nlspnmodel.py:344-357 and the backward of the normalisation (nlspnmodel.py:179-201,252-269).
+ *   g_list        HOST array of T device pointers, entry t = DIRECT upstream gradient
+ *                 [B,1,H,W] of list_feat[t]; a NULL entry means a zero gradient (not read)
+ *   g_offset_ext  [B,2KK,H,W]  upstream gradient of the `offset` output or NULL
+ *   g_aff_ext     [B,KK,H,W]   upstream gradient of the `aff` output or NULL
+ * Outputs (overwritten): g_feat_init [B,1,H,W], g_guidance [B,3N,H,W], g_confidence [B,1,H,W]
+ * (NULL iff conf_fixed is NULL), g_gamma: one double (device memory).
+ * `src` must be the S = T array written by the forward (S = 1 without confidence).
+ * Gradient wrt feat_fix is not produced (mask_fix is detached, nlspnmodel.py:330).
+ * The scatter uses fp32 atomics: summation order, hence the last bits, vary run to run,
+ * as in the reference (deformconv/test.py:627-631). */
+NLSPN_API size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K);
+NLSPN_API int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
+                   const float *offset, const float *aff, const float *conf_fixed,
+                   const float *src, int S, const float *list_feat, const float *const *g_list,
+                   const float *g_offset_ext, const float *g_aff_ext, float gamma, int affinity,
+                   unsigned flags, int B, int H, int W, int K, int T,
+                   float *g_feat_init, float *g_guidance, float *g_confidence, double *g_gamma,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- single-step operator: the reference's existing native boundary (B1) ---------------
+ * Same argument order and meaning as DCN.modulated_deform_conv_forward / _backward
+ * (src/model/deformconv/src/modulated_deform_conv.h:10-25,46-62; pybind names in
+ * src/model/deformconv/src/vision.cpp:9-10).  Supported domain = what nlspnmodel.py:107-121,
+ * 205-208 passes: C_in = C_out = 1, group = deformable_group = 1, stride 1, dilation 1,
+ * pad = (K-1)/2, kernel_h = kernel_w = K in {3,5,7}; any weight[1,1,K,K] and bias[1].
+ * Anything else returns NLSPN_ERR_DOMAIN (never a silent wrong answer).  im2col_step is
+ * accepted and ignored (no batch-divisibility restriction).
+ *   input [B,1,H,W], offset [B,2KK,H,W] (all KK taps deformable), mask [B,KK,H,W].
+ * backward overwrites grad_input, grad_offset, grad_mask, grad_weight[KK], grad_bias[1]. */
+NLSPN_API int nlspn_dcn_forward(const float *input, const float *weight, const float *bias,
+                      const float *offset, const float *mask,
+                      int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                      int dilation_h, int dilation_w, int group, int deformable_group,
+                      int im2col_step, int B, int C, int H, int W, float *output, void *stream);
+NLSPN_API int nlspn_dcn_backward(const float *input, const float *weight, const float *bias,
+                       const float *offset, const float *mask, const float *grad_output,
+                       int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                       int dilation_h, int dilation_w, int group, int deformable_group,
+                       int im2col_step, int B, int C, int H, int W,
+                       float *grad_input, float *grad_offset, float *grad_mask,
+                       float *grad_weight, float *grad_bias, void *stream);
+
+/* ---- debug: integer corners chosen for every tap (exact-index parity test) -------------
+ * idx [B,KK,3,H,W] int32: floor(h_im), floor(w_im), valid (validity test of cuh:180),
+ * with h_im = (float)(h - pad + i) + offset_h formed exactly as cuh:178-179. */
+NLSPN_API int nlspn_debug_indices(const float *offset, int B, int H, int W, int K, int32_t *idx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLSPN_B200_H */

@@ -1,0 +1,77 @@
+"""ctypes binding of libnlspn_b200.so (C ABI: include/nlspn_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised.  Build it with ``python -m nlspn_eccv20_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+from .build import LIB_PATH
+
+_c = ctypes
+_fp = _c.c_void_p  # every tensor argument is passed as a raw device address
+
+_lock = threading.Lock()
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/nlspn_b200.h one to one
+SIGNATURES = {
+    "nlspn_abi_version": (_c.c_int, []),
+    "nlspn_last_error": (_c.c_char_p, []),
+    "nlspn_launch_count": (_c.c_ulonglong, []),
+    "nlspn_device_info": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int)]),
+    "nlspn_prologue_fwd": (_c.c_int, [_fp, _fp, _fp, _fp, _c.c_float, _c.c_int, _c.c_uint,
+                                      _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                      _fp, _fp, _fp, _fp, _fp]),
+    "nlspn_propagate_fwd": (_c.c_int, [_fp, _fp, _fp, _fp, _c.c_uint,
+                                       _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                       _fp, _c.c_int, _fp, _fp]),
+    "nlspn_backward_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "nlspn_backward": (_c.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _c.c_int, _fp,
+                                  _c.POINTER(_c.c_void_p), _fp, _fp, _c.c_float, _c.c_int, _c.c_uint,
+                                  _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                  _fp, _fp, _fp, _fp, _fp, _c.c_size_t, _fp]),
+    "nlspn_dcn_forward": (_c.c_int, [_fp] * 5 + [_c.c_int] * 15 + [_fp, _fp]),
+    "nlspn_dcn_backward": (_c.c_int, [_fp] * 6 + [_c.c_int] * 15 + [_fp] * 6),
+    "nlspn_debug_indices": (_c.c_int, [_fp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _fp, _fp]),
+}
+
+AFFINITY = {"AS": 0, "ASS": 1, "TC": 2, "TGASS": 3}
+FLAG_PRESERVE_INPUT = 1
+FLAG_ALWAYS_CLIP = 2
+
+
+def lib_path() -> str:
+    return LIB_PATH
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    "nlspn_eccv20_b200: %s is missing -- the CUDA extension is REQUIRED (there is "
+                    "no CPU/PyTorch fallback). Build it: python -m nlspn_eccv20_b200.build" % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)  # AttributeError if the header and the .so disagree
+                fn.restype = res
+                fn.argtypes = args
+            if lib.nlspn_abi_version() != 1:
+                raise RuntimeError("libnlspn_b200.so ABI version mismatch")
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().nlspn_last_error().decode("utf-8", "replace")
+        kind = "validation error" if rc < 0 else "CUDA error"
+        raise RuntimeError("%s failed: %s %d: %s" % (what, kind, rc, msg))

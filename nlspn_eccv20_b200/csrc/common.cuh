@@ -1,0 +1,72 @@
+// common.cuh -- shared device helpers for the NLSPN propagation kernels (sm_100a).
+//
+// Arithmetic contract (SURVEY 0.4 / 7 hard-part 3): the sampling coordinate is formed as
+// (float)(h - pad + i) + offset with the integer part added first and ONE floating add, the
+// fractional weights as lh = h_im - floor(h_im), hh = 1 - lh, exactly like the reference
+// (modulated_deform_im2col_cuda.cuh:28-35,157-158,178-179).  Re-associating any of this
+// breaks the 1e-4 m bound at KITTI width.  No fast-math anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nlspn {
+
+constexpr int kBlock = 256;
+
+template <int K>
+struct Geo {
+    static constexpr int KK = K * K;
+    static constexpr int N = KK - 1;
+    static constexpr int REF = N / 2;       // nlspnmodel.py:91
+    static constexpr int PAD = (K - 1) / 2; // nlspnmodel.py:117
+};
+
+// in-range test of modulated_deform_im2col_cuda.cuh:180 (NaN -> false)
+__device__ __forceinline__ bool tap_valid(float h_im, float w_im, int H, int W)
+{
+    return h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;
+}
+
+// The four corner values of a zero-padded bilinear sample read straight from global memory
+// with the per-corner guards of cuh:37-48.  Precondition: tap_valid().
+struct Quad {
+    float v1, v2, v3, v4; // (hl,wl) (hl,wl+1) (hl+1,wl) (hl+1,wl+1)
+    float lh, lw;         // fractional parts
+    int hl, wl;
+};
+
+__device__ __forceinline__ Quad load_quad(const float *__restrict__ im, int H, int W, float h_im,
+                                          float w_im)
+{
+    Quad q;
+    const float hf = floorf(h_im), wf = floorf(w_im);
+    q.hl = (int)hf;
+    q.wl = (int)wf;
+    q.lh = h_im - hf;
+    q.lw = w_im - wf;
+    const bool top = q.hl >= 0, bot = q.hl + 1 <= H - 1;
+    const bool lef = q.wl >= 0, rig = q.wl + 1 <= W - 1;
+    const float *p = im + (long)q.hl * W + q.wl;
+    q.v1 = (top && lef) ? __ldg(p) : 0.f;
+    q.v2 = (top && rig) ? __ldg(p + 1) : 0.f;
+    q.v3 = (bot && lef) ? __ldg(p + W) : 0.f;
+    q.v4 = (bot && rig) ? __ldg(p + W + 1) : 0.f;
+    return q;
+}
+
+// cuh:50-52
+__device__ __forceinline__ float quad_value(const Quad &q)
+{
+    const float hh = 1.f - q.lh, hw = 1.f - q.lw;
+    const float w1 = hh * hw, w2 = hh * q.lw, w3 = q.lh * hw, w4 = q.lh * q.lw;
+    return w1 * q.v1 + w2 * q.v2 + w3 * q.v3 + w4 * q.v4;
+}
+
+// input-preserving blend, nlspnmodel.py:344,357 -- literal, so that fixed pixels are exact
+__device__ __forceinline__ float blend_fix(float v, float dep)
+{
+    const float m = dep > 0.f ? 1.f : 0.f;
+    return (1.f - m) * v + m * dep;
+}
+
+} // namespace nlspn

@@ -1,0 +1,444 @@
+// kernels_v1.cuh -- straightforward one-thread-per-pixel kernels (sm_100a).
+//
+// These are the CORRECTNESS BASELINE kernels: the prologue, a direct-gather forward iteration,
+// the reverse-replay backward iteration and the fused final/prologue-backward kernel.  They are
+// also what the single-step DCN boundary (B1) runs.  The tiled/persistent kernels in
+// kernels_tiled.cuh replace the two iteration kernels on the NLSPN path when shapes allow.
+#pragma once
+#include "common.cuh"
+
+namespace nlspn {
+
+enum : unsigned { kPreserve = 1u, kAlwaysClip = 2u };
+enum : int { kAS = 0, kASS = 1, kTC = 2, kTGASS = 3 };
+
+// ======================================================================================
+// Prologue.  nlspnmodel.py:252-259 (_off_insert), :179-201 (_affinity_normalization),
+// :261-269 (_aff_insert), :328-334 (mask_fix / confidence), :341-351 (first blend + premul).
+// ======================================================================================
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+prologue_fwd_kernel(const float *__restrict__ guidance, const float *__restrict__ conf,
+                    const float *__restrict__ init, const float *__restrict__ dep, float gamma,
+                    int affinity, unsigned flags, int P, float *__restrict__ offset,
+                    float *__restrict__ aff, float *__restrict__ conf_out, float *__restrict__ src0)
+{
+    using G = Geo<K>;
+    const int r = blockIdx.x * kBlock + threadIdx.x;
+    if (r >= P) return;
+    const long b = blockIdx.y;
+    const float *gb = guidance + b * 3 * G::N * P + r;
+    float *ob = offset + b * 2 * G::KK * P + r;
+    float *ab = aff + b * G::KK * P + r;
+
+#pragma unroll
+    for (int t = 0; t < G::KK; ++t) {
+        if (t == G::REF) {
+            ob[(long)(2 * t) * P] = 0.f;
+            ob[(long)(2 * t + 1) * P] = 0.f;
+        } else {
+            const int n = t < G::REF ? t : t - 1;
+            ob[(long)(2 * t) * P] = __ldg(gb + (long)(2 * n) * P);
+            ob[(long)(2 * t + 1) * P] = __ldg(gb + (long)(2 * n + 1) * P);
+        }
+    }
+
+    float a[G::N];
+    float abs_sum = 0.f;
+    const bool use_tanh = affinity == kTC || affinity == kTGASS;
+    const float g = affinity == kTGASS ? gamma + 1e-8f : gamma;
+#pragma unroll
+    for (int n = 0; n < G::N; ++n) {
+        float v = __ldg(gb + (long)(2 * G::N + n) * P);
+        if (use_tanh) v = tanhf(v) / g;
+        a[n] = v;
+        abs_sum += fabsf(v);
+    }
+    abs_sum += 1e-4f;
+    if ((affinity == kASS || affinity == kTGASS) && abs_sum < 1.0f) abs_sum = 1.0f;
+    float sum = 0.f;
+#pragma unroll
+    for (int n = 0; n < G::N; ++n) {
+        if (affinity != kTC) a[n] = a[n] / abs_sum;
+        sum += a[n];
+    }
+#pragma unroll
+    for (int t = 0; t < G::KK; ++t)
+        ab[(long)t * P] = t == G::REF ? 1.0f - sum : a[t < G::REF ? t : t - 1];
+
+    const long q = b * P + r;
+    const bool preserve = (flags & kPreserve) != 0;
+    const float d = preserve ? __ldg(dep + q) : 0.f;
+    float x = __ldg(init + q);
+    if (preserve) x = blend_fix(x, d);
+    if (flags & kAlwaysClip) x = fmaxf(x, 0.f);
+    if (conf) {
+        float c = __ldg(conf + q);
+        if (preserve) {
+            const float m = d > 0.f ? 1.f : 0.f;
+            c = (1.0f - m) * c + m;
+        }
+        conf_out[q] = c;
+        x = x * c;
+    }
+    src0[q] = x;
+}
+
+// ======================================================================================
+// One propagation iteration, direct gather from global memory.
+// CENTER_ZERO = true : NLSPN path; the centre tap has a structurally zero offset
+//                      (nlspnmodel.py:256) so it is the pixel's own value -- one coalesced
+//                      load instead of four gathered ones; weight = 1, bias = 0.
+// CENTER_ZERO = false: general single step (boundary B1): all KK taps deformable, weight
+//                      and bias applied (modulated_deform_conv_cuda.cu:112).
+// Epilogue (NLSPN path): blend, clamp, append to list_feat, pre-multiply for the next gather.
+// ======================================================================================
+template <int K, bool CENTER_ZERO>
+__global__ void __launch_bounds__(kBlock)
+iter_fwd_kernel(const float *__restrict__ src_prev, const float *__restrict__ offset,
+                const float *__restrict__ aff, const float *__restrict__ conf,
+                const float *__restrict__ dep, const float *__restrict__ weight,
+                const float *__restrict__ bias, unsigned flags, int H, int W,
+                float *__restrict__ out, float *__restrict__ src_next)
+{
+    using G = Geo<K>;
+    const int P = H * W;
+    const int r = blockIdx.x * kBlock + threadIdx.x;
+    if (r >= P) return;
+    const long b = blockIdx.y;
+    const int h = r / W, w = r - h * W;
+    const float *im = src_prev + b * P;
+    const float *ob = offset + b * 2 * G::KK * P + r;
+    const float *ab = aff + b * G::KK * P + r;
+
+    float acc = (!CENTER_ZERO && bias) ? __ldg(bias) : 0.f;
+#pragma unroll
+    for (int t = 0; t < G::KK; ++t) {
+        const int i = t / K, j = t % K;
+        const float a = __ldg(ab + (long)t * P);
+        float v;
+        if (CENTER_ZERO && t == G::REF) {
+            v = __ldg(im + r);
+        } else {
+            const float oh = __ldg(ob + (long)(2 * t) * P);
+            const float ow = __ldg(ob + (long)(2 * t + 1) * P);
+            const float h_im = (float)(h - G::PAD + i) + oh;
+            const float w_im = (float)(w - G::PAD + j) + ow;
+            v = 0.f;
+            if (tap_valid(h_im, w_im, H, W)) v = quad_value(load_quad(im, H, W, h_im, w_im));
+        }
+        if (!CENTER_ZERO && weight)
+            acc += __ldg(weight + t) * (v * a);
+        else
+            acc += v * a;
+    }
+
+    const long q = b * P + r;
+    if (CENTER_ZERO) {
+        if (flags & kPreserve) acc = blend_fix(acc, __ldg(dep + q));
+        if (flags & kAlwaysClip) acc = fmaxf(acc, 0.f);
+        out[q] = acc;
+        if (src_next) src_next[q] = conf ? acc * __ldg(conf + q) : acc;
+    } else {
+        out[q] = acc;
+    }
+}
+
+// ======================================================================================
+// One backward iteration (reverse replay).  Per pixel:
+//   carried gradient  G = g_list[t] + c * S_in        (S_in = scatter result of iteration t+1)
+//   g_conf_acc       += x_t * S_in                     (d(x*c)/dc, nlspnmodel.py:351)
+//   gy = (1-m) * G                                     (d blend, nlspnmodel.py:357)
+//   per tap: grad_aff += gy * bilinear                 (cuh:314-315)
+//            grad_off += gy * aff * d bilinear/d coord (cuh:316-323, mdmcn_get_coordinate_weight)
+//            S_out[corner] += gy * aff * corner weight (cuh:229-252, mdmcn_get_gradient_weight)
+// grad_off / grad_aff accumulate over the T iterations in place (`first` stores instead of
+// adding, so no memset); S_in is zeroed after it is read so the two scatter planes ping-pong.
+// CENTER_ZERO as in the forward kernel.  For CENTER_ZERO=false (B1) g_off is laid out
+// [B,2KK,P]; for the NLSPN path it is the offset part of g_guidance, [B,3N,P] with N pairs.
+// ======================================================================================
+template <int K, bool CENTER_ZERO>
+__global__ void __launch_bounds__(kBlock)
+iter_bwd_kernel(const float *__restrict__ src_prev, const float *__restrict__ offset,
+                const float *__restrict__ aff, const float *__restrict__ conf,
+                const float *__restrict__ dep, const float *__restrict__ x_t,
+                const float *__restrict__ g_ext, const float *__restrict__ weight,
+                float *__restrict__ s_in, float *__restrict__ s_out, float *__restrict__ g_off,
+                long g_off_batch_stride, float *__restrict__ g_aff, float *__restrict__ g_conf_acc,
+                unsigned flags, int first, int H, int W)
+{
+    using G = Geo<K>;
+    const int P = H * W;
+    const int r = blockIdx.x * kBlock + threadIdx.x;
+    if (r >= P) return;
+    const long b = blockIdx.y;
+    const long q = b * P + r;
+    const int h = r / W, w = r - h * W;
+
+    float Gx = g_ext ? __ldg(g_ext + q) : 0.f;
+    if (s_in) {
+        const float gs = s_in[q];
+        s_in[q] = 0.f;
+        if (conf) {
+            Gx += __ldg(conf + q) * gs;
+            g_conf_acc[q] += __ldg(x_t + q) * gs;
+        } else {
+            Gx += gs;
+        }
+    }
+    if (CENTER_ZERO) {
+        if ((flags & kAlwaysClip) && !(__ldg(x_t + q) > 0.f)) Gx = 0.f;
+        if (flags & kPreserve) Gx = (1.0f - (__ldg(dep + q) > 0.f ? 1.f : 0.f)) * Gx;
+    }
+    const float gy = Gx;
+
+    const float *im = src_prev + b * P;
+    float *so = s_out + b * P;
+    const float *ob = offset + b * 2 * G::KK * P + r;
+    const float *ab = aff + b * G::KK * P + r;
+    float *gob = g_off + b * g_off_batch_stride + r;
+    float *gab = g_aff + b * G::KK * P + r;
+
+#pragma unroll
+    for (int t = 0; t < G::KK; ++t) {
+        const int i = t / K, j = t % K;
+        const float a = __ldg(ab + (long)t * P);
+        const float col = (!CENTER_ZERO && weight) ? __ldg(weight + t) * gy : gy;
+        if (CENTER_ZERO && t == G::REF) {
+            const float ga = col * __ldg(im + r);
+            if (first) gab[(long)t * P] = ga; else gab[(long)t * P] += ga;
+            atomicAdd(so + r, col * a);
+            continue;
+        }
+        const float oh = __ldg(ob + (long)(2 * t) * P);
+        const float ow = __ldg(ob + (long)(2 * t + 1) * P);
+        const float h_im = (float)(h - G::PAD + i) + oh;
+        const float w_im = (float)(w - G::PAD + j) + ow;
+        float ga = 0.f, gh = 0.f, gw = 0.f;
+        if (tap_valid(h_im, w_im, H, W)) {
+            const Quad qd = load_quad(im, H, W, h_im, w_im);
+            ga = col * quad_value(qd);
+            const float top = col * a;
+            // mdmcn_get_coordinate_weight, cuh:101-122 (expressions kept literal)
+            const float wl1 = (float)(qd.wl + 1) - w_im, wl0 = w_im - (float)qd.wl;
+            const float hl1 = (float)(qd.hl + 1) - h_im, hl0 = h_im - (float)qd.hl;
+            const float dh = -1.f * wl1 * qd.v1 + -1.f * wl0 * qd.v2 + wl1 * qd.v3 + wl0 * qd.v4;
+            const float dw = -1.f * hl1 * qd.v1 + hl1 * qd.v2 + -1.f * hl0 * qd.v3 + hl0 * qd.v4;
+            gh = dh * top;
+            gw = dw * top;
+            // mdmcn_get_gradient_weight, cuh:71-79: (h+1-ah), (ah+1-h) per corner
+            const float th = (float)(qd.hl + 1) - h_im;            // top rows
+            const float bh = (h_im + 1.f) - (float)(qd.hl + 1);    // bottom rows
+            const float lw_ = (float)(qd.wl + 1) - w_im;           // left cols
+            const float rw = (w_im + 1.f) - (float)(qd.wl + 1);    // right cols
+            const bool topv = qd.hl >= 0, botv = qd.hl + 1 <= H - 1;
+            const bool lefv = qd.wl >= 0, rigv = qd.wl + 1 <= W - 1;
+            float *sp = so + (long)qd.hl * W + qd.wl;
+            if (topv && lefv) atomicAdd(sp, th * lw_ * top);
+            if (topv && rigv) atomicAdd(sp + 1, th * rw * top);
+            if (botv && lefv) atomicAdd(sp + W, bh * lw_ * top);
+            if (botv && rigv) atomicAdd(sp + W + 1, bh * rw * top);
+        }
+        // pair index inside g_off: NLSPN path skips the centre pair
+        const int pr = CENTER_ZERO ? (t < G::REF ? t : t - 1) : t;
+        if (first) {
+            gob[(long)(2 * pr) * P] = gh;
+            gob[(long)(2 * pr + 1) * P] = gw;
+            gab[(long)t * P] = ga;
+        } else {
+            gob[(long)(2 * pr) * P] += gh;
+            gob[(long)(2 * pr + 1) * P] += gw;
+            gab[(long)t * P] += ga;
+        }
+    }
+}
+
+// ======================================================================================
+// Final backward kernel: consumes the last scatter plane (gradient wrt src[0]) and runs the
+// backward of the prologue (formulas: SURVEY 3.2, derived from nlspnmodel.py:185-197,262-267).
+// g_guidance's offset part already holds the accumulated offset gradients.
+// ======================================================================================
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ init,
+                 const float *__restrict__ dep, const float *__restrict__ conf,
+                 const float *__restrict__ s_in, const float *__restrict__ g_aff,
+                 const float *__restrict__ g_conf_acc, const float *__restrict__ g_off_ext,
+                 const float *__restrict__ g_aff_ext, float gamma, int affinity, unsigned flags,
+                 int P, float *__restrict__ g_init, float *__restrict__ g_guidance,
+                 float *__restrict__ g_conf, double *__restrict__ g_gamma)
+{
+    using G = Geo<K>;
+    const int r = blockIdx.x * kBlock + threadIdx.x;
+    const long b = blockIdx.y;
+    double local_gamma = 0.0;
+    if (r < P) {
+        const long q = b * P + r;
+        const bool preserve = (flags & kPreserve) != 0;
+        const float d = preserve ? __ldg(dep + q) : 0.f;
+        const float m = d > 0.f ? 1.f : 0.f;
+        const float gs = __ldg(s_in + q);
+        float x0 = __ldg(init + q);
+        if (preserve) x0 = blend_fix(x0, d);
+        const bool clipped = (flags & kAlwaysClip) && x0 < 0.f;
+        if (flags & kAlwaysClip) x0 = fmaxf(x0, 0.f);
+        float Gx;
+        if (conf) {
+            const float gc = __ldg(g_conf_acc + q) + x0 * gs;
+            g_conf[q] = preserve ? (1.0f - m) * gc : gc;
+            Gx = __ldg(conf + q) * gs;
+        } else {
+            Gx = gs;
+        }
+        if (clipped) Gx = 0.f;
+        g_init[q] = preserve ? (1.0f - m) * Gx : Gx;
+
+        const float *gb = guidance + b * 3 * G::N * P + r;
+        float *ggb = g_guidance + b * 3 * G::N * P + r;
+        if (g_off_ext) {
+            const float *eb = g_off_ext + b * 2 * G::KK * P + r;
+#pragma unroll
+            for (int n = 0; n < G::N; ++n) {
+                const int t = n < G::REF ? n : n + 1;
+                ggb[(long)(2 * n) * P] += __ldg(eb + (long)(2 * t) * P);
+                ggb[(long)(2 * n + 1) * P] += __ldg(eb + (long)(2 * t + 1) * P);
+            }
+        }
+        const float *gab = g_aff + b * G::KK * P + r;
+        const float *eab = g_aff_ext ? g_aff_ext + b * G::KK * P + r : nullptr;
+        const bool use_tanh = affinity == kTC || affinity == kTGASS;
+        const float g = affinity == kTGASS ? gamma + 1e-8f : gamma;
+        float a[G::N], th[G::N], Gh[G::N];
+        float s0 = 0.f;
+#pragma unroll
+        for (int n = 0; n < G::N; ++n) {
+            const float rr = __ldg(gb + (long)(2 * G::N + n) * P);
+            th[n] = use_tanh ? tanhf(rr) : 0.f;
+            a[n] = use_tanh ? th[n] / g : rr;
+            s0 += fabsf(a[n]);
+        }
+        s0 += 1e-4f;
+        bool clamped = false;
+        float s = s0;
+        if ((affinity == kASS || affinity == kTGASS) && s0 < 1.0f) {
+            s = 1.0f;
+            clamped = true;
+        }
+        float Gref = __ldg(gab + (long)G::REF * P);
+        if (eab) Gref += __ldg(eab + (long)G::REF * P);
+        float dot = 0.f;
+#pragma unroll
+        for (int n = 0; n < G::N; ++n) {
+            const int t = n < G::REF ? n : n + 1;
+            float gv = __ldg(gab + (long)t * P);
+            if (eab) gv += __ldg(eab + (long)t * P);
+            Gh[n] = gv - Gref;
+            dot += Gh[n] * a[n];
+        }
+#pragma unroll
+        for (int n = 0; n < G::N; ++n) {
+            float da;
+            if (affinity == kTC) {
+                da = Gh[n];
+            } else {
+                da = Gh[n] / s;
+                if (!clamped) {
+                    const float sg = a[n] > 0.f ? 1.f : (a[n] < 0.f ? -1.f : 0.f);
+                    da -= sg * dot / (s * s);
+                }
+            }
+            float dr = da;
+            if (use_tanh) {
+                dr = da * (1.f - th[n] * th[n]) / g;
+                local_gamma += -(double)da * (double)th[n] / ((double)g * (double)g);
+            }
+            ggb[(long)(2 * G::N + n) * P] = dr;
+        }
+    }
+    // block reduction of the gamma gradient, one double atomic per block
+    if (affinity == kTGASS || affinity == kTC) {
+        __shared__ double red[kBlock / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local_gamma += __shfl_xor_sync(0xffffffffu, local_gamma, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local_gamma;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int i = 0; i < kBlock / 32; ++i) tot += red[i];
+            if (tot != 0.0) atomicAdd(g_gamma, tot);
+        }
+    }
+}
+
+// grad_weight / grad_bias of the single-step operator (modulated_deform_conv_cuda.cu:248,271-272)
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+dcn_wb_grad_kernel(const float *__restrict__ input, const float *__restrict__ offset,
+                   const float *__restrict__ mask, const float *__restrict__ gout, int H, int W,
+                   float *__restrict__ gw, float *__restrict__ gbias)
+{
+    using G = Geo<K>;
+    const int P = H * W;
+    const int r = blockIdx.x * kBlock + threadIdx.x;
+    const long b = blockIdx.y;
+    float part[G::KK + 1];
+#pragma unroll
+    for (int t = 0; t <= G::KK; ++t) part[t] = 0.f;
+    if (r < P) {
+        const int h = r / W, w = r - h * W;
+        const float g = __ldg(gout + b * P + r);
+        const float *im = input + b * P;
+        const float *ob = offset + b * 2 * G::KK * P + r;
+        const float *mb = mask + b * G::KK * P + r;
+        part[G::KK] = g;
+#pragma unroll
+        for (int t = 0; t < G::KK; ++t) {
+            const float h_im = (float)(h - G::PAD + t / K) + __ldg(ob + (long)(2 * t) * P);
+            const float w_im = (float)(w - G::PAD + t % K) + __ldg(ob + (long)(2 * t + 1) * P);
+            float v = 0.f;
+            if (tap_valid(h_im, w_im, H, W)) v = quad_value(load_quad(im, H, W, h_im, w_im));
+            part[t] = g * (v * __ldg(mb + (long)t * P));
+        }
+    }
+    __shared__ float red[kBlock / 32][G::KK + 1];
+#pragma unroll
+    for (int t = 0; t <= G::KK; ++t) {
+        float v = part[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x <= G::KK) {
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < kBlock / 32; ++i) tot += red[i][threadIdx.x];
+        atomicAdd(threadIdx.x == G::KK ? gbias : gw + threadIdx.x, tot);
+    }
+}
+
+// debug: integer corners per tap
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+debug_indices_kernel(const float *__restrict__ offset, int H, int W, int32_t *__restrict__ idx)
+{
+    using G = Geo<K>;
+    const int P = H * W;
+    const int r = blockIdx.x * kBlock + threadIdx.x;
+    if (r >= P) return;
+    const long b = blockIdx.y;
+    const int h = r / W, w = r - h * W;
+    const float *ob = offset + b * 2 * G::KK * P + r;
+#pragma unroll
+    for (int t = 0; t < G::KK; ++t) {
+        const float h_im = (float)(h - G::PAD + t / K) + __ldg(ob + (long)(2 * t) * P);
+        const float w_im = (float)(w - G::PAD + t % K) + __ldg(ob + (long)(2 * t + 1) * P);
+        int32_t *o = idx + ((b * G::KK + t) * 3) * P + r;
+        o[0] = (int32_t)floorf(h_im);
+        o[P] = (int32_t)floorf(w_im);
+        o[2 * (long)P] = tap_valid(h_im, w_im, H, W) ? 1 : 0;
+    }
+}
+
+} // namespace nlspn

@@ -1,0 +1,299 @@
+// nlspn_b200.cu -- C ABI (include/nlspn_b200.h) over the sm_100a kernels.
+// Host side only validates, picks a kernel variant and enqueues launches on the caller's
+// stream.  No allocation, no synchronisation, no torch/ATen.
+#include <cstdarg>
+#include <cstdio>
+#include <atomic>
+#include <mutex>
+
+#include "../../include/nlspn_b200.h"
+#include "kernels_v1.cuh"
+
+using namespace nlspn;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e;
+}
+
+#define NLSPN_CHECK_LAUNCH(what)                              \
+    do {                                                      \
+        cudaError_t e__ = cudaGetLastError();                 \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what);  \
+        g_launches.fetch_add(1, std::memory_order_relaxed);   \
+    } while (0)
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_shape(int B, int H, int W, int K, int T)
+{
+    if (B <= 0 || H <= 0 || W <= 0 || T <= 0)
+        return fail(NLSPN_ERR_SHAPE, "B, H, W, T must be positive (got %d, %d, %d, %d)", B, H, W, T);
+    if (K != 3 && K != 5 && K != 7)
+        return fail(NLSPN_ERR_KERNEL, "prop_kernel must be 3, 5 or 7 (got %d)", K);
+    if (B > 65535) return fail(NLSPN_ERR_SHAPE, "B > 65535 is not supported (got %d)", B);
+    // per-image plane index must fit int32; whole-tensor offsets are 64-bit
+    if ((long)H * W > (1L << 30))
+        return fail(NLSPN_ERR_SHAPE, "H*W too large (%ld)", (long)H * W);
+    return 0;
+}
+
+dim3 grid_for(int P, int B) { return dim3((unsigned)((P + kBlock - 1) / kBlock), (unsigned)B, 1); }
+
+#define DISPATCH_K(K_, ...)                                   \
+    switch (K_) {                                             \
+    case 3: { constexpr int KC = 3; __VA_ARGS__; } break;     \
+    case 5: { constexpr int KC = 5; __VA_ARGS__; } break;     \
+    case 7: { constexpr int KC = 7; __VA_ARGS__; } break;     \
+    default: return fail(NLSPN_ERR_KERNEL, "prop_kernel must be 3, 5 or 7 (got %d)", K_); \
+    }
+
+} // namespace
+
+extern "C" {
+
+int nlspn_abi_version(void) { return NLSPN_ABI_VERSION; }
+
+const char *nlspn_last_error(void) { return g_err; }
+
+unsigned long long nlspn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int nlspn_device_info(int device, int *sm_count, int *l2_bytes)
+{
+    static std::mutex mu;
+    static int cached_dev = -1, cached_sm = 0, cached_l2 = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cached_dev != device) {
+        int sm = 0, l2 = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(SM count)");
+        e = cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(L2 size)");
+        cached_dev = device;
+        cached_sm = sm;
+        cached_l2 = l2;
+    }
+    if (sm_count) *sm_count = cached_sm;
+    if (l2_bytes) *l2_bytes = cached_l2;
+    return 0;
+}
+
+int nlspn_prologue_fwd(const float *guidance, const float *confidence, const float *feat_init,
+                       const float *feat_fix, float gamma, int affinity, unsigned flags,
+                       int B, int H, int W, int K,
+                       float *offset, float *aff, float *conf_fixed, float *src0, void *stream)
+{
+    if (int rc = check_shape(B, H, W, K, 1)) return rc;
+    if (!guidance || !feat_init || !offset || !aff || !src0)
+        return fail(NLSPN_ERR_NULL, "prologue_fwd: guidance, feat_init, offset, aff, src0 are required");
+    if (confidence && !conf_fixed)
+        return fail(NLSPN_ERR_NULL, "prologue_fwd: conf_fixed is required when confidence is given");
+    if ((flags & NLSPN_FLAG_PRESERVE_INPUT) && !feat_fix)
+        return fail(NLSPN_ERR_NULL, "prologue_fwd: PRESERVE_INPUT needs feat_fix");
+    if (affinity < NLSPN_AFF_AS || affinity > NLSPN_AFF_TGASS)
+        return fail(NLSPN_ERR_AFFINITY, "unknown affinity mode %d", affinity);
+    const int P = H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_K(K, (prologue_fwd_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
+                      guidance, confidence, feat_init, feat_fix, gamma, affinity, flags, P, offset,
+                      aff, conf_fixed, src0)));
+    NLSPN_CHECK_LAUNCH("prologue_fwd_kernel");
+    return 0;
+}
+
+int nlspn_propagate_fwd(const float *offset, const float *aff, const float *conf_fixed,
+                        const float *feat_fix, unsigned flags, int B, int H, int W, int K, int T,
+                        float *src, int S, float *list_feat, void *stream)
+{
+    if (int rc = check_shape(B, H, W, K, T)) return rc;
+    if (!offset || !aff || !src || !list_feat)
+        return fail(NLSPN_ERR_NULL, "propagate_fwd: offset, aff, src, list_feat are required");
+    if ((flags & NLSPN_FLAG_PRESERVE_INPUT) && !feat_fix)
+        return fail(NLSPN_ERR_NULL, "propagate_fwd: PRESERVE_INPUT needs feat_fix");
+    if (S < 1 || (conf_fixed && T > 1 && S < 2))
+        return fail(NLSPN_ERR_SHAPE, "propagate_fwd: src needs S >= 2 planes with confidence (got %d)", S);
+    const int P = H * W;
+    const long BP = (long)B * P;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int t = 1; t <= T; ++t) {
+        const float *src_prev;
+        float *src_next = nullptr;
+        if (conf_fixed) {
+            src_prev = src + (long)((t - 1) % S) * BP;
+            if (t < T) src_next = src + (long)(t % S) * BP;
+        } else {
+            src_prev = t == 1 ? src : list_feat + (long)(t - 2) * BP;
+        }
+        float *out = list_feat + (long)(t - 1) * BP;
+        DISPATCH_K(K, (iter_fwd_kernel<KC, true><<<grid_for(P, B), kBlock, 0, st>>>(
+                          src_prev, offset, aff, conf_fixed, feat_fix, nullptr, nullptr, flags, H, W,
+                          out, src_next)));
+        NLSPN_CHECK_LAUNCH("iter_fwd_kernel");
+    }
+    return 0;
+}
+
+size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K)
+{
+    if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+    const size_t BP = (size_t)B * H * W;
+    // scatter planes A, B + confidence-gradient accumulator + affinity-gradient accumulator
+    return sizeof(float) * (3 * BP + (size_t)K * K * BP);
+}
+
+int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
+                   const float *offset, const float *aff, const float *conf_fixed,
+                   const float *src, int S, const float *list_feat, const float *const *g_list,
+                   const float *g_offset_ext, const float *g_aff_ext, float gamma, int affinity,
+                   unsigned flags, int B, int H, int W, int K, int T,
+                   float *g_feat_init, float *g_guidance, float *g_confidence, double *g_gamma,
+                   void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (int rc = check_shape(B, H, W, K, T)) return rc;
+    if (!guidance || !feat_init || !offset || !aff || !src || !list_feat || !g_list ||
+        !g_feat_init || !g_guidance || !g_gamma || !workspace)
+        return fail(NLSPN_ERR_NULL, "backward: a required pointer is NULL");
+    if (conf_fixed && !g_confidence)
+        return fail(NLSPN_ERR_NULL, "backward: g_confidence is required when conf_fixed is given");
+    if ((flags & NLSPN_FLAG_PRESERVE_INPUT) && !feat_fix)
+        return fail(NLSPN_ERR_NULL, "backward: PRESERVE_INPUT needs feat_fix");
+    if (affinity < NLSPN_AFF_AS || affinity > NLSPN_AFF_TGASS)
+        return fail(NLSPN_ERR_AFFINITY, "unknown affinity mode %d", affinity);
+    if (conf_fixed && S < T)
+        return fail(NLSPN_ERR_SHAPE, "backward: src must keep all T planes (S=%d, T=%d)", S, T);
+    if (workspace_bytes < nlspn_backward_workspace_bytes(B, H, W, K) || !aligned16(workspace))
+        return fail(NLSPN_ERR_WORKSPACE, "backward: workspace too small (%zu < %zu) or misaligned",
+                    workspace_bytes, nlspn_backward_workspace_bytes(B, H, W, K));
+    const int P = H * W;
+    const long BP = (long)B * P;
+    const int N = K * K - 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *ws = static_cast<float *>(workspace);
+    float *planeA = ws, *planeB = ws + BP, *g_conf_acc = ws + 2 * BP, *g_aff_acc = ws + 3 * BP;
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 3 * BP, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+    e = cudaMemsetAsync(g_gamma, 0, sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(g_gamma)");
+
+    for (int t = T; t >= 1; --t) {
+        const float *src_prev;
+        if (conf_fixed) src_prev = src + (long)(t - 1) * BP;
+        else src_prev = t == 1 ? src : list_feat + (long)(t - 2) * BP;
+        float *s_out = ((T - t) % 2 == 0) ? planeA : planeB;
+        float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? planeB : planeA);
+        DISPATCH_K(K, (iter_bwd_kernel<KC, true><<<grid_for(P, B), kBlock, 0, st>>>(
+                          src_prev, offset, aff, conf_fixed, feat_fix, list_feat + (long)(t - 1) * BP,
+                          g_list[t - 1], nullptr, s_in, s_out, g_guidance,
+                          (long)3 * N * P, g_aff_acc, g_conf_acc, flags, t == T ? 1 : 0, H, W)));
+        NLSPN_CHECK_LAUNCH("iter_bwd_kernel");
+    }
+    const float *s_last = ((T - 1) % 2 == 0) ? planeA : planeB;
+    DISPATCH_K(K, (final_bwd_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
+                      guidance, feat_init, feat_fix, conf_fixed, s_last, g_aff_acc, g_conf_acc,
+                      g_offset_ext, g_aff_ext, gamma, affinity, flags, P, g_feat_init, g_guidance,
+                      g_confidence, g_gamma)));
+    NLSPN_CHECK_LAUNCH("final_bwd_kernel");
+    return 0;
+}
+
+static int check_dcn_domain(int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h,
+                            int pad_w, int dilation_h, int dilation_w, int group,
+                            int deformable_group, int C)
+{
+    if (C != 1 || group != 1 || deformable_group != 1)
+        return fail(NLSPN_ERR_DOMAIN, "DCN: only C=1, group=1, deformable_group=1 (got %d, %d, %d)",
+                    C, group, deformable_group);
+    if (kernel_h != kernel_w) return fail(NLSPN_ERR_DOMAIN, "DCN: square kernels only");
+    if (stride_h != 1 || stride_w != 1 || dilation_h != 1 || dilation_w != 1)
+        return fail(NLSPN_ERR_DOMAIN, "DCN: stride 1 and dilation 1 only");
+    if (pad_h != (kernel_h - 1) / 2 || pad_w != (kernel_w - 1) / 2)
+        return fail(NLSPN_ERR_DOMAIN, "DCN: padding must be (K-1)/2");
+    return 0;
+}
+
+int nlspn_dcn_forward(const float *input, const float *weight, const float *bias,
+                      const float *offset, const float *mask,
+                      int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                      int dilation_h, int dilation_w, int group, int deformable_group,
+                      int im2col_step, int B, int C, int H, int W, float *output, void *stream)
+{
+    (void)im2col_step;
+    if (int rc = check_dcn_domain(kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h,
+                                  dilation_w, group, deformable_group, C))
+        return rc;
+    if (int rc = check_shape(B, H, W, kernel_h, 1)) return rc;
+    if (!input || !weight || !bias || !offset || !mask || !output)
+        return fail(NLSPN_ERR_NULL, "dcn_forward: a required pointer is NULL");
+    const int P = H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_K(kernel_h, (iter_fwd_kernel<KC, false><<<grid_for(P, B), kBlock, 0, st>>>(
+                             input, offset, mask, nullptr, nullptr, weight, bias, 0u, H, W, output,
+                             nullptr)));
+    NLSPN_CHECK_LAUNCH("iter_fwd_kernel<dcn>");
+    return 0;
+}
+
+int nlspn_dcn_backward(const float *input, const float *weight, const float *bias,
+                       const float *offset, const float *mask, const float *grad_output,
+                       int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                       int dilation_h, int dilation_w, int group, int deformable_group,
+                       int im2col_step, int B, int C, int H, int W,
+                       float *grad_input, float *grad_offset, float *grad_mask,
+                       float *grad_weight, float *grad_bias, void *stream)
+{
+    (void)im2col_step;
+    (void)bias;
+    if (int rc = check_dcn_domain(kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h,
+                                  dilation_w, group, deformable_group, C))
+        return rc;
+    if (int rc = check_shape(B, H, W, kernel_h, 1)) return rc;
+    if (!input || !weight || !offset || !mask || !grad_output || !grad_input || !grad_offset ||
+        !grad_mask || !grad_weight || !grad_bias)
+        return fail(NLSPN_ERR_NULL, "dcn_backward: a required pointer is NULL");
+    const int P = H * W;
+    const long BP = (long)B * P;
+    const int KK = kernel_h * kernel_h;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(float) * BP, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_input)");
+    e = cudaMemsetAsync(grad_weight, 0, sizeof(float) * KK, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_weight)");
+    e = cudaMemsetAsync(grad_bias, 0, sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_bias)");
+    DISPATCH_K(kernel_h, (iter_bwd_kernel<KC, false><<<grid_for(P, B), kBlock, 0, st>>>(
+                             input, offset, mask, nullptr, nullptr, nullptr, grad_output, weight,
+                             nullptr, grad_input, grad_offset, (long)2 * KK * P, grad_mask, nullptr,
+                             0u, 1, H, W)));
+    NLSPN_CHECK_LAUNCH("iter_bwd_kernel<dcn>");
+    DISPATCH_K(kernel_h, (dcn_wb_grad_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
+                             input, offset, mask, grad_output, H, W, grad_weight, grad_bias)));
+    NLSPN_CHECK_LAUNCH("dcn_wb_grad_kernel");
+    return 0;
+}
+
+int nlspn_debug_indices(const float *offset, int B, int H, int W, int K, int32_t *idx, void *stream)
+{
+    if (int rc = check_shape(B, H, W, K, 1)) return rc;
+    if (!offset || !idx) return fail(NLSPN_ERR_NULL, "debug_indices: NULL pointer");
+    DISPATCH_K(K, (debug_indices_kernel<KC><<<grid_for(H * W, B), kBlock, 0, (cudaStream_t)stream>>>(
+                      offset, H, W, idx)));
+    NLSPN_CHECK_LAUNCH("debug_indices_kernel");
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,189 @@
+"""Thin torch-facing wrappers over the C ABI: tensors in, tensors out, current stream.
+
+torch is plumbing here (device memory, streams); all arithmetic happens in libnlspn_b200.so.
+Every wrapper raises if a tensor is not a contiguous fp32 CUDA tensor -- there is no
+CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+__all__ = ["prologue_fwd", "propagate_fwd", "backward", "dcn_forward", "dcn_backward",
+           "debug_indices", "device_info"]
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(name, t, shape=None, optional=False):
+    if t is None:
+        if optional:
+            return None
+        raise RuntimeError("%s is required" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (nlspn_eccv20_b200 has no CPU path)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32 (got %s)" % (name, t.dtype))
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise RuntimeError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    return t.contiguous()
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _flags(preserve_input, always_clip):
+    return (_lib.FLAG_PRESERVE_INPUT if preserve_input else 0) | \
+           (_lib.FLAG_ALWAYS_CLIP if always_clip else 0)
+
+
+def device_info(device=None):
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    sm, l2 = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(_lib.load().nlspn_device_info(dev.index or 0, ctypes.byref(sm), ctypes.byref(l2)),
+               "nlspn_device_info")
+    return dict(sm_count=sm.value, l2_bytes=l2.value)
+
+
+def prologue_fwd(guidance, confidence, feat_init, feat_fix, gamma, K, affinity="TGASS",
+                 preserve_input=True, always_clip=False):
+    """-> (offset [B,2KK,H,W], aff [B,KK,H,W], conf_fixed [B,1,H,W] | None, src0 [B,1,H,W])."""
+    lib = _lib.load()
+    B, _, H, W = feat_init.shape
+    N = K * K - 1
+    feat_init = _chk("feat_init", feat_init, (B, 1, H, W))
+    guidance = _chk("guidance", guidance, (B, 3 * N, H, W))
+    confidence = _chk("confidence", confidence, (B, 1, H, W), optional=True)
+    feat_fix = _chk("feat_fix", feat_fix, (B, 1, H, W), optional=True)
+    preserve = bool(preserve_input and feat_fix is not None)
+    dev = feat_init.device
+    opt = dict(device=dev, dtype=torch.float32)
+    offset = torch.empty((B, 2 * K * K, H, W), **opt)
+    aff = torch.empty((B, K * K, H, W), **opt)
+    conf_fixed = torch.empty((B, 1, H, W), **opt) if confidence is not None else None
+    src0 = torch.empty((B, 1, H, W), **opt)
+    with torch.cuda.device(dev):
+        rc = lib.nlspn_prologue_fwd(_ptr(guidance), _ptr(confidence), _ptr(feat_init), _ptr(feat_fix),
+                                    float(gamma), _lib.AFFINITY[affinity], _flags(preserve, always_clip),
+                                    B, H, W, K, _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(src0),
+                                    _stream(dev))
+    _lib.check(rc, "nlspn_prologue_fwd")
+    return offset, aff, conf_fixed, src0
+
+
+def propagate_fwd(offset, aff, conf_fixed, feat_fix, src, list_feat, K, T,
+                  preserve_input=True, always_clip=False):
+    """Runs T iterations in place: src [S,B,1,H,W] (plane 0 filled), list_feat [T,B,1,H,W]."""
+    lib = _lib.load()
+    S, B, _, H, W = src.shape
+    offset = _chk("offset", offset, (B, 2 * K * K, H, W))
+    aff = _chk("aff", aff, (B, K * K, H, W))
+    conf_fixed = _chk("conf_fixed", conf_fixed, (B, 1, H, W), optional=True)
+    feat_fix = _chk("feat_fix", feat_fix, (B, 1, H, W), optional=True)
+    _chk("list_feat", list_feat, (T, B, 1, H, W))
+    if not (src.is_contiguous() and list_feat.is_contiguous()):
+        raise RuntimeError("src and list_feat must be contiguous (they are written in place)")
+    preserve = bool(preserve_input and feat_fix is not None)
+    dev = src.device
+    with torch.cuda.device(dev):
+        rc = lib.nlspn_propagate_fwd(_ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(feat_fix),
+                                     _flags(preserve, always_clip), B, H, W, K, T, _ptr(src), S,
+                                     _ptr(list_feat), _stream(dev))
+    _lib.check(rc, "nlspn_propagate_fwd")
+    return list_feat
+
+
+def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_feat, g_list,
+             gamma, K, T, affinity="TGASS", preserve_input=True, always_clip=False,
+             g_offset_ext=None, g_aff_ext=None):
+    """g_list: sequence of T tensors [B,1,H,W] or None.  -> (g_init, g_guidance, g_conf, g_gamma)."""
+    lib = _lib.load()
+    B, _, H, W = feat_init.shape
+    N = K * K - 1
+    S = src.shape[0]
+    dev = feat_init.device
+    opt = dict(device=dev, dtype=torch.float32)
+    feat_fix = _chk("feat_fix", feat_fix, (B, 1, H, W), optional=True)
+    preserve = bool(preserve_input and feat_fix is not None)
+    keep = [_chk("g_list[%d]" % i, g, (B, 1, H, W), optional=True) for i, g in enumerate(g_list)]
+    if len(keep) != T:
+        raise RuntimeError("g_list must have T entries")
+    ptrs = (ctypes.c_void_p * T)(*[(g.data_ptr() if g is not None else None) for g in keep])
+    g_offset_ext = _chk("g_offset_ext", g_offset_ext, (B, 2 * K * K, H, W), optional=True)
+    g_aff_ext = _chk("g_aff_ext", g_aff_ext, (B, K * K, H, W), optional=True)
+    g_init = torch.empty((B, 1, H, W), **opt)
+    g_guid = torch.empty((B, 3 * N, H, W), **opt)
+    g_conf = torch.empty((B, 1, H, W), **opt) if conf_fixed is not None else None
+    g_gamma = torch.empty((1,), device=dev, dtype=torch.float64)
+    nbytes = lib.nlspn_backward_workspace_bytes(B, H, W, K)
+    ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        rc = lib.nlspn_backward(_ptr(guidance.contiguous()), _ptr(feat_init.contiguous()), _ptr(feat_fix),
+                                _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(src), S, _ptr(list_feat),
+                                ptrs, _ptr(g_offset_ext), _ptr(g_aff_ext), float(gamma),
+                                _lib.AFFINITY[affinity], _flags(preserve, always_clip), B, H, W, K, T,
+                                _ptr(g_init), _ptr(g_guid), _ptr(g_conf), _ptr(g_gamma), _ptr(ws),
+                                nbytes, _stream(dev))
+    _lib.check(rc, "nlspn_backward")
+    return g_init, g_guid, g_conf, g_gamma
+
+
+_DCN_INTS = ("kernel_h", "kernel_w", "stride_h", "stride_w", "pad_h", "pad_w", "dilation_h",
+             "dilation_w", "group", "deformable_group", "im2col_step")
+
+
+def dcn_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride_h, stride_w,
+                pad_h, pad_w, dilation_h, dilation_w, group, deformable_group, im2col_step):
+    lib = _lib.load()
+    input = _chk("input", input)
+    B, C, H, W = input.shape
+    weight, bias, offset, mask = _chk("weight", weight), _chk("bias", bias), _chk("offset", offset), _chk("mask", mask)
+    KK = kernel_h * kernel_w
+    if tuple(offset.shape) != (B, 2 * KK, H, W) or tuple(mask.shape) != (B, KK, H, W):
+        raise RuntimeError("offset/mask shape does not match input and kernel size")
+    out = torch.empty_like(input)
+    dev = input.device
+    with torch.cuda.device(dev):
+        rc = lib.nlspn_dcn_forward(_ptr(input), _ptr(weight), _ptr(bias), _ptr(offset), _ptr(mask),
+                                   kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h,
+                                   dilation_w, group, deformable_group, im2col_step, B, C, H, W,
+                                   _ptr(out), _stream(dev))
+    _lib.check(rc, "nlspn_dcn_forward")
+    return out
+
+
+def dcn_backward(input, weight, bias, offset, mask, grad_output, kernel_h, kernel_w, stride_h,
+                 stride_w, pad_h, pad_w, dilation_h, dilation_w, group, deformable_group, im2col_step):
+    lib = _lib.load()
+    input = _chk("input", input)
+    B, C, H, W = input.shape
+    weight, bias, offset, mask = _chk("weight", weight), _chk("bias", bias), _chk("offset", offset), _chk("mask", mask)
+    grad_output = _chk("grad_output", grad_output, (B, C, H, W))
+    gi, go, gm = torch.empty_like(input), torch.empty_like(offset), torch.empty_like(mask)
+    gw, gb = torch.empty_like(weight), torch.empty_like(bias)
+    dev = input.device
+    with torch.cuda.device(dev):
+        rc = lib.nlspn_dcn_backward(_ptr(input), _ptr(weight), _ptr(bias), _ptr(offset), _ptr(mask),
+                                    _ptr(grad_output), kernel_h, kernel_w, stride_h, stride_w, pad_h,
+                                    pad_w, dilation_h, dilation_w, group, deformable_group, im2col_step,
+                                    B, C, H, W, _ptr(gi), _ptr(go), _ptr(gm), _ptr(gw), _ptr(gb),
+                                    _stream(dev))
+    _lib.check(rc, "nlspn_dcn_backward")
+    return gi, go, gm, gw, gb
+
+
+def debug_indices(offset, K):
+    lib = _lib.load()
+    offset = _chk("offset", offset)
+    B, _, H, W = offset.shape
+    idx = torch.empty((B, K * K, 3, H, W), device=offset.device, dtype=torch.int32)
+    with torch.cuda.device(offset.device):
+        rc = lib.nlspn_debug_indices(_ptr(offset), B, H, W, K, _ptr(idx), _stream(offset.device))
+    _lib.check(rc, "nlspn_debug_indices")
+    return idx

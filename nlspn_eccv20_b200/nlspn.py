@@ -1,0 +1,154 @@
+"""NLSPN -- drop-in module for the reference's propagation (nlspnmodel.py:323-377).
+
+``NLSPN.forward(feat_init, guidance, confidence, feat_fix, rgb)`` returns
+``(feat_result, list_feat, offset, aff, aff_const)`` (the north-star signature; in the
+reference fork the same five values are the output-dict entries 'pred' (pre-clamp),
+'pred_inter', 'offset', 'aff', 'gamma', nlspnmodel.py:379-381).  The body runs entirely in
+libnlspn_b200.so through one ``torch.autograd.Function``.
+
+Fork semantics (the parity target): the state is pre-multiplied by the confidence
+before EVERY gather (nlspnmodel.py:350-351), confidence is forced to 1 on fixed pixels (:334),
+and the input-preserving blend runs once before iteration 1 and after every iteration
+(:341-344,355-357).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import functional as F_
+
+__all__ = ["NLSPN", "NLSPNFunction", "nlspn_propagate"]
+
+
+class NLSPNFunction(torch.autograd.Function):
+    """(feat_init, guidance, confidence|None, feat_fix|None, gamma) ->
+    (list_feat[0..T-1], offset, aff, conf_fixed|None).  Backward: one fused reverse replay."""
+
+    @staticmethod
+    def forward(ctx, feat_init, guidance, confidence, feat_fix, gamma, K, T, affinity,
+                preserve_input, always_clip):
+        need_grad = any(t is not None and t.requires_grad for t in (feat_init, guidance, confidence, gamma))
+        gamma_val = float(gamma.detach().reshape(-1)[0]) if torch.is_tensor(gamma) else float(gamma)
+        feat_init_c = feat_init.detach().contiguous()
+        guidance_c = guidance.detach().contiguous()
+        conf_c = confidence.detach().contiguous() if confidence is not None else None
+        fix_c = feat_fix.detach().contiguous() if feat_fix is not None else None
+        preserve = bool(preserve_input and fix_c is not None)
+        offset, aff, conf_fixed, src0 = F_.prologue_fwd(guidance_c, conf_c, feat_init_c, fix_c, gamma_val,
+                                                        K, affinity, preserve, always_clip)
+        B, _, H, W = feat_init_c.shape
+        # src planes: all T kept when a backward may follow and confidence is used; else ping-pong
+        if conf_fixed is None:
+            S = 1
+        else:
+            S = T if need_grad else min(T, 2)
+        if S == 1:
+            src = src0.unsqueeze(0)
+        else:
+            src = torch.empty((S, B, 1, H, W), device=src0.device, dtype=torch.float32)
+            src[0].copy_(src0)
+        list_feat = torch.empty((T, B, 1, H, W), device=src0.device, dtype=torch.float32)
+        F_.propagate_fwd(offset, aff, conf_fixed, fix_c, src, list_feat, K, T, preserve, always_clip)
+        ctx.cfg = (K, T, affinity, preserve, always_clip, gamma_val)
+        ctx.has_conf = conf_fixed is not None
+        ctx.gamma_is_tensor = torch.is_tensor(gamma)
+        ctx.save_for_backward(feat_init_c, guidance_c, fix_c, offset, aff, conf_fixed, src, list_feat)
+        ctx.set_materialize_grads(False)
+        outs = tuple(list_feat[t] for t in range(T)) + (offset, aff)
+        if conf_fixed is not None:
+            outs = outs + (conf_fixed,)
+        return outs
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *grads):
+        K, T, affinity, preserve, always_clip, gamma_val = ctx.cfg
+        feat_init, guidance, feat_fix, offset, aff, conf_fixed, src, list_feat = ctx.saved_tensors
+        g_list = list(grads[:T])
+        g_off_ext, g_aff_ext = grads[T], grads[T + 1]
+        g_cf_ext = grads[T + 2] if ctx.has_conf else None
+        g_init, g_guid, g_conf, g_gamma = F_.backward(
+            guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_feat, g_list, gamma_val,
+            K, T, affinity, preserve, always_clip, g_off_ext, g_aff_ext)
+        if g_cf_ext is not None:
+            # conf_fixed = (1-m)*confidence + m, nlspnmodel.py:334
+            m = (feat_fix > 0).to(g_cf_ext.dtype) if preserve else 0.0
+            g_conf = g_conf + (1.0 - m) * g_cf_ext
+        g_gam = g_gamma.to(torch.float32) if ctx.gamma_is_tensor else None
+        return g_init, g_guid, (g_conf if ctx.has_conf else None), None, g_gam, \
+            None, None, None, None, None
+
+
+def nlspn_propagate(feat_init, guidance, confidence, feat_fix, gamma, prop_kernel=3, prop_time=18,
+                    affinity="TGASS", preserve_input=True, always_clip=False):
+    """Functional form.  -> (feat_result, list_feat, offset, aff, conf_fixed|None)."""
+    outs = NLSPNFunction.apply(feat_init, guidance, confidence, feat_fix, gamma, prop_kernel,
+                               prop_time, affinity, preserve_input, always_clip)
+    T = prop_time
+    list_feat = list(outs[:T])
+    conf_fixed = outs[T + 2] if len(outs) > T + 2 else None
+    return list_feat[-1], list_feat, outs[T], outs[T + 1], conf_fixed
+
+
+class NLSPN(nn.Module):
+    """Owns the same parameters, with the same names and shapes, as the reference model's
+    propagation state (nlspnmodel.py:93-121): ``aff_scale_const``, ``w``, ``b``, ``w_conf``.
+
+    ``args`` may be the reference's argparse Namespace (attributes prop_kernel, prop_time,
+    affinity, affinity_gamma, conf_prop, preserve_input, always_clip) or None with kwargs."""
+
+    def __init__(self, args=None, **kw):
+        super().__init__()
+
+        def opt(name, default):
+            if name in kw:
+                return kw[name]
+            return getattr(args, name, default) if args is not None else default
+
+        self.prop_kernel = int(opt("prop_kernel", 3))
+        self.prop_time = int(opt("prop_time", 18))
+        self.affinity = str(opt("affinity", "TGASS"))
+        self.affinity_gamma = float(opt("affinity_gamma", 0.5))
+        self.conf_prop = bool(opt("conf_prop", True))
+        self.preserve_input = bool(opt("preserve_input", True))
+        self.always_clip = bool(opt("always_clip", False))
+        assert (self.prop_kernel % 2) == 1, \
+            'only odd kernel is supported but k_f = {}'.format(self.prop_kernel)   # nlspnmodel.py:29-30
+        if self.prop_kernel not in (3, 5, 7):
+            raise NotImplementedError("prop_kernel must be 3, 5 or 7")
+        self.num_neighbors = self.prop_kernel * self.prop_kernel - 1              # :32
+        self.idx_ref = self.num_neighbors // 2                                    # :91
+        self.ch_f = 1
+        if self.affinity == 'TC':                                                 # :93-104
+            self.aff_scale_const = nn.Parameter(self.num_neighbors * torch.ones(1))
+            self.aff_scale_const.requires_grad = False
+        elif self.affinity == 'TGASS':
+            self.aff_scale_const = nn.Parameter(self.affinity_gamma * self.num_neighbors * torch.ones(1))
+        elif self.affinity in ('AS', 'ASS'):
+            self.aff_scale_const = nn.Parameter(torch.ones(1))
+            self.aff_scale_const.requires_grad = False
+        else:
+            raise NotImplementedError
+        # dummy gathering parameters kept for state-dict compatibility (:107-114)
+        self.w = nn.Parameter(torch.ones((self.ch_f, 1, self.prop_kernel, self.prop_kernel)))
+        self.b = nn.Parameter(torch.zeros(self.ch_f))
+        self.w.requires_grad = False
+        self.b.requires_grad = False
+        self.w_conf = nn.Parameter(torch.ones((1, 1, 1, 1)))
+        self.w_conf.requires_grad = False
+
+    def forward(self, feat_init, guidance, confidence=None, feat_fix=None, rgb=None):
+        assert self.ch_f == feat_init.shape[1]                                    # :318
+        if self.conf_prop:
+            assert confidence is not None                                         # :320-321
+        else:
+            confidence = None
+        if self.preserve_input:
+            assert feat_fix is not None and feat_init.shape == feat_fix.shape      # :329
+        else:
+            feat_fix = None
+        feat_result, list_feat, offset, aff, _ = nlspn_propagate(
+            feat_init, guidance, confidence, feat_fix, self.aff_scale_const, self.prop_kernel,
+            self.prop_time, self.affinity, self.preserve_input, self.always_clip)
+        return feat_result, list_feat, offset, aff, self.aff_scale_const.data

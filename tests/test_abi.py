@@ -1,0 +1,107 @@
+"""CPU: the C-ABI library loads, exports every symbol include/nlspn_b200.h declares, and
+rejects bad arguments with negative status codes BEFORE touching CUDA (no compute here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "nlspn_b200.h")).read()
+    return sorted(set(re.findall(r"NLSPN_API[^;(]*?\b(nlspn_[a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from nlspn_eccv20_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for s in ["nlspn_abi_version", "nlspn_last_error", "nlspn_prologue_fwd", "nlspn_propagate_fwd",
+              "nlspn_backward", "nlspn_backward_workspace_bytes", "nlspn_dcn_forward",
+              "nlspn_dcn_backward", "nlspn_debug_indices", "nlspn_device_info"]:
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from nlspn_eccv20_b200 import _lib
+    raw = ctypes.CDLL(_lib.lib_path())
+    for s in declared_symbols():
+        assert hasattr(raw, s), "libnlspn_b200.so does not export %s" % s
+        assert s in _lib.SIGNATURES, "python binding misses %s" % s
+    assert lib.nlspn_abi_version() == 1
+
+
+def test_library_has_sm100a_code_and_no_torch_dependency():
+    import subprocess
+    from nlspn_eccv20_b200 import _lib
+    out = subprocess.run(["ldd", _lib.lib_path()], capture_output=True, text=True).stdout
+    assert "torch" not in out and "c10" not in out
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if os.path.exists(cuobjdump):
+        o = subprocess.run([cuobjdump, "-lelf", _lib.lib_path()], capture_output=True, text=True).stdout
+        assert "sm_100a" in o
+
+
+def test_validation_errors_are_negative_and_described(lib):
+    P = ctypes.c_void_p
+    one = P(16)  # never dereferenced: validation fails first
+    # bad kernel size
+    rc = lib.nlspn_prologue_fwd(one, None, one, None, 4.0, 3, 0, 1, 4, 4, 4, one, one, None, one, None)
+    assert rc == -3 and b"prop_kernel" in lib.nlspn_last_error()
+    # missing required pointer
+    rc = lib.nlspn_prologue_fwd(None, None, one, None, 4.0, 3, 0, 1, 4, 4, 3, one, one, None, one, None)
+    assert rc == -1
+    # PRESERVE_INPUT without feat_fix
+    rc = lib.nlspn_prologue_fwd(one, None, one, None, 4.0, 3, 1, 1, 4, 4, 3, one, one, None, one, None)
+    assert rc == -1 and b"feat_fix" in lib.nlspn_last_error()
+    # bad affinity / bad shape
+    assert lib.nlspn_prologue_fwd(one, None, one, None, 4.0, 9, 0, 1, 4, 4, 3, one, one, None, one, None) == -6
+    assert lib.nlspn_prologue_fwd(one, None, one, None, 4.0, 3, 0, 0, 4, 4, 3, one, one, None, one, None) == -2
+    # confidence needs >= 2 src planes
+    assert lib.nlspn_propagate_fwd(one, one, one, None, 0, 1, 4, 4, 3, 5, one, 1, one, None) == -2
+    # DCN outside the NLSPN domain: C=2, stride 2, wrong padding
+    ints_ok = [3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 64]
+    def dcn(ints, C=1):
+        return lib.nlspn_dcn_forward(one, one, one, one, one, *ints, 1, C, 4, 4, one, None)
+    assert dcn(ints_ok, C=2) == -4
+    assert dcn([3, 3, 2, 2, 1, 1, 1, 1, 1, 1, 64]) == -4
+    assert dcn([3, 3, 1, 1, 0, 0, 1, 1, 1, 1, 64]) == -4
+    assert dcn([3, 3, 1, 1, 1, 1, 1, 1, 2, 1, 64]) == -4
+    assert lib.nlspn_backward_workspace_bytes(2, 8, 8, 3) == 4 * (3 + 9) * 2 * 64
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no file of the product package may reference it."""
+    pkg = os.path.join(ROOT, "nlspn_eccv20_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from nlspn_eccv20_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="REQUIRED"):
+        _lib.load()
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+    from nlspn_eccv20_b200 import NLSPN
+    m = NLSPN(prop_kernel=3, prop_time=2)
+    x = torch.zeros(1, 1, 4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(x, torch.zeros(1, 24, 4, 4), x, x)
+    assert list(m.state_dict().keys()) == ["aff_scale_const", "w", "b", "w_conf"]
+    assert float(m.aff_scale_const) == 4.0 and m.aff_scale_const.requires_grad
+    assert not m.w.requires_grad and tuple(m.w.shape) == (1, 1, 3, 3)
