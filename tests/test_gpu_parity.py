@@ -55,13 +55,13 @@ def _rel(a, b):
 def test_forward_matches_reference_golden(dev, name):
     g = load_golden(name)
     mod, _, (feat_result, list_feat, offset, aff, gamma), m = _run_module(g, dev)
-    assert torch.equal(offset.cpu(), torch.from_numpy(g["out_offset"]))          # offsets exact
-    np.testing.assert_allclose(aff.cpu().numpy(), g["out_aff"], rtol=0, atol=2e-6)
-    lf = torch.stack(list_feat, 0).cpu().numpy()
+    assert torch.equal(offset.detach().cpu(), torch.from_numpy(g["out_offset"]))          # offsets exact
+    np.testing.assert_allclose(aff.detach().cpu().numpy(), g["out_aff"], rtol=0, atol=2e-6)
+    lf = torch.stack(list_feat, 0).detach().cpu().numpy()
     scale = max(1.0, float(np.abs(g["out_list_feat"]).max()))
     tol = 1e-4 if "signed" not in name and "clip" not in name else 1e-5 * scale
     assert np.abs(lf - g["out_list_feat"]).max() <= tol
-    assert np.abs(feat_result.cpu().numpy() - g["out_feat_result"]).max() <= tol
+    assert np.abs(feat_result.detach().cpu().numpy() - g["out_feat_result"]).max() <= tol
     assert abs(float(gamma) - m["gamma"]) < 1e-6
     if m["preserve"]:
         fix = g["in_feat_fix"] > 0
@@ -70,7 +70,7 @@ def test_forward_matches_reference_golden(dev, name):
     # RMSE / MAE identical to 1e-5 (src/metric/nlspnmetric.py:53-60)
     from nlspn_eccv20_b200.synth import rmse_mae
     gt = torch.from_numpy(g["in_gt"])
-    a = rmse_mae(torch.clamp(feat_result.cpu(), min=0), gt)
+    a = rmse_mae(torch.clamp(feat_result.detach().cpu(), min=0), gt)
     b = rmse_mae(torch.from_numpy(g["out_pred"]), gt)
     assert abs(a[0] - b[0]) <= 1e-5 and abs(a[1] - b[1]) <= 1e-5
 
@@ -175,7 +175,7 @@ def test_against_oracle_seeded(dev, oracle, K, T, B, H, W, use_conf):
     feat_result, list_feat, offset, aff, _ = mod(fi, gd, cf, inp["feat_fix"].to(dev))
     lf = torch.stack(list_feat, 0).detach().cpu().numpy()
     assert np.abs(lf - ref["list_feat"]).max() <= 1e-4
-    assert np.array_equal(offset.cpu().numpy(), ref["offset"])
+    assert np.array_equal(offset.detach().cpu().numpy(), ref["offset"])
     np.testing.assert_allclose(aff.detach().cpu().numpy(), ref["aff"], rtol=0, atol=1e-6)
     # backward with a gradient on the final state and on one intermediate state
     gen = torch.Generator().manual_seed(5)
