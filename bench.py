@@ -281,11 +281,39 @@ def main():
     e2e_val = pix_iter_step * args.steps / (e2e_ms * 1e-3) / 1e9
     peaks, peak_kind = measured_peaks()
     N = K * K - 1
-    if train:
-        kern, kb, kms = "iter_bwd_kernel", (36 * N + 36), bwd_ms / T
-    else:
-        kern, kb, kms = "iter_fwd_kernel", (12 * N + 20), fwd_ms / T
-    achieved = kb * B * H * W / (kms * 1e-3) / 1e9
+
+    # ---- per-kernel split of the phases: a separate pass with the library's event hooks on
+    # (events around every launch perturb throughput, so this pass is NOT the one `value` is from;
+    # the kernel's average launch duration = phase time measured in the timed region x its share).
+    lib.nlspn_profile_enable(1)
+    for _ in range(max(1, min(args.steps, 3))):
+        step(dev_in)
+    torch.cuda.synchronize()
+    prof = _lib.profile_read()
+    lib.nlspn_profile_enable(0)
+    # algorithmic bytes per LAUNCH and pixel (fp32, DESIGN.md "kernels"): what the kernel must move
+    alg = {"prologue_fwd_kernel": 24 * N + 28,
+           "iter_fwd_kernel": 12 * N + 20,
+           "bwd_state_kernel": 12 * N + 40,
+           "bwd_param_kernel": 8 * T + 24 * N + 8,
+           "final_bwd_kernel": 8 * N + 4 * (N + 1) + 16 + 24,
+           "iter_bwd_kernel": 36 * N + 36}
+    fwd_names = ("prologue_fwd_kernel", "iter_fwd_kernel")
+    phase_prof = {"forward": sum(prof[k][0] for k in prof if k in fwd_names),
+                  "backward": sum(prof[k][0] for k in prof if k not in fwd_names)}
+    kernels = {}
+    for name, (ms, cnt) in prof.items():
+        ph = "forward" if name in fwd_names else "backward"
+        share = ms / phase_prof[ph] if phase_prof[ph] > 0 else 0.0
+        phase_ms = fwd_ms if ph == "forward" else bwd_ms
+        per_step = cnt / max(1, min(args.steps, 3))
+        launch_ms = phase_ms * share / per_step
+        gbs = alg.get(name, 0) * B * H * W / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+        kernels[name] = {"launches_per_step": per_step, "share_of_phase": share, "launch_ms": launch_ms,
+                         "alg_bytes_per_launch": alg.get(name, 0) * B * H * W, "achieved_gbs": gbs,
+                         "frac": gbs / peaks["hbm_gbs"], "step_ms": phase_ms * share}
+    kern = max(kernels, key=lambda k: kernels[k]["step_ms"])
+    kb, kms, achieved = kernels[kern]["alg_bytes_per_launch"], kernels[kern]["launch_ms"], kernels[kern]["achieved_gbs"]
     step_gbs = alg_bytes(K, T, args.mode) * (pix_iter_step / world) * args.steps / (total_ms * 1e-3) / 1e9
     line = {"metric": METRIC if train else "nlspn_propagation_fwd_gpix_iter_per_s", "value": value,
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -299,10 +327,12 @@ def main():
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                         "alg_bytes_per_launch": kb * B * H * W,
+                         "alg_bytes_per_launch": kb,
                          "launch_ms": kms,
-                         "note": "launch duration = CUDA-event time of the phase / T (includes the "
-                                 "fused final kernel and memsets: conservative)"},
+                         "note": "dominant kernel by time per step; launch duration = CUDA-event time of its "
+                                 "phase in the timed region x the kernel's share of that phase (event-bracketed "
+                                 "profile pass), / launches per step"},
+            "kernels": kernels,
             "roofline_step": {"alg_bytes_per_pix_iter": alg_bytes(K, T, args.mode), "achieved": step_gbs,
                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": step_gbs / peaks["hbm_gbs"]}}
 

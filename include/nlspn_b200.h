@@ -65,6 +65,10 @@ enum nlspn_affinity { NLSPN_AFF_AS = 0, NLSPN_AFF_ASS = 1, NLSPN_AFF_TC = 2, NLS
 /* flags */
 #define NLSPN_FLAG_PRESERVE_INPUT 1u /* args.preserve_input, nlspnmodel.py:328,341-344,355-357 (needs feat_fix) */
 #define NLSPN_FLAG_ALWAYS_CLIP    2u /* args.always_clip,    nlspnmodel.py:346-348,359-361                       */
+/* debugging aid: run the backward as T per-iteration kernels that re-read/re-write the
+ * gradient accumulators and scatter with scalar atomics (the reference's structure); results
+ * agree with the default two-pass backward up to fp32 summation order. */
+#define NLSPN_FLAG_BWD_PER_ITERATION 0x100u
 
 NLSPN_API int nlspn_abi_version(void);
 NLSPN_API const char *nlspn_last_error(void);
@@ -72,6 +76,17 @@ NLSPN_API const char *nlspn_last_error(void);
 /* Number of kernels this library has launched in this process so far (monotonic; used by
  * bench.py to report gpu_launches). */
 NLSPN_API unsigned long long nlspn_launch_count(void);
+
+/* Optional per-kernel timing for bench.py's roofline.  While enabled, every kernel launch of
+ * this library is bracketed by CUDA events on the caller's stream (this perturbs throughput a
+ * little: never enable it inside a timed region whose `value` is reported).
+ * nlspn_profile_enable(1) clears the table and starts, (0) stops.  nlspn_profile_read
+ * synchronises the recorded events and returns per-class summed milliseconds and launch counts
+ * (arrays of at least nlspn_profile_classes() entries). */
+NLSPN_API int nlspn_profile_enable(int on);
+NLSPN_API int nlspn_profile_classes(void);
+NLSPN_API const char *nlspn_profile_class_name(int cls);
+NLSPN_API int nlspn_profile_read(double *ms, long long *launches, int n);
 
 /* Device facts the host side sizes its shards with: SM count and L2 bytes of `device`. */
 NLSPN_API int nlspn_device_info(int device, int *sm_count, int *l2_bytes);
@@ -110,7 +125,7 @@ NLSPN_API int nlspn_propagate_fwd(const float *offset, const float *aff, const f
  * Gradient wrt feat_fix is not produced (mask_fix is detached, nlspnmodel.py:330).
  * The scatter uses fp32 atomics: summation order, hence the last bits, vary run to run,
  * as in the reference (deformconv/test.py:627-631). */
-NLSPN_API size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K);
+NLSPN_API size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T);
 NLSPN_API int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
                    const float *offset, const float *aff, const float *conf_fixed,
                    const float *src, int S, const float *list_feat, const float *const *g_list,

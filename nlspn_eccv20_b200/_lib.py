@@ -22,6 +22,10 @@ SIGNATURES = {
     "nlspn_abi_version": (_c.c_int, []),
     "nlspn_last_error": (_c.c_char_p, []),
     "nlspn_launch_count": (_c.c_ulonglong, []),
+    "nlspn_profile_enable": (_c.c_int, [_c.c_int]),
+    "nlspn_profile_classes": (_c.c_int, []),
+    "nlspn_profile_class_name": (_c.c_char_p, [_c.c_int]),
+    "nlspn_profile_read": (_c.c_int, [_c.POINTER(_c.c_double), _c.POINTER(_c.c_longlong), _c.c_int]),
     "nlspn_device_info": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int)]),
     "nlspn_prologue_fwd": (_c.c_int, [_fp, _fp, _fp, _fp, _c.c_float, _c.c_int, _c.c_uint,
                                       _c.c_int, _c.c_int, _c.c_int, _c.c_int,
@@ -29,7 +33,7 @@ SIGNATURES = {
     "nlspn_propagate_fwd": (_c.c_int, [_fp, _fp, _fp, _fp, _c.c_uint,
                                        _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                        _fp, _c.c_int, _fp, _fp]),
-    "nlspn_backward_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "nlspn_backward_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     "nlspn_backward": (_c.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _c.c_int, _fp,
                                   _c.POINTER(_c.c_void_p), _fp, _fp, _c.c_float, _c.c_int, _c.c_uint,
                                   _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
@@ -42,6 +46,7 @@ SIGNATURES = {
 AFFINITY = {"AS": 0, "ASS": 1, "TC": 2, "TGASS": 3}
 FLAG_PRESERVE_INPUT = 1
 FLAG_ALWAYS_CLIP = 2
+FLAG_BWD_PER_ITERATION = 0x100
 
 
 def lib_path() -> str:
@@ -75,3 +80,13 @@ def check(rc: int, what: str):
         msg = load().nlspn_last_error().decode("utf-8", "replace")
         kind = "validation error" if rc < 0 else "CUDA error"
         raise RuntimeError("%s failed: %s %d: %s" % (what, kind, rc, msg))
+
+
+def profile_read():
+    """-> {kernel class name: (total ms, launches)} for the launches recorded since profile_enable(1)."""
+    lib = load()
+    n = lib.nlspn_profile_classes()
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_longlong * n)()
+    check(lib.nlspn_profile_read(ms, cnt, n), "nlspn_profile_read")
+    return {lib.nlspn_profile_class_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i]}

@@ -69,4 +69,29 @@ __device__ __forceinline__ float blend_fix(float v, float dep)
     return (1.f - m) * v + m * dep;
 }
 
+// geometry of the blocked scatter planes of one image
+struct ScatterGeo {
+    int Hb, Wb;          // blocks per column / row
+    long plane;          // floats per phase plane (multiple of 4)
+    long image;          // floats per image = 4 * plane
+};
+
+__host__ __device__ inline ScatterGeo scatter_geo(int H, int W)
+{
+    ScatterGeo g;
+    g.Hb = H / 2 + 2;
+    g.Wb = W / 2 + 2;
+    g.plane = (long)g.Hb * g.Wb * 4;
+    g.image = 4 * g.plane;
+    return g;
+}
+
+// address of padded cell (Y, X) = (y+1, x+1) in phase plane (sy, sx)
+__device__ __forceinline__ long scatter_cell(const ScatterGeo &g, int sy, int sx, int Y, int X)
+{
+    const int by = (Y + sy) >> 1, ly = (Y + sy) & 1;
+    const int bx = (X + sx) >> 1, lx = (X + sx) & 1;
+    return (long)(sy * 2 + sx) * g.plane + ((long)by * g.Wb + bx) * 4 + ly * 2 + lx;
+}
+
 } // namespace nlspn

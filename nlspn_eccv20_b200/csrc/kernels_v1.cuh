@@ -258,17 +258,18 @@ iter_bwd_kernel(const float *__restrict__ src_prev, const float *__restrict__ of
 // backward of the prologue (formulas: SURVEY 3.2, derived from nlspnmodel.py:185-197,262-267).
 // g_guidance's offset part already holds the accumulated offset gradients.
 // ======================================================================================
-template <int K>
+template <int K, bool BLOCKED>
 __global__ void __launch_bounds__(kBlock)
 final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ init,
                  const float *__restrict__ dep, const float *__restrict__ conf,
                  const float *__restrict__ s_in, const float *__restrict__ g_aff,
                  const float *__restrict__ g_conf_acc, const float *__restrict__ g_off_ext,
                  const float *__restrict__ g_aff_ext, float gamma, int affinity, unsigned flags,
-                 int P, float *__restrict__ g_init, float *__restrict__ g_guidance,
+                 int H, int W, float *__restrict__ g_init, float *__restrict__ g_guidance,
                  float *__restrict__ g_conf, double *__restrict__ g_gamma)
 {
     using G = Geo<K>;
+    const int P = H * W;
     const int r = blockIdx.x * kBlock + threadIdx.x;
     const long b = blockIdx.y;
     double local_gamma = 0.0;
@@ -277,7 +278,17 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         const bool preserve = (flags & kPreserve) != 0;
         const float d = preserve ? __ldg(dep + q) : 0.f;
         const float m = d > 0.f ? 1.f : 0.f;
-        const float gs = __ldg(s_in + q);
+        float gs;
+        if (BLOCKED) {   // four phase copies of the 2x2-blocked scatter plane (kernels_v2.cuh)
+            const ScatterGeo sg = scatter_geo(H, W);
+            const float *sl = s_in + b * sg.image;
+            const int hh = r / W, ww = r - hh * W;
+            gs = 0.f;
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) gs += sl[scatter_cell(sg, ph >> 1, ph & 1, hh + 1, ww + 1)];
+        } else {
+            gs = __ldg(s_in + q);
+        }
         float x0 = __ldg(init + q);
         if (preserve) x0 = blend_fix(x0, d);
         const bool clipped = (flags & kAlwaysClip) && x0 < 0.f;

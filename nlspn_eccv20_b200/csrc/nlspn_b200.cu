@@ -5,9 +5,10 @@
 #include <cstdio>
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "../../include/nlspn_b200.h"
-#include "kernels_v1.cuh"
+#include "kernels_v2.cuh"
 
 using namespace nlspn;
 
@@ -15,6 +16,50 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+
+// ---- optional per-kernel-class timing (bench.py's roofline): CUDA events around every launch
+enum ProfClass { kProfPrologue = 0, kProfIterFwd, kProfBwdState, kProfBwdParam, kProfFinalBwd,
+                 kProfIterBwdV1, kProfDcnFwd, kProfDcnBwd, kProfClasses };
+const char *const kProfNames[kProfClasses] = {"prologue_fwd_kernel", "iter_fwd_kernel", "bwd_state_kernel",
+                                              "bwd_param_kernel", "final_bwd_kernel", "iter_bwd_kernel",
+                                              "dcn_forward", "dcn_backward"};
+struct ProfRec { int cls; cudaEvent_t e0, e1; };
+std::mutex g_prof_mu;
+std::atomic<int> g_prof_on{0};
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+
+cudaEvent_t prof_event()
+{
+    if (!g_prof_pool.empty()) {
+        cudaEvent_t e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ProfScope {
+    cudaStream_t st;
+    int idx = -1;
+    ProfScope(int cls, cudaStream_t s) : st(s)
+    {
+        if (!g_prof_on.load(std::memory_order_relaxed)) return;
+        std::lock_guard<std::mutex> lock(g_prof_mu);
+        ProfRec r{cls, prof_event(), prof_event()};
+        cudaEventRecord(r.e0, st);
+        g_prof_recs.push_back(r);
+        idx = (int)g_prof_recs.size() - 1;
+    }
+    ~ProfScope()
+    {
+        if (idx < 0) return;
+        std::lock_guard<std::mutex> lock(g_prof_mu);
+        if (idx < (int)g_prof_recs.size()) cudaEventRecord(g_prof_recs[idx].e1, st);
+    }
+};
 
 int fail(int code, const char *fmt, ...)
 {
@@ -73,6 +118,39 @@ const char *nlspn_last_error(void) { return g_err; }
 
 unsigned long long nlspn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int nlspn_profile_enable(int on)
+{
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    for (auto &r : g_prof_recs) {
+        g_prof_pool.push_back(r.e0);
+        g_prof_pool.push_back(r.e1);
+    }
+    g_prof_recs.clear();
+    g_prof_on.store(on ? 1 : 0);
+    return 0;
+}
+
+int nlspn_profile_classes(void) { return kProfClasses; }
+
+const char *nlspn_profile_class_name(int cls) { return cls >= 0 && cls < kProfClasses ? kProfNames[cls] : ""; }
+
+int nlspn_profile_read(double *ms, long long *launches, int n)
+{
+    if (!ms || !launches || n < kProfClasses) return fail(NLSPN_ERR_NULL, "profile_read: need %d slots", kProfClasses);
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    for (int i = 0; i < n; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    for (auto &r : g_prof_recs) {
+        cudaError_t e = cudaEventSynchronize(r.e1);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(profile)");
+        float t = 0.f;
+        e = cudaEventElapsedTime(&t, r.e0, r.e1);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime(profile)");
+        ms[r.cls] += t;
+        launches[r.cls] += 1;
+    }
+    return 0;
+}
+
 int nlspn_device_info(int device, int *sm_count, int *l2_bytes)
 {
     static std::mutex mu;
@@ -109,9 +187,10 @@ int nlspn_prologue_fwd(const float *guidance, const float *confidence, const flo
         return fail(NLSPN_ERR_AFFINITY, "unknown affinity mode %d", affinity);
     const int P = H * W;
     cudaStream_t st = (cudaStream_t)stream;
+    { ProfScope prof__(kProfPrologue, st);
     DISPATCH_K(K, (prologue_fwd_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
                       guidance, confidence, feat_init, feat_fix, gamma, affinity, flags, P, offset,
-                      aff, conf_fixed, src0)));
+                      aff, conf_fixed, src0))); }
     NLSPN_CHECK_LAUNCH("prologue_fwd_kernel");
     return 0;
 }
@@ -140,20 +219,36 @@ int nlspn_propagate_fwd(const float *offset, const float *aff, const float *conf
             src_prev = t == 1 ? src : list_feat + (long)(t - 2) * BP;
         }
         float *out = list_feat + (long)(t - 1) * BP;
+        { ProfScope prof__(kProfIterFwd, st);
         DISPATCH_K(K, (iter_fwd_kernel<KC, true><<<grid_for(P, B), kBlock, 0, st>>>(
                           src_prev, offset, aff, conf_fixed, feat_fix, nullptr, nullptr, flags, H, W,
-                          out, src_next)));
+                          out, src_next))); }
         NLSPN_CHECK_LAUNCH("iter_fwd_kernel");
     }
     return 0;
 }
 
-size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K)
+static size_t ws_bytes_v1(int B, int H, int W, int K)
 {
-    if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
     const size_t BP = (size_t)B * H * W;
     // scatter planes A, B + confidence-gradient accumulator + affinity-gradient accumulator
     return sizeof(float) * (3 * BP + (size_t)K * K * BP);
+}
+
+static size_t ws_bytes_v2(int B, int H, int W, int K, int T)
+{
+    const size_t BP = (size_t)B * H * W;
+    const ScatterGeo sg = scatter_geo(H, W);
+    // two sets of four phase planes + confidence-gradient accumulator + gy for every iteration
+    // + raw affinity-gradient accumulator
+    return sizeof(float) * (2 * (size_t)B * sg.image + BP + (size_t)T * BP + (size_t)K * K * BP);
+}
+
+size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T)
+{
+    if (B <= 0 || H <= 0 || W <= 0 || K <= 0 || T <= 0) return 0;
+    const size_t a = ws_bytes_v1(B, H, W, K), b = ws_bytes_v2(B, H, W, K, T);
+    return a > b ? a : b;
 }
 
 int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
@@ -176,37 +271,78 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         return fail(NLSPN_ERR_AFFINITY, "unknown affinity mode %d", affinity);
     if (conf_fixed && S < T)
         return fail(NLSPN_ERR_SHAPE, "backward: src must keep all T planes (S=%d, T=%d)", S, T);
-    if (workspace_bytes < nlspn_backward_workspace_bytes(B, H, W, K) || !aligned16(workspace))
+    if (workspace_bytes < nlspn_backward_workspace_bytes(B, H, W, K, T) || !aligned16(workspace))
         return fail(NLSPN_ERR_WORKSPACE, "backward: workspace too small (%zu < %zu) or misaligned",
-                    workspace_bytes, nlspn_backward_workspace_bytes(B, H, W, K));
+                    workspace_bytes, nlspn_backward_workspace_bytes(B, H, W, K, T));
     const int P = H * W;
     const long BP = (long)B * P;
     const int N = K * K - 1;
     cudaStream_t st = (cudaStream_t)stream;
     float *ws = static_cast<float *>(workspace);
-    float *planeA = ws, *planeB = ws + BP, *g_conf_acc = ws + 2 * BP, *g_aff_acc = ws + 3 * BP;
-    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 3 * BP, st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
-    e = cudaMemsetAsync(g_gamma, 0, sizeof(double), st);
+    cudaError_t e = cudaMemsetAsync(g_gamma, 0, sizeof(double), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(g_gamma)");
 
-    for (int t = T; t >= 1; --t) {
-        const float *src_prev;
-        if (conf_fixed) src_prev = src + (long)(t - 1) * BP;
-        else src_prev = t == 1 ? src : list_feat + (long)(t - 2) * BP;
-        float *s_out = ((T - t) % 2 == 0) ? planeA : planeB;
-        float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? planeB : planeA);
-        DISPATCH_K(K, (iter_bwd_kernel<KC, true><<<grid_for(P, B), kBlock, 0, st>>>(
-                          src_prev, offset, aff, conf_fixed, feat_fix, list_feat + (long)(t - 1) * BP,
-                          g_list[t - 1], nullptr, s_in, s_out, g_guidance,
-                          (long)3 * N * P, g_aff_acc, g_conf_acc, flags, t == T ? 1 : 0, H, W)));
-        NLSPN_CHECK_LAUNCH("iter_bwd_kernel");
+    if (flags & NLSPN_FLAG_BWD_PER_ITERATION) {
+        // ---- v1: per-iteration accumulator RMW + scalar atomics (kept for cross-checking)
+        float *planeA = ws, *planeB = ws + BP, *g_conf_acc = ws + 2 * BP, *g_aff_acc = ws + 3 * BP;
+        e = cudaMemsetAsync(ws, 0, sizeof(float) * 3 * BP, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+        for (int t = T; t >= 1; --t) {
+            const float *src_prev;
+            if (conf_fixed) src_prev = src + (long)(t - 1) * BP;
+            else src_prev = t == 1 ? src : list_feat + (long)(t - 2) * BP;
+            float *s_out = ((T - t) % 2 == 0) ? planeA : planeB;
+            float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? planeB : planeA);
+            { ProfScope prof__(kProfIterBwdV1, st);
+            DISPATCH_K(K, (iter_bwd_kernel<KC, true><<<grid_for(P, B), kBlock, 0, st>>>(
+                              src_prev, offset, aff, conf_fixed, feat_fix, list_feat + (long)(t - 1) * BP,
+                              g_list[t - 1], nullptr, s_in, s_out, g_guidance,
+                              (long)3 * N * P, g_aff_acc, g_conf_acc, flags, t == T ? 1 : 0, H, W))); }
+            NLSPN_CHECK_LAUNCH("iter_bwd_kernel");
+        }
+        const float *s_last = ((T - 1) % 2 == 0) ? planeA : planeB;
+        { ProfScope prof__(kProfFinalBwd, st);
+        DISPATCH_K(K, (final_bwd_kernel<KC, false><<<grid_for(P, B), kBlock, 0, st>>>(
+                          guidance, feat_init, feat_fix, conf_fixed, s_last, g_aff_acc, g_conf_acc,
+                          g_offset_ext, g_aff_ext, gamma, affinity, flags, H, W, g_feat_init, g_guidance,
+                          g_confidence, g_gamma))); }
+        NLSPN_CHECK_LAUNCH("final_bwd_kernel");
+        return 0;
     }
-    const float *s_last = ((T - 1) % 2 == 0) ? planeA : planeB;
-    DISPATCH_K(K, (final_bwd_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
+
+    // ---- v2: pass A (state gradient, T launches, REDx4 scatter) + pass B (one launch)
+    const ScatterGeo sg = scatter_geo(H, W);
+    float *setA = ws, *setB = ws + (long)B * sg.image;
+    float *g_conf_acc = ws + 2 * (long)B * sg.image;
+    float *gy_all = g_conf_acc + BP;
+    float *g_aff_acc = gy_all + (long)T * BP;
+    e = cudaMemsetAsync(ws, 0, sizeof(float) * (2 * (size_t)B * sg.image + BP), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+    for (int t = T; t >= 1; --t) {
+        float *s_out = ((T - t) % 2 == 0) ? setA : setB;
+        float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? setB : setA);
+        { ProfScope prof__(kProfBwdState, st);
+        DISPATCH_K(K, (bwd_state_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
+                          offset, aff, conf_fixed, feat_fix, list_feat + (long)(t - 1) * BP, g_list[t - 1],
+                          s_in, s_out, gy_all + (long)(t - 1) * BP, g_conf_acc, flags, H, W))); }
+        NLSPN_CHECK_LAUNCH("bwd_state_kernel");
+    }
+    const float *s_last = ((T - 1) % 2 == 0) ? setA : setB;
+    {
+        constexpr int C = 9;
+        const int nch = (K * K + C - 1) / C;
+        dim3 grid((unsigned)((P + kParamBlock - 1) / kParamBlock), (unsigned)B, (unsigned)nch);
+        { ProfScope prof__(kProfBwdParam, st);
+        DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
+                          offset, aff, src, list_feat, gy_all, conf_fixed ? 1 : 0, H, W, T, BP, g_guidance,
+                          g_aff_acc))); }
+        NLSPN_CHECK_LAUNCH("bwd_param_kernel");
+    }
+    { ProfScope prof__(kProfFinalBwd, st);
+    DISPATCH_K(K, (final_bwd_kernel<KC, true><<<grid_for(P, B), kBlock, 0, st>>>(
                       guidance, feat_init, feat_fix, conf_fixed, s_last, g_aff_acc, g_conf_acc,
-                      g_offset_ext, g_aff_ext, gamma, affinity, flags, P, g_feat_init, g_guidance,
-                      g_confidence, g_gamma)));
+                      g_offset_ext, g_aff_ext, gamma, affinity, flags, H, W, g_feat_init, g_guidance,
+                      g_confidence, g_gamma))); }
     NLSPN_CHECK_LAUNCH("final_bwd_kernel");
     return 0;
 }
@@ -241,9 +377,10 @@ int nlspn_dcn_forward(const float *input, const float *weight, const float *bias
         return fail(NLSPN_ERR_NULL, "dcn_forward: a required pointer is NULL");
     const int P = H * W;
     cudaStream_t st = (cudaStream_t)stream;
+    { ProfScope prof__(kProfDcnFwd, st);
     DISPATCH_K(kernel_h, (iter_fwd_kernel<KC, false><<<grid_for(P, B), kBlock, 0, st>>>(
                              input, offset, mask, nullptr, nullptr, weight, bias, 0u, H, W, output,
-                             nullptr)));
+                             nullptr))); }
     NLSPN_CHECK_LAUNCH("iter_fwd_kernel<dcn>");
     return 0;
 }
@@ -275,10 +412,11 @@ int nlspn_dcn_backward(const float *input, const float *weight, const float *bia
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_weight)");
     e = cudaMemsetAsync(grad_bias, 0, sizeof(float), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_bias)");
+    { ProfScope prof__(kProfDcnBwd, st);
     DISPATCH_K(kernel_h, (iter_bwd_kernel<KC, false><<<grid_for(P, B), kBlock, 0, st>>>(
                              input, offset, mask, nullptr, nullptr, nullptr, grad_output, weight,
                              nullptr, grad_input, grad_offset, (long)2 * KK * P, grad_mask, nullptr,
-                             0u, 1, H, W)));
+                             0u, 1, H, W))); }
     NLSPN_CHECK_LAUNCH("iter_bwd_kernel<dcn>");
     DISPATCH_K(kernel_h, (dcn_wb_grad_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
                              input, offset, mask, grad_output, H, W, grad_weight, grad_bias)));

@@ -101,7 +101,7 @@ def propagate_fwd(offset, aff, conf_fixed, feat_fix, src, list_feat, K, T,
 
 def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_feat, g_list,
              gamma, K, T, affinity="TGASS", preserve_input=True, always_clip=False,
-             g_offset_ext=None, g_aff_ext=None):
+             g_offset_ext=None, g_aff_ext=None, per_iteration=False):
     """g_list: sequence of T tensors [B,1,H,W] or None.  -> (g_init, g_guidance, g_conf, g_gamma)."""
     lib = _lib.load()
     B, _, H, W = feat_init.shape
@@ -121,14 +121,15 @@ def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_f
     g_guid = torch.empty((B, 3 * N, H, W), **opt)
     g_conf = torch.empty((B, 1, H, W), **opt) if conf_fixed is not None else None
     g_gamma = torch.empty((1,), device=dev, dtype=torch.float64)
-    nbytes = lib.nlspn_backward_workspace_bytes(B, H, W, K)
+    nbytes = lib.nlspn_backward_workspace_bytes(B, H, W, K, T)
     ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
     with torch.cuda.device(dev):
         rc = lib.nlspn_backward(_ptr(guidance.contiguous()), _ptr(feat_init.contiguous()), _ptr(feat_fix),
                                 _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(src), S, _ptr(list_feat),
                                 ptrs, _ptr(g_offset_ext), _ptr(g_aff_ext), float(gamma),
-                                _lib.AFFINITY[affinity], _flags(preserve, always_clip), B, H, W, K, T,
-                                _ptr(g_init), _ptr(g_guid), _ptr(g_conf), _ptr(g_gamma), _ptr(ws),
+                                _lib.AFFINITY[affinity],
+                                _flags(preserve, always_clip) | (_lib.FLAG_BWD_PER_ITERATION if per_iteration else 0),
+                                B, H, W, K, T, _ptr(g_init), _ptr(g_guid), _ptr(g_conf), _ptr(g_gamma), _ptr(ws),
                                 nbytes, _stream(dev))
     _lib.check(rc, "nlspn_backward")
     return g_init, g_guid, g_conf, g_gamma

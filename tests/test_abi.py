@@ -74,7 +74,9 @@ def test_validation_errors_are_negative_and_described(lib):
     assert dcn([3, 3, 2, 2, 1, 1, 1, 1, 1, 1, 64]) == -4
     assert dcn([3, 3, 1, 1, 0, 0, 1, 1, 1, 1, 64]) == -4
     assert dcn([3, 3, 1, 1, 1, 1, 1, 1, 2, 1, 64]) == -4
-    assert lib.nlspn_backward_workspace_bytes(2, 8, 8, 3) == 4 * (3 + 9) * 2 * 64
+    assert lib.nlspn_backward_workspace_bytes(2, 8, 8, 3, 1) >= 4 * (3 + 9) * 2 * 64
+    assert lib.nlspn_backward_workspace_bytes(2, 8, 8, 3, 40) >= 4 * 40 * 2 * 64
+    assert lib.nlspn_backward_workspace_bytes(0, 8, 8, 3, 1) == 0
 
 
 def test_product_never_imports_the_oracle():

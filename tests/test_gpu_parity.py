@@ -269,3 +269,34 @@ def test_fused_path_equals_unfused_reference_statements(dev):
             x = Fn.apply(x * c, offset, aff, mod.w, mod.b, 1, 1, 1, 1, 1, 64)
             x = (1 - m) * x + m * dep
             assert float((x - lf[t]).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("K,T,use_conf", [(3, 6, True), (5, 3, True), (3, 4, False), (7, 2, True)])
+def test_two_pass_backward_equals_per_iteration_backward(dev, K, T, use_conf):
+    """The default backward (pass A with REDx4 scatter + pass B in registers) against the
+    per-iteration formulation (accumulator RMW + scalar atomics) on the same saved tensors."""
+    from nlspn_eccv20_b200 import functional as F_
+    from nlspn_eccv20_b200.synth import make_inputs
+    B, H, W = 2, 38, 45
+    inp = make_inputs(B, H, W, K, seed=77 + K, device=dev, conf_mean=2.0)
+    gamma = 0.5 * (K * K - 1)
+    conf = inp["confidence"] if use_conf else None
+    offset, aff, cfx, src0 = F_.prologue_fwd(inp["guidance"], conf, inp["feat_init"], inp["feat_fix"], gamma, K)
+    S = T if use_conf else 1
+    src = torch.empty((S, B, 1, H, W), device=dev)
+    src[0].copy_(src0)
+    lf = torch.empty((T, B, 1, H, W), device=dev)
+    F_.propagate_fwd(offset, aff, cfx, inp["feat_fix"], src, lf, K, T)
+    g = torch.Generator().manual_seed(1)
+    g_list = [torch.randn(B, 1, H, W, generator=g).to(dev) if t % 2 == 1 or t == T - 1 else None for t in range(T)]
+    goe = torch.randn(offset.shape, generator=g).to(dev)
+    gae = torch.randn(aff.shape, generator=g).to(dev)
+    args = (inp["guidance"], inp["feat_init"], inp["feat_fix"], offset, aff, cfx, src, lf, g_list, gamma, K, T)
+    a = F_.backward(*args, g_offset_ext=goe, g_aff_ext=gae)
+    b = F_.backward(*args, g_offset_ext=goe, g_aff_ext=gae, per_iteration=True)
+    for x, y, name in zip(a, b, ["g_init", "g_guidance", "g_conf", "g_gamma"]):
+        if x is None:
+            assert y is None
+            continue
+        s = float(y.abs().max())
+        assert float((x - y).abs().max()) <= 2e-5 * max(s, 1e-20), name
