@@ -23,6 +23,8 @@
  *   offset      [B,2KK,H,W]  offsets after the zero centre pair was inserted (nlspnmodel.py:252-259)
  *   aff         [B,KK,H,W]   normalised affinities incl. the centre weight    (nlspnmodel.py:179-201,261-269)
  *   conf_fixed  [B,1,H,W]    (1-m)*confidence + m, m = [feat_fix>0]          (nlspnmodel.py:328-334)
+ *   gamma       [1]          aff_scale_const, a DEVICE scalar (nlspnmodel.py:93-104); passing the
+ *                            parameter's device address avoids a host sync per call
  *   list_feat   [T,B,1,H,W]  state after every iteration    (list_pred, nlspnmodel.py:363)
  *   src         [S,B,1,H,W]  the planes the gather read: src[t] = x_t * conf_fixed (x_0 = blended
  *                            feat_init).  S = T keeps all of them for backward; S = 2 ping-pongs
@@ -98,7 +100,7 @@ NLSPN_API int nlspn_device_info(int device, int *sm_count, int *l2_bytes);
  * Writes offset, aff, conf_fixed (if confidence != NULL) and src0 = x_0 * conf_fixed where
  * x_0 = blend(feat_init) (clamped at 0 under ALWAYS_CLIP). */
 NLSPN_API int nlspn_prologue_fwd(const float *guidance, const float *confidence, const float *feat_init,
-                       const float *feat_fix, float gamma, int affinity, unsigned flags,
+                       const float *feat_fix, const float *gamma, int affinity, unsigned flags,
                        int B, int H, int W, int K,
                        float *offset, float *aff, float *conf_fixed, float *src0, void *stream);
 
@@ -110,6 +112,17 @@ NLSPN_API int nlspn_prologue_fwd(const float *guidance, const float *confidence,
 NLSPN_API int nlspn_propagate_fwd(const float *offset, const float *aff, const float *conf_fixed,
                         const float *feat_fix, unsigned flags, int B, int H, int W, int K, int T,
                         float *src, int S, float *list_feat, void *stream);
+
+/* ---- fused forward: prologue + T iterations in one call ---------------------------------
+ * Same results as nlspn_prologue_fwd followed by nlspn_propagate_fwd, but enqueued group-major
+ * (all T iterations of a group of images before the next group) so a group's offsets and
+ * affinities are still in L2 when the iterations read them.  This is what the NLSPN module
+ * calls. */
+NLSPN_API int nlspn_forward(const float *guidance, const float *confidence, const float *feat_init,
+                            const float *feat_fix, const float *gamma, int affinity, unsigned flags,
+                            int B, int H, int W, int K, int T,
+                            float *offset, float *aff, float *conf_fixed, float *src, int S,
+                            float *list_feat, void *stream);
 
 /* ---- backward of prologue + loop ------------------------------------------------------
  * Replaces T x ModulatedDeformConvFunction.backward (modulated_deform_conv_func.py:38-56 ->
@@ -129,7 +142,7 @@ NLSPN_API size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int 
 NLSPN_API int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
                    const float *offset, const float *aff, const float *conf_fixed,
                    const float *src, int S, const float *list_feat, const float *const *g_list,
-                   const float *g_offset_ext, const float *g_aff_ext, float gamma, int affinity,
+                   const float *g_offset_ext, const float *g_aff_ext, const float *gamma, int affinity,
                    unsigned flags, int B, int H, int W, int K, int T,
                    float *g_feat_init, float *g_guidance, float *g_confidence, double *g_gamma,
                    void *workspace, size_t workspace_bytes, void *stream);

@@ -27,15 +27,18 @@ SIGNATURES = {
     "nlspn_profile_class_name": (_c.c_char_p, [_c.c_int]),
     "nlspn_profile_read": (_c.c_int, [_c.POINTER(_c.c_double), _c.POINTER(_c.c_longlong), _c.c_int]),
     "nlspn_device_info": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int)]),
-    "nlspn_prologue_fwd": (_c.c_int, [_fp, _fp, _fp, _fp, _c.c_float, _c.c_int, _c.c_uint,
+    "nlspn_prologue_fwd": (_c.c_int, [_fp, _fp, _fp, _fp, _fp, _c.c_int, _c.c_uint,
                                       _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                       _fp, _fp, _fp, _fp, _fp]),
     "nlspn_propagate_fwd": (_c.c_int, [_fp, _fp, _fp, _fp, _c.c_uint,
                                        _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                        _fp, _c.c_int, _fp, _fp]),
+    "nlspn_forward": (_c.c_int, [_fp, _fp, _fp, _fp, _fp, _c.c_int, _c.c_uint,
+                                 _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                 _fp, _fp, _fp, _fp, _c.c_int, _fp, _fp]),
     "nlspn_backward_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     "nlspn_backward": (_c.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _c.c_int, _fp,
-                                  _c.POINTER(_c.c_void_p), _fp, _fp, _c.c_float, _c.c_int, _c.c_uint,
+                                  _c.POINTER(_c.c_void_p), _fp, _fp, _fp, _c.c_int, _c.c_uint,
                                   _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                   _fp, _fp, _fp, _fp, _fp, _c.c_size_t, _fp]),
     "nlspn_dcn_forward": (_c.c_int, [_fp] * 5 + [_c.c_int] * 15 + [_fp, _fp]),

@@ -19,8 +19,8 @@ enum : int { kAS = 0, kASS = 1, kTC = 2, kTGASS = 3 };
 template <int K>
 __global__ void __launch_bounds__(kBlock)
 prologue_fwd_kernel(const float *__restrict__ guidance, const float *__restrict__ conf,
-                    const float *__restrict__ init, const float *__restrict__ dep, float gamma,
-                    int affinity, unsigned flags, int P, float *__restrict__ offset,
+                    const float *__restrict__ init, const float *__restrict__ dep,
+                    const float *__restrict__ gamma_ptr, int affinity, unsigned flags, int P, float *__restrict__ offset,
                     float *__restrict__ aff, float *__restrict__ conf_out, float *__restrict__ src0)
 {
     using G = Geo<K>;
@@ -46,6 +46,7 @@ prologue_fwd_kernel(const float *__restrict__ guidance, const float *__restrict_
     float a[G::N];
     float abs_sum = 0.f;
     const bool use_tanh = affinity == kTC || affinity == kTGASS;
+    const float gamma = __ldg(gamma_ptr);
     const float g = affinity == kTGASS ? gamma + 1e-8f : gamma;
 #pragma unroll
     for (int n = 0; n < G::N; ++n) {
@@ -264,8 +265,8 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
                  const float *__restrict__ dep, const float *__restrict__ conf,
                  const float *__restrict__ s_in, const float *__restrict__ g_aff,
                  const float *__restrict__ g_conf_acc, const float *__restrict__ g_off_ext,
-                 const float *__restrict__ g_aff_ext, float gamma, int affinity, unsigned flags,
-                 int H, int W, float *__restrict__ g_init, float *__restrict__ g_guidance,
+                 const float *__restrict__ g_aff_ext, const float *__restrict__ gamma_ptr, int affinity,
+                 unsigned flags, int H, int W, float *__restrict__ g_init, float *__restrict__ g_guidance,
                  float *__restrict__ g_conf, double *__restrict__ g_gamma)
 {
     using G = Geo<K>;
@@ -318,6 +319,7 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         const float *gab = g_aff + b * G::KK * P + r;
         const float *eab = g_aff_ext ? g_aff_ext + b * G::KK * P + r : nullptr;
         const bool use_tanh = affinity == kTC || affinity == kTGASS;
+        const float gamma = __ldg(gamma_ptr);
         const float g = affinity == kTGASS ? gamma + 1e-8f : gamma;
         float a[G::N], th[G::N], Gh[G::N];
         float s0 = 0.f;

@@ -126,7 +126,7 @@ template <int K, int C>
 __global__ void __launch_bounds__(kParamBlock)
 bwd_param_kernel(const float *__restrict__ offset, const float *__restrict__ aff,
                  const float *__restrict__ src, const float *__restrict__ list_feat,
-                 const float *__restrict__ gy_all, int has_conf, int H, int W, int T, long BP,
+                 const float *__restrict__ gy_all, int has_conf, int H, int W, int T, long BP, long GP,
                  float *__restrict__ g_guidance, float *__restrict__ g_aff_acc)
 {
     using G = Geo<K>;
@@ -155,7 +155,7 @@ bwd_param_kernel(const float *__restrict__ offset, const float *__restrict__ aff
         }
     }
     for (int t = T; t >= 1; --t) {
-        const float gy = __ldg(gy_all + (long)(t - 1) * BP + q);
+        const float gy = __ldg(gy_all + (long)(t - 1) * GP + q);
         if (gy == 0.f) continue;
         const float *im;
         if (has_conf) im = src + (long)(t - 1) * BP + b * P;

@@ -3,6 +3,7 @@
 // stream.  No allocation, no synchronisation, no torch/ATen.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -171,61 +172,145 @@ int nlspn_device_info(int device, int *sm_count, int *l2_bytes)
     return 0;
 }
 
+// ---- image groups -----------------------------------------------------------------------
+// Batch images propagate independently, so the host loop is GROUP-major: all T
+// iterations of a group of G images are enqueued before the next group starts.  G is sized so
+// that a group's offsets + affinities (+ the blocked scatter planes in the backward) stay
+// resident in L2 across the iterations: HBM then sees each byte of them once per pass instead of
+// once per iteration, and the backward's vector REDs hit L2 instead of missing to DRAM (ncu on
+// the batch-major order: 958 us per bwd_state launch, long_scoreboard/lg_throttle stalls with
+// every unit < 20 % busy; see profiles/).
+static int group_images(int B, int H, int W, int K, bool backward)
+{
+    if (const char *e = getenv("NLSPN_GROUP_IMAGES")) {
+        const int g = atoi(e);
+        if (g > 0) return g < B ? g : B;
+    }
+    int dev = 0, l2 = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, nullptr, &l2) != 0 || l2 <= 0)
+        l2 = 64 << 20;
+    const double per_image = (double)H * W * 4.0 * (3.0 * K * K + (backward ? 14.0 : 4.0));
+    int g = (int)(0.45 * (double)l2 / per_image);
+    if (g < 1) g = 1;
+    if (g > B) g = B;
+    const int ngroups = (B + g - 1) / g;
+    return (B + ngroups - 1) / ngroups;   // balanced groups
+}
+
+struct FwdCall {
+    const float *guidance, *confidence, *feat_init, *feat_fix;
+    const float *gamma;
+    int affinity;
+    unsigned flags;
+    int B, H, W, K, T;
+    float *offset, *aff, *conf_fixed, *src;
+    int S;
+    float *list_feat;
+    cudaStream_t st;
+};
+
+static int launch_prologue(const FwdCall &c, int b0, int nb)
+{
+    const int P = c.H * c.W, KK = c.K * c.K, N = KK - 1;
+    const long o1 = (long)b0 * P;
+    ProfScope prof__(kProfPrologue, c.st);
+    DISPATCH_K(c.K, (prologue_fwd_kernel<KC><<<grid_for(P, nb), kBlock, 0, c.st>>>(
+                        c.guidance + o1 * 3 * N, c.confidence ? c.confidence + o1 : nullptr,
+                        c.feat_init + o1, c.feat_fix ? c.feat_fix + o1 : nullptr, c.gamma, c.affinity,
+                        c.flags, P, c.offset + o1 * 2 * KK, c.aff + o1 * KK,
+                        c.conf_fixed ? c.conf_fixed + o1 : nullptr, c.src + o1)));
+    NLSPN_CHECK_LAUNCH("prologue_fwd_kernel");
+    return 0;
+}
+
+static int launch_iter_fwd(const FwdCall &c, int b0, int nb, int t)
+{
+    const int P = c.H * c.W, KK = c.K * c.K;
+    const long BP = (long)c.B * P, o1 = (long)b0 * P;
+    const float *src_prev;
+    float *src_next = nullptr;
+    if (c.conf_fixed) {
+        src_prev = c.src + (long)((t - 1) % c.S) * BP + o1;
+        if (t < c.T) src_next = c.src + (long)(t % c.S) * BP + o1;
+    } else {
+        src_prev = (t == 1 ? c.src : c.list_feat + (long)(t - 2) * BP) + o1;
+    }
+    float *out = c.list_feat + (long)(t - 1) * BP + o1;
+    ProfScope prof__(kProfIterFwd, c.st);
+    DISPATCH_K(c.K, (iter_fwd_kernel<KC, true><<<grid_for(P, nb), kBlock, 0, c.st>>>(
+                        src_prev, c.offset + o1 * 2 * KK, c.aff + o1 * KK,
+                        c.conf_fixed ? c.conf_fixed + o1 : nullptr, c.feat_fix ? c.feat_fix + o1 : nullptr,
+                        nullptr, nullptr, c.flags, c.H, c.W, out, src_next)));
+    NLSPN_CHECK_LAUNCH("iter_fwd_kernel");
+    return 0;
+}
+
+static int check_fwd(const FwdCall &c, bool prologue, bool iters)
+{
+    if (int rc = check_shape(c.B, c.H, c.W, c.K, c.T)) return rc;
+    if ((c.flags & NLSPN_FLAG_PRESERVE_INPUT) && !c.feat_fix)
+        return fail(NLSPN_ERR_NULL, "PRESERVE_INPUT needs feat_fix");
+    if (prologue) {
+        if (!c.guidance || !c.feat_init || !c.offset || !c.aff || !c.src || !c.gamma)
+            return fail(NLSPN_ERR_NULL, "prologue: guidance, feat_init, gamma, offset, aff, src are required");
+        if (c.confidence && !c.conf_fixed)
+            return fail(NLSPN_ERR_NULL, "prologue: conf_fixed is required when confidence is given");
+        if (c.affinity < NLSPN_AFF_AS || c.affinity > NLSPN_AFF_TGASS)
+            return fail(NLSPN_ERR_AFFINITY, "unknown affinity mode %d", c.affinity);
+    }
+    if (iters) {
+        if (!c.offset || !c.aff || !c.src || !c.list_feat)
+            return fail(NLSPN_ERR_NULL, "propagate: offset, aff, src, list_feat are required");
+        if (c.S < 1 || (c.conf_fixed && c.T > 1 && c.S < 2))
+            return fail(NLSPN_ERR_SHAPE, "propagate: src needs S >= 2 planes with confidence (got %d)", c.S);
+    }
+    return 0;
+}
+
+static int run_forward(const FwdCall &c, bool prologue, bool iters)
+{
+    if (int rc = check_fwd(c, prologue, iters)) return rc;
+    const int G = group_images(c.B, c.H, c.W, c.K, false);
+    for (int b0 = 0; b0 < c.B; b0 += G) {
+        const int nb = c.B - b0 < G ? c.B - b0 : G;
+        if (prologue)
+            if (int rc = launch_prologue(c, b0, nb)) return rc;
+        if (iters)
+            for (int t = 1; t <= c.T; ++t)
+                if (int rc = launch_iter_fwd(c, b0, nb, t)) return rc;
+    }
+    return 0;
+}
+
 int nlspn_prologue_fwd(const float *guidance, const float *confidence, const float *feat_init,
-                       const float *feat_fix, float gamma, int affinity, unsigned flags,
+                       const float *feat_fix, const float *gamma, int affinity, unsigned flags,
                        int B, int H, int W, int K,
                        float *offset, float *aff, float *conf_fixed, float *src0, void *stream)
 {
-    if (int rc = check_shape(B, H, W, K, 1)) return rc;
-    if (!guidance || !feat_init || !offset || !aff || !src0)
-        return fail(NLSPN_ERR_NULL, "prologue_fwd: guidance, feat_init, offset, aff, src0 are required");
-    if (confidence && !conf_fixed)
-        return fail(NLSPN_ERR_NULL, "prologue_fwd: conf_fixed is required when confidence is given");
-    if ((flags & NLSPN_FLAG_PRESERVE_INPUT) && !feat_fix)
-        return fail(NLSPN_ERR_NULL, "prologue_fwd: PRESERVE_INPUT needs feat_fix");
-    if (affinity < NLSPN_AFF_AS || affinity > NLSPN_AFF_TGASS)
-        return fail(NLSPN_ERR_AFFINITY, "unknown affinity mode %d", affinity);
-    const int P = H * W;
-    cudaStream_t st = (cudaStream_t)stream;
-    { ProfScope prof__(kProfPrologue, st);
-    DISPATCH_K(K, (prologue_fwd_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
-                      guidance, confidence, feat_init, feat_fix, gamma, affinity, flags, P, offset,
-                      aff, conf_fixed, src0))); }
-    NLSPN_CHECK_LAUNCH("prologue_fwd_kernel");
-    return 0;
+    FwdCall c{guidance, confidence, feat_init, feat_fix, gamma, affinity, flags, B, H, W, K, 1,
+              offset, aff, conf_fixed, src0, 1, nullptr, (cudaStream_t)stream};
+    return run_forward(c, true, false);
 }
 
 int nlspn_propagate_fwd(const float *offset, const float *aff, const float *conf_fixed,
                         const float *feat_fix, unsigned flags, int B, int H, int W, int K, int T,
                         float *src, int S, float *list_feat, void *stream)
 {
-    if (int rc = check_shape(B, H, W, K, T)) return rc;
-    if (!offset || !aff || !src || !list_feat)
-        return fail(NLSPN_ERR_NULL, "propagate_fwd: offset, aff, src, list_feat are required");
-    if ((flags & NLSPN_FLAG_PRESERVE_INPUT) && !feat_fix)
-        return fail(NLSPN_ERR_NULL, "propagate_fwd: PRESERVE_INPUT needs feat_fix");
-    if (S < 1 || (conf_fixed && T > 1 && S < 2))
-        return fail(NLSPN_ERR_SHAPE, "propagate_fwd: src needs S >= 2 planes with confidence (got %d)", S);
-    const int P = H * W;
-    const long BP = (long)B * P;
-    cudaStream_t st = (cudaStream_t)stream;
-    for (int t = 1; t <= T; ++t) {
-        const float *src_prev;
-        float *src_next = nullptr;
-        if (conf_fixed) {
-            src_prev = src + (long)((t - 1) % S) * BP;
-            if (t < T) src_next = src + (long)(t % S) * BP;
-        } else {
-            src_prev = t == 1 ? src : list_feat + (long)(t - 2) * BP;
-        }
-        float *out = list_feat + (long)(t - 1) * BP;
-        { ProfScope prof__(kProfIterFwd, st);
-        DISPATCH_K(K, (iter_fwd_kernel<KC, true><<<grid_for(P, B), kBlock, 0, st>>>(
-                          src_prev, offset, aff, conf_fixed, feat_fix, nullptr, nullptr, flags, H, W,
-                          out, src_next))); }
-        NLSPN_CHECK_LAUNCH("iter_fwd_kernel");
-    }
-    return 0;
+    FwdCall c{nullptr, nullptr, nullptr, feat_fix, nullptr, 0, flags, B, H, W, K, T,
+              const_cast<float *>(offset), const_cast<float *>(aff), const_cast<float *>(conf_fixed), src, S,
+              list_feat, (cudaStream_t)stream};
+    return run_forward(c, false, true);
+}
+
+int nlspn_forward(const float *guidance, const float *confidence, const float *feat_init,
+                  const float *feat_fix, const float *gamma, int affinity, unsigned flags,
+                  int B, int H, int W, int K, int T,
+                  float *offset, float *aff, float *conf_fixed, float *src, int S, float *list_feat,
+                  void *stream)
+{
+    FwdCall c{guidance, confidence, feat_init, feat_fix, gamma, affinity, flags, B, H, W, K, T,
+              offset, aff, conf_fixed, src, S, list_feat, (cudaStream_t)stream};
+    return run_forward(c, true, true);
 }
 
 static size_t ws_bytes_v1(int B, int H, int W, int K)
@@ -240,7 +325,7 @@ static size_t ws_bytes_v2(int B, int H, int W, int K, int T)
     const size_t BP = (size_t)B * H * W;
     const ScatterGeo sg = scatter_geo(H, W);
     // two sets of four phase planes + confidence-gradient accumulator + gy for every iteration
-    // + raw affinity-gradient accumulator
+    // + raw affinity-gradient accumulator (sized for the whole batch; a group uses a prefix)
     return sizeof(float) * (2 * (size_t)B * sg.image + BP + (size_t)T * BP + (size_t)K * K * BP);
 }
 
@@ -254,13 +339,13 @@ size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T)
 int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
                    const float *offset, const float *aff, const float *conf_fixed,
                    const float *src, int S, const float *list_feat, const float *const *g_list,
-                   const float *g_offset_ext, const float *g_aff_ext, float gamma, int affinity,
+                   const float *g_offset_ext, const float *g_aff_ext, const float *gamma, int affinity,
                    unsigned flags, int B, int H, int W, int K, int T,
                    float *g_feat_init, float *g_guidance, float *g_confidence, double *g_gamma,
                    void *workspace, size_t workspace_bytes, void *stream)
 {
     if (int rc = check_shape(B, H, W, K, T)) return rc;
-    if (!guidance || !feat_init || !offset || !aff || !src || !list_feat || !g_list ||
+    if (!guidance || !feat_init || !offset || !aff || !src || !list_feat || !g_list || !gamma ||
         !g_feat_init || !g_guidance || !g_gamma || !workspace)
         return fail(NLSPN_ERR_NULL, "backward: a required pointer is NULL");
     if (conf_fixed && !g_confidence)
@@ -274,9 +359,9 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     if (workspace_bytes < nlspn_backward_workspace_bytes(B, H, W, K, T) || !aligned16(workspace))
         return fail(NLSPN_ERR_WORKSPACE, "backward: workspace too small (%zu < %zu) or misaligned",
                     workspace_bytes, nlspn_backward_workspace_bytes(B, H, W, K, T));
-    const int P = H * W;
+    const int P = H * W, KK = K * K;
     const long BP = (long)B * P;
-    const int N = K * K - 1;
+    const int N = KK - 1;
     cudaStream_t st = (cudaStream_t)stream;
     float *ws = static_cast<float *>(workspace);
     cudaError_t e = cudaMemsetAsync(g_gamma, 0, sizeof(double), st);
@@ -293,57 +378,69 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             else src_prev = t == 1 ? src : list_feat + (long)(t - 2) * BP;
             float *s_out = ((T - t) % 2 == 0) ? planeA : planeB;
             float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? planeB : planeA);
-            { ProfScope prof__(kProfIterBwdV1, st);
+            ProfScope prof__(kProfIterBwdV1, st);
             DISPATCH_K(K, (iter_bwd_kernel<KC, true><<<grid_for(P, B), kBlock, 0, st>>>(
                               src_prev, offset, aff, conf_fixed, feat_fix, list_feat + (long)(t - 1) * BP,
                               g_list[t - 1], nullptr, s_in, s_out, g_guidance,
-                              (long)3 * N * P, g_aff_acc, g_conf_acc, flags, t == T ? 1 : 0, H, W))); }
+                              (long)3 * N * P, g_aff_acc, g_conf_acc, flags, t == T ? 1 : 0, H, W)));
             NLSPN_CHECK_LAUNCH("iter_bwd_kernel");
         }
         const float *s_last = ((T - 1) % 2 == 0) ? planeA : planeB;
-        { ProfScope prof__(kProfFinalBwd, st);
+        ProfScope prof__(kProfFinalBwd, st);
         DISPATCH_K(K, (final_bwd_kernel<KC, false><<<grid_for(P, B), kBlock, 0, st>>>(
                           guidance, feat_init, feat_fix, conf_fixed, s_last, g_aff_acc, g_conf_acc,
                           g_offset_ext, g_aff_ext, gamma, affinity, flags, H, W, g_feat_init, g_guidance,
-                          g_confidence, g_gamma))); }
+                          g_confidence, g_gamma)));
         NLSPN_CHECK_LAUNCH("final_bwd_kernel");
         return 0;
     }
 
-    // ---- v2: pass A (state gradient, T launches, REDx4 scatter) + pass B (one launch)
+    // ---- v2: group-major; per group: pass A (state gradient, T launches, REDx4 scatter),
+    //      pass B (parameter gradients, one launch), final (prologue backward)
     const ScatterGeo sg = scatter_geo(H, W);
-    float *setA = ws, *setB = ws + (long)B * sg.image;
-    float *g_conf_acc = ws + 2 * (long)B * sg.image;
-    float *gy_all = g_conf_acc + BP;
-    float *g_aff_acc = gy_all + (long)T * BP;
-    e = cudaMemsetAsync(ws, 0, sizeof(float) * (2 * (size_t)B * sg.image + BP), st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
-    for (int t = T; t >= 1; --t) {
-        float *s_out = ((T - t) % 2 == 0) ? setA : setB;
-        float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? setB : setA);
-        { ProfScope prof__(kProfBwdState, st);
-        DISPATCH_K(K, (bwd_state_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
-                          offset, aff, conf_fixed, feat_fix, list_feat + (long)(t - 1) * BP, g_list[t - 1],
-                          s_in, s_out, gy_all + (long)(t - 1) * BP, g_conf_acc, flags, H, W))); }
-        NLSPN_CHECK_LAUNCH("bwd_state_kernel");
+    const int G = group_images(B, H, W, K, true);
+    float *setA = ws, *setB = setA + (long)G * sg.image;
+    float *g_conf_acc = setB + (long)G * sg.image;
+    float *gy_all = g_conf_acc + (long)G * P;          // [T, G, P]
+    float *g_aff_acc = gy_all + (long)T * G * P;       // [G, KK, P]
+    for (int b0 = 0; b0 < B; b0 += G) {
+        const int nb = B - b0 < G ? B - b0 : G;
+        const long o1 = (long)b0 * P;
+        const long GP = (long)nb * P;                   // gy planes of this group are [T, nb, P]
+        e = cudaMemsetAsync(setA, 0, sizeof(float) * (2 * (size_t)G * sg.image + (size_t)G * P), st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+        const float *cf = conf_fixed ? conf_fixed + o1 : nullptr;
+        const float *fx = feat_fix ? feat_fix + o1 : nullptr;
+        for (int t = T; t >= 1; --t) {
+            float *s_out = ((T - t) % 2 == 0) ? setA : setB;
+            float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? setB : setA);
+            ProfScope prof__(kProfBwdState, st);
+            DISPATCH_K(K, (bwd_state_kernel<KC><<<grid_for(P, nb), kBlock, 0, st>>>(
+                              offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, list_feat + (long)(t - 1) * BP + o1,
+                              g_list[t - 1] ? g_list[t - 1] + o1 : nullptr, s_in, s_out,
+                              gy_all + (long)(t - 1) * GP, g_conf_acc, flags, H, W)));
+            NLSPN_CHECK_LAUNCH("bwd_state_kernel");
+        }
+        const float *s_last = ((T - 1) % 2 == 0) ? setA : setB;
+        {
+            constexpr int C = 9;
+            const int nch = (KK + C - 1) / C;
+            dim3 grid((unsigned)((P + kParamBlock - 1) / kParamBlock), (unsigned)nb, (unsigned)nch);
+            ProfScope prof__(kProfBwdParam, st);
+            DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
+                              offset + o1 * 2 * KK, aff + o1 * KK, src + o1, list_feat + o1, gy_all,
+                              conf_fixed ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc)));
+            NLSPN_CHECK_LAUNCH("bwd_param_kernel");
+        }
+        ProfScope prof__(kProfFinalBwd, st);
+        DISPATCH_K(K, (final_bwd_kernel<KC, true><<<grid_for(P, nb), kBlock, 0, st>>>(
+                          guidance + o1 * 3 * N, feat_init + o1, fx, cf, s_last, g_aff_acc, g_conf_acc,
+                          g_offset_ext ? g_offset_ext + o1 * 2 * KK : nullptr,
+                          g_aff_ext ? g_aff_ext + o1 * KK : nullptr, gamma, affinity, flags, H, W,
+                          g_feat_init + o1, g_guidance + o1 * 3 * N, g_confidence ? g_confidence + o1 : nullptr,
+                          g_gamma)));
+        NLSPN_CHECK_LAUNCH("final_bwd_kernel");
     }
-    const float *s_last = ((T - 1) % 2 == 0) ? setA : setB;
-    {
-        constexpr int C = 9;
-        const int nch = (K * K + C - 1) / C;
-        dim3 grid((unsigned)((P + kParamBlock - 1) / kParamBlock), (unsigned)B, (unsigned)nch);
-        { ProfScope prof__(kProfBwdParam, st);
-        DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
-                          offset, aff, src, list_feat, gy_all, conf_fixed ? 1 : 0, H, W, T, BP, g_guidance,
-                          g_aff_acc))); }
-        NLSPN_CHECK_LAUNCH("bwd_param_kernel");
-    }
-    { ProfScope prof__(kProfFinalBwd, st);
-    DISPATCH_K(K, (final_bwd_kernel<KC, true><<<grid_for(P, B), kBlock, 0, st>>>(
-                      guidance, feat_init, feat_fix, conf_fixed, s_last, g_aff_acc, g_conf_acc,
-                      g_offset_ext, g_aff_ext, gamma, affinity, flags, H, W, g_feat_init, g_guidance,
-                      g_confidence, g_gamma))); }
-    NLSPN_CHECK_LAUNCH("final_bwd_kernel");
     return 0;
 }
 

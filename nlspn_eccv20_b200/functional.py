@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["prologue_fwd", "propagate_fwd", "backward", "dcn_forward", "dcn_backward",
+__all__ = ["forward", "prologue_fwd", "propagate_fwd", "backward", "dcn_forward", "dcn_backward",
            "debug_indices", "device_info"]
 
 
@@ -32,6 +32,16 @@ def _chk(name, t, shape=None, optional=False):
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise RuntimeError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
     return t.contiguous()
+
+
+def _gamma(gamma, dev):
+    """gamma as a 1-element fp32 device tensor (no host sync when it already is one)."""
+    if torch.is_tensor(gamma):
+        g = gamma.detach().reshape(-1)[:1]
+        if g.device != dev or g.dtype != torch.float32:
+            g = g.to(device=dev, dtype=torch.float32)
+        return g.contiguous()
+    return torch.full((1,), float(gamma), device=dev, dtype=torch.float32)
 
 
 def _stream(dev):
@@ -68,13 +78,44 @@ def prologue_fwd(guidance, confidence, feat_init, feat_fix, gamma, K, affinity="
     aff = torch.empty((B, K * K, H, W), **opt)
     conf_fixed = torch.empty((B, 1, H, W), **opt) if confidence is not None else None
     src0 = torch.empty((B, 1, H, W), **opt)
+    gam = _gamma(gamma, dev)
     with torch.cuda.device(dev):
         rc = lib.nlspn_prologue_fwd(_ptr(guidance), _ptr(confidence), _ptr(feat_init), _ptr(feat_fix),
-                                    float(gamma), _lib.AFFINITY[affinity], _flags(preserve, always_clip),
+                                    _ptr(gam), _lib.AFFINITY[affinity], _flags(preserve, always_clip),
                                     B, H, W, K, _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(src0),
                                     _stream(dev))
     _lib.check(rc, "nlspn_prologue_fwd")
     return offset, aff, conf_fixed, src0
+
+
+def forward(guidance, confidence, feat_init, feat_fix, gamma, K, T, affinity="TGASS",
+            preserve_input=True, always_clip=False, keep_src=True):
+    """Fused prologue + T iterations (group-major).
+    -> (offset, aff, conf_fixed | None, src [S,B,1,H,W], list_feat [T,B,1,H,W])."""
+    lib = _lib.load()
+    B, _, H, W = feat_init.shape
+    N = K * K - 1
+    feat_init = _chk("feat_init", feat_init, (B, 1, H, W))
+    guidance = _chk("guidance", guidance, (B, 3 * N, H, W))
+    confidence = _chk("confidence", confidence, (B, 1, H, W), optional=True)
+    feat_fix = _chk("feat_fix", feat_fix, (B, 1, H, W), optional=True)
+    preserve = bool(preserve_input and feat_fix is not None)
+    dev = feat_init.device
+    opt = dict(device=dev, dtype=torch.float32)
+    offset = torch.empty((B, 2 * K * K, H, W), **opt)
+    aff = torch.empty((B, K * K, H, W), **opt)
+    conf_fixed = torch.empty((B, 1, H, W), **opt) if confidence is not None else None
+    S = 1 if confidence is None else (T if keep_src else min(T, 2))
+    src = torch.empty((S, B, 1, H, W), **opt)
+    list_feat = torch.empty((T, B, 1, H, W), **opt)
+    gam = _gamma(gamma, dev)
+    with torch.cuda.device(dev):
+        rc = lib.nlspn_forward(_ptr(guidance), _ptr(confidence), _ptr(feat_init), _ptr(feat_fix),
+                               _ptr(gam), _lib.AFFINITY[affinity], _flags(preserve, always_clip),
+                               B, H, W, K, T, _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(src), S,
+                               _ptr(list_feat), _stream(dev))
+    _lib.check(rc, "nlspn_forward")
+    return offset, aff, conf_fixed, src, list_feat
 
 
 def propagate_fwd(offset, aff, conf_fixed, feat_fix, src, list_feat, K, T,
@@ -123,10 +164,11 @@ def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_f
     g_gamma = torch.empty((1,), device=dev, dtype=torch.float64)
     nbytes = lib.nlspn_backward_workspace_bytes(B, H, W, K, T)
     ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+    gam = _gamma(gamma, dev)
     with torch.cuda.device(dev):
         rc = lib.nlspn_backward(_ptr(guidance.contiguous()), _ptr(feat_init.contiguous()), _ptr(feat_fix),
                                 _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(src), S, _ptr(list_feat),
-                                ptrs, _ptr(g_offset_ext), _ptr(g_aff_ext), float(gamma),
+                                ptrs, _ptr(g_offset_ext), _ptr(g_aff_ext), _ptr(gam),
                                 _lib.AFFINITY[affinity],
                                 _flags(preserve, always_clip) | (_lib.FLAG_BWD_PER_ITERATION if per_iteration else 0),
                                 B, H, W, K, T, _ptr(g_init), _ptr(g_guid), _ptr(g_conf), _ptr(g_gamma), _ptr(ws),

@@ -29,27 +29,15 @@ class NLSPNFunction(torch.autograd.Function):
     def forward(ctx, feat_init, guidance, confidence, feat_fix, gamma, K, T, affinity,
                 preserve_input, always_clip):
         need_grad = any(t is not None and t.requires_grad for t in (feat_init, guidance, confidence, gamma))
-        gamma_val = float(gamma.detach().reshape(-1)[0]) if torch.is_tensor(gamma) else float(gamma)
+        gamma_val = gamma.detach() if torch.is_tensor(gamma) else float(gamma)   # stays on the device
         feat_init_c = feat_init.detach().contiguous()
         guidance_c = guidance.detach().contiguous()
         conf_c = confidence.detach().contiguous() if confidence is not None else None
         fix_c = feat_fix.detach().contiguous() if feat_fix is not None else None
         preserve = bool(preserve_input and fix_c is not None)
-        offset, aff, conf_fixed, src0 = F_.prologue_fwd(guidance_c, conf_c, feat_init_c, fix_c, gamma_val,
-                                                        K, affinity, preserve, always_clip)
-        B, _, H, W = feat_init_c.shape
-        # src planes: all T kept when a backward may follow and confidence is used; else ping-pong
-        if conf_fixed is None:
-            S = 1
-        else:
-            S = T if need_grad else min(T, 2)
-        if S == 1:
-            src = src0.unsqueeze(0)
-        else:
-            src = torch.empty((S, B, 1, H, W), device=src0.device, dtype=torch.float32)
-            src[0].copy_(src0)
-        list_feat = torch.empty((T, B, 1, H, W), device=src0.device, dtype=torch.float32)
-        F_.propagate_fwd(offset, aff, conf_fixed, fix_c, src, list_feat, K, T, preserve, always_clip)
+        offset, aff, conf_fixed, src, list_feat = F_.forward(
+            guidance_c, conf_c, feat_init_c, fix_c, gamma_val, K, T, affinity, preserve, always_clip,
+            keep_src=need_grad)
         ctx.cfg = (K, T, affinity, preserve, always_clip, gamma_val)
         ctx.has_conf = conf_fixed is not None
         ctx.gamma_is_tensor = torch.is_tensor(gamma)

@@ -42,7 +42,7 @@ def test_library_has_sm100a_code_and_no_torch_dependency():
     import subprocess
     from nlspn_eccv20_b200 import _lib
     out = subprocess.run(["ldd", _lib.lib_path()], capture_output=True, text=True).stdout
-    assert "torch" not in out and "c10" not in out
+    assert "libtorch" not in out and "libc10" not in out
     cuobjdump = "/usr/local/cuda/bin/cuobjdump"
     if os.path.exists(cuobjdump):
         o = subprocess.run([cuobjdump, "-lelf", _lib.lib_path()], capture_output=True, text=True).stdout
@@ -53,17 +53,17 @@ def test_validation_errors_are_negative_and_described(lib):
     P = ctypes.c_void_p
     one = P(16)  # never dereferenced: validation fails first
     # bad kernel size
-    rc = lib.nlspn_prologue_fwd(one, None, one, None, 4.0, 3, 0, 1, 4, 4, 4, one, one, None, one, None)
+    rc = lib.nlspn_prologue_fwd(one, None, one, None, one, 3, 0, 1, 4, 4, 4, one, one, None, one, None)
     assert rc == -3 and b"prop_kernel" in lib.nlspn_last_error()
     # missing required pointer
-    rc = lib.nlspn_prologue_fwd(None, None, one, None, 4.0, 3, 0, 1, 4, 4, 3, one, one, None, one, None)
+    rc = lib.nlspn_prologue_fwd(None, None, one, None, one, 3, 0, 1, 4, 4, 3, one, one, None, one, None)
     assert rc == -1
     # PRESERVE_INPUT without feat_fix
-    rc = lib.nlspn_prologue_fwd(one, None, one, None, 4.0, 3, 1, 1, 4, 4, 3, one, one, None, one, None)
+    rc = lib.nlspn_prologue_fwd(one, None, one, None, one, 3, 1, 1, 4, 4, 3, one, one, None, one, None)
     assert rc == -1 and b"feat_fix" in lib.nlspn_last_error()
     # bad affinity / bad shape
-    assert lib.nlspn_prologue_fwd(one, None, one, None, 4.0, 9, 0, 1, 4, 4, 3, one, one, None, one, None) == -6
-    assert lib.nlspn_prologue_fwd(one, None, one, None, 4.0, 3, 0, 0, 4, 4, 3, one, one, None, one, None) == -2
+    assert lib.nlspn_prologue_fwd(one, None, one, None, one, 9, 0, 1, 4, 4, 3, one, one, None, one, None) == -6
+    assert lib.nlspn_prologue_fwd(one, None, one, None, one, 3, 0, 0, 4, 4, 3, one, one, None, one, None) == -2
     # confidence needs >= 2 src planes
     assert lib.nlspn_propagate_fwd(one, one, one, None, 0, 1, 4, 4, 3, 5, one, 1, one, None) == -2
     # DCN outside the NLSPN domain: C=2, stride 2, wrong padding
