@@ -35,7 +35,15 @@ namespace nlspn {
 //   gy   = (1-m) * G  [clip mask]   -> stored for pass B            (nlspnmodel.py:357,361)
 //   S_out[footprint(tap)] += gy * aff[tap] * corner weights          (cuh:229-252, 71-79)
 // ======================================================================================
-template <int K>
+// load with an optional "stream once" (evict-first) hint: used for offsets/affinities when the
+// image group is too large to stay L2-resident across iterations
+template <bool STREAM>
+__device__ __forceinline__ float ld_geo(const float *p)
+{
+    return STREAM ? __ldcs(p) : __ldg(p);
+}
+
+template <int K, bool STREAM>
 __global__ void __launch_bounds__(kBlock)
 bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff,
                  const float *__restrict__ conf, const float *__restrict__ dep,
@@ -52,48 +60,58 @@ bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff
     const int h = r / W, w = r - h * W;
     const ScatterGeo sg = scatter_geo(H, W);
 
-    // the streamed geometry first: these loads do not depend on the previous launch
+    // ---- stage 1: issue EVERY load before the first store, so one memory round trip covers
+    // the streamed geometry, the four scatter cells and the per-pixel planes
     const float *ob = offset + b * 2 * G::KK * P + r;
     const float *ab = aff + b * G::KK * P + r;
     float oh[G::KK], ow[G::KK], av[G::KK];
 #pragma unroll
     for (int t = 0; t < G::KK; ++t) {
-        av[t] = __ldg(ab + (long)t * P);
+        av[t] = ld_geo<STREAM>(ab + (long)t * P);
         if (t != G::REF) {
-            oh[t] = __ldg(ob + (long)(2 * t) * P);
-            ow[t] = __ldg(ob + (long)(2 * t + 1) * P);
+            oh[t] = ld_geo<STREAM>(ob + (long)(2 * t) * P);
+            ow[t] = ld_geo<STREAM>(ob + (long)(2 * t + 1) * P);
         }
     }
-
-    float Gx = g_ext ? __ldg(g_ext + q) : 0.f;
-    if (s_in) {
-        float *si = s_in + b * sg.image;
-        float gs = 0.f;
+    float *si = s_in ? s_in + b * sg.image : nullptr;
+    long cell[4];
+    float cv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ph = 0; ph < 4; ++ph) {
-            const long c = scatter_cell(sg, ph >> 1, ph & 1, h + 1, w + 1);
-            gs += si[c];
-            si[c] = 0.f;
-        }
-        if (conf) {
-            Gx += __ldg(conf + q) * gs;
-            g_conf_acc[q] += __ldg(x_t + q) * gs;
-        } else {
-            Gx += gs;
-        }
+    for (int ph = 0; ph < 4; ++ph) {
+        cell[ph] = scatter_cell(sg, ph >> 1, ph & 1, h + 1, w + 1);
+        if (si) cv[ph] = __ldcg(si + cell[ph]);
     }
-    if ((flags & kAlwaysClip) && !(__ldg(x_t + q) > 0.f)) Gx = 0.f;
-    if (flags & kPreserve) Gx = (1.0f - (__ldg(dep + q) > 0.f ? 1.f : 0.f)) * Gx;
+    const float gext = g_ext ? __ldg(g_ext + q) : 0.f;
+    const float cf = conf ? __ldg(conf + q) : 1.f;
+    const bool need_x = (si && conf) || (flags & kAlwaysClip);
+    const float xt = need_x ? __ldg(x_t + q) : 1.f;
+    const float dp = (flags & kPreserve) ? __ldg(dep + q) : 0.f;
+    const float gca = (si && conf) ? g_conf_acc[q] : 0.f;
+
+    // ---- stage 2: arithmetic
+    const float gs = ((cv[0] + cv[1]) + cv[2]) + cv[3];
+    float Gx = gext;
+    if (si) Gx += conf ? cf * gs : gs;
+    if ((flags & kAlwaysClip) && !(xt > 0.f)) Gx = 0.f;
+    if (flags & kPreserve) Gx = (1.0f - (dp > 0.f ? 1.f : 0.f)) * Gx;
     const float gy = Gx;
+
+    // ---- stage 3: plain stores
+    if (si) {
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) si[cell[ph]] = 0.f;
+        if (conf) g_conf_acc[q] = gca + xt * gs;
+    }
     gy_out[q] = gy;
     if (gy == 0.f) return; // fixed pixels (and exact zeros) contribute nothing to the scatter
 
+    // ---- stage 4: one vector RED per tap
     float *so = s_out + b * sg.image;
 #pragma unroll
     for (int t = 0; t < G::KK; ++t) {
         const float top = gy * av[t];
         if (t == G::REF) {
-            atomicAdd(so + scatter_cell(sg, 0, 0, h + 1, w + 1), top);
+            atomicAdd(so + cell[0], top);
             continue;
         }
         const float h_im = (float)(h - G::PAD + t / K) + oh[t];

@@ -399,6 +399,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     //      pass B (parameter gradients, one launch), final (prologue backward)
     const ScatterGeo sg = scatter_geo(H, W);
     const int G = group_images(B, H, W, K, true);
+    const bool stream_hint = getenv("NLSPN_STREAM_HINT") && atoi(getenv("NLSPN_STREAM_HINT")) != 0;
     float *setA = ws, *setB = setA + (long)G * sg.image;
     float *g_conf_acc = setB + (long)G * sg.image;
     float *gy_all = g_conf_acc + (long)G * P;          // [T, G, P]
@@ -415,10 +416,17 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             float *s_out = ((T - t) % 2 == 0) ? setA : setB;
             float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? setB : setA);
             ProfScope prof__(kProfBwdState, st);
-            DISPATCH_K(K, (bwd_state_kernel<KC><<<grid_for(P, nb), kBlock, 0, st>>>(
-                              offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, list_feat + (long)(t - 1) * BP + o1,
-                              g_list[t - 1] ? g_list[t - 1] + o1 : nullptr, s_in, s_out,
-                              gy_all + (long)(t - 1) * GP, g_conf_acc, flags, H, W)));
+            if (stream_hint) {
+                DISPATCH_K(K, (bwd_state_kernel<KC, true><<<grid_for(P, nb), kBlock, 0, st>>>(
+                                  offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, list_feat + (long)(t - 1) * BP + o1,
+                                  g_list[t - 1] ? g_list[t - 1] + o1 : nullptr, s_in, s_out,
+                                  gy_all + (long)(t - 1) * GP, g_conf_acc, flags, H, W)));
+            } else {
+                DISPATCH_K(K, (bwd_state_kernel<KC, false><<<grid_for(P, nb), kBlock, 0, st>>>(
+                                  offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, list_feat + (long)(t - 1) * BP + o1,
+                                  g_list[t - 1] ? g_list[t - 1] + o1 : nullptr, s_in, s_out,
+                                  gy_all + (long)(t - 1) * GP, g_conf_acc, flags, H, W)));
+            }
             NLSPN_CHECK_LAUNCH("bwd_state_kernel");
         }
         const float *s_last = ((T - 1) % 2 == 0) ? setA : setB;
