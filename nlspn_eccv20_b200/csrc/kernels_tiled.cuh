@@ -1,0 +1,246 @@
+// kernels_tiled.cuh -- TMA-tiled gather kernels (sm_100a).
+//
+// ncu on the direct-gather kernels (profiles/r01_v1_*): the 4*K^2 bilinear corner loads are
+// uncoalesced LDGs averaging ~13 sectors per request and L1 is the busiest unit (67 %), while
+// DRAM idles at 48 %.  Here each CTA owns a TW x TH pixel tile; the plane it gathers from
+// arrives in shared memory as ONE halo'd (TW+2R) x (TH+2R) box moved by the Tensor Memory
+// Accelerator (cp.async.bulk.tensor.3d, completion on an mbarrier).  TMA zero-fills whatever
+// lies outside the image, which is precisely the sampler's zero padding, so the gather loop has
+// no image-border guards; the only test left is "does the 2x2 footprint lie inside my box".
+// Taps that leave the box (|offset| > R-1 px) fall back to guarded global loads, so results are
+// identical for arbitrary offsets -- the box only makes the common case cheap.
+//
+//   iter_fwd_tiled_kernel   one propagation iteration (same epilogue as iter_fwd_kernel)
+//   bwd_param_tiled_kernel  pass B of the backward: loops t = T..1 with a 2-deep TMA pipeline
+//                           (plane t-1 is in flight while plane t is consumed)
+#pragma once
+#include "kernels_v2.cuh"
+#include "tma.cuh"
+
+namespace nlspn {
+
+constexpr int kHalo = 8;          // R: box halo in pixels
+constexpr int kTileW = 32;        // one warp per tile row: coalesced per-pixel planes
+constexpr int kBoxW = kTileW + 2 * kHalo;
+
+template <int TH>
+struct TileGeo {
+    static constexpr int BoxH = TH + 2 * kHalo;
+    static constexpr int BoxFloats = BoxH * kBoxW;
+    static constexpr int BoxBytes = BoxFloats * 4;
+};
+
+// four corner values of a sample from the shared-memory box, falling back to global memory
+// when the footprint is not inside the box.  box(0,0) is pixel (y0 - R, x0 - R).
+template <int TH>
+__device__ __forceinline__ Quad box_quad(const float *__restrict__ box, int y0, int x0,
+                                         const float *__restrict__ im, int H, int W, float h_im, float w_im)
+{
+    const float hf = floorf(h_im), wf = floorf(w_im);
+    const int hl = (int)hf, wl = (int)wf;
+    const int ty = hl - (y0 - kHalo), tx = wl - (x0 - kHalo);
+    if ((unsigned)ty < (unsigned)(TileGeo<TH>::BoxH - 1) && (unsigned)tx < (unsigned)(kBoxW - 1)) {
+        Quad q;
+        q.hl = hl;
+        q.wl = wl;
+        q.lh = h_im - hf;
+        q.lw = w_im - wf;
+        const float *p = box + ty * kBoxW + tx;
+        q.v1 = p[0];
+        q.v2 = p[1];
+        q.v3 = p[kBoxW];
+        q.v4 = p[kBoxW + 1];
+        return q;
+    }
+    return load_quad(im, H, W, h_im, w_im);
+}
+
+// ======================================================================================
+// Forward iteration, tiled.  grid = (tiles_x, tiles_y, nb), block = (32, TH).
+// plane_z = index of the source plane of image 0 of this launch inside the tensor map.
+// ======================================================================================
+template <int K, int TH, bool STREAM>
+__global__ void __launch_bounds__(kTileW * TH)
+iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
+                      const float *__restrict__ src_prev, const float *__restrict__ offset,
+                      const float *__restrict__ aff, const float *__restrict__ conf,
+                      const float *__restrict__ dep, unsigned flags, int H, int W,
+                      float *__restrict__ out, float *__restrict__ src_next)
+{
+    using G = Geo<K>;
+    using TG = TileGeo<TH>;
+    __shared__ __align__(128) float box[TG::BoxFloats];
+    __shared__ __align__(8) uint64_t bar;
+    const int P = H * W;
+    const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * TH;
+    const long b = blockIdx.z;
+    const int tid = threadIdx.y * kTileW + threadIdx.x;
+    if (tid == 0) {
+        tma::mbar_init(&bar, 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_arrive_expect_tx(&bar, TG::BoxBytes);
+        tma::load_3d(box, &src_map, &bar, x0 - kHalo, y0 - kHalo, plane_z + (int)b);
+    }
+    const int w = x0 + threadIdx.x, h = y0 + threadIdx.y;
+    const bool inside = w < W && h < H;
+    const int r = h * W + w;
+    // streamed geometry: independent of the box, issued before waiting for it
+    float oh[G::KK], ow[G::KK], av[G::KK];
+    float dp = 0.f, cf = 1.f;
+    if (inside) {
+        const float *ob = offset + b * 2 * G::KK * P + r;
+        const float *ab = aff + b * G::KK * P + r;
+#pragma unroll
+        for (int t = 0; t < G::KK; ++t) {
+            av[t] = ld_geo<STREAM>(ab + (long)t * P);
+            oh[t] = ow[t] = 0.f;
+            if (t != G::REF) {
+                oh[t] = ld_geo<STREAM>(ob + (long)(2 * t) * P);
+                ow[t] = ld_geo<STREAM>(ob + (long)(2 * t + 1) * P);
+            }
+        }
+        if (flags & kPreserve) dp = __ldg(dep + b * P + r);
+        if (conf && src_next) cf = __ldg(conf + b * P + r);
+    }
+    tma::mbar_wait(&bar, 0);
+    if (!inside) return;
+
+    const float *im = src_prev + b * P;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < G::KK; ++t) {
+        float v;
+        if (t == G::REF) {
+            v = box[(threadIdx.y + kHalo) * kBoxW + threadIdx.x + kHalo];
+        } else {
+            const float h_im = (float)(h - G::PAD + t / K) + oh[t];
+            const float w_im = (float)(w - G::PAD + t % K) + ow[t];
+            v = 0.f;
+            if (tap_valid(h_im, w_im, H, W)) v = quad_value(box_quad<TH>(box, y0, x0, im, H, W, h_im, w_im));
+        }
+        acc += v * av[t];
+    }
+    const long q = b * P + r;
+    if (flags & kPreserve) acc = blend_fix(acc, dp);
+    if (flags & kAlwaysClip) acc = fmaxf(acc, 0.f);
+    out[q] = acc;
+    if (src_next) src_next[q] = conf ? acc * cf : acc;
+}
+
+// ======================================================================================
+// Pass B of the backward, tiled.  grid = (tiles_x, tiles_y, nb * NCH), block = (32, TH).
+// For iteration t the gather source is plane  z_t  of one of two tensor maps:
+//   with confidence:     src_map,  z = (t-1)*Bsrc + b0 + b
+//   without confidence:  t == 1 -> src_map, z = b0 + b ; t >= 2 -> list_map, z = (t-2)*Bsrc + b0 + b
+// ======================================================================================
+template <int K, int C, int TH>
+__global__ void __launch_bounds__(kTileW * TH)
+bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
+                       const __grid_constant__ CUtensorMap list_map, int Bsrc, int b0,
+                       const float *__restrict__ offset, const float *__restrict__ aff,
+                       const float *__restrict__ src, const float *__restrict__ list_feat,
+                       const float *__restrict__ gy_all, int has_conf, int H, int W, int T, long BP,
+                       long GP, float *__restrict__ g_guidance, float *__restrict__ g_aff_acc)
+{
+    using G = Geo<K>;
+    using TG = TileGeo<TH>;
+    constexpr int NCH = (G::KK + C - 1) / C;
+    __shared__ __align__(128) float box[2][TG::BoxFloats];
+    __shared__ __align__(8) uint64_t bar[2];
+    const int P = H * W;
+    const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * TH;
+    const int b = NCH == 1 ? (int)blockIdx.z : (int)blockIdx.z / NCH;
+    const int k0 = NCH == 1 ? 0 : ((int)blockIdx.z % NCH) * C;
+    const int tid = threadIdx.y * kTileW + threadIdx.x;
+    if (tid == 0) {
+        tma::mbar_init(&bar[0], 1);
+        tma::mbar_init(&bar[1], 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t, int buf) {   // thread 0 only
+        tma::mbar_arrive_expect_tx(&bar[buf], TG::BoxBytes);
+        const bool use_src = has_conf || t == 1;
+        const int z = use_src ? (has_conf ? (t - 1) * Bsrc : 0) + b0 + b : (t - 2) * Bsrc + b0 + b;
+        tma::load_3d(box[buf], use_src ? &src_map : &list_map, &bar[buf], x0 - kHalo, y0 - kHalo, z);
+    };
+    if (tid == 0) issue(T, 0);
+
+    const int w = x0 + threadIdx.x, h = y0 + threadIdx.y;
+    const bool inside = w < W && h < H;
+    const int r = inside ? h * W + w : 0;
+    const long q = (long)b * P + r;
+    float oh[C], ow[C], av[C], acc_h[C], acc_w[C], acc_a[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int k = k0 + c;
+        oh[c] = ow[c] = av[c] = 0.f;
+        acc_h[c] = acc_w[c] = acc_a[c] = 0.f;
+        if (inside && k < G::KK) {
+            av[c] = __ldg(aff + ((long)b * G::KK + k) * P + r);
+            if (k != G::REF) {
+                oh[c] = __ldg(offset + ((long)b * 2 * G::KK + 2 * k) * P + r);
+                ow[c] = __ldg(offset + ((long)b * 2 * G::KK + 2 * k + 1) * P + r);
+            }
+        }
+    }
+    float gy_next = inside ? __ldg(gy_all + (long)(T - 1) * GP + q) : 0.f;
+    uint32_t phase_bits = 0u;   // bit i = parity the next wait on bar[i] expects
+    for (int t = T; t >= 1; --t) {
+        const int cur = (T - t) & 1;
+        // everyone is done reading box[cur^1] (consumed in the previous trip): refill it
+        __syncthreads();
+        if (tid == 0 && t > 1) issue(t - 1, cur ^ 1);
+        const float gy = gy_next;
+        if (t > 1) gy_next = inside ? __ldg(gy_all + (long)(t - 2) * GP + q) : 0.f;
+        tma::mbar_wait(&bar[cur], (phase_bits >> cur) & 1u);
+        phase_bits ^= 1u << cur;
+        if (gy == 0.f) continue;
+        const float *bx = box[cur];
+        const float *im;
+        if (has_conf) im = src + (long)(t - 1) * BP + (long)b * P;
+        else im = (t == 1 ? src : list_feat + (long)(t - 2) * BP) + (long)b * P;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int k = k0 + c;
+            if (k >= G::KK) continue;
+            if (k == G::REF) {
+                acc_a[c] += gy * bx[(threadIdx.y + kHalo) * kBoxW + threadIdx.x + kHalo];
+                continue;
+            }
+            const float h_im = (float)(h - G::PAD + k / K) + oh[c];
+            const float w_im = (float)(w - G::PAD + k % K) + ow[c];
+            if (!tap_valid(h_im, w_im, H, W)) continue;
+            const Quad qd = box_quad<TH>(bx, y0, x0, im, H, W, h_im, w_im);
+            acc_a[c] += gy * quad_value(qd);                       // cuh:314-315
+            const float top = gy * av[c];
+            // mdmcn_get_coordinate_weight, cuh:101-122 (expressions kept literal)
+            const float wl1 = (float)(qd.wl + 1) - w_im, wl0 = w_im - (float)qd.wl;
+            const float hl1 = (float)(qd.hl + 1) - h_im, hl0 = h_im - (float)qd.hl;
+            const float dh = -1.f * wl1 * qd.v1 + -1.f * wl0 * qd.v2 + wl1 * qd.v3 + wl0 * qd.v4;
+            const float dw = -1.f * hl1 * qd.v1 + hl1 * qd.v2 + -1.f * hl0 * qd.v3 + hl0 * qd.v4;
+            acc_h[c] += dh * top;
+            acc_w[c] += dw * top;
+        }
+    }
+    if (!inside) return;
+    float *ggb = g_guidance + (long)b * 3 * G::N * P + r;
+    float *gab = g_aff_acc + (long)b * G::KK * P + r;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int k = k0 + c;
+        if (k >= G::KK) continue;
+        gab[(long)k * P] = acc_a[c];
+        if (k != G::REF) {
+            const int n = k < G::REF ? k : k - 1;
+            ggb[(long)(2 * n) * P] = acc_h[c];
+            ggb[(long)(2 * n + 1) * P] = acc_w[c];
+        }
+    }
+}
+
+} // namespace nlspn

@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../include/nlspn_b200.h"
-#include "kernels_v2.cuh"
+#include "kernels_tiled.cuh"
 
 using namespace nlspn;
 
@@ -186,15 +186,71 @@ static int group_images(int B, int H, int W, int K, bool backward)
         const int g = atoi(e);
         if (g > 0) return g < B ? g : B;
     }
+    // Measured on B200 (KITTI, B=8, K=3, T=18; profiles/): once every load of a thread is issued
+    // before its first store the kernels no longer care whether a group is L2-resident
+    // (G=1: 6.58, G=2: 6.82, G=4: 6.89, G=8: 7.09 Gpix*iter/s), and smaller groups cost launch
+    // tails.  Default: the whole batch is one group.
+    (void)H; (void)W; (void)K; (void)backward;
+    return B;
+}
+
+// ---- TMA tensor maps -----------------------------------------------------------------------
+// A [planes, H, W] fp32 array viewed as a 3-D tensor; box = one halo'd tile of one plane.
+// cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so the
+// library needs no link-time dependency on libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+static bool tiled_enabled()
+{
+    const char *e = getenv("NLSPN_TILED");
+    return !(e && atoi(e) == 0);
+}
+
+// true when the tiled (TMA) kernels can serve this shape
+static bool tiled_ok(const void *base, int W)
+{
+    return tiled_enabled() && (W % 4) == 0 && aligned16(base) && encode_tiled_fn() != nullptr;
+}
+
+static int make_plane_map(CUtensorMap *map, const float *base, long planes, int H, int W, int box_h)
+{
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kBoxW, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims,
+                                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NLSPN_ERR_SHAPE, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return 0;
+}
+
+constexpr int kFwdTH = 16;    // forward tile: 32 x 16 pixels, 512 threads
+constexpr int kParamTH = 8;   // pass-B tile: 32 x 8 pixels, 256 threads (register-heavy)
+
+static bool stream_hint_for(int B, int H, int W, int K)
+{
+    if (const char *e = getenv("NLSPN_STREAM_HINT")) return atoi(e) != 0;
     int dev = 0, l2 = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, nullptr, &l2) != 0 || l2 <= 0)
-        l2 = 64 << 20;
-    const double per_image = (double)H * W * 4.0 * (3.0 * K * K + (backward ? 14.0 : 4.0));
-    int g = (int)(0.45 * (double)l2 / per_image);
-    if (g < 1) g = 1;
-    if (g > B) g = B;
-    const int ngroups = (B + g - 1) / g;
-    return (B + ngroups - 1) / ngroups;   // balanced groups
+    if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, nullptr, &l2) != 0) return true;
+    return (double)B * H * W * 4.0 * 3.0 * K * K > 0.5 * (double)l2;   // geometry does not fit L2
 }
 
 struct FwdCall {
@@ -223,23 +279,48 @@ static int launch_prologue(const FwdCall &c, int b0, int nb)
     return 0;
 }
 
-static int launch_iter_fwd(const FwdCall &c, int b0, int nb, int t)
+static int launch_iter_fwd(const FwdCall &c, int b0, int nb, int t, const CUtensorMap *src_map,
+                           const CUtensorMap *list_map, bool stream)
 {
     const int P = c.H * c.W, KK = c.K * c.K;
     const long BP = (long)c.B * P, o1 = (long)b0 * P;
     const float *src_prev;
     float *src_next = nullptr;
+    const CUtensorMap *map = src_map;
+    int plane_z;
     if (c.conf_fixed) {
         src_prev = c.src + (long)((t - 1) % c.S) * BP + o1;
+        plane_z = ((t - 1) % c.S) * c.B + b0;
         if (t < c.T) src_next = c.src + (long)(t % c.S) * BP + o1;
+    } else if (t == 1) {
+        src_prev = c.src + o1;
+        plane_z = b0;
     } else {
-        src_prev = (t == 1 ? c.src : c.list_feat + (long)(t - 2) * BP) + o1;
+        src_prev = c.list_feat + (long)(t - 2) * BP + o1;
+        plane_z = (t - 2) * c.B + b0;
+        map = list_map;
     }
     float *out = c.list_feat + (long)(t - 1) * BP + o1;
+    const float *cf = c.conf_fixed ? c.conf_fixed + o1 : nullptr;
+    const float *fx = c.feat_fix ? c.feat_fix + o1 : nullptr;
     ProfScope prof__(kProfIterFwd, c.st);
+    if (map) {
+        dim3 grid((unsigned)((c.W + kTileW - 1) / kTileW), (unsigned)((c.H + kFwdTH - 1) / kFwdTH), (unsigned)nb);
+        dim3 block(kTileW, kFwdTH);
+        if (stream) {
+            DISPATCH_K(c.K, (iter_fwd_tiled_kernel<KC, kFwdTH, true><<<grid, block, 0, c.st>>>(
+                                *map, plane_z, src_prev, c.offset + o1 * 2 * KK, c.aff + o1 * KK, cf, fx,
+                                c.flags, c.H, c.W, out, src_next)));
+        } else {
+            DISPATCH_K(c.K, (iter_fwd_tiled_kernel<KC, kFwdTH, false><<<grid, block, 0, c.st>>>(
+                                *map, plane_z, src_prev, c.offset + o1 * 2 * KK, c.aff + o1 * KK, cf, fx,
+                                c.flags, c.H, c.W, out, src_next)));
+        }
+        NLSPN_CHECK_LAUNCH("iter_fwd_tiled_kernel");
+        return 0;
+    }
     DISPATCH_K(c.K, (iter_fwd_kernel<KC, true><<<grid_for(P, nb), kBlock, 0, c.st>>>(
-                        src_prev, c.offset + o1 * 2 * KK, c.aff + o1 * KK,
-                        c.conf_fixed ? c.conf_fixed + o1 : nullptr, c.feat_fix ? c.feat_fix + o1 : nullptr,
+                        src_prev, c.offset + o1 * 2 * KK, c.aff + o1 * KK, cf, fx,
                         nullptr, nullptr, c.flags, c.H, c.W, out, src_next)));
     NLSPN_CHECK_LAUNCH("iter_fwd_kernel");
     return 0;
@@ -271,13 +352,22 @@ static int run_forward(const FwdCall &c, bool prologue, bool iters)
 {
     if (int rc = check_fwd(c, prologue, iters)) return rc;
     const int G = group_images(c.B, c.H, c.W, c.K, false);
+    CUtensorMap src_map, list_map;
+    const CUtensorMap *psrc = nullptr, *plist = nullptr;
+    if (iters && tiled_ok(c.src, c.W) && aligned16(c.list_feat)) {
+        if (int rc = make_plane_map(&src_map, c.src, (long)c.S * c.B, c.H, c.W, TileGeo<kFwdTH>::BoxH)) return rc;
+        if (int rc = make_plane_map(&list_map, c.list_feat, (long)c.T * c.B, c.H, c.W, TileGeo<kFwdTH>::BoxH)) return rc;
+        psrc = &src_map;
+        plist = &list_map;
+    }
+    const bool stream = stream_hint_for(G, c.H, c.W, c.K);
     for (int b0 = 0; b0 < c.B; b0 += G) {
         const int nb = c.B - b0 < G ? c.B - b0 : G;
         if (prologue)
             if (int rc = launch_prologue(c, b0, nb)) return rc;
         if (iters)
             for (int t = 1; t <= c.T; ++t)
-                if (int rc = launch_iter_fwd(c, b0, nb, t)) return rc;
+                if (int rc = launch_iter_fwd(c, b0, nb, t, psrc, plist, stream)) return rc;
     }
     return 0;
 }
@@ -399,7 +489,13 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     //      pass B (parameter gradients, one launch), final (prologue backward)
     const ScatterGeo sg = scatter_geo(H, W);
     const int G = group_images(B, H, W, K, true);
-    const bool stream_hint = getenv("NLSPN_STREAM_HINT") && atoi(getenv("NLSPN_STREAM_HINT")) != 0;
+    const bool stream_hint = stream_hint_for(G, H, W, K);
+    CUtensorMap src_map, list_map;
+    const bool use_tiled = tiled_ok(src, W) && aligned16(list_feat);
+    if (use_tiled) {
+        if (int rc = make_plane_map(&src_map, src, (long)(conf_fixed ? T : 1) * B, H, W, TileGeo<kParamTH>::BoxH)) return rc;
+        if (int rc = make_plane_map(&list_map, list_feat, (long)T * B, H, W, TileGeo<kParamTH>::BoxH)) return rc;
+    }
     float *setA = ws, *setB = setA + (long)G * sg.image;
     float *g_conf_acc = setB + (long)G * sg.image;
     float *gy_all = g_conf_acc + (long)G * P;          // [T, G, P]
@@ -435,10 +531,21 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             const int nch = (KK + C - 1) / C;
             dim3 grid((unsigned)((P + kParamBlock - 1) / kParamBlock), (unsigned)nb, (unsigned)nch);
             ProfScope prof__(kProfBwdParam, st);
-            DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
-                              offset + o1 * 2 * KK, aff + o1 * KK, src + o1, list_feat + o1, gy_all,
-                              conf_fixed ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc)));
-            NLSPN_CHECK_LAUNCH("bwd_param_kernel");
+            if (use_tiled) {
+                dim3 tgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + kParamTH - 1) / kParamTH),
+                           (unsigned)(nb * nch));
+                dim3 tblock(kTileW, kParamTH);
+                DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, kParamTH><<<tgrid, tblock, 0, st>>>(
+                                  src_map, list_map, B, b0, offset + o1 * 2 * KK, aff + o1 * KK, src + o1,
+                                  list_feat + o1, gy_all, conf_fixed ? 1 : 0, H, W, T, BP, GP,
+                                  g_guidance + o1 * 3 * N, g_aff_acc)));
+                NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
+            } else {
+                DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
+                                  offset + o1 * 2 * KK, aff + o1 * KK, src + o1, list_feat + o1, gy_all,
+                                  conf_fixed ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc)));
+                NLSPN_CHECK_LAUNCH("bwd_param_kernel");
+            }
         }
         ProfScope prof__(kProfFinalBwd, st);
         DISPATCH_K(K, (final_bwd_kernel<KC, true><<<grid_for(P, nb), kBlock, 0, st>>>(
