@@ -80,14 +80,13 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
         tma::fence_barrier_init();
     }
     __syncthreads();
-    if (tid == 0) {
-        tma::mbar_arrive_expect_tx(&bar, TG::BoxBytes);
-        tma::load_3d(box, &src_map, &bar, x0 - kHalo, y0 - kHalo, plane_z + (int)b);
-    }
+    // PDL: let the next iteration's CTAs become resident as soon as ours have started; they
+    // only prefetch their (iteration-independent) geometry before their own grid_dependency_wait
+    tma::grid_launch_dependents();
     const int w = x0 + threadIdx.x, h = y0 + threadIdx.y;
     const bool inside = w < W && h < H;
     const int r = h * W + w;
-    // streamed geometry: independent of the box, issued before waiting for it
+    // streamed geometry: independent of the previous iteration, issued before waiting for it
     float oh[G::KK], ow[G::KK], av[G::KK];
     float dp = 0.f, cf = 1.f;
     if (inside) {
@@ -104,6 +103,12 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
         }
         if (flags & kPreserve) dp = __ldg(dep + b * P + r);
         if (conf && src_next) cf = __ldg(conf + b * P + r);
+    }
+    // everything below depends on the previous iteration's output
+    tma::grid_dependency_wait();
+    if (tid == 0) {
+        tma::mbar_arrive_expect_tx(&bar, TG::BoxBytes);
+        tma::load_3d(box, &src_map, &bar, x0 - kHalo, y0 - kHalo, plane_z + (int)b);
     }
     tma::mbar_wait(&bar, 0);
     if (!inside) return;
@@ -135,6 +140,14 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
 // For iteration t the gather source is plane  z_t  of one of two tensor maps:
 //   with confidence:     src_map,  z = (t-1)*Bsrc + b0 + b
 //   without confidence:  t == 1 -> src_map, z = b0 + b ; t >= 2 -> list_map, z = (t-2)*Bsrc + b0 + b
+//
+// The sampling geometry of a tap does not depend on t, so everything derived from the offsets
+// (box index of the footprint, fractional weights, validity) is computed ONCE and kept in
+// registers; the t loop is 4 LDS + ~20 FP instructions per tap.  Each tap is classified once:
+//   FAST  footprint inside the box and the tap passes the validity test of cuh:180
+//   SLOW  valid but outside the box  -> guarded global loads every iteration
+//   SKIP  invalid (cuh:308-311: contributes nothing)
+// A warp whose lanes are all-FAST runs a branch-free loop.
 // ======================================================================================
 template <int K, int C, int TH>
 __global__ void __launch_bounds__(kTileW * TH)
@@ -174,57 +187,123 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
     const bool inside = w < W && h < H;
     const int r = inside ? h * W + w : 0;
     const long q = (long)b * P + r;
-    float oh[C], ow[C], av[C], acc_h[C], acc_w[C], acc_a[C];
+
+    // ---- per-tap geometry, computed once
+    int idx[C];                         // box index of the footprint's top-left corner (FAST taps)
+    float lh[C], lw[C], hl1[C], wl1[C]; // hl0 == lh, wl0 == lw (same expressions as cuh:101-122)
+    float av[C];
+    float acc_h[C], acc_w[C], acc_a[C];
+    unsigned slow_bits = 0u, skip_bits = 0u;
+    constexpr int kCenterIdx = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const int k = k0 + c;
-        oh[c] = ow[c] = av[c] = 0.f;
+        idx[c] = kCenterIdx;
+        lh[c] = lw[c] = hl1[c] = wl1[c] = av[c] = 0.f;
         acc_h[c] = acc_w[c] = acc_a[c] = 0.f;
-        if (inside && k < G::KK) {
-            av[c] = __ldg(aff + ((long)b * G::KK + k) * P + r);
-            if (k != G::REF) {
-                oh[c] = __ldg(offset + ((long)b * 2 * G::KK + 2 * k) * P + r);
-                ow[c] = __ldg(offset + ((long)b * 2 * G::KK + 2 * k + 1) * P + r);
-            }
+        if (!inside || k >= G::KK) {
+            skip_bits |= 1u << c;
+            continue;
+        }
+        av[c] = __ldg(aff + ((long)b * G::KK + k) * P + r);
+        if (k == G::REF) {
+            idx[c] = (threadIdx.y + kHalo) * kBoxW + threadIdx.x + kHalo;
+            continue;
+        }
+        const float o_h = __ldg(offset + ((long)b * 2 * G::KK + 2 * k) * P + r);
+        const float o_w = __ldg(offset + ((long)b * 2 * G::KK + 2 * k + 1) * P + r);
+        const float h_im = (float)(h - G::PAD + k / K) + o_h;
+        const float w_im = (float)(w - G::PAD + k % K) + o_w;
+        if (!tap_valid(h_im, w_im, H, W)) {
+            skip_bits |= 1u << c;
+            continue;
+        }
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int hl = (int)hf, wl = (int)wf;
+        lh[c] = h_im - hf;                       // == h_im - (float)hl
+        lw[c] = w_im - wf;
+        hl1[c] = (float)(hl + 1) - h_im;
+        wl1[c] = (float)(wl + 1) - w_im;
+        const int ty = hl - (y0 - kHalo), tx = wl - (x0 - kHalo);
+        if ((unsigned)ty < (unsigned)(TG::BoxH - 1) && (unsigned)tx < (unsigned)(kBoxW - 1)) {
+            idx[c] = ty * kBoxW + tx;
+        } else {
+            slow_bits |= 1u << c;
+            idx[c] = hl * W + wl;                // image index of the corner (may be negative)
         }
     }
-    float gy_next = inside ? __ldg(gy_all + (long)(T - 1) * GP + q) : 0.f;
+    const bool warp_fast = __all_sync(0xffffffffu, (slow_bits | skip_bits) == 0u);
+
+    float gy_n1 = inside ? __ldg(gy_all + (long)(T - 1) * GP + q) : 0.f;
+    float gy_n2 = (inside && T > 1) ? __ldg(gy_all + (long)(T - 2) * GP + q) : 0.f;
     uint32_t phase_bits = 0u;   // bit i = parity the next wait on bar[i] expects
     for (int t = T; t >= 1; --t) {
         const int cur = (T - t) & 1;
         // everyone is done reading box[cur^1] (consumed in the previous trip): refill it
         __syncthreads();
         if (tid == 0 && t > 1) issue(t - 1, cur ^ 1);
-        const float gy = gy_next;
-        if (t > 1) gy_next = inside ? __ldg(gy_all + (long)(t - 2) * GP + q) : 0.f;
+        const float gy = gy_n1;
+        gy_n1 = gy_n2;
+        if (t > 2) gy_n2 = inside ? __ldg(gy_all + (long)(t - 3) * GP + q) : 0.f;
         tma::mbar_wait(&bar[cur], (phase_bits >> cur) & 1u);
         phase_bits ^= 1u << cur;
-        if (gy == 0.f) continue;
         const float *bx = box[cur];
-        const float *im;
-        if (has_conf) im = src + (long)(t - 1) * BP + (long)b * P;
-        else im = (t == 1 ? src : list_feat + (long)(t - 2) * BP) + (long)b * P;
+        if (warp_fast) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const int k = k0 + c;
-            if (k >= G::KK) continue;
-            if (k == G::REF) {
-                acc_a[c] += gy * bx[(threadIdx.y + kHalo) * kBoxW + threadIdx.x + kHalo];
-                continue;
+            for (int c = 0; c < C; ++c) {
+                const int k = k0 + c;
+                const float *p = bx + idx[c];
+                if (k == G::REF) {
+                    acc_a[c] += gy * p[0];
+                    continue;
+                }
+                const float v1 = p[0], v2 = p[1], v3 = p[kBoxW], v4 = p[kBoxW + 1];
+                const float hh = 1.f - lh[c], hw = 1.f - lw[c];
+                const float bil = (hh * hw) * v1 + (hh * lw[c]) * v2 + (lh[c] * hw) * v3 + (lh[c] * lw[c]) * v4;
+                acc_a[c] += gy * bil;                                            // cuh:314-315
+                const float top = gy * av[c];
+                const float dh = -1.f * wl1[c] * v1 + -1.f * lw[c] * v2 + wl1[c] * v3 + lw[c] * v4;
+                const float dw = -1.f * hl1[c] * v1 + hl1[c] * v2 + -1.f * lh[c] * v3 + lh[c] * v4;
+                acc_h[c] += dh * top;
+                acc_w[c] += dw * top;
             }
-            const float h_im = (float)(h - G::PAD + k / K) + oh[c];
-            const float w_im = (float)(w - G::PAD + k % K) + ow[c];
-            if (!tap_valid(h_im, w_im, H, W)) continue;
-            const Quad qd = box_quad<TH>(bx, y0, x0, im, H, W, h_im, w_im);
-            acc_a[c] += gy * quad_value(qd);                       // cuh:314-315
-            const float top = gy * av[c];
-            // mdmcn_get_coordinate_weight, cuh:101-122 (expressions kept literal)
-            const float wl1 = (float)(qd.wl + 1) - w_im, wl0 = w_im - (float)qd.wl;
-            const float hl1 = (float)(qd.hl + 1) - h_im, hl0 = h_im - (float)qd.hl;
-            const float dh = -1.f * wl1 * qd.v1 + -1.f * wl0 * qd.v2 + wl1 * qd.v3 + wl0 * qd.v4;
-            const float dw = -1.f * hl1 * qd.v1 + hl1 * qd.v2 + -1.f * hl0 * qd.v3 + hl0 * qd.v4;
-            acc_h[c] += dh * top;
-            acc_w[c] += dw * top;
+        } else if (gy != 0.f) {
+            const float *im;
+            if (has_conf) im = src + (long)(t - 1) * BP + (long)b * P;
+            else im = (t == 1 ? src : list_feat + (long)(t - 2) * BP) + (long)b * P;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int k = k0 + c;
+                if (skip_bits & (1u << c)) continue;
+                if (k == G::REF) {
+                    acc_a[c] += gy * bx[idx[c]];
+                    continue;
+                }
+                float v1, v2, v3, v4;
+                if (slow_bits & (1u << c)) {
+                    // guarded global loads (cuh:37-48); idx = hl*W + wl
+                    const int hl = (int)floorf((float)(h - G::PAD + k / K) +
+                                               __ldg(offset + ((long)b * 2 * G::KK + 2 * k) * P + r));
+                    const int wl = idx[c] - hl * W;
+                    const bool tp = hl >= 0, bt = hl + 1 <= H - 1, lf = wl >= 0, rg = wl + 1 <= W - 1;
+                    const float *pg = im + idx[c];
+                    v1 = (tp && lf) ? __ldg(pg) : 0.f;
+                    v2 = (tp && rg) ? __ldg(pg + 1) : 0.f;
+                    v3 = (bt && lf) ? __ldg(pg + W) : 0.f;
+                    v4 = (bt && rg) ? __ldg(pg + W + 1) : 0.f;
+                } else {
+                    const float *p = bx + idx[c];
+                    v1 = p[0]; v2 = p[1]; v3 = p[kBoxW]; v4 = p[kBoxW + 1];
+                }
+                const float hh = 1.f - lh[c], hw = 1.f - lw[c];
+                const float bil = (hh * hw) * v1 + (hh * lw[c]) * v2 + (lh[c] * hw) * v3 + (lh[c] * lw[c]) * v4;
+                acc_a[c] += gy * bil;
+                const float top = gy * av[c];
+                const float dh = -1.f * wl1[c] * v1 + -1.f * lw[c] * v2 + wl1[c] * v3 + lw[c] * v4;
+                const float dw = -1.f * hl1[c] * v1 + hl1[c] * v2 + -1.f * lh[c] * v3 + lh[c] * v4;
+                acc_h[c] += dh * top;
+                acc_w[c] += dw * top;
+            }
         }
     }
     if (!inside) return;

@@ -25,6 +25,7 @@
 // 36N+36 = 324 B of the per-iteration formulation (K=3).
 #pragma once
 #include "kernels_v1.cuh"
+#include "tma.cuh"
 
 namespace nlspn {
 
@@ -61,7 +62,10 @@ bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff
     const ScatterGeo sg = scatter_geo(H, W);
 
     // ---- stage 1: issue EVERY load before the first store, so one memory round trip covers
-    // the streamed geometry, the four scatter cells and the per-pixel planes
+    // the streamed geometry, the four scatter cells and the per-pixel planes.
+    // PDL: the loads that do not depend on the previous backward iteration go first; the next
+    // launch may start prefetching its own geometry while this grid drains.
+    tma::grid_launch_dependents();
     const float *ob = offset + b * 2 * G::KK * P + r;
     const float *ab = aff + b * G::KK * P + r;
     float oh[G::KK], ow[G::KK], av[G::KK];
@@ -73,6 +77,12 @@ bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff
             ow[t] = ld_geo<STREAM>(ob + (long)(2 * t + 1) * P);
         }
     }
+    const float gext = g_ext ? __ldg(g_ext + q) : 0.f;
+    const float cf = conf ? __ldg(conf + q) : 1.f;
+    const bool need_x = (s_in && conf) || (flags & kAlwaysClip);
+    const float xt = need_x ? __ldg(x_t + q) : 1.f;
+    const float dp = (flags & kPreserve) ? __ldg(dep + q) : 0.f;
+    tma::grid_dependency_wait();   // s_in / s_out / g_conf_acc belong to the previous launch
     float *si = s_in ? s_in + b * sg.image : nullptr;
     long cell[4];
     float cv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -81,11 +91,6 @@ bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff
         cell[ph] = scatter_cell(sg, ph >> 1, ph & 1, h + 1, w + 1);
         if (si) cv[ph] = __ldcg(si + cell[ph]);
     }
-    const float gext = g_ext ? __ldg(g_ext + q) : 0.f;
-    const float cf = conf ? __ldg(conf + q) : 1.f;
-    const bool need_x = (si && conf) || (flags & kAlwaysClip);
-    const float xt = need_x ? __ldg(x_t + q) : 1.f;
-    const float dp = (flags & kPreserve) ? __ldg(dep + q) : 0.f;
     const float gca = (si && conf) ? g_conf_acc[q] : 0.f;
 
     // ---- stage 2: arithmetic

@@ -242,8 +242,37 @@ static int make_plane_map(CUtensorMap *map, const float *base, long planes, int 
     return 0;
 }
 
+// Launch with programmatic stream serialisation (PDL): the grid may become resident while the
+// previous kernel in the stream is still draining; the kernel itself orders its dependent
+// accesses with griddepcontrol.wait (tma::grid_dependency_wait).
+static bool pdl_enabled()
+{
+    const char *e = getenv("NLSPN_PDL");
+    return !(e && atoi(e) == 0);
+}
+
+} // extern "C" (templates need C++ linkage)
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+extern "C" {
+
 constexpr int kFwdTH = 16;    // forward tile: 32 x 16 pixels, 512 threads
-constexpr int kParamTH = 8;   // pass-B tile: 32 x 8 pixels, 256 threads (register-heavy)
+constexpr int kParamTH = 16;  // pass-B tile: 32 x 16 pixels, 512 threads (<= 128 registers)
 
 static bool stream_hint_for(int B, int H, int W, int K)
 {
@@ -308,11 +337,11 @@ static int launch_iter_fwd(const FwdCall &c, int b0, int nb, int t, const CUtens
         dim3 grid((unsigned)((c.W + kTileW - 1) / kTileW), (unsigned)((c.H + kFwdTH - 1) / kFwdTH), (unsigned)nb);
         dim3 block(kTileW, kFwdTH);
         if (stream) {
-            DISPATCH_K(c.K, (iter_fwd_tiled_kernel<KC, kFwdTH, true><<<grid, block, 0, c.st>>>(
+            DISPATCH_K(c.K, (launch_pdl(iter_fwd_tiled_kernel<KC, kFwdTH, true>, grid, block, c.st,
                                 *map, plane_z, src_prev, c.offset + o1 * 2 * KK, c.aff + o1 * KK, cf, fx,
                                 c.flags, c.H, c.W, out, src_next)));
         } else {
-            DISPATCH_K(c.K, (iter_fwd_tiled_kernel<KC, kFwdTH, false><<<grid, block, 0, c.st>>>(
+            DISPATCH_K(c.K, (launch_pdl(iter_fwd_tiled_kernel<KC, kFwdTH, false>, grid, block, c.st,
                                 *map, plane_z, src_prev, c.offset + o1 * 2 * KK, c.aff + o1 * KK, cf, fx,
                                 c.flags, c.H, c.W, out, src_next)));
         }
@@ -512,16 +541,17 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             float *s_out = ((T - t) % 2 == 0) ? setA : setB;
             float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? setB : setA);
             ProfScope prof__(kProfBwdState, st);
+            const float *xt = list_feat + (long)(t - 1) * BP + o1;
+            const float *ge = g_list[t - 1] ? g_list[t - 1] + o1 : nullptr;
+            float *gyo = gy_all + (long)(t - 1) * GP;
             if (stream_hint) {
-                DISPATCH_K(K, (bwd_state_kernel<KC, true><<<grid_for(P, nb), kBlock, 0, st>>>(
-                                  offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, list_feat + (long)(t - 1) * BP + o1,
-                                  g_list[t - 1] ? g_list[t - 1] + o1 : nullptr, s_in, s_out,
-                                  gy_all + (long)(t - 1) * GP, g_conf_acc, flags, H, W)));
+                DISPATCH_K(K, (launch_pdl(bwd_state_kernel<KC, true>, grid_for(P, nb), dim3(kBlock), st,
+                                  offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, xt, ge, s_in, s_out, gyo,
+                                  g_conf_acc, flags, H, W)));
             } else {
-                DISPATCH_K(K, (bwd_state_kernel<KC, false><<<grid_for(P, nb), kBlock, 0, st>>>(
-                                  offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, list_feat + (long)(t - 1) * BP + o1,
-                                  g_list[t - 1] ? g_list[t - 1] + o1 : nullptr, s_in, s_out,
-                                  gy_all + (long)(t - 1) * GP, g_conf_acc, flags, H, W)));
+                DISPATCH_K(K, (launch_pdl(bwd_state_kernel<KC, false>, grid_for(P, nb), dim3(kBlock), st,
+                                  offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, xt, ge, s_in, s_out, gyo,
+                                  g_conf_acc, flags, H, W)));
             }
             NLSPN_CHECK_LAUNCH("bwd_state_kernel");
         }

@@ -6,6 +6,7 @@
 // :37-48), so every per-corner image-border guard disappears from the gather loop.
 #pragma once
 #include <cuda.h>
+// (this header is also included by the non-TMA kernels for the PDL helpers)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
