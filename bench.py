@@ -51,7 +51,9 @@ def parse():
     p.add_argument("--mode", default="fwdbwd", choices=["fwdbwd", "fwd"])
     p.add_argument("--smooth-offsets", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-images", type=int, default=None, help="images in the CPU sample")
+    p.add_argument("--cpu-images", type=int, default=None, help="frames in the CPU sample (default: min(cores, 8))")
+    p.add_argument("--cpu-rows", type=int, default=48,
+                   help="rows of each frame in the CPU sample (full width; bounds the CPU leg's run time)")
     return p.parse_args()
 
 
@@ -107,7 +109,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.004)
 
     def start(self):
         if self._nvml is not None:
@@ -125,7 +127,9 @@ class ClockSampler:
 
 
 def cpu_reference_run(args, H, W, md, n_images, steps, warmup):
-    """Times oracle/torchvision_port.py (the reference path over torchvision) on host cores."""
+    """Times oracle/torchvision_port.py (the reference path over torchvision) on host cores.
+    Sample: n_images frames of min(H, --cpu-rows) rows x full width, one frame per host thread."""
+    H = min(H, args.cpu_rows)
     import torch
     from nlspn_eccv20_b200.synth import make_inputs
     from oracle import torchvision_port as TP
@@ -149,7 +153,7 @@ def cpu_reference_run(args, H, W, md, n_images, steps, warmup):
     mean = sum(times) / len(times)
     pix_iter = n_images * H * W * T
     return dict(value=pix_iter / mean / 1e9, best=pix_iter / best / 1e9, seconds=mean, cores=workers,
-                host_cores=cores, n_images=n_images)
+                host_cores=cores, n_images=n_images, rows=H)
 
 
 def main():
@@ -167,7 +171,8 @@ def main():
               "affinity": "TGASS", "conf_prop": True, "preserve_input": True,
               "offsets": "smooth" if args.smooth_offsets else "iid N(0,2^2) px",
               "sharding": "batch shard per GPU, no collective on the data path",
-              "l2": "inputs exceed L2 (guidance alone is %.0f MB per GPU)" % (B * 3 * (K * K - 1) * H * W * 4 / 1e6)}
+              "l2": ("inputs exceed L2 (guidance alone is %.0f MB per GPU vs 126 MB L2)" if B * 3 * (K * K - 1) * H * W * 4 > 126e6
+                     else "inputs (%.0f MB guidance per GPU) fit L2: a 256 MB buffer is written between steps") % (B * 3 * (K * K - 1) * H * W * 4 / 1e6)}
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -180,10 +185,11 @@ def main():
                 "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                 "sample": "%d full %dx%d frames per step, one frame per host thread "
-                                           "(torchvision deform_conv2d stand-in, fwd%s), %d host cores"
-                                           % (r["n_images"], H, W, "+bwd" if args.mode == "fwdbwd" else "",
-                                              r["host_cores"])},
+                                 "sample": "%d frames x %d rows x %d cols per step (full-width strips of the %dx%d "
+                                           "frame), one frame per host thread, torchvision deform_conv2d "
+                                           "stand-in (oracle/torchvision_port.py), fwd%s, %d host cores"
+                                           % (r["n_images"], r["rows"], W, H, W,
+                                              "+bwd" if args.mode == "fwdbwd" else "", r["host_cores"])},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -257,16 +263,54 @@ def main():
     fwd_ms = sum(a.elapsed_time(b) for a, b, _ in rec) / len(rec)
     bwd_ms = sum(b.elapsed_time(c) for _, b, c in rec) / len(rec)
 
-    # ---- end to end: pinned host inputs -> H2D -> module -> D2H of the loss, every step
+    # ---- end to end: pinned host inputs -> H2D -> module -> D2H of the loss, every step.
+    # The batch shard is fed in chunks of frames: a copy stream uploads chunk i+1 while the
+    # compute stream runs the module on chunk i (images are independent, so the chunked step is
+    # the same computation; this is the double-buffered prefetch a pinned DataLoader does).
     h2d = sum(host[k].numel() * 4 for k in names)
+    chunk = max(1, min(B, int(os.environ.get("NLSPN_E2E_CHUNK", "2"))))
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    gt_chunks = [gt[i:i + chunk] for i in range(0, B, chunk)]
+
+    def e2e_step():
+        pending = None
+        losses = []
+
+        def upload(i):
+            with torch.cuda.stream(copy_stream):
+                inp = {k: host[k][i:i + chunk].to(dev, non_blocking=True) for k in names}
+                evt = torch.cuda.Event()
+                evt.record(copy_stream)
+            return inp, evt
+
+        pending = upload(0)
+        for ci, i in enumerate(range(0, B, chunk)):
+            inp, evt = pending
+            pending = upload(i + chunk) if i + chunk < B else None
+            main_stream.wait_event(evt)
+            for t_ in inp.values():
+                t_.record_stream(main_stream)
+            fi, gd, cf = inp["feat_init"], inp["guidance"], inp["confidence"]
+            if train:
+                fi, gd, cf = (t_.requires_grad_(True) for t_ in (fi, gd, cf))
+            with torch.set_grad_enabled(train):
+                feat_result = mod(fi, gd, cf, inp["feat_fix"])[0]
+                loss = (torch.clamp(feat_result, min=0) - gt_chunks[ci]).abs().sum()
+            if train:
+                loss.backward()
+            losses.append(loss)
+        return float(torch.stack(losses).sum())      # D2H of the result + sync
+
     for _ in range(min(2, args.warmup)):
-        float(step({k: host[k].to(dev, non_blocking=True) for k in names}))
+        mod.aff_scale_const.grad = None
+        e2e_step()
     sync_all()
     e_start, e_end = ev(), ev()
     e_start.record()
     for _ in range(args.steps):
-        inp = {k: host[k].to(dev, non_blocking=True) for k in names}
-        loss_host = float(step(inp))           # D2H of the result + sync
+        mod.aff_scale_const.grad = None
+        loss_host = e2e_step()
     e_end.record()
     sync_all()
     e2e_ms = e_start.elapsed_time(e_end)
@@ -302,16 +346,19 @@ def main():
     phase_prof = {"forward": sum(prof[k][0] for k in prof if k in fwd_names),
                   "backward": sum(prof[k][0] for k in prof if k not in fwd_names)}
     kernels = {}
+    nprof = max(1, min(args.steps, 3))
+    per_iter = ("iter_fwd_kernel", "bwd_state_kernel", "iter_bwd_kernel")
     for name, (ms, cnt) in prof.items():
         ph = "forward" if name in fwd_names else "backward"
         share = ms / phase_prof[ph] if phase_prof[ph] > 0 else 0.0
         phase_ms = fwd_ms if ph == "forward" else bwd_ms
-        per_step = cnt / max(1, min(args.steps, 3))
-        launch_ms = phase_ms * share / per_step
-        gbs = alg.get(name, 0) * B * H * W / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
-        kernels[name] = {"launches_per_step": per_step, "share_of_phase": share, "launch_ms": launch_ms,
-                         "alg_bytes_per_launch": alg.get(name, 0) * B * H * W, "achieved_gbs": gbs,
-                         "frac": gbs / peaks["hbm_gbs"], "step_ms": phase_ms * share}
+        per_step = cnt / nprof
+        step_ms = phase_ms * share
+        bytes_step = alg.get(name, 0) * B * H * W * (T if name in per_iter else 1)
+        gbs = bytes_step / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0
+        kernels[name] = {"launches_per_step": per_step, "share_of_phase": share, "step_ms": step_ms,
+                         "launch_ms": step_ms / per_step, "alg_bytes_per_launch": bytes_step / per_step,
+                         "achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"]}
     kern = max(kernels, key=lambda k: kernels[k]["step_ms"])
     kb, kms, achieved = kernels[kern]["alg_bytes_per_launch"], kernels[kern]["launch_ms"], kernels[kern]["achieved_gbs"]
     step_gbs = alg_bytes(K, T, args.mode) * (pix_iter_step / world) * args.steps / (total_ms * 1e-3) / 1e9
@@ -338,11 +385,13 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_img = args.cpu_images or min(os.cpu_count() or 1, 8)
-        r = cpu_reference_run(args, H, W, md, n_img, 1, 0)
+        r = cpu_reference_run(args, H, W, md, n_img, 2, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                "sample": "%d full %dx%d frames, one per host thread, fwd%s, torchvision "
-                                          "deform_conv2d stand-in (oracle/torchvision_port.py), %d host cores, %.1f s"
-                                          % (r["n_images"], H, W, "+bwd" if train else "", r["host_cores"], r["seconds"])}
+                                "sample": "%d frames x %d rows x %d cols (full-width strips of the %dx%d frame), one "
+                                          "frame per host thread, fwd%s, torchvision deform_conv2d stand-in "
+                                          "(oracle/torchvision_port.py), %d host cores, %.1f s per pass"
+                                          % (r["n_images"], r["rows"], W, H, W, "+bwd" if train else "",
+                                             r["host_cores"], r["seconds"])}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
