@@ -178,7 +178,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        n_img = args.cpu_images or min(os.cpu_count() or 1, 8)
+        n_img = args.cpu_images or min(os.cpu_count() or 1, 32)
         r = cpu_reference_run(args, H, W, md, n_img, max(1, args.steps), max(0, args.warmup))
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -384,7 +384,7 @@ def main():
                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": step_gbs / peaks["hbm_gbs"]}}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_img = args.cpu_images or min(os.cpu_count() or 1, 8)
+        n_img = args.cpu_images or min(os.cpu_count() or 1, 32)
         r = cpu_reference_run(args, H, W, md, n_img, 2, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                 "sample": "%d frames x %d rows x %d cols (full-width strips of the %dx%d frame), one "

@@ -113,20 +113,52 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
     tma::mbar_wait(&bar, 0);
     if (!inside) return;
 
-    const float *im = src_prev + b * P;
-    float acc = 0.f;
+    // Footprint (rows hl, hl+1; cols wl, wl+1) lies inside the box  <=>  ylo <= h_im < yhi and
+    // xlo <= w_im < xhi (NaN -> false).  Inside the box the validity test of cuh:180 is implied by
+    // TMA's zero fill: an out-of-image footprint reads zeros, and a coordinate of exactly -1 puts
+    // all its weight (lh = 0) on the zero row.
+    const float ylo = (float)(y0 - kHalo), yhi = (float)(y0 - kHalo + TG::BoxH - 1);
+    const float xlo = (float)(x0 - kHalo), xhi = (float)(x0 - kHalo + kBoxW - 1);
+    float hi[G::KK], wi[G::KK];
+    bool all_in = true;
 #pragma unroll
     for (int t = 0; t < G::KK; ++t) {
-        float v;
-        if (t == G::REF) {
-            v = box[(threadIdx.y + kHalo) * kBoxW + threadIdx.x + kHalo];
-        } else {
-            const float h_im = (float)(h - G::PAD + t / K) + oh[t];
-            const float w_im = (float)(w - G::PAD + t % K) + ow[t];
-            v = 0.f;
-            if (tap_valid(h_im, w_im, H, W)) v = quad_value(box_quad<TH>(box, y0, x0, im, H, W, h_im, w_im));
+        if (t == G::REF) continue;
+        hi[t] = (float)(h - G::PAD + t / K) + oh[t];
+        wi[t] = (float)(w - G::PAD + t % K) + ow[t];
+        all_in = all_in && hi[t] >= ylo && hi[t] < yhi && wi[t] >= xlo && wi[t] < xhi;
+    }
+    const float *im = src_prev + b * P;
+    float acc = 0.f;
+    if (__all_sync(__activemask(), all_in)) {
+        // branch-free: every tap of every lane of this warp reads the box
+#pragma unroll
+        for (int t = 0; t < G::KK; ++t) {
+            float v;
+            if (t == G::REF) {
+                v = box[(threadIdx.y + kHalo) * kBoxW + threadIdx.x + kHalo];
+            } else {
+                const float hf = floorf(hi[t]), wf = floorf(wi[t]);
+                const float lh = hi[t] - hf, lw = wi[t] - wf;
+                const float hh = 1.f - lh, hw = 1.f - lw;
+                const float *p = box + ((int)hf - (y0 - kHalo)) * kBoxW + ((int)wf - (x0 - kHalo));
+                v = (hh * hw) * p[0] + (hh * lw) * p[1] + (lh * hw) * p[kBoxW] + (lh * lw) * p[kBoxW + 1];
+            }
+            acc += v * av[t];
         }
-        acc += v * av[t];
+    } else {
+#pragma unroll
+        for (int t = 0; t < G::KK; ++t) {
+            float v;
+            if (t == G::REF) {
+                v = box[(threadIdx.y + kHalo) * kBoxW + threadIdx.x + kHalo];
+            } else {
+                v = 0.f;
+                if (tap_valid(hi[t], wi[t], H, W))
+                    v = quad_value(box_quad<TH>(box, y0, x0, im, H, W, hi[t], wi[t]));
+            }
+            acc += v * av[t];
+        }
     }
     const long q = b * P + r;
     if (flags & kPreserve) acc = blend_fix(acc, dp);

@@ -339,7 +339,7 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         }
         float Gref = __ldg(gab + (long)G::REF * P);
         if (eab) Gref += __ldg(eab + (long)G::REF * P);
-        float dot = 0.f;
+        float dot = 0.f, gsum = 0.f;
 #pragma unroll
         for (int n = 0; n < G::N; ++n) {
             const int t = n < G::REF ? n : n + 1;
@@ -363,10 +363,12 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
             float dr = da;
             if (use_tanh) {
                 dr = da * (1.f - th[n] * th[n]) / g;
-                local_gamma += -(double)da * (double)th[n] / ((double)g * (double)g);
+                gsum += da * th[n];
             }
             ggb[(long)(2 * G::N + n) * P] = dr;
         }
+        // d a_n / d gamma = -tanh(r_n) / g^2 ; one fp64 conversion per thread (fp64 ALUs are scarce)
+        local_gamma = -(double)gsum / ((double)g * (double)g);
     }
     // block reduction of the gamma gradient, one double atomic per block
     if (affinity == kTGASS || affinity == kTC) {
