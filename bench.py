@@ -360,6 +360,12 @@ def main():
                          "launch_ms": step_ms / per_step, "alg_bytes_per_launch": bytes_step / per_step,
                          "achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"]}
     kern = max(kernels, key=lambda k: kernels[k]["step_ms"])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("%s_%dx%d_B%d_per_gpu_K%d_T%d" % (args.workload, H, W, B, K, T), {}).get(kern)
+    except Exception:
+        traffic = None
     kb, kms, achieved = kernels[kern]["alg_bytes_per_launch"], kernels[kern]["launch_ms"], kernels[kern]["achieved_gbs"]
     step_gbs = alg_bytes(K, T, args.mode) * (pix_iter_step / world) * args.steps / (total_ms * 1e-3) / 1e9
     line = {"metric": METRIC if train else "nlspn_propagation_fwd_gpix_iter_per_s", "value": value,
@@ -372,7 +378,7 @@ def main():
             "phases_ms": {"forward": fwd_ms, "backward": bwd_ms,
                           "forward_gpix_iter_per_s": pix_iter_step / world / (fwd_ms * 1e-3) / 1e9},
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
                          "alg_bytes_per_launch": kb,
                          "launch_ms": kms,
