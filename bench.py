@@ -300,7 +300,7 @@ def main():
             if train:
                 loss.backward()
             losses.append(loss)
-        return float(torch.stack(losses).sum())      # D2H of the result + sync
+        return float(torch.stack(losses).sum().detach())      # D2H of the result + sync
 
     for _ in range(min(2, args.warmup)):
         mod.aff_scale_const.grad = None
@@ -373,7 +373,8 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
+                    "chunk_frames": chunk},
             "gpu_launches": int(launches),
             "phases_ms": {"forward": fwd_ms, "backward": bwd_ms,
                           "forward_gpix_iter_per_s": pix_iter_step / world / (fwd_ms * 1e-3) / 1e9},

@@ -271,7 +271,24 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
 
 extern "C" {
 
-constexpr int kFwdTH = 16;    // forward tile: 32 x 16 pixels, 512 threads
+constexpr int kFwdTH = 16;    // default forward tile: 32 x 16 pixels, 512 threads
+
+// forward tile height: 8, 16 or 32 rows (NLSPN_FWD_TH overrides the default; tuning knob)
+static int fwd_tile_h()
+{
+    if (const char *e = getenv("NLSPN_FWD_TH")) {
+        const int v = atoi(e);
+        if (v == 8 || v == 16 || v == 32) return v;
+    }
+    return kFwdTH;
+}
+
+#define DISPATCH_TH(TH_, ...)                                  \
+    switch (TH_) {                                             \
+    case 8: { constexpr int THC = 8; __VA_ARGS__; } break;     \
+    case 32: { constexpr int THC = 32; __VA_ARGS__; } break;   \
+    default: { constexpr int THC = 16; __VA_ARGS__; } break;   \
+    }
 constexpr int kParamTH = 16;  // pass-B tile: 32 x 16 pixels, 512 threads (<= 128 registers)
 
 static bool stream_hint_for(int B, int H, int W, int K)
@@ -334,16 +351,17 @@ static int launch_iter_fwd(const FwdCall &c, int b0, int nb, int t, const CUtens
     const float *fx = c.feat_fix ? c.feat_fix + o1 : nullptr;
     ProfScope prof__(kProfIterFwd, c.st);
     if (map) {
-        dim3 grid((unsigned)((c.W + kTileW - 1) / kTileW), (unsigned)((c.H + kFwdTH - 1) / kFwdTH), (unsigned)nb);
-        dim3 block(kTileW, kFwdTH);
+        const int th = fwd_tile_h();
+        dim3 grid((unsigned)((c.W + kTileW - 1) / kTileW), (unsigned)((c.H + th - 1) / th), (unsigned)nb);
+        dim3 block(kTileW, th);
         if (stream) {
-            DISPATCH_K(c.K, (launch_pdl(iter_fwd_tiled_kernel<KC, kFwdTH, true>, grid, block, c.st,
+            DISPATCH_TH(th, DISPATCH_K(c.K, (launch_pdl(iter_fwd_tiled_kernel<KC, THC, true>, grid, block, c.st,
                                 *map, plane_z, src_prev, c.offset + o1 * 2 * KK, c.aff + o1 * KK, cf, fx,
-                                c.flags, c.H, c.W, out, src_next)));
+                                c.flags, c.H, c.W, out, src_next))));
         } else {
-            DISPATCH_K(c.K, (launch_pdl(iter_fwd_tiled_kernel<KC, kFwdTH, false>, grid, block, c.st,
+            DISPATCH_TH(th, DISPATCH_K(c.K, (launch_pdl(iter_fwd_tiled_kernel<KC, THC, false>, grid, block, c.st,
                                 *map, plane_z, src_prev, c.offset + o1 * 2 * KK, c.aff + o1 * KK, cf, fx,
-                                c.flags, c.H, c.W, out, src_next)));
+                                c.flags, c.H, c.W, out, src_next))));
         }
         NLSPN_CHECK_LAUNCH("iter_fwd_tiled_kernel");
         return 0;
@@ -384,8 +402,8 @@ static int run_forward(const FwdCall &c, bool prologue, bool iters)
     CUtensorMap src_map, list_map;
     const CUtensorMap *psrc = nullptr, *plist = nullptr;
     if (iters && tiled_ok(c.src, c.W) && aligned16(c.list_feat)) {
-        if (int rc = make_plane_map(&src_map, c.src, (long)c.S * c.B, c.H, c.W, TileGeo<kFwdTH>::BoxH)) return rc;
-        if (int rc = make_plane_map(&list_map, c.list_feat, (long)c.T * c.B, c.H, c.W, TileGeo<kFwdTH>::BoxH)) return rc;
+        if (int rc = make_plane_map(&src_map, c.src, (long)c.S * c.B, c.H, c.W, fwd_tile_h() + 2 * kHalo)) return rc;
+        if (int rc = make_plane_map(&list_map, c.list_feat, (long)c.T * c.B, c.H, c.W, fwd_tile_h() + 2 * kHalo)) return rc;
         psrc = &src_map;
         plist = &list_map;
     }
