@@ -278,18 +278,28 @@ static int fwd_tile_h()
 {
     if (const char *e = getenv("NLSPN_FWD_TH")) {
         const int v = atoi(e);
-        if (v == 8 || v == 16 || v == 32) return v;
+        if (v == 4 || v == 8 || v == 16 || v == 32) return v;
     }
     return kFwdTH;
 }
 
 #define DISPATCH_TH(TH_, ...)                                  \
     switch (TH_) {                                             \
+    case 4: { constexpr int THC = 4; __VA_ARGS__; } break;     \
     case 8: { constexpr int THC = 8; __VA_ARGS__; } break;     \
     case 32: { constexpr int THC = 32; __VA_ARGS__; } break;   \
     default: { constexpr int THC = 16; __VA_ARGS__; } break;   \
     }
-constexpr int kParamTH = 16;  // pass-B tile: 32 x 16 pixels, 512 threads (<= 128 registers)
+constexpr int kParamTH = 16;  // default pass-B tile: 32 x 16 pixels, 512 threads (<= 128 registers)
+
+static int param_tile_h()
+{
+    if (const char *e = getenv("NLSPN_PARAM_TH")) {
+        const int v = atoi(e);
+        if (v == 4 || v == 8 || v == 16) return v;
+    }
+    return kParamTH;
+}
 
 static bool stream_hint_for(int B, int H, int W, int K)
 {
@@ -540,8 +550,8 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     CUtensorMap src_map, list_map;
     const bool use_tiled = tiled_ok(src, W) && aligned16(list_feat);
     if (use_tiled) {
-        if (int rc = make_plane_map(&src_map, src, (long)(conf_fixed ? T : 1) * B, H, W, TileGeo<kParamTH>::BoxH)) return rc;
-        if (int rc = make_plane_map(&list_map, list_feat, (long)T * B, H, W, TileGeo<kParamTH>::BoxH)) return rc;
+        if (int rc = make_plane_map(&src_map, src, (long)(conf_fixed ? T : 1) * B, H, W, param_tile_h() + 2 * kHalo)) return rc;
+        if (int rc = make_plane_map(&list_map, list_feat, (long)T * B, H, W, param_tile_h() + 2 * kHalo)) return rc;
     }
     float *setA = ws, *setB = setA + (long)G * sg.image;
     float *g_conf_acc = setB + (long)G * sg.image;
@@ -580,13 +590,14 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             dim3 grid((unsigned)((P + kParamBlock - 1) / kParamBlock), (unsigned)nb, (unsigned)nch);
             ProfScope prof__(kProfBwdParam, st);
             if (use_tiled) {
-                dim3 tgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + kParamTH - 1) / kParamTH),
+                const int pth = param_tile_h();
+                dim3 tgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + pth - 1) / pth),
                            (unsigned)(nb * nch));
-                dim3 tblock(kTileW, kParamTH);
-                DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, kParamTH><<<tgrid, tblock, 0, st>>>(
+                dim3 tblock(kTileW, pth);
+                DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, THC><<<tgrid, tblock, 0, st>>>(
                                   src_map, list_map, B, b0, offset + o1 * 2 * KK, aff + o1 * KK, src + o1,
                                   list_feat + o1, gy_all, conf_fixed ? 1 : 0, H, W, T, BP, GP,
-                                  g_guidance + o1 * 3 * N, g_aff_acc)));
+                                  g_guidance + o1 * 3 * N, g_aff_acc))));
                 NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
             } else {
                 DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
