@@ -44,8 +44,8 @@ __device__ __forceinline__ float ld_geo(const float *p)
     return STREAM ? __ldcs(p) : __ldg(p);
 }
 
-template <int K, bool STREAM>
-__global__ void __launch_bounds__(kBlock)
+template <int K, bool STREAM, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
 bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff,
                  const float *__restrict__ conf, const float *__restrict__ dep,
                  const float *__restrict__ x_t, const float *__restrict__ g_ext,

@@ -271,7 +271,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
 
 extern "C" {
 
-constexpr int kFwdTH = 16;    // default forward tile: 32 x 16 pixels, 512 threads
+constexpr int kFwdTH = 4;     // default forward tile: 32 x 4 pixels (B200 sweep: TH 4: 45.0, 8: 44.2, 16: 36.5, 32: 26.1 Gpix*iter/s)
 
 // forward tile height: 8, 16 or 32 rows (NLSPN_FWD_TH overrides the default; tuning knob)
 static int fwd_tile_h()
@@ -285,12 +285,12 @@ static int fwd_tile_h()
 
 #define DISPATCH_TH(TH_, ...)                                  \
     switch (TH_) {                                             \
-    case 4: { constexpr int THC = 4; __VA_ARGS__; } break;     \
     case 8: { constexpr int THC = 8; __VA_ARGS__; } break;     \
     case 32: { constexpr int THC = 32; __VA_ARGS__; } break;   \
-    default: { constexpr int THC = 16; __VA_ARGS__; } break;   \
+    case 16: { constexpr int THC = 16; __VA_ARGS__; } break;   \
+    default: { constexpr int THC = 4; __VA_ARGS__; } break;    \
     }
-constexpr int kParamTH = 16;  // default pass-B tile: 32 x 16 pixels, 512 threads (<= 128 registers)
+constexpr int kParamTH = 4;   // default pass-B tile: 32 x 4 pixels (B200 sweep: TH 4: 1.02, 8: 1.10, 16: 1.27 ms)
 
 static int param_tile_h()
 {
@@ -547,6 +547,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     const ScatterGeo sg = scatter_geo(H, W);
     const int G = group_images(B, H, W, K, true);
     const bool stream_hint = stream_hint_for(G, H, W, K);
+    const int state_minb = getenv("NLSPN_STATE_MINB") ? atoi(getenv("NLSPN_STATE_MINB")) : 4;
     CUtensorMap src_map, list_map;
     const bool use_tiled = tiled_ok(src, W) && aligned16(list_feat);
     if (use_tiled) {
@@ -572,15 +573,26 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             const float *xt = list_feat + (long)(t - 1) * BP + o1;
             const float *ge = g_list[t - 1] ? g_list[t - 1] + o1 : nullptr;
             float *gyo = gy_all + (long)(t - 1) * GP;
+#define STATE_LAUNCH(SH_, MB_)                                                                          \
+    DISPATCH_K(K, (launch_pdl(bwd_state_kernel<KC, SH_, MB_>, grid_for(P, nb), dim3(kBlock), st,           \
+                              offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, xt, ge, s_in, s_out, gyo,       \
+                              g_conf_acc, flags, H, W)))
             if (stream_hint) {
-                DISPATCH_K(K, (launch_pdl(bwd_state_kernel<KC, true>, grid_for(P, nb), dim3(kBlock), st,
-                                  offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, xt, ge, s_in, s_out, gyo,
-                                  g_conf_acc, flags, H, W)));
+                switch (state_minb) {
+                case 5: STATE_LAUNCH(true, 5); break;
+                case 6: STATE_LAUNCH(true, 6); break;
+                case 8: STATE_LAUNCH(true, 8); break;
+                default: STATE_LAUNCH(true, 4); break;
+                }
             } else {
-                DISPATCH_K(K, (launch_pdl(bwd_state_kernel<KC, false>, grid_for(P, nb), dim3(kBlock), st,
-                                  offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, xt, ge, s_in, s_out, gyo,
-                                  g_conf_acc, flags, H, W)));
+                switch (state_minb) {
+                case 5: STATE_LAUNCH(false, 5); break;
+                case 6: STATE_LAUNCH(false, 6); break;
+                case 8: STATE_LAUNCH(false, 8); break;
+                default: STATE_LAUNCH(false, 4); break;
+                }
             }
+#undef STATE_LAUNCH
             NLSPN_CHECK_LAUNCH("bwd_state_kernel");
         }
         const float *s_last = ((T - 1) % 2 == 0) ? setA : setB;
