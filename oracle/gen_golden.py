@@ -192,7 +192,7 @@ def case_paths():
             o[0, 12, H - 1, :] = 0.0  # tap 6 (after insert tap 7) dh: row H-1 -> h_im = H
             o[1, 2, 3, :] = 1.0
             o[1, 4:6, 7, :] = 40.0   # far out of range
-        with_grad = "clip" not in name
+        with_grad = True
         rec = run_path(model, inp, with_grad=with_grad, use_conf=use_conf)
         a = model.args
         save(name, {k: v for k, v in inp.items() if use_conf or k != "confidence"}, rec,

@@ -75,7 +75,7 @@ def test_forward_matches_reference_golden(dev, name):
     assert abs(a[0] - b[0]) <= 1e-5 and abs(a[1] - b[1]) <= 1e-5
 
 
-@pytest.mark.parametrize("name", [n for n in PATHS if "fullmodel" not in n and "clip" not in n])
+@pytest.mark.parametrize("name", [n for n in PATHS if "fullmodel" not in n])
 def test_backward_matches_reference_autograd(dev, name):
     g = load_golden(name)
     mod, (fi, gd, cf), (feat_result, list_feat, offset, aff, _), m = _run_module(g, dev, grad=True)
