@@ -19,27 +19,33 @@
 
 namespace nlspn {
 
-constexpr int kHalo = 8;          // R: box halo in pixels
 constexpr int kTileW = 32;        // one warp per tile row: coalesced per-pixel planes
-constexpr int kBoxW = kTileW + 2 * kHalo;
 
-template <int TH>
+// box halo R in pixels: covers the tap displacement (K-1)/2 plus |offset| <= 7 (3.5 sigma of the
+// sigma = 2 px offsets of SURVEY 8d); even, so that the box row is a multiple of 16 bytes
+__host__ __device__ constexpr int halo_for(int K) { return K == 3 ? 8 : (K == 5 ? 10 : 12); }
+
+template <int K, int TH>
 struct TileGeo {
-    static constexpr int BoxH = TH + 2 * kHalo;
-    static constexpr int BoxFloats = BoxH * kBoxW;
+    static constexpr int R = halo_for(K);
+    static constexpr int BoxW = kTileW + 2 * R;
+    static constexpr int BoxH = TH + 2 * R;
+    static constexpr int BoxFloats = BoxH * BoxW;
     static constexpr int BoxBytes = BoxFloats * 4;
 };
 
 // four corner values of a sample from the shared-memory box, falling back to global memory
 // when the footprint is not inside the box.  box(0,0) is pixel (y0 - R, x0 - R).
-template <int TH>
+template <int K, int TH>
 __device__ __forceinline__ Quad box_quad(const float *__restrict__ box, int y0, int x0,
                                          const float *__restrict__ im, int H, int W, float h_im, float w_im)
 {
+    constexpr int kHalo = TileGeo<K, TH>::R;
+    constexpr int kBoxW = TileGeo<K, TH>::BoxW;
     const float hf = floorf(h_im), wf = floorf(w_im);
     const int hl = (int)hf, wl = (int)wf;
     const int ty = hl - (y0 - kHalo), tx = wl - (x0 - kHalo);
-    if ((unsigned)ty < (unsigned)(TileGeo<TH>::BoxH - 1) && (unsigned)tx < (unsigned)(kBoxW - 1)) {
+    if ((unsigned)ty < (unsigned)(TileGeo<K, TH>::BoxH - 1) && (unsigned)tx < (unsigned)(kBoxW - 1)) {
         Quad q;
         q.hl = hl;
         q.wl = wl;
@@ -68,7 +74,9 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
                       float *__restrict__ out, float *__restrict__ src_next)
 {
     using G = Geo<K>;
-    using TG = TileGeo<TH>;
+    using TG = TileGeo<K, TH>;
+    constexpr int kHalo = TG::R;
+    constexpr int kBoxW = TG::BoxW;
     __shared__ __align__(128) float box[TG::BoxFloats];
     __shared__ __align__(8) uint64_t bar;
     const int P = H * W;
@@ -155,7 +163,7 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
             } else {
                 v = 0.f;
                 if (tap_valid(hi[t], wi[t], H, W))
-                    v = quad_value(box_quad<TH>(box, y0, x0, im, H, W, hi[t], wi[t]));
+                    v = quad_value(box_quad<K, TH>(box, y0, x0, im, H, W, hi[t], wi[t]));
             }
             acc += v * av[t];
         }
@@ -182,7 +190,7 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
 // A warp whose lanes are all-FAST runs a branch-free loop.
 // ======================================================================================
 template <int K, int C, int TH>
-__global__ void __launch_bounds__(kTileW * TH)
+__global__ void __launch_bounds__(kTileW * TH, (TH >= 16 ? 1 : 16 / TH))   // <= 128 registers
 bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
                        const __grid_constant__ CUtensorMap list_map, int Bsrc, int b0,
                        const float *__restrict__ offset, const float *__restrict__ aff,
@@ -191,7 +199,9 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
                        long GP, float *__restrict__ g_guidance, float *__restrict__ g_aff_acc)
 {
     using G = Geo<K>;
-    using TG = TileGeo<TH>;
+    using TG = TileGeo<K, TH>;
+    constexpr int kHalo = TG::R;
+    constexpr int kBoxW = TG::BoxW;
     constexpr int NCH = (G::KK + C - 1) / C;
     __shared__ __align__(128) float box[2][TG::BoxFloats];
     __shared__ __align__(8) uint64_t bar[2];

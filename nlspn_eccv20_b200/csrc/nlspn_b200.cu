@@ -228,11 +228,11 @@ static bool tiled_ok(const void *base, int W)
     return tiled_enabled() && (W % 4) == 0 && aligned16(base) && encode_tiled_fn() != nullptr;
 }
 
-static int make_plane_map(CUtensorMap *map, const float *base, long planes, int H, int W, int box_h)
+static int make_plane_map(CUtensorMap *map, const float *base, long planes, int H, int W, int box_w, int box_h)
 {
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)kBoxW, (cuuint32_t)box_h, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims,
                                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -412,8 +412,8 @@ static int run_forward(const FwdCall &c, bool prologue, bool iters)
     CUtensorMap src_map, list_map;
     const CUtensorMap *psrc = nullptr, *plist = nullptr;
     if (iters && tiled_ok(c.src, c.W) && aligned16(c.list_feat)) {
-        if (int rc = make_plane_map(&src_map, c.src, (long)c.S * c.B, c.H, c.W, fwd_tile_h() + 2 * kHalo)) return rc;
-        if (int rc = make_plane_map(&list_map, c.list_feat, (long)c.T * c.B, c.H, c.W, fwd_tile_h() + 2 * kHalo)) return rc;
+        if (int rc = make_plane_map(&src_map, c.src, (long)c.S * c.B, c.H, c.W, kTileW + 2 * halo_for(c.K), fwd_tile_h() + 2 * halo_for(c.K))) return rc;
+        if (int rc = make_plane_map(&list_map, c.list_feat, (long)c.T * c.B, c.H, c.W, kTileW + 2 * halo_for(c.K), fwd_tile_h() + 2 * halo_for(c.K))) return rc;
         psrc = &src_map;
         plist = &list_map;
     }
@@ -551,8 +551,8 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     CUtensorMap src_map, list_map;
     const bool use_tiled = tiled_ok(src, W) && aligned16(list_feat);
     if (use_tiled) {
-        if (int rc = make_plane_map(&src_map, src, (long)(conf_fixed ? T : 1) * B, H, W, param_tile_h() + 2 * kHalo)) return rc;
-        if (int rc = make_plane_map(&list_map, list_feat, (long)T * B, H, W, param_tile_h() + 2 * kHalo)) return rc;
+        if (int rc = make_plane_map(&src_map, src, (long)(conf_fixed ? T : 1) * B, H, W, kTileW + 2 * halo_for(K), param_tile_h() + 2 * halo_for(K))) return rc;
+        if (int rc = make_plane_map(&list_map, list_feat, (long)T * B, H, W, kTileW + 2 * halo_for(K), param_tile_h() + 2 * halo_for(K))) return rc;
     }
     float *setA = ws, *setB = setA + (long)G * sg.image;
     float *g_conf_acc = setB + (long)G * sg.image;
