@@ -22,8 +22,10 @@ namespace nlspn {
 constexpr int kTileW = 32;        // one warp per tile row: coalesced per-pixel planes
 
 // box halo R in pixels: covers the tap displacement (K-1)/2 plus |offset| <= 7 (3.5 sigma of the
-// sigma = 2 px offsets of SURVEY 8d); even, so that the box row is a multiple of 16 bytes
-__host__ __device__ constexpr int halo_for(int K) { return K == 3 ? 8 : (K == 5 ? 10 : 12); }
+// sigma = 2 px offsets of SURVEY 8d).  R is a multiple of 4 so that a box row is a multiple of
+// 32 bytes: a 208-byte row (R = 10) made cp.async.bulk.tensor trap with error 715 on B200,
+// 192- and 224-byte rows are fine.
+__host__ __device__ constexpr int halo_for(int K) { return K == 3 ? 8 : 12; }
 
 template <int K, int TH>
 struct TileGeo {
