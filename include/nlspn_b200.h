@@ -67,6 +67,10 @@ enum nlspn_affinity { NLSPN_AFF_AS = 0, NLSPN_AFF_ASS = 1, NLSPN_AFF_TC = 2, NLS
 /* flags */
 #define NLSPN_FLAG_PRESERVE_INPUT 1u /* args.preserve_input, nlspnmodel.py:328,341-344,355-357 (needs feat_fix) */
 #define NLSPN_FLAG_ALWAYS_CLIP    2u /* args.always_clip,    nlspnmodel.py:346-348,359-361                       */
+/* args.offset == False (the fork's default, src/config.py:272-275): fixed-local propagation,
+ * nlspnmodel.py:209-224 -- 3x3 replicate-padded weighted sum instead of the deformable gather.
+ * guidance is then [B,N,H,W] (raw affinities only), `offset`/`g_offset_ext` are NULL, K must be 3. */
+#define NLSPN_FLAG_NO_OFFSET 4u
 /* debugging aid: run the backward as T per-iteration kernels that re-read/re-write the
  * gradient accumulators and scatter with scalar atomics (the reference's structure); results
  * agree with the default two-pass backward up to fp32 summation order. */

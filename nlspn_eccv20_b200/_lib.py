@@ -49,6 +49,7 @@ SIGNATURES = {
 AFFINITY = {"AS": 0, "ASS": 1, "TC": 2, "TGASS": 3}
 FLAG_PRESERVE_INPUT = 1
 FLAG_ALWAYS_CLIP = 2
+FLAG_NO_OFFSET = 4
 FLAG_BWD_PER_ITERATION = 0x100
 
 

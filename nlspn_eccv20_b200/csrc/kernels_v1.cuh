@@ -9,7 +9,7 @@
 
 namespace nlspn {
 
-enum : unsigned { kPreserve = 1u, kAlwaysClip = 2u };
+enum : unsigned { kPreserve = 1u, kAlwaysClip = 2u, kNoOffset = 4u };
 enum : int { kAS = 0, kASS = 1, kTC = 2, kTGASS = 3 };
 
 // ======================================================================================
@@ -27,12 +27,16 @@ prologue_fwd_kernel(const float *__restrict__ guidance, const float *__restrict_
     const int r = blockIdx.x * kBlock + threadIdx.x;
     if (r >= P) return;
     const long b = blockIdx.y;
-    const float *gb = guidance + b * 3 * G::N * P + r;
+    // fixed-local mode (args.offset False): guidance holds the N raw affinities only
+    const bool no_off = (flags & kNoOffset) != 0;
+    const float *gb = guidance + b * (no_off ? 1 : 3) * G::N * P + r;
     float *ob = offset + b * 2 * G::KK * P + r;
     float *ab = aff + b * G::KK * P + r;
+    const int aff_ch0 = no_off ? 0 : 2 * G::N;   // first raw-affinity channel of guidance
 
 #pragma unroll
     for (int t = 0; t < G::KK; ++t) {
+        if (no_off) break;
         if (t == G::REF) {
             ob[(long)(2 * t) * P] = 0.f;
             ob[(long)(2 * t + 1) * P] = 0.f;
@@ -50,7 +54,7 @@ prologue_fwd_kernel(const float *__restrict__ guidance, const float *__restrict_
     const float g = affinity == kTGASS ? gamma + 1e-8f : gamma;
 #pragma unroll
     for (int n = 0; n < G::N; ++n) {
-        float v = __ldg(gb + (long)(2 * G::N + n) * P);
+        float v = __ldg(gb + (long)(aff_ch0 + n) * P);
         if (use_tanh) v = tanhf(v) / g;
         a[n] = v;
         abs_sum += fabsf(v);
@@ -305,9 +309,11 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         if (clipped) Gx = 0.f;
         g_init[q] = preserve ? (1.0f - m) * Gx : Gx;
 
-        const float *gb = guidance + b * 3 * G::N * P + r;
-        float *ggb = g_guidance + b * 3 * G::N * P + r;
-        if (g_off_ext) {
+        const bool no_off = (flags & kNoOffset) != 0;
+        const int aff_ch0 = no_off ? 0 : 2 * G::N;
+        const float *gb = guidance + b * (no_off ? 1 : 3) * G::N * P + r;
+        float *ggb = g_guidance + b * (no_off ? 1 : 3) * G::N * P + r;
+        if (g_off_ext && !no_off) {
             const float *eb = g_off_ext + b * 2 * G::KK * P + r;
 #pragma unroll
             for (int n = 0; n < G::N; ++n) {
@@ -325,7 +331,7 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         float s0 = 0.f;
 #pragma unroll
         for (int n = 0; n < G::N; ++n) {
-            const float rr = __ldg(gb + (long)(2 * G::N + n) * P);
+            const float rr = __ldg(gb + (long)(aff_ch0 + n) * P);
             th[n] = use_tanh ? tanhf(rr) : 0.f;
             a[n] = use_tanh ? th[n] / g : rr;
             s0 += fabsf(a[n]);
@@ -365,7 +371,7 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
                 dr = da * (1.f - th[n] * th[n]) / g;
                 gsum += da * th[n];
             }
-            ggb[(long)(2 * G::N + n) * P] = dr;
+            ggb[(long)(aff_ch0 + n) * P] = dr;
         }
         // d a_n / d gamma = -tanh(r_n) / g^2 ; one fp64 conversion per thread (fp64 ALUs are scarce)
         local_gamma = -(double)gsum / ((double)g * (double)g);

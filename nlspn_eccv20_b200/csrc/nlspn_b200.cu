@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/nlspn_b200.h"
+#include "kernels_fixed.cuh"
 #include "kernels_tiled.cuh"
 
 using namespace nlspn;
@@ -326,10 +327,11 @@ static int launch_prologue(const FwdCall &c, int b0, int nb)
     const int P = c.H * c.W, KK = c.K * c.K, N = KK - 1;
     const long o1 = (long)b0 * P;
     ProfScope prof__(kProfPrologue, c.st);
+    const bool no_off = (c.flags & NLSPN_FLAG_NO_OFFSET) != 0;
     DISPATCH_K(c.K, (prologue_fwd_kernel<KC><<<grid_for(P, nb), kBlock, 0, c.st>>>(
-                        c.guidance + o1 * 3 * N, c.confidence ? c.confidence + o1 : nullptr,
+                        c.guidance + o1 * (no_off ? 1 : 3) * N, c.confidence ? c.confidence + o1 : nullptr,
                         c.feat_init + o1, c.feat_fix ? c.feat_fix + o1 : nullptr, c.gamma, c.affinity,
-                        c.flags, P, c.offset + o1 * 2 * KK, c.aff + o1 * KK,
+                        c.flags, P, no_off ? nullptr : c.offset + o1 * 2 * KK, c.aff + o1 * KK,
                         c.conf_fixed ? c.conf_fixed + o1 : nullptr, c.src + o1)));
     NLSPN_CHECK_LAUNCH("prologue_fwd_kernel");
     return 0;
@@ -360,6 +362,18 @@ static int launch_iter_fwd(const FwdCall &c, int b0, int nb, int t, const CUtens
     const float *cf = c.conf_fixed ? c.conf_fixed + o1 : nullptr;
     const float *fx = c.feat_fix ? c.feat_fix + o1 : nullptr;
     ProfScope prof__(kProfIterFwd, c.st);
+    if (c.flags & NLSPN_FLAG_NO_OFFSET) {
+        cudaError_t e;
+        if (stream)
+            e = launch_pdl(fixed_fwd_kernel<true>, grid_for(P, nb), dim3(kBlock), c.st, src_prev,
+                           c.aff + o1 * KK, cf, fx, c.flags, c.H, c.W, out, src_next);
+        else
+            e = launch_pdl(fixed_fwd_kernel<false>, grid_for(P, nb), dim3(kBlock), c.st, src_prev,
+                           c.aff + o1 * KK, cf, fx, c.flags, c.H, c.W, out, src_next);
+        if (e != cudaSuccess) return cuda_fail(e, "fixed_fwd_kernel");
+        NLSPN_CHECK_LAUNCH("fixed_fwd_kernel");
+        return 0;
+    }
     if (map) {
         const int th = fwd_tile_h();
         dim3 grid((unsigned)((c.W + kTileW - 1) / kTileW), (unsigned)((c.H + th - 1) / th), (unsigned)nb);
@@ -388,8 +402,11 @@ static int check_fwd(const FwdCall &c, bool prologue, bool iters)
     if (int rc = check_shape(c.B, c.H, c.W, c.K, c.T)) return rc;
     if ((c.flags & NLSPN_FLAG_PRESERVE_INPUT) && !c.feat_fix)
         return fail(NLSPN_ERR_NULL, "PRESERVE_INPUT needs feat_fix");
+    const bool no_off = (c.flags & NLSPN_FLAG_NO_OFFSET) != 0;
+    if (no_off && c.K != 3)
+        return fail(NLSPN_ERR_KERNEL, "fixed-local propagation (NO_OFFSET) is 3x3 only, as in the reference (got K=%d)", c.K);
     if (prologue) {
-        if (!c.guidance || !c.feat_init || !c.offset || !c.aff || !c.src || !c.gamma)
+        if (!c.guidance || !c.feat_init || (!c.offset && !no_off) || !c.aff || !c.src || !c.gamma)
             return fail(NLSPN_ERR_NULL, "prologue: guidance, feat_init, gamma, offset, aff, src are required");
         if (c.confidence && !c.conf_fixed)
             return fail(NLSPN_ERR_NULL, "prologue: conf_fixed is required when confidence is given");
@@ -397,7 +414,7 @@ static int check_fwd(const FwdCall &c, bool prologue, bool iters)
             return fail(NLSPN_ERR_AFFINITY, "unknown affinity mode %d", c.affinity);
     }
     if (iters) {
-        if (!c.offset || !c.aff || !c.src || !c.list_feat)
+        if ((!c.offset && !no_off) || !c.aff || !c.src || !c.list_feat)
             return fail(NLSPN_ERR_NULL, "propagate: offset, aff, src, list_feat are required");
         if (c.S < 1 || (c.conf_fixed && c.T > 1 && c.S < 2))
             return fail(NLSPN_ERR_SHAPE, "propagate: src needs S >= 2 planes with confidence (got %d)", c.S);
@@ -411,7 +428,7 @@ static int run_forward(const FwdCall &c, bool prologue, bool iters)
     const int G = group_images(c.B, c.H, c.W, c.K, false);
     CUtensorMap src_map, list_map;
     const CUtensorMap *psrc = nullptr, *plist = nullptr;
-    if (iters && tiled_ok(c.src, c.W) && aligned16(c.list_feat)) {
+    if (iters && !(c.flags & NLSPN_FLAG_NO_OFFSET) && tiled_ok(c.src, c.W) && aligned16(c.list_feat)) {
         if (int rc = make_plane_map(&src_map, c.src, (long)c.S * c.B, c.H, c.W, kTileW + 2 * halo_for(c.K), fwd_tile_h() + 2 * halo_for(c.K))) return rc;
         if (int rc = make_plane_map(&list_map, c.list_feat, (long)c.T * c.B, c.H, c.W, kTileW + 2 * halo_for(c.K), fwd_tile_h() + 2 * halo_for(c.K))) return rc;
         psrc = &src_map;
@@ -492,7 +509,10 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                    void *workspace, size_t workspace_bytes, void *stream)
 {
     if (int rc = check_shape(B, H, W, K, T)) return rc;
-    if (!guidance || !feat_init || !offset || !aff || !src || !list_feat || !g_list || !gamma ||
+    const bool no_off = (flags & NLSPN_FLAG_NO_OFFSET) != 0;
+    if (no_off && K != 3)
+        return fail(NLSPN_ERR_KERNEL, "fixed-local propagation (NO_OFFSET) is 3x3 only (got K=%d)", K);
+    if (!guidance || !feat_init || (!offset && !no_off) || !aff || !src || !list_feat || !g_list || !gamma ||
         !g_feat_init || !g_guidance || !g_gamma || !workspace)
         return fail(NLSPN_ERR_NULL, "backward: a required pointer is NULL");
     if (conf_fixed && !g_confidence)
@@ -513,6 +533,43 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     float *ws = static_cast<float *>(workspace);
     cudaError_t e = cudaMemsetAsync(g_gamma, 0, sizeof(double), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(g_gamma)");
+
+    if (no_off) {
+        // ---- fixed-local propagation (nlspnmodel.py:209-224): plain scatter planes, scalar REDs
+        float *planeA = ws, *planeB = ws + BP, *g_conf_acc = ws + 2 * BP;
+        float *gy_all = ws + 3 * BP, *g_aff_acc = gy_all + (long)T * BP;
+        e = cudaMemsetAsync(ws, 0, sizeof(float) * 3 * BP, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+        const bool sh = stream_hint_for(B, H, W, K);
+        for (int t = T; t >= 1; --t) {
+            float *s_out = ((T - t) % 2 == 0) ? planeA : planeB;
+            float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? planeB : planeA);
+            ProfScope prof__(kProfBwdState, st);
+            if (sh)
+                e = launch_pdl(fixed_state_kernel<true>, grid_for(P, B), dim3(kBlock), st, aff, conf_fixed,
+                               feat_fix, list_feat + (long)(t - 1) * BP, g_list[t - 1], s_in, s_out,
+                               gy_all + (long)(t - 1) * BP, g_conf_acc, flags, H, W);
+            else
+                e = launch_pdl(fixed_state_kernel<false>, grid_for(P, B), dim3(kBlock), st, aff, conf_fixed,
+                               feat_fix, list_feat + (long)(t - 1) * BP, g_list[t - 1], s_in, s_out,
+                               gy_all + (long)(t - 1) * BP, g_conf_acc, flags, H, W);
+            if (e != cudaSuccess) return cuda_fail(e, "fixed_state_kernel");
+            NLSPN_CHECK_LAUNCH("fixed_state_kernel");
+        }
+        const float *s_last = ((T - 1) % 2 == 0) ? planeA : planeB;
+        {
+            ProfScope prof__(kProfBwdParam, st);
+            fixed_param_kernel<<<grid_for(P, B), kBlock, 0, st>>>(src, list_feat, gy_all, conf_fixed ? 1 : 0,
+                                                                  H, W, T, BP, BP, g_aff_acc);
+            NLSPN_CHECK_LAUNCH("fixed_param_kernel");
+        }
+        ProfScope prof__(kProfFinalBwd, st);
+        final_bwd_kernel<3, false><<<grid_for(P, B), kBlock, 0, st>>>(
+            guidance, feat_init, feat_fix, conf_fixed, s_last, g_aff_acc, g_conf_acc, nullptr, g_aff_ext, gamma,
+            affinity, flags, H, W, g_feat_init, g_guidance, g_confidence, g_gamma);
+        NLSPN_CHECK_LAUNCH("final_bwd_kernel");
+        return 0;
+    }
 
     if (flags & NLSPN_FLAG_BWD_PER_ITERATION) {
         // ---- v1: per-iteration accumulator RMW + scalar atomics (kept for cross-checking)

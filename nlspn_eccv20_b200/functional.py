@@ -48,9 +48,10 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def _flags(preserve_input, always_clip):
+def _flags(preserve_input, always_clip, use_offset=True):
     return (_lib.FLAG_PRESERVE_INPUT if preserve_input else 0) | \
-           (_lib.FLAG_ALWAYS_CLIP if always_clip else 0)
+           (_lib.FLAG_ALWAYS_CLIP if always_clip else 0) | \
+           (0 if use_offset else _lib.FLAG_NO_OFFSET)
 
 
 def device_info(device=None):
@@ -89,20 +90,21 @@ def prologue_fwd(guidance, confidence, feat_init, feat_fix, gamma, K, affinity="
 
 
 def forward(guidance, confidence, feat_init, feat_fix, gamma, K, T, affinity="TGASS",
-            preserve_input=True, always_clip=False, keep_src=True):
+            preserve_input=True, always_clip=False, keep_src=True, use_offset=True):
     """Fused prologue + T iterations (group-major).
-    -> (offset, aff, conf_fixed | None, src [S,B,1,H,W], list_feat [T,B,1,H,W])."""
+    -> (offset | None, aff, conf_fixed | None, src [S,B,1,H,W], list_feat [T,B,1,H,W]).
+    use_offset=False: fixed-local propagation (nlspnmodel.py:209-224), guidance is [B,N,H,W]."""
     lib = _lib.load()
     B, _, H, W = feat_init.shape
     N = K * K - 1
     feat_init = _chk("feat_init", feat_init, (B, 1, H, W))
-    guidance = _chk("guidance", guidance, (B, 3 * N, H, W))
+    guidance = _chk("guidance", guidance, (B, (3 if use_offset else 1) * N, H, W))
     confidence = _chk("confidence", confidence, (B, 1, H, W), optional=True)
     feat_fix = _chk("feat_fix", feat_fix, (B, 1, H, W), optional=True)
     preserve = bool(preserve_input and feat_fix is not None)
     dev = feat_init.device
     opt = dict(device=dev, dtype=torch.float32)
-    offset = torch.empty((B, 2 * K * K, H, W), **opt)
+    offset = torch.empty((B, 2 * K * K, H, W), **opt) if use_offset else None
     aff = torch.empty((B, K * K, H, W), **opt)
     conf_fixed = torch.empty((B, 1, H, W), **opt) if confidence is not None else None
     S = 1 if confidence is None else (T if keep_src else min(T, 2))
@@ -111,7 +113,7 @@ def forward(guidance, confidence, feat_init, feat_fix, gamma, K, T, affinity="TG
     gam = _gamma(gamma, dev)
     with torch.cuda.device(dev):
         rc = lib.nlspn_forward(_ptr(guidance), _ptr(confidence), _ptr(feat_init), _ptr(feat_fix),
-                               _ptr(gam), _lib.AFFINITY[affinity], _flags(preserve, always_clip),
+                               _ptr(gam), _lib.AFFINITY[affinity], _flags(preserve, always_clip, use_offset),
                                B, H, W, K, T, _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(src), S,
                                _ptr(list_feat), _stream(dev))
     _lib.check(rc, "nlspn_forward")
@@ -142,7 +144,7 @@ def propagate_fwd(offset, aff, conf_fixed, feat_fix, src, list_feat, K, T,
 
 def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_feat, g_list,
              gamma, K, T, affinity="TGASS", preserve_input=True, always_clip=False,
-             g_offset_ext=None, g_aff_ext=None, per_iteration=False):
+             g_offset_ext=None, g_aff_ext=None, per_iteration=False, use_offset=True):
     """g_list: sequence of T tensors [B,1,H,W] or None.  -> (g_init, g_guidance, g_conf, g_gamma)."""
     lib = _lib.load()
     B, _, H, W = feat_init.shape
@@ -159,7 +161,7 @@ def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_f
     g_offset_ext = _chk("g_offset_ext", g_offset_ext, (B, 2 * K * K, H, W), optional=True)
     g_aff_ext = _chk("g_aff_ext", g_aff_ext, (B, K * K, H, W), optional=True)
     g_init = torch.empty((B, 1, H, W), **opt)
-    g_guid = torch.empty((B, 3 * N, H, W), **opt)
+    g_guid = torch.empty((B, (3 if use_offset else 1) * N, H, W), **opt)
     g_conf = torch.empty((B, 1, H, W), **opt) if conf_fixed is not None else None
     g_gamma = torch.empty((1,), device=dev, dtype=torch.float64)
     nbytes = lib.nlspn_backward_workspace_bytes(B, H, W, K, T)
@@ -170,7 +172,7 @@ def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_f
                                 _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(src), S, _ptr(list_feat),
                                 ptrs, _ptr(g_offset_ext), _ptr(g_aff_ext), _ptr(gam),
                                 _lib.AFFINITY[affinity],
-                                _flags(preserve, always_clip) | (_lib.FLAG_BWD_PER_ITERATION if per_iteration else 0),
+                                _flags(preserve, always_clip, use_offset) | (_lib.FLAG_BWD_PER_ITERATION if per_iteration else 0),
                                 B, H, W, K, T, _ptr(g_init), _ptr(g_guid), _ptr(g_conf), _ptr(g_gamma), _ptr(ws),
                                 nbytes, _stream(dev))
     _lib.check(rc, "nlspn_backward")

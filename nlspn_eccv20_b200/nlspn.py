@@ -27,7 +27,7 @@ class NLSPNFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat_init, guidance, confidence, feat_fix, gamma, K, T, affinity,
-                preserve_input, always_clip):
+                preserve_input, always_clip, use_offset=True):
         need_grad = any(t is not None and t.requires_grad for t in (feat_init, guidance, confidence, gamma))
         gamma_val = gamma.detach() if torch.is_tensor(gamma) else float(gamma)   # stays on the device
         feat_init_c = feat_init.detach().contiguous()
@@ -37,13 +37,17 @@ class NLSPNFunction(torch.autograd.Function):
         preserve = bool(preserve_input and fix_c is not None)
         offset, aff, conf_fixed, src, list_feat = F_.forward(
             guidance_c, conf_c, feat_init_c, fix_c, gamma_val, K, T, affinity, preserve, always_clip,
-            keep_src=need_grad)
+            keep_src=need_grad, use_offset=use_offset)
         ctx.cfg = (K, T, affinity, preserve, always_clip, gamma_val)
+        ctx.use_offset = bool(use_offset)
         ctx.has_conf = conf_fixed is not None
         ctx.gamma_is_tensor = torch.is_tensor(gamma)
         ctx.save_for_backward(feat_init_c, guidance_c, fix_c, offset, aff, conf_fixed, src, list_feat)
         ctx.set_materialize_grads(False)
-        outs = tuple(list_feat[t] for t in range(T)) + (offset, aff)
+        # outputs: T states, aff, [offset], [conf_fixed]
+        outs = tuple(list_feat[t] for t in range(T)) + (aff,)
+        if offset is not None:
+            outs = outs + (offset,)
         if conf_fixed is not None:
             outs = outs + (conf_fixed,)
         return outs
@@ -54,29 +58,42 @@ class NLSPNFunction(torch.autograd.Function):
         K, T, affinity, preserve, always_clip, gamma_val = ctx.cfg
         feat_init, guidance, feat_fix, offset, aff, conf_fixed, src, list_feat = ctx.saved_tensors
         g_list = list(grads[:T])
-        g_off_ext, g_aff_ext = grads[T], grads[T + 1]
-        g_cf_ext = grads[T + 2] if ctx.has_conf else None
+        g_aff_ext = grads[T]
+        i = T + 1
+        g_off_ext = None
+        if ctx.use_offset:
+            g_off_ext = grads[i]
+            i += 1
+        g_cf_ext = grads[i] if ctx.has_conf else None
         g_init, g_guid, g_conf, g_gamma = F_.backward(
             guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_feat, g_list, gamma_val,
-            K, T, affinity, preserve, always_clip, g_off_ext, g_aff_ext)
+            K, T, affinity, preserve, always_clip, g_off_ext, g_aff_ext, use_offset=ctx.use_offset)
         if g_cf_ext is not None:
             # conf_fixed = (1-m)*confidence + m, nlspnmodel.py:334
             m = (feat_fix > 0).to(g_cf_ext.dtype) if preserve else 0.0
             g_conf = g_conf + (1.0 - m) * g_cf_ext
         g_gam = g_gamma.to(torch.float32) if ctx.gamma_is_tensor else None
         return g_init, g_guid, (g_conf if ctx.has_conf else None), None, g_gam, \
-            None, None, None, None, None
+            None, None, None, None, None, None
 
 
 def nlspn_propagate(feat_init, guidance, confidence, feat_fix, gamma, prop_kernel=3, prop_time=18,
-                    affinity="TGASS", preserve_input=True, always_clip=False):
-    """Functional form.  -> (feat_result, list_feat, offset, aff, conf_fixed|None)."""
+                    affinity="TGASS", preserve_input=True, always_clip=False, use_offset=True):
+    """Functional form.  -> (feat_result, list_feat, offset|None, aff, conf_fixed|None).
+    use_offset=False selects the fork's fixed-local propagation (nlspnmodel.py:209-224); guidance
+    then holds the N raw affinities only and `offset` is None (as in nlspnmodel.py:306-308)."""
     outs = NLSPNFunction.apply(feat_init, guidance, confidence, feat_fix, gamma, prop_kernel,
-                               prop_time, affinity, preserve_input, always_clip)
+                               prop_time, affinity, preserve_input, always_clip, use_offset)
     T = prop_time
     list_feat = list(outs[:T])
-    conf_fixed = outs[T + 2] if len(outs) > T + 2 else None
-    return list_feat[-1], list_feat, outs[T], outs[T + 1], conf_fixed
+    aff = outs[T]
+    i = T + 1
+    offset = None
+    if use_offset:
+        offset = outs[i]
+        i += 1
+    conf_fixed = outs[i] if len(outs) > i else None
+    return list_feat[-1], list_feat, offset, aff, conf_fixed
 
 
 class NLSPN(nn.Module):
@@ -101,6 +118,9 @@ class NLSPN(nn.Module):
         self.conf_prop = bool(opt("conf_prop", True))
         self.preserve_input = bool(opt("preserve_input", True))
         self.always_clip = bool(opt("always_clip", False))
+        # args.offset: deformable gather (True; the north-star path) or the fork's fixed-local 3x3
+        # propagation (False; the fork's command-line default, src/config.py:272-275)
+        self.offset = bool(opt("offset", True))
         assert (self.prop_kernel % 2) == 1, \
             'only odd kernel is supported but k_f = {}'.format(self.prop_kernel)   # nlspnmodel.py:29-30
         if self.prop_kernel not in (3, 5, 7):
@@ -138,5 +158,5 @@ class NLSPN(nn.Module):
             feat_fix = None
         feat_result, list_feat, offset, aff, _ = nlspn_propagate(
             feat_init, guidance, confidence, feat_fix, self.aff_scale_const, self.prop_kernel,
-            self.prop_time, self.affinity, self.preserve_input, self.always_clip)
+            self.prop_time, self.affinity, self.preserve_input, self.always_clip, self.offset)
         return feat_result, list_feat, offset, aff, self.aff_scale_const.data

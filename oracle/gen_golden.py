@@ -70,17 +70,23 @@ def loss_fn(out, gt):
 def run_path(model, inp, with_grad=True, use_conf=True):
     N = model.num_neighbors
     fi = inp["feat_init"].clone().requires_grad_(with_grad)
+    if not model.args.offset:
+        inp["guidance"] = inp["guidance"][:, 2 * N:].contiguous()   # raw affinities only (:306-308)
     gd = inp["guidance"].clone().requires_grad_(with_grad)
     cf = inp["confidence"].clone().requires_grad_(with_grad) if use_conf else None
     if with_grad and model.aff_scale_const.requires_grad:
         model.aff_scale_const.grad = None
-    out = RH.reference_propagate(model, fi, gd[:, :2 * N], gd[:, 2 * N:], cf, inp["feat_fix"])
+    if model.args.offset:
+        out = RH.reference_propagate(model, fi, gd[:, :2 * N], gd[:, 2 * N:], cf, inp["feat_fix"])
+    else:
+        out = RH.reference_propagate(model, fi, None, gd, cf, inp["feat_fix"])
     rec = dict(
         feat_result=out["feat_result"].detach(), pred=out["pred"].detach(),
         list_feat=torch.stack([p.detach() for p in out["pred_inter"]], 0),
-        offset=out["offset"].detach(), aff=out["aff"].detach(),
-        gamma=out["gamma"].clone(),
+        aff=out["aff"].detach(), gamma=out["gamma"].clone(),
     )
+    if out["offset"] is not None:
+        rec["offset"] = out["offset"].detach()
     if use_conf:
         rec["conf_fixed"] = out["confidence"].detach()
     if with_grad:
@@ -178,6 +184,9 @@ def case_paths():
         ("path_ASS_k3_t4", 1, 12, 16, 3, 4, dict(), dict(affinity="ASS"), True),
         ("path_TC_k3_t4", 1, 12, 16, 3, 4, dict(), dict(affinity="TC"), True),
         ("path_clip_k3_t4", 1, 12, 16, 3, 4, dict(signed=True), dict(always_clip=True), True),
+        # the fork's default: no offsets -> fixed-local 3x3 propagation (nlspnmodel.py:209-224)
+        ("path_fixedlocal_k3_t6", 2, 14, 20, 3, 6, dict(), dict(offset=False), True),
+        ("path_fixedlocal_noconf_k3_t3", 1, 9, 13, 3, 3, dict(signed=True), dict(offset=False, conf_prop=False), False),
     ]
     for name, B, H, W, K, T, ikw, mkw, use_conf in specs:
         g = torch.Generator().manual_seed(SEED + len(name))
@@ -197,7 +206,7 @@ def case_paths():
         a = model.args
         save(name, {k: v for k, v in inp.items() if use_conf or k != "confidence"}, rec,
              dict(K=K, T=T, affinity=a.affinity, preserve=int(a.preserve_input),
-                  use_conf=int(use_conf), always_clip=int(a.always_clip),
+                  use_conf=int(use_conf), always_clip=int(a.always_clip), use_offset=int(a.offset),
                   gamma=float(model.aff_scale_const)))
 
     # zero guidance (zero_init_aff, config.py:233-236): every top/left border tap on -1

@@ -88,12 +88,24 @@ def insert_center_offset(off, K):
     return torch.cat([o[:, :N // 2], z, o[:, N // 2:]], 1).reshape(B, 2 * K * K, H, W)
 
 
+def fixed_local_step(x, aff):
+    """nlspnmodel.py:209-224: replicate-pad by one, weight the 9 shifted copies, sum."""
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1), mode="replicate")
+    H, W = x.shape[2], x.shape[3]
+    cols = [xp[:, :, i:i + H, j:j + W] for i in range(3) for j in range(3)]
+    return (torch.cat(cols, 1) * aff).sum(1, keepdim=True)
+
+
 def propagate(feat_init, guidance, confidence, feat_fix, gamma, K, T, affinity="TGASS",
-              preserve_input=True, always_clip=False):
+              preserve_input=True, always_clip=False, use_offset=True):
     """-> dict(feat_result, list_feat (list of T), offset, aff, confidence)."""
     N = K * K - 1
-    offset = insert_center_offset(guidance[:, :2 * N], K)
-    aff = normalize_affinity(guidance[:, 2 * N:], gamma, affinity)
+    if use_offset:
+        offset = insert_center_offset(guidance[:, :2 * N], K)
+        aff = normalize_affinity(guidance[:, 2 * N:], gamma, affinity)
+    else:
+        offset = None
+        aff = normalize_affinity(guidance, gamma, affinity)
     preserve = preserve_input and feat_fix is not None
     if preserve:
         m = (feat_fix > 0).to(feat_init.dtype)
@@ -109,7 +121,7 @@ def propagate(feat_init, guidance, confidence, feat_fix, gamma, K, T, affinity="
     out = []
     for _ in range(T):
         s = x * confidence if confidence is not None else x
-        x = DeformStep.apply(s, offset, aff, w, b, K)
+        x = DeformStep.apply(s, offset, aff, w, b, K) if use_offset else fixed_local_step(s, aff)
         if preserve:
             x = (1.0 - m) * x + m * feat_fix
         if always_clip:

@@ -29,7 +29,8 @@ def dev():
 def _meta(g):
     return dict(K=int(g["meta_K"]), T=int(g["meta_T"]), affinity=str(g["meta_affinity"]),
                 preserve=bool(int(g["meta_preserve"])), use_conf=bool(int(g["meta_use_conf"])),
-                always_clip=bool(int(g.get("meta_always_clip", 0))), gamma=float(g["meta_gamma"]))
+                always_clip=bool(int(g.get("meta_always_clip", 0))), gamma=float(g["meta_gamma"]),
+                use_offset=bool(int(g.get("meta_use_offset", 1))))
 
 
 def _run_module(g, dev, grad=False):
@@ -37,7 +38,7 @@ def _run_module(g, dev, grad=False):
     m = _meta(g)
     mod = NLSPN(prop_kernel=m["K"], prop_time=m["T"], affinity=m["affinity"],
                 conf_prop=m["use_conf"], preserve_input=m["preserve"],
-                always_clip=m["always_clip"]).to(dev)
+                always_clip=m["always_clip"], offset=m["use_offset"]).to(dev)
     with torch.no_grad():
         mod.aff_scale_const.fill_(m["gamma"])
     t = lambda k: torch.from_numpy(g[k]).to(dev)
@@ -55,7 +56,10 @@ def _rel(a, b):
 def test_forward_matches_reference_golden(dev, name):
     g = load_golden(name)
     mod, _, (feat_result, list_feat, offset, aff, gamma), m = _run_module(g, dev)
-    assert torch.equal(offset.detach().cpu(), torch.from_numpy(g["out_offset"]))          # offsets exact
+    if m["use_offset"]:
+        assert torch.equal(offset.detach().cpu(), torch.from_numpy(g["out_offset"]))      # offsets exact
+    else:
+        assert offset is None                                                              # nlspnmodel.py:307
     np.testing.assert_allclose(aff.detach().cpu().numpy(), g["out_aff"], rtol=0, atol=2e-6)
     lf = torch.stack(list_feat, 0).detach().cpu().numpy()
     scale = max(1.0, float(np.abs(g["out_list_feat"]).max()))
@@ -84,6 +88,11 @@ def test_backward_matches_reference_autograd(dev, name):
     N = m["K"] ** 2 - 1
     assert _rel(fi.grad.cpu().numpy(), g["out_g_feat_init"]) < 1e-4
     gg = gd.grad.cpu().numpy()
+    if not m["use_offset"]:
+        assert _rel(gg, g["out_g_guidance"]) < 2e-4
+        if m["use_conf"]:
+            assert _rel(cf.grad.cpu().numpy(), g["out_g_confidence"]) < 1e-4
+        return
     assert _rel(gg[:, 2 * N:], g["out_g_guidance"][:, 2 * N:]) < 2e-4
     if m["use_conf"]:
         assert _rel(cf.grad.cpu().numpy(), g["out_g_confidence"]) < 1e-4

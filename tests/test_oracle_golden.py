@@ -7,13 +7,15 @@ import pytest
 
 from conftest import golden_names, load_golden
 
-PATHS = golden_names("path_") + golden_names("fullmodel_")
+ALL_PATHS = golden_names("path_") + golden_names("fullmodel_")
+PATHS = [n for n in ALL_PATHS if "fixedlocal" not in n]     # the C oracle restates the deformable path only
 
 
 def _meta(g):
     return dict(K=int(g["meta_K"]), T=int(g["meta_T"]), affinity=str(g["meta_affinity"]),
                 preserve=bool(int(g["meta_preserve"])), use_conf=bool(int(g["meta_use_conf"])),
-                always_clip=bool(int(g.get("meta_always_clip", 0))), gamma=float(g["meta_gamma"]))
+                always_clip=bool(int(g.get("meta_always_clip", 0))), gamma=float(g["meta_gamma"]),
+                use_offset=bool(int(g.get("meta_use_offset", 1))))
 
 
 def _fwd(oracle, g, dtype=np.float32):
@@ -96,7 +98,7 @@ def test_dcn_step_matches_reference_function(oracle, name):
     np.testing.assert_allclose(gb, g["out_gb"], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("name", [n for n in PATHS if "fullmodel" not in n])
+@pytest.mark.parametrize("name", [n for n in ALL_PATHS if "fullmodel" not in n])
 def test_torchvision_port_matches_reference(name):
     """oracle/torchvision_port.py (the CPU-baseline restatement) against the golden vectors."""
     import torch
@@ -109,12 +111,15 @@ def test_torchvision_port_matches_reference(name):
     cf = t("in_confidence").requires_grad_(grad) if m["use_conf"] else None
     gam = torch.tensor([m["gamma"]], requires_grad=grad and m["affinity"] == "TGASS")
     out = TP.propagate(fi, gd, cf, t("in_feat_fix") if True else None, gam, m["K"], m["T"],
-                       m["affinity"], m["preserve"], m["always_clip"])
+                       m["affinity"], m["preserve"], m["always_clip"], use_offset=m["use_offset"])
     lf = torch.stack(out["list_feat"], 0).detach().numpy()
     # same ops in the same order as the reference => bit-exact on CPU
     assert np.array_equal(lf, g["out_list_feat"])
     assert np.array_equal(out["aff"].detach().numpy(), g["out_aff"])
-    assert np.array_equal(out["offset"].detach().numpy(), g["out_offset"])
+    if m["use_offset"]:
+        assert np.array_equal(out["offset"].detach().numpy(), g["out_offset"])
+    else:
+        assert out["offset"] is None
     if grad:
         gl = t("out_g_list")
         torch.autograd.backward(out["list_feat"], [gl[i] for i in range(m["T"])])
