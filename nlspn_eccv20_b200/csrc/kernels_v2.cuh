@@ -122,10 +122,14 @@ bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff
         const float h_im = (float)(h - G::PAD + t / K) + oh[t];
         const float w_im = (float)(w - G::PAD + t % K) + ow[t];
         if (!tap_valid(h_im, w_im, H, W)) continue;
-        const int hl = (int)floorf(h_im), wl = (int)floorf(w_im);
-        // mdmcn_get_gradient_weight, cuh:71-79 (expressions kept literal)
-        const float th = (float)(hl + 1) - h_im, bh = (h_im + 1.f) - (float)(hl + 1);
-        const float lw_ = (float)(wl + 1) - w_im, rw = (w_im + 1.f) - (float)(wl + 1);
+        float hf, wf;
+        int hl, wl;
+        floor_small(h_im, hf, hl);
+        floor_small(w_im, wf, wl);
+        // mdmcn_get_gradient_weight, cuh:71-79 (expressions kept literal; (float)(hl+1) == hf + 1 exactly)
+        const float h1 = hf + 1.f, w1 = wf + 1.f;
+        const float th = h1 - h_im, bh = (h_im + 1.f) - h1;
+        const float lw_ = w1 - w_im, rw = (w_im + 1.f) - w1;
         const int Y = hl + 1, X = wl + 1;         // padded coordinates of the top-left corner
         const int sy = Y & 1, sx = X & 1;
         float4 *blk = reinterpret_cast<float4 *>(
