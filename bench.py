@@ -268,7 +268,7 @@ def main():
     # compute stream runs the module on chunk i (images are independent, so the chunked step is
     # the same computation; this is the double-buffered prefetch a pinned DataLoader does).
     h2d = sum(host[k].numel() * 4 for k in names)
-    chunk = max(1, min(B, int(os.environ.get("NLSPN_E2E_CHUNK", "2"))))
+    chunk = max(1, min(B, int(os.environ.get("NLSPN_E2E_CHUNK", "1"))))
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     gt_chunks = [gt[i:i + chunk] for i in range(0, B, chunk)]
