@@ -11,6 +11,7 @@ namespace nlspn {
 
 enum : unsigned { kPreserve = 1u, kAlwaysClip = 2u, kNoOffset = 4u };
 enum : int { kAS = 0, kASS = 1, kTC = 2, kTGASS = 3 };
+constexpr int kGammaSlots = 64;   // partial sums of d loss / d gamma (final_bwd_kernel -> gamma_reduce_kernel)
 
 // ======================================================================================
 // Prologue.  nlspnmodel.py:252-259 (_off_insert), :179-201 (_affinity_normalization),
@@ -387,9 +388,20 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
             double tot = 0.0;
 #pragma unroll
             for (int i = 0; i < kBlock / 32; ++i) tot += red[i];
-            if (tot != 0.0) atomicAdd(g_gamma, tot);
+            // spread over kGammaSlots addresses: thousands of same-address fp64 atomics serialise in L2
+            if (tot != 0.0) atomicAdd(g_gamma + (blockIdx.x + blockIdx.y * gridDim.x) % kGammaSlots, tot);
         }
     }
+}
+
+// sums the kGammaSlots partial gamma gradients into the caller's scalar (one warp, fixed order)
+__global__ void gamma_reduce_kernel(const double *__restrict__ slots, double *__restrict__ g_gamma)
+{
+    double v = 0.0;
+    for (int i = threadIdx.x; i < kGammaSlots; i += 32) v += slots[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) *g_gamma = v;
 }
 
 // grad_weight / grad_bias of the single-step operator (modulated_deform_conv_cuda.cu:248,271-272)

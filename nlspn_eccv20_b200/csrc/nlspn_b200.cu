@@ -497,7 +497,7 @@ size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T)
 {
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0 || T <= 0) return 0;
     const size_t a = ws_bytes_v1(B, H, W, K), b = ws_bytes_v2(B, H, W, K, T);
-    return a > b ? a : b;
+    return (a > b ? a : b) + sizeof(double) * kGammaSlots;
 }
 
 int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
@@ -530,9 +530,17 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     const long BP = (long)B * P;
     const int N = KK - 1;
     cudaStream_t st = (cudaStream_t)stream;
-    float *ws = static_cast<float *>(workspace);
-    cudaError_t e = cudaMemsetAsync(g_gamma, 0, sizeof(double), st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(g_gamma)");
+    // workspace head: kGammaSlots fp64 partial sums of the gamma gradient
+    double *gamma_slots = static_cast<double *>(workspace);
+    float *ws = static_cast<float *>(workspace) + 2 * kGammaSlots;
+    cudaError_t e = cudaMemsetAsync(gamma_slots, 0, sizeof(double) * kGammaSlots, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(gamma slots)");
+    struct GammaReduce {   // runs on every return path after the final kernel was enqueued
+        double *slots, *out;
+        cudaStream_t st;
+        bool armed = false;
+        ~GammaReduce() { if (armed) gamma_reduce_kernel<<<1, 32, 0, st>>>(slots, out); }
+    } gamma_reduce{gamma_slots, g_gamma, st};
 
     if (no_off) {
         // ---- fixed-local propagation (nlspnmodel.py:209-224): plain scatter planes, scalar REDs
@@ -566,8 +574,9 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         ProfScope prof__(kProfFinalBwd, st);
         final_bwd_kernel<3, false><<<grid_for(P, B), kBlock, 0, st>>>(
             guidance, feat_init, feat_fix, conf_fixed, s_last, g_aff_acc, g_conf_acc, nullptr, g_aff_ext, gamma,
-            affinity, flags, H, W, g_feat_init, g_guidance, g_confidence, g_gamma);
+            affinity, flags, H, W, g_feat_init, g_guidance, g_confidence, gamma_slots);
         NLSPN_CHECK_LAUNCH("final_bwd_kernel");
+        gamma_reduce.armed = true;
         return 0;
     }
 
@@ -594,8 +603,9 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         DISPATCH_K(K, (final_bwd_kernel<KC, false><<<grid_for(P, B), kBlock, 0, st>>>(
                           guidance, feat_init, feat_fix, conf_fixed, s_last, g_aff_acc, g_conf_acc,
                           g_offset_ext, g_aff_ext, gamma, affinity, flags, H, W, g_feat_init, g_guidance,
-                          g_confidence, g_gamma)));
+                          g_confidence, gamma_slots)));
         NLSPN_CHECK_LAUNCH("final_bwd_kernel");
+        gamma_reduce.armed = true;
         return 0;
     }
 
@@ -681,9 +691,10 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                           g_offset_ext ? g_offset_ext + o1 * 2 * KK : nullptr,
                           g_aff_ext ? g_aff_ext + o1 * KK : nullptr, gamma, affinity, flags, H, W,
                           g_feat_init + o1, g_guidance + o1 * 3 * N, g_confidence ? g_confidence + o1 : nullptr,
-                          g_gamma)));
+                          gamma_slots)));
         NLSPN_CHECK_LAUNCH("final_bwd_kernel");
     }
+    gamma_reduce.armed = true;
     return 0;
 }
 

@@ -90,10 +90,14 @@ int main(int argc, char** argv)
     dim3 grid((P + 255) / 256, B);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const char* names[5] = {"4x RED.F32", "2x RED.F32x2 (shifted planes)", "1x RED.F32x4 (blocked planes)", "1x ST.128 (no atomics)", "math only"};
+    float* d_flush; const size_t flush_bytes = 512u << 20;
+    CK(cudaMalloc(&d_flush, flush_bytes));
+    const int cold = argc > 3 ? atoi(argv[3]) : 0;   // 1: evict the scatter planes from L2 before each run
     for (int mode = 0; mode < 5; ++mode) {
         float best = 1e9f;
         for (int rep = 0; rep < 6; ++rep) {
             CK(cudaMemsetAsync(d_S, 0, (size_t)B * 4 * plane_stride * 4));
+            if (cold) CK(cudaMemsetAsync(d_flush, 1, flush_bytes));
             cudaEventRecord(e0);
             switch (mode) {
             case 0: scatter<0><<<grid, 256>>>(d_off, d_gy, d_S, H, W, plane_stride); break;
@@ -107,7 +111,7 @@ int main(int argc, char** argv)
             if (rep > 0 && ms < best) best = ms;
         }
         CK(cudaGetLastError());
-        printf("sigma=%.1f smooth=%d  %-34s %8.3f ms  %7.2f Gpix/s  %7.1f G corner-adds/s\n", sigma, smooth,
+        printf("cold=%d sigma=%.1f smooth=%d  %-34s %8.3f ms  %7.2f Gpix/s  %7.1f G corner-adds/s\n", cold, sigma, smooth,
                names[mode], best, (double)B * P / best / 1e6, (double)B * P * 32 / best / 1e6);
     }
     return 0;
