@@ -328,13 +328,17 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         const bool use_tanh = affinity == kTC || affinity == kTGASS;
         const float gamma = __ldg(gamma_ptr);
         const float g = affinity == kTGASS ? gamma + 1e-8f : gamma;
+        // Three IEEE divisions per pixel instead of 4N: the denominators g, s and s^2 are shared by
+        // all N affinities, and a gradient tolerates the last-bit difference of x * (1/d) vs x / d
+        // (the FORWARD prologue keeps true divisions: its outputs are API-visible values).
+        const float inv_g = 1.0f / g;
         float a[G::N], th[G::N], Gh[G::N];
         float s0 = 0.f;
 #pragma unroll
         for (int n = 0; n < G::N; ++n) {
             const float rr = __ldg(gb + (long)(aff_ch0 + n) * P);
             th[n] = use_tanh ? tanhf(rr) : 0.f;
-            a[n] = use_tanh ? th[n] / g : rr;
+            a[n] = use_tanh ? th[n] * inv_g : rr;
             s0 += fabsf(a[n]);
         }
         s0 += 1e-4f;
@@ -344,6 +348,7 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
             s = 1.0f;
             clamped = true;
         }
+        const float inv_s = 1.0f / s;
         float Gref = __ldg(gab + (long)G::REF * P);
         if (eab) Gref += __ldg(eab + (long)G::REF * P);
         float dot = 0.f, gsum = 0.f;
@@ -355,21 +360,19 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
             Gh[n] = gv - Gref;
             dot += Gh[n] * a[n];
         }
+        const float corr = clamped ? 0.f : dot * inv_s * inv_s;
 #pragma unroll
         for (int n = 0; n < G::N; ++n) {
             float da;
             if (affinity == kTC) {
                 da = Gh[n];
             } else {
-                da = Gh[n] / s;
-                if (!clamped) {
-                    const float sg = a[n] > 0.f ? 1.f : (a[n] < 0.f ? -1.f : 0.f);
-                    da -= sg * dot / (s * s);
-                }
+                const float sg = a[n] > 0.f ? 1.f : (a[n] < 0.f ? -1.f : 0.f);
+                da = Gh[n] * inv_s - sg * corr;
             }
             float dr = da;
             if (use_tanh) {
-                dr = da * (1.f - th[n] * th[n]) / g;
+                dr = da * (1.f - th[n] * th[n]) * inv_g;
                 gsum += da * th[n];
             }
             ggb[(long)(aff_ch0 + n) * P] = dr;
