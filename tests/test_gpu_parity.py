@@ -309,3 +309,70 @@ def test_two_pass_backward_equals_per_iteration_backward(dev, K, T, use_conf):
             continue
         s = float(y.abs().max())
         assert float((x - y).abs().max()) <= 2e-5 * max(s, 1e-20), name
+
+
+def test_non_default_stream_and_concurrent_threads(dev):
+    """Boundary B1/B2 threading contract: work is enqueued on the caller's CURRENT
+    stream, and two host threads (the reference's test() uses nn.DataParallel worker threads,
+    src/main.py:366) may call concurrently.  Results must equal the serial default-stream run."""
+    import threading
+    from nlspn_eccv20_b200 import NLSPN
+    from nlspn_eccv20_b200.synth import make_inputs
+    K, T = 3, 5
+    mod = NLSPN(prop_kernel=K, prop_time=T).to(dev)
+    inps = [make_inputs(2, 36, 44, K, seed=500 + i, device=dev, conf_mean=2.0) for i in range(2)]
+
+    def run(inp):
+        fi = inp["feat_init"].clone().requires_grad_(True)
+        out = mod(fi, inp["guidance"], inp["confidence"], inp["feat_fix"])
+        out[0].square().sum().backward()
+        return out[0].detach().clone(), fi.grad.clone()
+
+    serial = [run(i) for i in inps]
+    torch.cuda.synchronize()
+    results = [None, None]
+
+    def worker(i):
+        s = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(s):
+            results[i] = run(inps[i])
+        s.synchronize()
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for (a, ga), (b, gb) in zip(serial, results):
+        assert torch.equal(a, b)                                       # forward is deterministic
+        assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max())   # atomics: order only
+
+
+def test_unusual_inputs(dev):
+    """Non-contiguous / expanded inputs, offsets far outside the image, inf-free zeros."""
+    from nlspn_eccv20_b200 import NLSPN
+    from nlspn_eccv20_b200.synth import make_inputs
+    K, T = 3, 4
+    inp = make_inputs(1, 32, 40, K, seed=8, device=dev)
+    mod = NLSPN(prop_kernel=K, prop_time=T).to(dev)
+    with torch.no_grad():
+        ref = mod(inp["feat_init"], inp["guidance"], inp["confidence"], inp["feat_fix"])[0]
+        # channels-last style non-contiguous guidance must give the same answer
+        g_nc = inp["guidance"].permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        assert not g_nc.is_contiguous()
+        assert torch.equal(mod(inp["feat_init"], g_nc, inp["confidence"], inp["feat_fix"])[0], ref)
+        # every offset far outside: only the centre tap survives => x_t = blend(a_ref * x_{t-1} * c)
+        g_far = inp["guidance"].clone()
+        g_far[:, :2 * (K * K - 1)] = 1.0e4
+        out = mod(inp["feat_init"], g_far, inp["confidence"], inp["feat_fix"])
+        aff = out[3]
+        m = (inp["feat_fix"] > 0).float()
+        c = (1 - m) * inp["confidence"] + m
+        x = (1 - m) * inp["feat_init"] + m * inp["feat_fix"]
+        for t in range(T):
+            x = (1 - m) * (aff[:, 4:5] * (x * c)) + m * inp["feat_fix"]
+            assert float((out[1][t] - x).abs().max()) <= 1e-6
+    with pytest.raises(RuntimeError):
+        mod(inp["feat_init"], inp["guidance"][:, :-1], inp["confidence"], inp["feat_fix"])
+    with pytest.raises(RuntimeError):
+        mod(inp["feat_init"].double(), inp["guidance"], inp["confidence"], inp["feat_fix"])
