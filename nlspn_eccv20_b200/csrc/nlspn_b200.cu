@@ -10,6 +10,7 @@
 
 #include "../../include/nlspn_b200.h"
 #include "kernels_fixed.cuh"
+#include "kernels_persist.cuh"
 #include "kernels_tiled.cuh"
 
 using namespace nlspn;
@@ -397,6 +398,50 @@ static int launch_iter_fwd(const FwdCall &c, int b0, int nb, int t, const CUtens
     return 0;
 }
 
+// Persistent forward (kernels_persist.cuh): used when every pixel of the batch can own a
+// co-resident thread.  *tried = 1 when the whole forward was enqueued here.
+static int persist_capacity(int K, int *blocks_per_sm)
+{
+    int n = 0;
+    cudaError_t e = cudaSuccess;
+    DISPATCH_K(K, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, persist_fwd_kernel<KC>, kPersistBlock, 0));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    *blocks_per_sm = n;
+    return 0;
+}
+
+static int try_persistent_forward(const FwdCall &c, bool prologue, int *tried)
+{
+    *tried = 0;
+    if (c.K != 3) return 0;   // 24 / 48 taps of geometry do not fit the register file
+    if (const char *e = getenv("NLSPN_PERSIST"))
+        if (atoi(e) == 0) return 0;
+    int dev = 0, sms = 0, coop = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, &sms, nullptr) != 0) return 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) return 0;
+    int per_sm = 0;
+    if (int rc = persist_capacity(c.K, &per_sm)) return rc;
+    const long BP = (long)c.B * c.H * c.W;
+    const long capacity = (long)sms * per_sm * kPersistBlock;
+    if (per_sm <= 0 || BP > capacity) return 0;
+    if (prologue)
+        if (int rc = launch_prologue(c, 0, c.B)) return rc;
+    const unsigned blocks = (unsigned)((BP + kPersistBlock - 1) / kPersistBlock);
+    const float *offset = c.offset, *aff = c.aff, *conf = c.conf_fixed, *dep = c.feat_fix;
+    unsigned flags = c.flags;
+    int H = c.H, W = c.W, B = c.B, T = c.T, S = c.S;
+    float *src = c.src, *list_feat = c.list_feat;
+    void *args[] = {&offset, &aff, &conf, &dep, &flags, &H, &W, &B, &T, &src, &S, &list_feat};
+    ProfScope prof__(kProfIterFwd, c.st);
+    cudaError_t e = cudaSuccess;
+    DISPATCH_K(c.K, e = cudaLaunchCooperativeKernel((const void *)persist_fwd_kernel<KC>, dim3(blocks),
+                                                    dim3(kPersistBlock), args, 0, c.st));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(persist_fwd_kernel)");
+    NLSPN_CHECK_LAUNCH("persist_fwd_kernel");
+    *tried = 1;
+    return 0;
+}
+
 static int check_fwd(const FwdCall &c, bool prologue, bool iters)
 {
     if (int rc = check_shape(c.B, c.H, c.W, c.K, c.T)) return rc;
@@ -435,6 +480,11 @@ static int run_forward(const FwdCall &c, bool prologue, bool iters)
         plist = &list_map;
     }
     const bool stream = stream_hint_for(G, c.H, c.W, c.K);
+    if (iters && !(c.flags & NLSPN_FLAG_NO_OFFSET)) {
+        int tried = 0;
+        if (int rc = try_persistent_forward(c, prologue, &tried)) return rc;
+        if (tried) return 0;
+    }
     for (int b0 = 0; b0 < c.B; b0 += G) {
         const int nb = c.B - b0 < G ? c.B - b0 : G;
         if (prologue)

@@ -376,3 +376,28 @@ def test_unusual_inputs(dev):
         mod(inp["feat_init"], inp["guidance"][:, :-1], inp["confidence"], inp["feat_fix"])
     with pytest.raises(RuntimeError):
         mod(inp["feat_init"].double(), inp["guidance"], inp["confidence"], inp["feat_fix"])
+
+
+def test_persistent_forward_equals_per_iteration_forward(dev, monkeypatch):
+    """One NYU-sized frame takes the persistent cooperative kernel (geometry in registers, grid
+    barrier per iteration); NLSPN_PERSIST=0 forces the per-iteration kernels.  Same arithmetic."""
+    from nlspn_eccv20_b200 import NLSPN
+    from nlspn_eccv20_b200.synth import workload
+    inp = workload("nyu", 1, 3, device=dev, conf_mean=3.0)
+    mod = NLSPN(prop_kernel=3, prop_time=18).to(dev)
+    with torch.no_grad():
+        a = mod(inp["feat_init"], inp["guidance"], inp["confidence"], inp["feat_fix"])
+        monkeypatch.setenv("NLSPN_PERSIST", "0")
+        b = mod(inp["feat_init"], inp["guidance"], inp["confidence"], inp["feat_fix"])
+    for x, y in zip(a[1], b[1]):
+        assert float((x - y).abs().max()) <= 2e-6
+    # and with gradients (all src planes kept): backward consumes what the persistent kernel saved
+    monkeypatch.delenv("NLSPN_PERSIST")
+    fi = inp["feat_init"].clone().requires_grad_(True)
+    out = mod(fi, inp["guidance"], inp["confidence"], inp["feat_fix"])
+    out[0].sum().backward()
+    g1 = fi.grad.clone()
+    monkeypatch.setenv("NLSPN_PERSIST", "0")
+    fi2 = inp["feat_init"].clone().requires_grad_(True)
+    mod(fi2, inp["guidance"], inp["confidence"], inp["feat_fix"])[0].sum().backward()
+    assert float((g1 - fi2.grad).abs().max()) <= 1e-5 * float(g1.abs().max())
