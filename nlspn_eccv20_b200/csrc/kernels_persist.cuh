@@ -54,27 +54,45 @@ persist_fwd_kernel(const float *__restrict__ offset, const float *__restrict__ a
     const int r = active ? (int)(q - (long)b * P) : 0;
     const int h = r / W, w = r - h * W;
 
-    // ---- the pixel's geometry: loaded once, register-resident for all T iterations
-    float hi[G::KK], wi[G::KK], av[G::KK];
-    bool ok[G::KK];
+    // ---- the pixel's geometry: loaded once, register-resident for all T iterations.
+    // Per tap: image index of the footprint's top-left corner, the two fractional weights and four
+    // corner-valid bits (validity test of cuh:180 AND the per-corner guards of cuh:37-48), so the
+    // iteration body is branch-free: 4 predicated L2 loads + 8 FP ops per tap, all 32 loads of a
+    // pixel in flight at once.
+    int idx[G::KK];
+    float lh[G::KK], lw[G::KK], av[G::KK];
+    unsigned cmask = 0u;   // bit 4k+c: corner c of tap k is read
     float dp = 0.f, cf = 1.f;
+#pragma unroll
+    for (int t = 0; t < G::KK; ++t) {
+        idx[t] = 0;
+        lh[t] = lw[t] = av[t] = 0.f;
+    }
     if (active) {
         const float *ob = offset + (long)b * 2 * G::KK * P + r;
         const float *ab = aff + (long)b * G::KK * P + r;
 #pragma unroll
         for (int t = 0; t < G::KK; ++t) {
             av[t] = __ldg(ab + (long)t * P);
-            hi[t] = wi[t] = 0.f;
-            ok[t] = true;
-            if (t != G::REF) {
-                hi[t] = (float)(h - G::PAD + t / K) + __ldg(ob + (long)(2 * t) * P);
-                wi[t] = (float)(w - G::PAD + t % K) + __ldg(ob + (long)(2 * t + 1) * P);
-                ok[t] = tap_valid(hi[t], wi[t], H, W);
-            }
+            if (t == G::REF) continue;
+            const float h_im = (float)(h - G::PAD + t / K) + __ldg(ob + (long)(2 * t) * P);
+            const float w_im = (float)(w - G::PAD + t % K) + __ldg(ob + (long)(2 * t + 1) * P);
+            if (!tap_valid(h_im, w_im, H, W)) continue;
+            const float hf = floorf(h_im), wf = floorf(w_im);
+            const int hl = (int)hf, wl = (int)wf;
+            lh[t] = h_im - hf;
+            lw[t] = w_im - wf;
+            idx[t] = hl * W + wl;
+            const bool top = hl >= 0, bot = hl + 1 <= H - 1, lef = wl >= 0, rig = wl + 1 <= W - 1;
+            cmask |= ((top && lef) ? 1u : 0u) << (4 * (t < G::REF ? t : t - 1) + 0);
+            cmask |= ((top && rig) ? 1u : 0u) << (4 * (t < G::REF ? t : t - 1) + 1);
+            cmask |= ((bot && lef) ? 1u : 0u) << (4 * (t < G::REF ? t : t - 1) + 2);
+            cmask |= ((bot && rig) ? 1u : 0u) << (4 * (t < G::REF ? t : t - 1) + 3);
         }
         if (flags & kPreserve) dp = __ldg(dep + q);
         if (conf) cf = __ldg(conf + q);
     }
+    static_assert(K == 3, "corner mask packs 8 deformable taps into 32 bits");
 
     for (int t = 1; t <= T; ++t) {
         const float *src_prev;
@@ -90,9 +108,19 @@ persist_fwd_kernel(const float *__restrict__ offset, const float *__restrict__ a
             float acc = 0.f;
 #pragma unroll
             for (int k = 0; k < G::KK; ++k) {
-                float v = 0.f;
-                if (k == G::REF) v = __ldcg(im + r);
-                else if (ok[k]) v = quad_value(load_quad_cg(im, H, W, hi[k], wi[k]));
+                float v;
+                if (k == G::REF) {
+                    v = __ldcg(im + r);
+                } else {
+                    const int n = k < G::REF ? k : k - 1;       // slot of this tap in cmask
+                    const float *p = im + idx[k];
+                    const float v1 = (cmask >> (4 * n + 0)) & 1u ? __ldcg(p) : 0.f;
+                    const float v2 = (cmask >> (4 * n + 1)) & 1u ? __ldcg(p + 1) : 0.f;
+                    const float v3 = (cmask >> (4 * n + 2)) & 1u ? __ldcg(p + W) : 0.f;
+                    const float v4 = (cmask >> (4 * n + 3)) & 1u ? __ldcg(p + W + 1) : 0.f;
+                    const float hh = 1.f - lh[k], hw = 1.f - lw[k];
+                    v = (hh * hw) * v1 + (hh * lw[k]) * v2 + (lh[k] * hw) * v3 + (lh[k] * lw[k]) * v4;
+                }
                 acc += v * av[k];
             }
             if (flags & kPreserve) acc = blend_fix(acc, dp);

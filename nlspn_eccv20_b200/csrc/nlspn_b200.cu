@@ -402,9 +402,9 @@ static int launch_iter_fwd(const FwdCall &c, int b0, int nb, int t, const CUtens
 // co-resident thread.  *tried = 1 when the whole forward was enqueued here.
 static int persist_capacity(int K, int *blocks_per_sm)
 {
+    (void)K;   // K == 3 only (checked by the caller)
     int n = 0;
-    cudaError_t e = cudaSuccess;
-    DISPATCH_K(K, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, persist_fwd_kernel<KC>, kPersistBlock, 0));
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, persist_fwd_kernel<3>, kPersistBlock, 0);
     if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     *blocks_per_sm = n;
     return 0;
@@ -434,8 +434,8 @@ static int try_persistent_forward(const FwdCall &c, bool prologue, int *tried)
     void *args[] = {&offset, &aff, &conf, &dep, &flags, &H, &W, &B, &T, &src, &S, &list_feat};
     ProfScope prof__(kProfIterFwd, c.st);
     cudaError_t e = cudaSuccess;
-    DISPATCH_K(c.K, e = cudaLaunchCooperativeKernel((const void *)persist_fwd_kernel<KC>, dim3(blocks),
-                                                    dim3(kPersistBlock), args, 0, c.st));
+    e = cudaLaunchCooperativeKernel((const void *)persist_fwd_kernel<3>, dim3(blocks), dim3(kPersistBlock),
+                                    args, 0, c.st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(persist_fwd_kernel)");
     NLSPN_CHECK_LAUNCH("persist_fwd_kernel");
     *tried = 1;
