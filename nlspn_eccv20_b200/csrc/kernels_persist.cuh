@@ -15,53 +15,42 @@
 
 namespace nlspn {
 
-constexpr int kPersistBlock = 256;
+constexpr int kPersistTH = 8;                       // tile: 32 x 8 pixels, one pixel per thread
+constexpr int kPersistBlock = 32 * kPersistTH;
+constexpr int kPersistHalo = 8;
+constexpr int kPersistBoxW = 32 + 2 * kPersistHalo;
+constexpr int kPersistBoxH = kPersistTH + 2 * kPersistHalo;
 
-// corner values with the guards of cuh:37-48, read through L2 (ld.global.cg): the plane was
-// written by other SMs earlier in THIS launch, so the (incoherent) L1 must be bypassed
-__device__ __forceinline__ Quad load_quad_cg(const float *im, int H, int W, float h_im, float w_im)
-{
-    Quad q;
-    const float hf = floorf(h_im), wf = floorf(w_im);
-    q.hl = (int)hf;
-    q.wl = (int)wf;
-    q.lh = h_im - hf;
-    q.lw = w_im - wf;
-    const bool top = q.hl >= 0, bot = q.hl + 1 <= H - 1;
-    const bool lef = q.wl >= 0, rig = q.wl + 1 <= W - 1;
-    const float *p = im + (long)q.hl * W + q.wl;
-    q.v1 = (top && lef) ? __ldcg(p) : 0.f;
-    q.v2 = (top && rig) ? __ldcg(p + 1) : 0.f;
-    q.v3 = (bot && lef) ? __ldcg(p + W) : 0.f;
-    q.v4 = (bot && rig) ? __ldcg(p + W + 1) : 0.f;
-    return q;
-}
-
+// grid = (ceil(W/32), ceil(H/8), B), block = (32, 8); cooperative launch (all CTAs co-resident)
 template <int K>
-__global__ void __launch_bounds__(kPersistBlock)
+__global__ void __launch_bounds__(kPersistBlock, 2)
 persist_fwd_kernel(const float *__restrict__ offset, const float *__restrict__ aff,
                    const float *__restrict__ conf, const float *__restrict__ dep, unsigned flags, int H,
                    int W, int B, int T, float *src, int S, float *list_feat)
 {
     namespace cg = cooperative_groups;
     using G = Geo<K>;
+    static_assert(K == 3, "slow/skip masks pack 8 deformable taps");
     cg::grid_group grid = cg::this_grid();
+    __shared__ float box[kPersistBoxH * kPersistBoxW];
     const int P = H * W;
     const long BP = (long)B * P;
-    const long q = (long)blockIdx.x * kPersistBlock + threadIdx.x;   // one pixel per thread
-    const bool active = q < BP;
-    const int b = active ? (int)(q / P) : 0;
-    const int r = active ? (int)(q - (long)b * P) : 0;
-    const int h = r / W, w = r - h * W;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * kPersistTH;
+    const int b = blockIdx.z;
+    const int w = x0 + threadIdx.x, h = y0 + threadIdx.y;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const bool active = w < W && h < H;
+    const int r = active ? h * W + w : 0;
+    const long q = (long)b * P + r;
 
     // ---- the pixel's geometry: loaded once, register-resident for all T iterations.
-    // Per tap: image index of the footprint's top-left corner, the two fractional weights and four
-    // corner-valid bits (validity test of cuh:180 AND the per-corner guards of cuh:37-48), so the
-    // iteration body is branch-free: 4 predicated L2 loads + 8 FP ops per tap, all 32 loads of a
-    // pixel in flight at once.
+    // Per tap: index of the footprint's top-left corner (in the shared-memory box when the
+    // footprint lies inside it, else in the image), the two fractional weights, and for the
+    // out-of-box taps four corner-valid bits (guards of cuh:37-48).  Invalid taps (cuh:180) get
+    // zero weights and the box origin as index, so the common path is branch-free.
     int idx[G::KK];
     float lh[G::KK], lw[G::KK], av[G::KK];
-    unsigned cmask = 0u;   // bit 4k+c: corner c of tap k is read
+    unsigned slow = 0u, cmask = 0u;
     float dp = 0.f, cf = 1.f;
 #pragma unroll
     for (int t = 0; t < G::KK; ++t) {
@@ -73,26 +62,36 @@ persist_fwd_kernel(const float *__restrict__ offset, const float *__restrict__ a
         const float *ab = aff + (long)b * G::KK * P + r;
 #pragma unroll
         for (int t = 0; t < G::KK; ++t) {
-            av[t] = __ldg(ab + (long)t * P);
-            if (t == G::REF) continue;
+            if (t == G::REF) {
+                av[t] = __ldg(ab + (long)t * P);
+                idx[t] = (threadIdx.y + kPersistHalo) * kPersistBoxW + threadIdx.x + kPersistHalo;
+                continue;
+            }
             const float h_im = (float)(h - G::PAD + t / K) + __ldg(ob + (long)(2 * t) * P);
             const float w_im = (float)(w - G::PAD + t % K) + __ldg(ob + (long)(2 * t + 1) * P);
-            if (!tap_valid(h_im, w_im, H, W)) continue;
+            if (!tap_valid(h_im, w_im, H, W)) continue;      // av stays 0: the tap contributes nothing
+            av[t] = __ldg(ab + (long)t * P);
             const float hf = floorf(h_im), wf = floorf(w_im);
             const int hl = (int)hf, wl = (int)wf;
             lh[t] = h_im - hf;
             lw[t] = w_im - wf;
-            idx[t] = hl * W + wl;
-            const bool top = hl >= 0, bot = hl + 1 <= H - 1, lef = wl >= 0, rig = wl + 1 <= W - 1;
-            cmask |= ((top && lef) ? 1u : 0u) << (4 * (t < G::REF ? t : t - 1) + 0);
-            cmask |= ((top && rig) ? 1u : 0u) << (4 * (t < G::REF ? t : t - 1) + 1);
-            cmask |= ((bot && lef) ? 1u : 0u) << (4 * (t < G::REF ? t : t - 1) + 2);
-            cmask |= ((bot && rig) ? 1u : 0u) << (4 * (t < G::REF ? t : t - 1) + 3);
+            const int ty = hl - (y0 - kPersistHalo), tx = wl - (x0 - kPersistHalo);
+            if ((unsigned)ty < (unsigned)(kPersistBoxH - 1) && (unsigned)tx < (unsigned)(kPersistBoxW - 1)) {
+                idx[t] = ty * kPersistBoxW + tx;
+            } else {
+                const int n = t < G::REF ? t : t - 1;
+                slow |= 1u << n;
+                idx[t] = hl * W + wl;
+                const bool top = hl >= 0, bot = hl + 1 <= H - 1, lef = wl >= 0, rig = wl + 1 <= W - 1;
+                cmask |= ((top && lef) ? 1u : 0u) << (4 * n + 0);
+                cmask |= ((top && rig) ? 1u : 0u) << (4 * n + 1);
+                cmask |= ((bot && lef) ? 1u : 0u) << (4 * n + 2);
+                cmask |= ((bot && rig) ? 1u : 0u) << (4 * n + 3);
+            }
         }
         if (flags & kPreserve) dp = __ldg(dep + q);
         if (conf) cf = __ldg(conf + q);
     }
-    static_assert(K == 3, "corner mask packs 8 deformable taps into 32 bits");
 
     for (int t = 1; t <= T; ++t) {
         const float *src_prev;
@@ -103,21 +102,35 @@ persist_fwd_kernel(const float *__restrict__ offset, const float *__restrict__ a
         } else {
             src_prev = t == 1 ? src : list_feat + (long)(t - 2) * BP;
         }
+        const float *im = src_prev + (long)b * P;
+        // stage the halo'd tile of the plane: coalesced L2 reads (ld.global.cg -- the plane was
+        // written by other SMs in this launch), zero outside the image (= the sampler's padding)
+        for (int i = tid; i < kPersistBoxH * kPersistBoxW; i += kPersistBlock) {
+            const int by = i / kPersistBoxW, bx = i - by * kPersistBoxW;
+            const int yy = y0 - kPersistHalo + by, xx = x0 - kPersistHalo + bx;
+            box[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldcg(im + yy * W + xx) : 0.f;
+        }
+        __syncthreads();
         if (active) {
-            const float *im = src_prev + (long)b * P;
             float acc = 0.f;
 #pragma unroll
             for (int k = 0; k < G::KK; ++k) {
                 float v;
                 if (k == G::REF) {
-                    v = __ldcg(im + r);
+                    v = box[idx[k]];
                 } else {
-                    const int n = k < G::REF ? k : k - 1;       // slot of this tap in cmask
-                    const float *p = im + idx[k];
-                    const float v1 = (cmask >> (4 * n + 0)) & 1u ? __ldcg(p) : 0.f;
-                    const float v2 = (cmask >> (4 * n + 1)) & 1u ? __ldcg(p + 1) : 0.f;
-                    const float v3 = (cmask >> (4 * n + 2)) & 1u ? __ldcg(p + W) : 0.f;
-                    const float v4 = (cmask >> (4 * n + 3)) & 1u ? __ldcg(p + W + 1) : 0.f;
+                    const int n = k < G::REF ? k : k - 1;
+                    float v1, v2, v3, v4;
+                    if (slow & (1u << n)) {
+                        const float *p = im + idx[k];
+                        v1 = (cmask >> (4 * n + 0)) & 1u ? __ldcg(p) : 0.f;
+                        v2 = (cmask >> (4 * n + 1)) & 1u ? __ldcg(p + 1) : 0.f;
+                        v3 = (cmask >> (4 * n + 2)) & 1u ? __ldcg(p + W) : 0.f;
+                        v4 = (cmask >> (4 * n + 3)) & 1u ? __ldcg(p + W + 1) : 0.f;
+                    } else {
+                        const float *p = box + idx[k];
+                        v1 = p[0]; v2 = p[1]; v3 = p[kPersistBoxW]; v4 = p[kPersistBoxW + 1];
+                    }
                     const float hh = 1.f - lh[k], hw = 1.f - lw[k];
                     v = (hh * hw) * v1 + (hh * lw[k]) * v2 + (lh[k] * hw) * v3 + (lh[k] * lw[k]) * v4;
                 }
@@ -128,7 +141,7 @@ persist_fwd_kernel(const float *__restrict__ offset, const float *__restrict__ a
             list_feat[(long)(t - 1) * BP + q] = acc;
             if (src_next) src_next[q] = acc * cf;
         }
-        if (t < T) grid.sync();   // every pixel of iteration t is written (and fenced) before t+1 gathers
+        if (t < T) grid.sync();   // iteration t fully written (and fenced); also frees the box for refill
     }
 }
 

@@ -421,12 +421,11 @@ static int try_persistent_forward(const FwdCall &c, bool prologue, int *tried)
     if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) return 0;
     int per_sm = 0;
     if (int rc = persist_capacity(c.K, &per_sm)) return rc;
-    const long BP = (long)c.B * c.H * c.W;
-    const long capacity = (long)sms * per_sm * kPersistBlock;
-    if (per_sm <= 0 || BP > capacity) return 0;
+    const dim3 pgrid((unsigned)((c.W + 31) / 32), (unsigned)((c.H + kPersistTH - 1) / kPersistTH), (unsigned)c.B);
+    const long blocks_needed = (long)pgrid.x * pgrid.y * pgrid.z;
+    if (per_sm <= 0 || blocks_needed > (long)sms * per_sm) return 0;   // not co-resident: per-iteration path
     if (prologue)
         if (int rc = launch_prologue(c, 0, c.B)) return rc;
-    const unsigned blocks = (unsigned)((BP + kPersistBlock - 1) / kPersistBlock);
     const float *offset = c.offset, *aff = c.aff, *conf = c.conf_fixed, *dep = c.feat_fix;
     unsigned flags = c.flags;
     int H = c.H, W = c.W, B = c.B, T = c.T, S = c.S;
@@ -434,8 +433,8 @@ static int try_persistent_forward(const FwdCall &c, bool prologue, int *tried)
     void *args[] = {&offset, &aff, &conf, &dep, &flags, &H, &W, &B, &T, &src, &S, &list_feat};
     ProfScope prof__(kProfIterFwd, c.st);
     cudaError_t e = cudaSuccess;
-    e = cudaLaunchCooperativeKernel((const void *)persist_fwd_kernel<3>, dim3(blocks), dim3(kPersistBlock),
-                                    args, 0, c.st);
+    e = cudaLaunchCooperativeKernel((const void *)persist_fwd_kernel<3>, pgrid, dim3(32, kPersistTH), args, 0,
+                                    c.st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(persist_fwd_kernel)");
     NLSPN_CHECK_LAUNCH("persist_fwd_kernel");
     *tried = 1;
