@@ -87,18 +87,11 @@ __device__ __forceinline__ float blend_fix(float v, float dep)
     return (1.f - m) * v + m * dep;
 }
 
-// Geometry of the blocked scatter planes of one image (backward pass A, kernels_v2.cuh).
-// The gradient plane is kept in FOUR copies made of 2x2-pixel blocks, one per block phase
-// (sy, sx) in {0,1}^2, so that any bilinear footprint (rows Y, Y+1; cols X, X+1 in padded
-// coordinates Y = y+1, X = x+1) is exactly one aligned 16-byte block of the copy with
-// sy = Y&1, sx = X&1.  The two column phases are interleaved block by block: the footprints at
-// X = 2m and X = 2m+1 (neighbouring lanes when the offsets are spatially smooth) are the two
-// halves of ONE 32-byte sector, which halves the sectors a warp-wide vector RED ships when the
-// offsets are coherent (iid offsets: no change).
+// geometry of the blocked scatter planes of one image
 struct ScatterGeo {
-    int Hb, Wb;          // block rows / block-pair columns
-    long plane;          // floats per row-phase plane = Hb * Wb * 8
-    long image;          // floats per image = 2 * plane
+    int Hb, Wb;          // blocks per column / row
+    long plane;          // floats per phase plane (multiple of 4)
+    long image;          // floats per image = 4 * plane
 };
 
 __host__ __device__ inline ScatterGeo scatter_geo(int H, int W)
@@ -106,24 +99,17 @@ __host__ __device__ inline ScatterGeo scatter_geo(int H, int W)
     ScatterGeo g;
     g.Hb = H / 2 + 2;
     g.Wb = W / 2 + 2;
-    g.plane = (long)g.Hb * g.Wb * 8;
-    g.image = 2 * g.plane;
+    g.plane = (long)g.Hb * g.Wb * 4;
+    g.image = 4 * g.plane;
     return g;
 }
 
-// first float of the block that holds padded cell (Y, X) in phase (sy, sx); (X + sx) / 2 - sx >= 0
-// for every footprint (sx = X&1) and for every reader (X >= 1)
-__device__ __forceinline__ long scatter_block(const ScatterGeo &g, int sy, int sx, int Y, int X)
-{
-    const int by = (Y + sy) >> 1;
-    const int bxp = ((X + sx) >> 1) - sx;
-    return (long)sy * g.plane + (((long)by * g.Wb + bxp) * 2 + sx) * 4;
-}
-
-// address of padded cell (Y, X) = (y+1, x+1) in phase (sy, sx)
+// address of padded cell (Y, X) = (y+1, x+1) in phase plane (sy, sx)
 __device__ __forceinline__ long scatter_cell(const ScatterGeo &g, int sy, int sx, int Y, int X)
 {
-    return scatter_block(g, sy, sx, Y, X) + ((Y + sy) & 1) * 2 + ((X + sx) & 1);
+    const int by = (Y + sy) >> 1, ly = (Y + sy) & 1;
+    const int bx = (X + sx) >> 1, lx = (X + sx) & 1;
+    return (long)(sy * 2 + sx) * g.plane + ((long)by * g.Wb + bx) * 4 + ly * 2 + lx;
 }
 
 } // namespace nlspn

@@ -132,7 +132,8 @@ bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff
         const float lw_ = w1 - w_im, rw = (w_im + 1.f) - w1;
         const int Y = hl + 1, X = wl + 1;         // padded coordinates of the top-left corner
         const int sy = Y & 1, sx = X & 1;
-        float4 *blk = reinterpret_cast<float4 *>(so + scatter_block(sg, sy, sx, Y, X));
+        float4 *blk = reinterpret_cast<float4 *>(
+            so + (long)(sy * 2 + sx) * sg.plane + ((long)((Y + sy) >> 1) * sg.Wb + ((X + sx) >> 1)) * 4);
         atomicAdd(blk, make_float4(th * lw_ * top, th * rw * top, bh * lw_ * top, bh * rw * top));
     }
 }
