@@ -197,19 +197,14 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
                        const __grid_constant__ CUtensorMap list_map, int Bsrc, int b0,
                        const float *__restrict__ offset, const float *__restrict__ aff,
                        const float *__restrict__ src, const float *__restrict__ list_feat,
-                       const float *__restrict__ gy_all, int has_conf, int H, int W, int t_hi, int t_lo,
-                       int accumulate, long BP, long GP, float *__restrict__ g_guidance,
-                       float *__restrict__ g_aff_acc)
+                       const float *__restrict__ gy_all, int has_conf, int H, int W, int T, long BP,
+                       long GP, float *__restrict__ g_guidance, float *__restrict__ g_aff_acc)
 {
-    // Handles iterations t_hi .. t_lo (descending).  The host may split the T iterations into
-    // slices that run on a side stream while pass A is still producing gy for later slices;
-    // slices after the first add to the outputs of the previous ones (accumulate != 0).
     using G = Geo<K>;
     using TG = TileGeo<K, TH>;
     constexpr int kHalo = TG::R;
     constexpr int kBoxW = TG::BoxW;
     constexpr int NCH = (G::KK + C - 1) / C;
-    const int T = t_hi;
     __shared__ __align__(128) float box[2][TG::BoxFloats];
     __shared__ __align__(8) uint64_t bar[2];
     const int P = H * W;
@@ -284,16 +279,16 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
     const bool warp_fast = __all_sync(0xffffffffu, (slow_bits | skip_bits) == 0u);
 
     float gy_n1 = inside ? __ldg(gy_all + (long)(T - 1) * GP + q) : 0.f;
-    float gy_n2 = (inside && T > t_lo) ? __ldg(gy_all + (long)(T - 2) * GP + q) : 0.f;
+    float gy_n2 = (inside && T > 1) ? __ldg(gy_all + (long)(T - 2) * GP + q) : 0.f;
     uint32_t phase_bits = 0u;   // bit i = parity the next wait on bar[i] expects
-    for (int t = T; t >= t_lo; --t) {
+    for (int t = T; t >= 1; --t) {
         const int cur = (T - t) & 1;
         // everyone is done reading box[cur^1] (consumed in the previous trip): refill it
         __syncthreads();
-        if (tid == 0 && t > t_lo) issue(t - 1, cur ^ 1);
+        if (tid == 0 && t > 1) issue(t - 1, cur ^ 1);
         const float gy = gy_n1;
         gy_n1 = gy_n2;
-        if (t > t_lo + 1) gy_n2 = inside ? __ldg(gy_all + (long)(t - 3) * GP + q) : 0.f;
+        if (t > 2) gy_n2 = inside ? __ldg(gy_all + (long)(t - 3) * GP + q) : 0.f;
         tma::mbar_wait(&bar[cur], (phase_bits >> cur) & 1u);
         phase_bits ^= 1u << cur;
         const float *bx = box[cur];
@@ -362,14 +357,9 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
     for (int c = 0; c < C; ++c) {
         const int k = k0 + c;
         if (k >= G::KK) continue;
-        if (accumulate) acc_a[c] += gab[(long)k * P];
         gab[(long)k * P] = acc_a[c];
         if (k != G::REF) {
             const int n = k < G::REF ? k : k - 1;
-            if (accumulate) {
-                acc_h[c] += ggb[(long)(2 * n) * P];
-                acc_w[c] += ggb[(long)(2 * n + 1) * P];
-            }
             ggb[(long)(2 * n) * P] = acc_h[c];
             ggb[(long)(2 * n + 1) * P] = acc_w[c];
         }

@@ -88,20 +88,6 @@ int cuda_fail(cudaError_t e, const char *what)
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// One lazily created non-blocking side stream per device: pass B of the backward runs on it,
-// overlapped with pass A (different bottlenecks: instruction issue vs the SM->L2 write path).
-cudaStream_t side_stream()
-{
-    static std::mutex mu;
-    static cudaStream_t streams[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess)
-        streams[dev] = nullptr;
-    return streams[dev];
-}
-
 int check_shape(int B, int H, int W, int K, int T)
 {
     if (B <= 0 || H <= 0 || W <= 0 || T <= 0)
@@ -696,37 +682,9 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
         const float *cf = conf_fixed ? conf_fixed + o1 : nullptr;
         const float *fx = feat_fix ? feat_fix + o1 : nullptr;
-        // ---- pass B slicing: the T iterations are cut into `slices` ranges; the range whose gy
-        // planes are complete is handed to a side stream while pass A continues on `st`
-        int slices = 1;
-        if (use_tiled) {
-            slices = T >= 12 ? 3 : (T >= 6 ? 2 : 1);
-            if (const char *ev = getenv("NLSPN_PARAM_SLICES")) slices = atoi(ev) > 0 ? atoi(ev) : 1;
-            if (slices > T) slices = T;
-        }
-        cudaStream_t side = slices > 1 ? side_stream() : nullptr;
-        if (!side) slices = 1;
-        constexpr int C = 9;
-        const int nch = (KK + C - 1) / C;
-        int next_slice = 0;            // slices are numbered from the highest iterations down
-        auto slice_hi = [&](int s_) { return T - (int)((long)T * s_ / slices); };          // inclusive
-        auto slice_lo = [&](int s_) { return T - (int)((long)T * (s_ + 1) / slices) + 1; };  // inclusive
-        auto launch_param_slice = [&](int s_, cudaStream_t ps) -> int {
-            const int pth = param_tile_h();
-            dim3 tgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + pth - 1) / pth), (unsigned)(nb * nch));
-            dim3 tblock(kTileW, pth);
-            ProfScope prof__(kProfBwdParam, ps);
-            DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, THC><<<tgrid, tblock, 0, ps>>>(
-                              src_map, list_map, B, b0, offset + o1 * 2 * KK, aff + o1 * KK, src + o1,
-                              list_feat + o1, gy_all, conf_fixed ? 1 : 0, H, W, slice_hi(s_), slice_lo(s_),
-                              s_ > 0 ? 1 : 0, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc))));
-            NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
-            return 0;
-        };
         for (int t = T; t >= 1; --t) {
             float *s_out = ((T - t) % 2 == 0) ? setA : setB;
             float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? setB : setA);
-            {
             ProfScope prof__(kProfBwdState, st);
             const float *xt = list_feat + (long)(t - 1) * BP + o1;
             const float *ge = g_list[t - 1] ? g_list[t - 1] + o1 : nullptr;
@@ -752,46 +710,29 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             }
 #undef STATE_LAUNCH
             NLSPN_CHECK_LAUNCH("bwd_state_kernel");
-            }
-            // gy for every iteration of slice `next_slice` is now enqueued: fork it to the side stream
-            if (slices > 1 && next_slice < slices - 1 && t == slice_lo(next_slice)) {
-                cudaEvent_t ready;
-                if ((e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)) != cudaSuccess)
-                    return cuda_fail(e, "cudaEventCreate");
-                cudaEventRecord(ready, st);
-                cudaStreamWaitEvent(side, ready, 0);
-                cudaEventDestroy(ready);
-                if (int rc = launch_param_slice(next_slice, side)) return rc;
-                ++next_slice;
-            }
         }
         const float *s_last = ((T - 1) % 2 == 0) ? setA : setB;
-        if (use_tiled) {
-            if (slices > 1) {
-                // the last slice also runs on the side stream (after the earlier slices: their
-                // outputs are accumulated), then the caller's stream joins
-                cudaEvent_t ready, done;
-                if ((e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)) != cudaSuccess)
-                    return cuda_fail(e, "cudaEventCreate");
-                if ((e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming)) != cudaSuccess)
-                    return cuda_fail(e, "cudaEventCreate");
-                cudaEventRecord(ready, st);
-                cudaStreamWaitEvent(side, ready, 0);
-                if (int rc = launch_param_slice(slices - 1, side)) return rc;
-                cudaEventRecord(done, side);
-                cudaStreamWaitEvent(st, done, 0);
-                cudaEventDestroy(ready);
-                cudaEventDestroy(done);
-            } else {
-                if (int rc = launch_param_slice(0, st)) return rc;
-            }
-        } else {
+        {
+            constexpr int C = 9;
+            const int nch = (KK + C - 1) / C;
             dim3 grid((unsigned)((P + kParamBlock - 1) / kParamBlock), (unsigned)nb, (unsigned)nch);
             ProfScope prof__(kProfBwdParam, st);
-            DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
-                              offset + o1 * 2 * KK, aff + o1 * KK, src + o1, list_feat + o1, gy_all,
-                              conf_fixed ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc)));
-            NLSPN_CHECK_LAUNCH("bwd_param_kernel");
+            if (use_tiled) {
+                const int pth = param_tile_h();
+                dim3 tgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + pth - 1) / pth),
+                           (unsigned)(nb * nch));
+                dim3 tblock(kTileW, pth);
+                DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, THC><<<tgrid, tblock, 0, st>>>(
+                                  src_map, list_map, B, b0, offset + o1 * 2 * KK, aff + o1 * KK, src + o1,
+                                  list_feat + o1, gy_all, conf_fixed ? 1 : 0, H, W, T, BP, GP,
+                                  g_guidance + o1 * 3 * N, g_aff_acc))));
+                NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
+            } else {
+                DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
+                                  offset + o1 * 2 * KK, aff + o1 * KK, src + o1, list_feat + o1, gy_all,
+                                  conf_fixed ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc)));
+                NLSPN_CHECK_LAUNCH("bwd_param_kernel");
+            }
         }
         ProfScope prof__(kProfFinalBwd, st);
         DISPATCH_K(K, (final_bwd_kernel<KC, true><<<grid_for(P, nb), kBlock, 0, st>>>(
