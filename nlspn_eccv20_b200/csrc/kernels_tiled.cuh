@@ -366,4 +366,113 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
     }
 }
 
+// ======================================================================================
+// Pass A with the streamed geometry delivered by TMA.
+// ncu on bwd_state_kernel: the SM->L2 request port is the busiest unit (l1tex2xbar request cycles
+// 70-80 %): besides the 9 REDs, every thread issues 25 coalesced geometry loads = 100 sector
+// requests per warp.  Here ONE thread per CTA asks the Tensor Memory Accelerator for the CTA's
+// whole geometry -- a {32 px, TH rows, 2K^2 channels} box of `offset` and a {32, TH, K^2} box of
+// `aff` -- which travels as bulk requests and lands in shared memory without touching the
+// register file; the threads then read it conflict-free (lane = pixel).  Everything else is
+// bwd_state_kernel.  grid = (ceil(W/32), ceil(H/TH), nb), block = (32, TH).
+// ======================================================================================
+template <int K, int TH>
+__global__ void __launch_bounds__(kTileW * TH)
+bwd_state_tma_kernel(const __grid_constant__ CUtensorMap off_map, const __grid_constant__ CUtensorMap aff_map,
+                     int b0, const float *__restrict__ conf, const float *__restrict__ dep,
+                     const float *__restrict__ x_t, const float *__restrict__ g_ext, float *__restrict__ s_in,
+                     float *__restrict__ s_out, float *__restrict__ gy_out, float *__restrict__ g_conf_acc,
+                     unsigned flags, int H, int W)
+{
+    using G = Geo<K>;
+    __shared__ __align__(128) float s_off[2 * G::KK][TH][kTileW];
+    __shared__ __align__(128) float s_aff[G::KK][TH][kTileW];
+    __shared__ __align__(8) uint64_t bar;
+    const int P = H * W;
+    const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * TH;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.y * kTileW + threadIdx.x;
+    if (tid == 0) {
+        tma::mbar_init(&bar, 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {   // the geometry does not depend on the previous launch: fetch it right away
+        tma::mbar_arrive_expect_tx(&bar, (uint32_t)(sizeof(s_off) + sizeof(s_aff)));
+        tma::load_4d(s_off, &off_map, &bar, x0, y0, 0, b0 + b);
+        tma::load_4d(s_aff, &aff_map, &bar, x0, y0, 0, b0 + b);
+    }
+    tma::grid_launch_dependents();
+    const int w = x0 + threadIdx.x, h = y0 + threadIdx.y;
+    const bool inside = w < W && h < H;
+    const int r = inside ? h * W + w : 0;
+    const long q = (long)b * P + r;
+    const ScatterGeo sg = scatter_geo(H, W);
+
+    float gext = 0.f, cf = 1.f, xt = 1.f, dp = 0.f;
+    const bool need_x = (s_in && conf) || (flags & kAlwaysClip);
+    if (inside) {
+        gext = g_ext ? __ldg(g_ext + q) : 0.f;
+        cf = conf ? __ldg(conf + q) : 1.f;
+        xt = need_x ? __ldg(x_t + q) : 1.f;
+        dp = (flags & kPreserve) ? __ldg(dep + q) : 0.f;
+    }
+    tma::grid_dependency_wait();   // s_in / s_out / g_conf_acc belong to the previous launch
+    float *si = s_in ? s_in + (long)b * sg.image : nullptr;
+    long cell[4];
+    float cv[4] = {0.f, 0.f, 0.f, 0.f};
+    float gca = 0.f;
+    if (inside) {
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            cell[ph] = scatter_cell(sg, ph >> 1, ph & 1, h + 1, w + 1);
+            if (si) cv[ph] = __ldcg(si + cell[ph]);
+        }
+        if (si && conf) gca = g_conf_acc[q];
+    }
+    tma::mbar_wait(&bar, 0);
+    if (!inside) return;
+
+    const float gs = ((cv[0] + cv[1]) + cv[2]) + cv[3];
+    float Gx = gext;
+    if (si) Gx += conf ? cf * gs : gs;
+    if ((flags & kAlwaysClip) && !(xt > 0.f)) Gx = 0.f;
+    if (flags & kPreserve) Gx = (1.0f - (dp > 0.f ? 1.f : 0.f)) * Gx;
+    const float gy = Gx;
+    if (si) {
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) si[cell[ph]] = 0.f;
+        if (conf) g_conf_acc[q] = gca + xt * gs;
+    }
+    gy_out[q] = gy;
+    if (gy == 0.f) return;
+
+    float *so = s_out + (long)b * sg.image;
+    const int ty = threadIdx.y, tx = threadIdx.x;
+#pragma unroll
+    for (int t = 0; t < G::KK; ++t) {
+        const float top = gy * s_aff[t][ty][tx];
+        if (t == G::REF) {
+            atomicAdd(so + cell[0], top);
+            continue;
+        }
+        const float h_im = (float)(h - G::PAD + t / K) + s_off[2 * t][ty][tx];
+        const float w_im = (float)(w - G::PAD + t % K) + s_off[2 * t + 1][ty][tx];
+        if (!tap_valid(h_im, w_im, H, W)) continue;
+        float hf, wf;
+        int hl, wl;
+        floor_small(h_im, hf, hl);
+        floor_small(w_im, wf, wl);
+        // mdmcn_get_gradient_weight, cuh:71-79 (expressions kept literal; (float)(hl+1) == hf + 1 exactly)
+        const float h1 = hf + 1.f, w1 = wf + 1.f;
+        const float th = h1 - h_im, bh = (h_im + 1.f) - h1;
+        const float lw_ = w1 - w_im, rw = (w_im + 1.f) - w1;
+        const int Y = hl + 1, X = wl + 1;
+        const int sy = Y & 1, sx = X & 1;
+        float4 *blk = reinterpret_cast<float4 *>(
+            so + (long)(sy * 2 + sx) * sg.plane + ((long)((Y + sy) >> 1) * sg.Wb + ((X + sx) >> 1)) * 4);
+        atomicAdd(blk, make_float4(th * lw_ * top, th * rw * top, bh * lw_ * top, bh * rw * top));
+    }
+}
+
 } // namespace nlspn

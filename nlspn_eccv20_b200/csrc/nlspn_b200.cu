@@ -292,6 +292,22 @@ static int fwd_tile_h()
     case 16: { constexpr int THC = 16; __VA_ARGS__; } break;   \
     default: { constexpr int THC = 4; __VA_ARGS__; } break;    \
     }
+// [B, C, H, W] fp32 tensor viewed 4-D; box = {32 px, box_h rows, all C channels, 1 image}
+static int make_geometry_map(CUtensorMap *map, const float *base, int B, int C, int H, int W, int box_h)
+{
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)kTileW, (cuuint32_t)box_h, (cuuint32_t)C, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims,
+                                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NLSPN_ERR_SHAPE, "cuTensorMapEncodeTiled(4d) failed (CUresult %d)", (int)r);
+    return 0;
+}
+
+constexpr int kStateTH = 4;   // pass-A TMA tile: 32 x 4 pixels
 constexpr int kParamTH = 4;   // default pass-B tile: 32 x 4 pixels (B200 sweep: TH 4: 1.02, 8: 1.10, 16: 1.27 ms)
 
 static int param_tile_h()
@@ -670,6 +686,14 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         if (int rc = make_plane_map(&src_map, src, (long)(conf_fixed ? T : 1) * B, H, W, kTileW + 2 * halo_for(K), param_tile_h() + 2 * halo_for(K))) return rc;
         if (int rc = make_plane_map(&list_map, list_feat, (long)T * B, H, W, kTileW + 2 * halo_for(K), param_tile_h() + 2 * halo_for(K))) return rc;
     }
+    // pass A with TMA-delivered geometry: K = 3, 5 (K = 7 would need 75 KB of shared memory per CTA)
+    CUtensorMap off_map, aff_map;
+    bool state_tma = use_tiled && K <= 5 && aligned16(offset) && aligned16(aff) &&
+                     !(getenv("NLSPN_STATE_TMA") && atoi(getenv("NLSPN_STATE_TMA")) == 0);
+    if (state_tma) {
+        if (int rc = make_geometry_map(&off_map, offset, B, 2 * KK, H, W, kStateTH)) return rc;
+        if (int rc = make_geometry_map(&aff_map, aff, B, KK, H, W, kStateTH)) return rc;
+    }
     float *setA = ws, *setB = setA + (long)G * sg.image;
     float *g_conf_acc = setB + (long)G * sg.image;
     float *gy_all = g_conf_acc + (long)G * P;          // [T, G, P]
@@ -693,7 +717,17 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     DISPATCH_K(K, (launch_pdl(bwd_state_kernel<KC, SH_, MB_>, grid_for(P, nb), dim3(kBlock), st,           \
                               offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, xt, ge, s_in, s_out, gyo,       \
                               g_conf_acc, flags, H, W)))
-            if (stream_hint) {
+            if (state_tma) {
+                dim3 sgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + kStateTH - 1) / kStateTH), (unsigned)nb);
+                if (K == 3) {
+                    e = launch_pdl(bwd_state_tma_kernel<3, kStateTH>, sgrid, dim3(kTileW, kStateTH), st, off_map,
+                                   aff_map, b0, cf, fx, xt, ge, s_in, s_out, gyo, g_conf_acc, flags, H, W);
+                } else {
+                    e = launch_pdl(bwd_state_tma_kernel<5, kStateTH>, sgrid, dim3(kTileW, kStateTH), st, off_map,
+                                   aff_map, b0, cf, fx, xt, ge, s_in, s_out, gyo, g_conf_acc, flags, H, W);
+                }
+                if (e != cudaSuccess) return cuda_fail(e, "bwd_state_tma_kernel");
+            } else if (stream_hint) {
                 switch (state_minb) {
                 case 5: STATE_LAUNCH(true, 5); break;
                 case 6: STATE_LAUNCH(true, 6); break;

@@ -66,6 +66,17 @@ __device__ __forceinline__ void load_3d(void *smem_dst, const CUtensorMap *map, 
         : "memory");
 }
 
+// 4-D tiled load: coordinates (x = W, y = H, c = channel, n = batch image)
+__device__ __forceinline__ void load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y,
+                                        int c, int n)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(c),
+        "r"(n)
+        : "memory");
+}
+
 __device__ __forceinline__ void prefetch_descriptor(const CUtensorMap *map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
