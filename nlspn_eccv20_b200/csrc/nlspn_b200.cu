@@ -686,10 +686,14 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         if (int rc = make_plane_map(&src_map, src, (long)(conf_fixed ? T : 1) * B, H, W, kTileW + 2 * halo_for(K), param_tile_h() + 2 * halo_for(K))) return rc;
         if (int rc = make_plane_map(&list_map, list_feat, (long)T * B, H, W, kTileW + 2 * halo_for(K), param_tile_h() + 2 * halo_for(K))) return rc;
     }
-    // pass A with TMA-delivered geometry: K = 3, 5 (K = 7 would need 75 KB of shared memory per CTA)
+    // pass A with TMA-delivered geometry.  Measured on B200 (KITTI B=8): K=3 3.37 ms vs 3.28 ms with
+    // plain coalesced loads (no gain: the RED sectors, not the load requests, bound the kernel);
+    // K=5, T=36 16.5 ms vs 18.9 ms (24 taps of geometry no longer live in registers).  Default:
+    // K=5 only; NLSPN_STATE_TMA=1/0 forces it on (K<=5; K=7 would need 75 KB of smem per CTA) / off.
     CUtensorMap off_map, aff_map;
-    bool state_tma = use_tiled && K <= 5 && aligned16(offset) && aligned16(aff) &&
-                     !(getenv("NLSPN_STATE_TMA") && atoi(getenv("NLSPN_STATE_TMA")) == 0);
+    bool state_tma = use_tiled && K == 5 && aligned16(offset) && aligned16(aff);
+    if (const char *ev = getenv("NLSPN_STATE_TMA"))
+        state_tma = use_tiled && K <= 5 && aligned16(offset) && aligned16(aff) && atoi(ev) != 0;
     if (state_tma) {
         if (int rc = make_geometry_map(&off_map, offset, B, 2 * KK, H, W, kStateTH)) return rc;
         if (int rc = make_geometry_map(&aff_map, aff, B, KK, H, W, kStateTH)) return rc;
