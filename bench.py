@@ -50,6 +50,8 @@ def parse():
     p.add_argument("--iters", type=int, default=18)
     p.add_argument("--mode", default="fwdbwd", choices=["fwdbwd", "fwd"])
     p.add_argument("--smooth-offsets", action="store_true")
+    p.add_argument("--flush-l2", default="auto", choices=["auto", "on", "off"],
+                   help="write a 256 MB buffer between timed steps (auto: when the inputs fit L2)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-images", type=int, default=None, help="frames in the CPU sample (default: min(cores, 8))")
     p.add_argument("--cpu-rows", type=int, default=48,
@@ -171,8 +173,12 @@ def main():
               "affinity": "TGASS", "conf_prop": True, "preserve_input": True,
               "offsets": "smooth" if args.smooth_offsets else "iid N(0,2^2) px",
               "sharding": "batch shard per GPU, no collective on the data path",
-              "l2": ("inputs exceed L2 (guidance alone is %.0f MB per GPU vs 126 MB L2)" if B * 3 * (K * K - 1) * H * W * 4 > 126e6
-                     else "inputs (%.0f MB guidance per GPU) fit L2: a 256 MB buffer is written between steps") % (B * 3 * (K * K - 1) * H * W * 4 / 1e6)}
+              "l2": None}
+    guid_mb = B * 3 * (K * K - 1) * H * W * 4 / 1e6
+    flush = args.flush_l2 == "on" or (args.flush_l2 == "auto" and guid_mb <= 126.0)
+    config["l2"] = ("a 256 MB buffer is written between timed steps (L2 flush; inputs are %.0f MB per GPU)" % guid_mb
+                    if flush else
+                    "inputs exceed L2 (guidance alone is %.0f MB per GPU vs 126 MB L2): no flush" % guid_mb)
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -252,14 +258,20 @@ def main():
     rec = []
     n0 = lib.nlspn_launch_count()
     t_start, t_end = ev(), ev()
+    flush_buf = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32) if flush else None
     t_start.record()
     for _ in range(args.steps):
+        if flush:
+            flush_buf.fill_(1.0)           # evicts L2; excluded from the step time below
         step(dev_in, rec)
     t_end.record()
     sync_all()
     launches = lib.nlspn_launch_count() - n0
     clocks = sampler.stop()
-    total_ms = t_start.elapsed_time(t_end)
+    if flush:   # steps are timed individually (forward + backward events), the flush is not counted
+        total_ms = sum(a.elapsed_time(c) for a, _, c in rec)
+    else:
+        total_ms = t_start.elapsed_time(t_end)
     fwd_ms = sum(a.elapsed_time(b) for a, b, _ in rec) / len(rec)
     bwd_ms = sum(b.elapsed_time(c) for _, b, c in rec) / len(rec)
 
