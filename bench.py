@@ -280,7 +280,10 @@ def main():
     # compute stream runs the module on chunk i (images are independent, so the chunked step is
     # the same computation; this is the double-buffered prefetch a pinned DataLoader does).
     h2d = sum(host[k].numel() * 4 for k in names)
-    chunk = max(1, min(B, int(os.environ.get("NLSPN_E2E_CHUNK", "1"))))
+    # chunk of frames per upload: about one KITTI frame's worth of pixels (small frames are grouped so
+    # the per-chunk launches stay above the launch-bound regime)
+    auto_chunk = max(1, -(-400000 // (H * W)))
+    chunk = max(1, min(B, int(os.environ.get("NLSPN_E2E_CHUNK", str(auto_chunk)))))
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     gt_chunks = [gt[i:i + chunk] for i in range(0, B, chunk)]
