@@ -71,6 +71,20 @@ enum nlspn_affinity { NLSPN_AFF_AS = 0, NLSPN_AFF_ASS = 1, NLSPN_AFF_TC = 2, NLS
  * nlspnmodel.py:209-224 -- 3x3 replicate-padded weighted sum instead of the deformable gather.
  * guidance is then [B,N,H,W] (raw affinities only), `offset`/`g_offset_ext` are NULL, K must be 3. */
 #define NLSPN_FLAG_NO_OFFSET 4u
+/* UPSTREAM (zzangjinsun/NLSPN_ECCV20) semantics, the ones BASELINE.json's north-star prose describes
+ * (right-hand column).  PARITY UNPINNED: that code is not in the reference tree; these
+ * modes are checked against oracle/torchvision_port.py's restatement only.
+ *   BLEND_PRE     the input-preserving blend runs BEFORE every gather only; list_feat[t] and
+ *                 feat_result are the raw gathers (the fork blends after every iteration).
+ *   CONF_SAMPLED  the confidence is not multiplied into the state; instead each neighbour's affinity
+ *                 is multiplied, before the abs-sum normalisation, by the confidence sampled with a
+ *                 1x1 deformable gather at that neighbour's offset.  `confidence` is then required by
+ *                 nlspn_backward too, `conf_fixed` must be NULL, and g_confidence receives a scatter.
+ *   LEGACY        with CONF_SAMPLED: add the tap displacement to the sampling offset (--legacy).
+ * Not combinable with ALWAYS_CLIP, NO_OFFSET, BWD_PER_ITERATION. */
+#define NLSPN_FLAG_BLEND_PRE    8u
+#define NLSPN_FLAG_CONF_SAMPLED 16u
+#define NLSPN_FLAG_LEGACY       32u
 /* debugging aid: run the backward as T per-iteration kernels that re-read/re-write the
  * gradient accumulators and scatter with scalar atomics (the reference's structure); results
  * agree with the default two-pass backward up to fp32 summation order. */
@@ -136,6 +150,7 @@ NLSPN_API int nlspn_forward(const float *guidance, const float *confidence, cons
  *                 [B,1,H,W] of list_feat[t]; a NULL entry means a zero gradient (not read)
  *   g_offset_ext  [B,2KK,H,W]  upstream gradient of the `offset` output or NULL
  *   g_aff_ext     [B,KK,H,W]   upstream gradient of the `aff` output or NULL
+ * `confidence` (raw) is read only under NLSPN_FLAG_CONF_SAMPLED and may be NULL otherwise.
  * Outputs (overwritten): g_feat_init [B,1,H,W], g_guidance [B,3N,H,W], g_confidence [B,1,H,W]
  * (NULL iff conf_fixed is NULL), g_gamma: one double (device memory).
  * `src` must be the S = T array written by the forward (S = 1 without confidence).
@@ -144,7 +159,7 @@ NLSPN_API int nlspn_forward(const float *guidance, const float *confidence, cons
  * as in the reference (deformconv/test.py:627-631). */
 NLSPN_API size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T);
 NLSPN_API int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
-                   const float *offset, const float *aff, const float *conf_fixed,
+                   const float *confidence, const float *offset, const float *aff, const float *conf_fixed,
                    const float *src, int S, const float *list_feat, const float *const *g_list,
                    const float *g_offset_ext, const float *g_aff_ext, const float *gamma, int affinity,
                    unsigned flags, int B, int H, int W, int K, int T,

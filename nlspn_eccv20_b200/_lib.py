@@ -37,7 +37,7 @@ SIGNATURES = {
                                  _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                  _fp, _fp, _fp, _fp, _c.c_int, _fp, _fp]),
     "nlspn_backward_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
-    "nlspn_backward": (_c.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _c.c_int, _fp,
+    "nlspn_backward": (_c.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _c.c_int, _fp,
                                   _c.POINTER(_c.c_void_p), _fp, _fp, _fp, _c.c_int, _c.c_uint,
                                   _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                   _fp, _fp, _fp, _fp, _fp, _c.c_size_t, _fp]),
@@ -50,6 +50,9 @@ AFFINITY = {"AS": 0, "ASS": 1, "TC": 2, "TGASS": 3}
 FLAG_PRESERVE_INPUT = 1
 FLAG_ALWAYS_CLIP = 2
 FLAG_NO_OFFSET = 4
+FLAG_BLEND_PRE = 8
+FLAG_CONF_SAMPLED = 16
+FLAG_LEGACY = 32
 FLAG_BWD_PER_ITERATION = 0x100
 
 

@@ -171,6 +171,11 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
         }
     }
     const long q = b * P + r;
+    if (flags & kBlendPre) {   // upstream order: raw gather to the list, blended state to the next gather
+        out[q] = acc;
+        if (src_next) src_next[q] = (flags & kPreserve) ? blend_fix(acc, dp) : acc;
+        return;
+    }
     if (flags & kPreserve) acc = blend_fix(acc, dp);
     if (flags & kAlwaysClip) acc = fmaxf(acc, 0.f);
     out[q] = acc;
@@ -435,9 +440,13 @@ bwd_state_tma_kernel(const __grid_constant__ CUtensorMap off_map, const __grid_c
 
     const float gs = ((cv[0] + cv[1]) + cv[2]) + cv[3];
     float Gx = gext;
-    if (si) Gx += conf ? cf * gs : gs;
-    if ((flags & kAlwaysClip) && !(xt > 0.f)) Gx = 0.f;
-    if (flags & kPreserve) Gx = (1.0f - (dp > 0.f ? 1.f : 0.f)) * Gx;
+    if (flags & kBlendPre) {   // upstream order: the blend sits on the gather's INPUT
+        if (si) Gx += (flags & kPreserve) ? (1.0f - (dp > 0.f ? 1.f : 0.f)) * gs : gs;
+    } else {
+        if (si) Gx += conf ? cf * gs : gs;
+        if ((flags & kAlwaysClip) && !(xt > 0.f)) Gx = 0.f;
+        if (flags & kPreserve) Gx = (1.0f - (dp > 0.f ? 1.f : 0.f)) * Gx;
+    }
     const float gy = Gx;
     if (si) {
 #pragma unroll

@@ -9,9 +9,36 @@
 
 namespace nlspn {
 
-enum : unsigned { kPreserve = 1u, kAlwaysClip = 2u, kNoOffset = 4u };
+enum : unsigned { kPreserve = 1u, kAlwaysClip = 2u, kNoOffset = 4u, kBlendPre = 8u, kConfSampled = 16u,
+                  kLegacy = 32u };
 enum : int { kAS = 0, kASS = 1, kTC = 2, kTGASS = 3 };
 constexpr int kGammaSlots = 64;   // partial sums of d loss / d gamma (final_bwd_kernel -> gamma_reduce_kernel)
+
+// Upstream conf_prop (right column; restated from the north-star prose -- parity
+// unpinned): the confidence seen by neighbour n is the confidence map sampled by a 1x1 modulated
+// deformable gather (pad 0, unit mask/weight, zero bias) at that neighbour's offset; the tap
+// displacement is added to the offset only in --legacy mode.  Returns the sampled value and, if
+// asked, the sampling coordinates.
+template <int K>
+__device__ __forceinline__ float sample_conf(const float *__restrict__ conf_img, const float *__restrict__ gb,
+                                             int n, int h, int w, int H, int W, int P, bool legacy,
+                                             float *h_out = nullptr, float *w_out = nullptr)
+{
+    using G = Geo<K>;
+    const int t = n < G::REF ? n : n + 1;
+    float oh = __ldg(gb + (long)(2 * n) * P), ow = __ldg(gb + (long)(2 * n + 1) * P);
+    if (legacy) {
+        oh = oh + (float)(t / K - G::PAD);
+        ow = ow + (float)(t % K - G::PAD);
+    }
+    const float h_im = (float)h + oh, w_im = (float)w + ow;
+    if (h_out) {
+        *h_out = h_im;
+        *w_out = w_im;
+    }
+    if (!tap_valid(h_im, w_im, H, W)) return 0.f;
+    return quad_value(load_quad(conf_img, H, W, h_im, w_im));
+}
 
 // ======================================================================================
 // Prologue.  nlspnmodel.py:252-259 (_off_insert), :179-201 (_affinity_normalization),
@@ -21,10 +48,12 @@ template <int K>
 __global__ void __launch_bounds__(kBlock)
 prologue_fwd_kernel(const float *__restrict__ guidance, const float *__restrict__ conf,
                     const float *__restrict__ init, const float *__restrict__ dep,
-                    const float *__restrict__ gamma_ptr, int affinity, unsigned flags, int P, float *__restrict__ offset,
-                    float *__restrict__ aff, float *__restrict__ conf_out, float *__restrict__ src0)
+                    const float *__restrict__ gamma_ptr, int affinity, unsigned flags, int H, int W,
+                    float *__restrict__ offset, float *__restrict__ aff, float *__restrict__ conf_out,
+                    float *__restrict__ src0)
 {
     using G = Geo<K>;
+    const int P = H * W;
     const int r = blockIdx.x * kBlock + threadIdx.x;
     if (r >= P) return;
     const long b = blockIdx.y;
@@ -53,10 +82,13 @@ prologue_fwd_kernel(const float *__restrict__ guidance, const float *__restrict_
     const bool use_tanh = affinity == kTC || affinity == kTGASS;
     const float gamma = __ldg(gamma_ptr);
     const float g = affinity == kTGASS ? gamma + 1e-8f : gamma;
+    const bool sampled = (flags & kConfSampled) != 0;     // upstream conf_prop (parity unpinned)
+    const int hh0 = r / W, ww0 = r - hh0 * W;
 #pragma unroll
     for (int n = 0; n < G::N; ++n) {
         float v = __ldg(gb + (long)(aff_ch0 + n) * P);
         if (use_tanh) v = tanhf(v) / g;
+        if (sampled) v *= sample_conf<K>(conf + b * P, gb, n, hh0, ww0, H, W, P, (flags & kLegacy) != 0);
         a[n] = v;
         abs_sum += fabsf(v);
     }
@@ -78,7 +110,7 @@ prologue_fwd_kernel(const float *__restrict__ guidance, const float *__restrict_
     float x = __ldg(init + q);
     if (preserve) x = blend_fix(x, d);
     if (flags & kAlwaysClip) x = fmaxf(x, 0.f);
-    if (conf) {
+    if (conf && !sampled) {
         float c = __ldg(conf + q);
         if (preserve) {
             const float m = d > 0.f ? 1.f : 0.f;
@@ -141,10 +173,16 @@ iter_fwd_kernel(const float *__restrict__ src_prev, const float *__restrict__ of
 
     const long q = b * P + r;
     if (CENTER_ZERO) {
-        if (flags & kPreserve) acc = blend_fix(acc, __ldg(dep + q));
-        if (flags & kAlwaysClip) acc = fmaxf(acc, 0.f);
-        out[q] = acc;
-        if (src_next) src_next[q] = conf ? acc * __ldg(conf + q) : acc;
+        if (flags & kBlendPre) {
+            // upstream order: the list gets the raw gather, the NEXT gather reads the blended state
+            out[q] = acc;
+            if (src_next) src_next[q] = (flags & kPreserve) ? blend_fix(acc, __ldg(dep + q)) : acc;
+        } else {
+            if (flags & kPreserve) acc = blend_fix(acc, __ldg(dep + q));
+            if (flags & kAlwaysClip) acc = fmaxf(acc, 0.f);
+            out[q] = acc;
+            if (src_next) src_next[q] = conf ? acc * __ldg(conf + q) : acc;
+        }
     } else {
         out[q] = acc;
     }
@@ -272,8 +310,11 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
                  const float *__restrict__ g_conf_acc, const float *__restrict__ g_off_ext,
                  const float *__restrict__ g_aff_ext, const float *__restrict__ gamma_ptr, int affinity,
                  unsigned flags, int H, int W, float *__restrict__ g_init, float *__restrict__ g_guidance,
-                 float *__restrict__ g_conf, double *__restrict__ g_gamma)
+                 float *__restrict__ g_conf, double *__restrict__ g_gamma,
+                 const float *__restrict__ conf_raw = nullptr)
 {
+    // conf_raw: only for kConfSampled (upstream conf_prop): the raw confidence the prologue sampled;
+    // its gradient is SCATTERED into g_conf (zeroed by the host) with the bilinear corner weights.
     using G = Geo<K>;
     const int P = H * W;
     const int r = blockIdx.x * kBlock + threadIdx.x;
@@ -332,6 +373,8 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         // all N affinities, and a gradient tolerates the last-bit difference of x * (1/d) vs x / d
         // (the FORWARD prologue keeps true divisions: its outputs are API-visible values).
         const float inv_g = 1.0f / g;
+        const bool sampled = (flags & kConfSampled) != 0;
+        const int ph = r / W, pw = r - ph * W;
         float a[G::N], th[G::N], Gh[G::N];
         float s0 = 0.f;
 #pragma unroll
@@ -339,6 +382,7 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
             const float rr = __ldg(gb + (long)(aff_ch0 + n) * P);
             th[n] = use_tanh ? tanhf(rr) : 0.f;
             a[n] = use_tanh ? th[n] * inv_g : rr;
+            if (sampled) a[n] *= sample_conf<K>(conf_raw + b * P, gb, n, ph, pw, H, W, P, (flags & kLegacy) != 0);
             s0 += fabsf(a[n]);
         }
         s0 += 1e-4f;
@@ -369,6 +413,27 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
             } else {
                 const float sg = a[n] > 0.f ? 1.f : (a[n] < 0.f ? -1.f : 0.f);
                 da = Gh[n] * inv_s - sg * corr;
+            }
+            if (sampled) {
+                // a_n = u_n * c_n with u_n = tanh(r_n)/g and c_n the sampled confidence
+                float hc, wc;
+                const float cs = sample_conf<K>(conf_raw + b * P, gb, n, ph, pw, H, W, P, (flags & kLegacy) != 0,
+                                                &hc, &wc);
+                const float un = use_tanh ? th[n] * inv_g : __ldg(gb + (long)(aff_ch0 + n) * P);
+                const float gcs = da * un;            // d loss / d c_n
+                if (tap_valid(hc, wc, H, W) && gcs != 0.f) {
+                    // grad_input of the 1x1 gather: mdmcn_get_gradient_weight, cuh:56-81
+                    const int hl = (int)floorf(hc), wl = (int)floorf(wc);
+                    const float tw = (float)(hl + 1) - hc, bw = (hc + 1.f) - (float)(hl + 1);
+                    const float lw_ = (float)(wl + 1) - wc, rw = (wc + 1.f) - (float)(wl + 1);
+                    float *gp = g_conf + b * P + (long)hl * W + wl;
+                    const bool tp = hl >= 0, bt = hl + 1 <= H - 1, lf = wl >= 0, rg = wl + 1 <= W - 1;
+                    if (tp && lf) atomicAdd(gp, tw * lw_ * gcs);
+                    if (tp && rg) atomicAdd(gp + 1, tw * rw * gcs);
+                    if (bt && lf) atomicAdd(gp + W, bw * lw_ * gcs);
+                    if (bt && rg) atomicAdd(gp + W + 1, bw * rw * gcs);
+                }
+                da *= cs;                              // d loss / d u_n
             }
             float dr = da;
             if (use_tanh) {

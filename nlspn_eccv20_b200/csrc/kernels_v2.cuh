@@ -96,9 +96,13 @@ bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff
     // ---- stage 2: arithmetic
     const float gs = ((cv[0] + cv[1]) + cv[2]) + cv[3];
     float Gx = gext;
-    if (si) Gx += conf ? cf * gs : gs;
-    if ((flags & kAlwaysClip) && !(xt > 0.f)) Gx = 0.f;
-    if (flags & kPreserve) Gx = (1.0f - (dp > 0.f ? 1.f : 0.f)) * Gx;
+    if (flags & kBlendPre) {   // upstream order: the blend sits on the gather's INPUT
+        if (si) Gx += (flags & kPreserve) ? (1.0f - (dp > 0.f ? 1.f : 0.f)) * gs : gs;
+    } else {
+        if (si) Gx += conf ? cf * gs : gs;
+        if ((flags & kAlwaysClip) && !(xt > 0.f)) Gx = 0.f;
+        if (flags & kPreserve) Gx = (1.0f - (dp > 0.f ? 1.f : 0.f)) * Gx;
+    }
     const float gy = Gx;
 
     // ---- stage 3: plain stores

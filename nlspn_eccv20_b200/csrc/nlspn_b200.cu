@@ -348,7 +348,7 @@ static int launch_prologue(const FwdCall &c, int b0, int nb)
     DISPATCH_K(c.K, (prologue_fwd_kernel<KC><<<grid_for(P, nb), kBlock, 0, c.st>>>(
                         c.guidance + o1 * (no_off ? 1 : 3) * N, c.confidence ? c.confidence + o1 : nullptr,
                         c.feat_init + o1, c.feat_fix ? c.feat_fix + o1 : nullptr, c.gamma, c.affinity,
-                        c.flags, P, no_off ? nullptr : c.offset + o1 * 2 * KK, c.aff + o1 * KK,
+                        c.flags, c.H, c.W, no_off ? nullptr : c.offset + o1 * 2 * KK, c.aff + o1 * KK,
                         c.conf_fixed ? c.conf_fixed + o1 : nullptr, c.src + o1)));
     NLSPN_CHECK_LAUNCH("prologue_fwd_kernel");
     return 0;
@@ -363,7 +363,8 @@ static int launch_iter_fwd(const FwdCall &c, int b0, int nb, int t, const CUtens
     float *src_next = nullptr;
     const CUtensorMap *map = src_map;
     int plane_z;
-    if (c.conf_fixed) {
+    const bool use_src = c.conf_fixed || (c.flags & NLSPN_FLAG_BLEND_PRE);   // gather source != list_feat
+    if (use_src) {
         src_prev = c.src + (long)((t - 1) % c.S) * BP + o1;
         plane_z = ((t - 1) % c.S) * c.B + b0;
         if (t < c.T) src_next = c.src + (long)(t % c.S) * BP + o1;
@@ -430,6 +431,7 @@ static int try_persistent_forward(const FwdCall &c, bool prologue, int *tried)
 {
     *tried = 0;
     if (c.K != 3) return 0;   // 24 / 48 taps of geometry do not fit the register file
+    if (c.flags & NLSPN_FLAG_BLEND_PRE) return 0;   // upstream ordering: per-iteration kernels only
     if (const char *e = getenv("NLSPN_PERSIST"))
         if (atoi(e) == 0) return 0;
     int dev = 0, sms = 0, coop = 0;
@@ -457,6 +459,18 @@ static int try_persistent_forward(const FwdCall &c, bool prologue, int *tried)
     return 0;
 }
 
+// flag combinations the kernels implement
+static int check_mode_flags(unsigned flags)
+{
+    const bool pre = flags & NLSPN_FLAG_BLEND_PRE, sampled = flags & NLSPN_FLAG_CONF_SAMPLED;
+    if ((pre || sampled) && (flags & (NLSPN_FLAG_ALWAYS_CLIP | NLSPN_FLAG_NO_OFFSET | NLSPN_FLAG_BWD_PER_ITERATION)))
+        return fail(NLSPN_ERR_DOMAIN, "BLEND_PRE / CONF_SAMPLED (upstream semantics) cannot be combined with "
+                                      "ALWAYS_CLIP, NO_OFFSET or BWD_PER_ITERATION");
+    if ((flags & NLSPN_FLAG_LEGACY) && !sampled)
+        return fail(NLSPN_ERR_DOMAIN, "LEGACY only modifies CONF_SAMPLED");
+    return 0;
+}
+
 static int check_fwd(const FwdCall &c, bool prologue, bool iters)
 {
     if (int rc = check_shape(c.B, c.H, c.W, c.K, c.T)) return rc;
@@ -465,10 +479,13 @@ static int check_fwd(const FwdCall &c, bool prologue, bool iters)
     const bool no_off = (c.flags & NLSPN_FLAG_NO_OFFSET) != 0;
     if (no_off && c.K != 3)
         return fail(NLSPN_ERR_KERNEL, "fixed-local propagation (NO_OFFSET) is 3x3 only, as in the reference (got K=%d)", c.K);
+    if (int rc = check_mode_flags(c.flags)) return rc;
+    if (prologue && (c.flags & NLSPN_FLAG_CONF_SAMPLED) && (!c.confidence || c.conf_fixed))
+        return fail(NLSPN_ERR_NULL, "CONF_SAMPLED needs `confidence` and a NULL `conf_fixed` (the loop does not pre-multiply)");
     if (prologue) {
         if (!c.guidance || !c.feat_init || (!c.offset && !no_off) || !c.aff || !c.src || !c.gamma)
             return fail(NLSPN_ERR_NULL, "prologue: guidance, feat_init, gamma, offset, aff, src are required");
-        if (c.confidence && !c.conf_fixed)
+        if (c.confidence && !c.conf_fixed && !(c.flags & NLSPN_FLAG_CONF_SAMPLED))
             return fail(NLSPN_ERR_NULL, "prologue: conf_fixed is required when confidence is given");
         if (c.affinity < NLSPN_AFF_AS || c.affinity > NLSPN_AFF_TGASS)
             return fail(NLSPN_ERR_AFFINITY, "unknown affinity mode %d", c.affinity);
@@ -476,8 +493,8 @@ static int check_fwd(const FwdCall &c, bool prologue, bool iters)
     if (iters) {
         if ((!c.offset && !no_off) || !c.aff || !c.src || !c.list_feat)
             return fail(NLSPN_ERR_NULL, "propagate: offset, aff, src, list_feat are required");
-        if (c.S < 1 || (c.conf_fixed && c.T > 1 && c.S < 2))
-            return fail(NLSPN_ERR_SHAPE, "propagate: src needs S >= 2 planes with confidence (got %d)", c.S);
+        if (c.S < 1 || ((c.conf_fixed || (c.flags & NLSPN_FLAG_BLEND_PRE)) && c.T > 1 && c.S < 2))
+            return fail(NLSPN_ERR_SHAPE, "propagate: src needs S >= 2 planes with confidence / BLEND_PRE (got %d)", c.S);
     }
     return 0;
 }
@@ -566,7 +583,7 @@ size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T)
 }
 
 int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
-                   const float *offset, const float *aff, const float *conf_fixed,
+                   const float *confidence, const float *offset, const float *aff, const float *conf_fixed,
                    const float *src, int S, const float *list_feat, const float *const *g_list,
                    const float *g_offset_ext, const float *g_aff_ext, const float *gamma, int affinity,
                    unsigned flags, int B, int H, int W, int K, int T,
@@ -580,13 +597,18 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     if (!guidance || !feat_init || (!offset && !no_off) || !aff || !src || !list_feat || !g_list || !gamma ||
         !g_feat_init || !g_guidance || !g_gamma || !workspace)
         return fail(NLSPN_ERR_NULL, "backward: a required pointer is NULL");
-    if (conf_fixed && !g_confidence)
-        return fail(NLSPN_ERR_NULL, "backward: g_confidence is required when conf_fixed is given");
+    if (int rc = check_mode_flags(flags)) return rc;
+    const bool sampled = (flags & NLSPN_FLAG_CONF_SAMPLED) != 0;
+    const bool use_src = conf_fixed || (flags & NLSPN_FLAG_BLEND_PRE);
+    if (sampled && (!confidence || conf_fixed))
+        return fail(NLSPN_ERR_NULL, "backward: CONF_SAMPLED needs `confidence` and a NULL `conf_fixed`");
+    if ((conf_fixed || sampled) && !g_confidence)
+        return fail(NLSPN_ERR_NULL, "backward: g_confidence is required when confidence is used");
     if ((flags & NLSPN_FLAG_PRESERVE_INPUT) && !feat_fix)
         return fail(NLSPN_ERR_NULL, "backward: PRESERVE_INPUT needs feat_fix");
     if (affinity < NLSPN_AFF_AS || affinity > NLSPN_AFF_TGASS)
         return fail(NLSPN_ERR_AFFINITY, "unknown affinity mode %d", affinity);
-    if (conf_fixed && S < T)
+    if (use_src && S < T)
         return fail(NLSPN_ERR_SHAPE, "backward: src must keep all T planes (S=%d, T=%d)", S, T);
     if (workspace_bytes < nlspn_backward_workspace_bytes(B, H, W, K, T) || !aligned16(workspace))
         return fail(NLSPN_ERR_WORKSPACE, "backward: workspace too small (%zu < %zu) or misaligned",
@@ -683,7 +705,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     CUtensorMap src_map, list_map;
     const bool use_tiled = tiled_ok(src, W) && aligned16(list_feat);
     if (use_tiled) {
-        if (int rc = make_plane_map(&src_map, src, (long)(conf_fixed ? T : 1) * B, H, W, kTileW + 2 * halo_for(K), param_tile_h() + 2 * halo_for(K))) return rc;
+        if (int rc = make_plane_map(&src_map, src, (long)(use_src ? T : 1) * B, H, W, kTileW + 2 * halo_for(K), param_tile_h() + 2 * halo_for(K))) return rc;
         if (int rc = make_plane_map(&list_map, list_feat, (long)T * B, H, W, kTileW + 2 * halo_for(K), param_tile_h() + 2 * halo_for(K))) return rc;
     }
     // pass A with TMA-delivered geometry.  Measured on B200 (KITTI B=8): K=3 3.37 ms vs 3.28 ms with
@@ -762,15 +784,19 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                 dim3 tblock(kTileW, pth);
                 DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, THC><<<tgrid, tblock, 0, st>>>(
                                   src_map, list_map, B, b0, offset + o1 * 2 * KK, aff + o1 * KK, src + o1,
-                                  list_feat + o1, gy_all, conf_fixed ? 1 : 0, H, W, T, BP, GP,
+                                  list_feat + o1, gy_all, use_src ? 1 : 0, H, W, T, BP, GP,
                                   g_guidance + o1 * 3 * N, g_aff_acc))));
                 NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
             } else {
                 DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
                                   offset + o1 * 2 * KK, aff + o1 * KK, src + o1, list_feat + o1, gy_all,
-                                  conf_fixed ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc)));
+                                  use_src ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc)));
                 NLSPN_CHECK_LAUNCH("bwd_param_kernel");
             }
+        }
+        if (sampled) {   // the confidence gradient is scattered by the final kernel
+            e = cudaMemsetAsync(g_confidence + o1, 0, sizeof(float) * (size_t)nb * P, st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(g_confidence)");
         }
         ProfScope prof__(kProfFinalBwd, st);
         DISPATCH_K(K, (final_bwd_kernel<KC, true><<<grid_for(P, nb), kBlock, 0, st>>>(
@@ -778,7 +804,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                           g_offset_ext ? g_offset_ext + o1 * 2 * KK : nullptr,
                           g_aff_ext ? g_aff_ext + o1 * KK : nullptr, gamma, affinity, flags, H, W,
                           g_feat_init + o1, g_guidance + o1 * 3 * N, g_confidence ? g_confidence + o1 : nullptr,
-                          gamma_slots)));
+                          gamma_slots, sampled ? confidence + o1 : nullptr)));
         NLSPN_CHECK_LAUNCH("final_bwd_kernel");
     }
     gamma_reduce.armed = true;

@@ -48,10 +48,15 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def _flags(preserve_input, always_clip, use_offset=True):
+def _flags(preserve_input, always_clip, use_offset=True, conf_mode="premul", blend="post", legacy=False):
+    if conf_mode not in ("premul", "sampled", "none") or blend not in ("post", "pre"):
+        raise ValueError("conf_mode must be premul|sampled|none and blend post|pre")
     return (_lib.FLAG_PRESERVE_INPUT if preserve_input else 0) | \
            (_lib.FLAG_ALWAYS_CLIP if always_clip else 0) | \
-           (0 if use_offset else _lib.FLAG_NO_OFFSET)
+           (0 if use_offset else _lib.FLAG_NO_OFFSET) | \
+           (_lib.FLAG_BLEND_PRE if blend == "pre" else 0) | \
+           (_lib.FLAG_CONF_SAMPLED if conf_mode == "sampled" else 0) | \
+           (_lib.FLAG_LEGACY if (legacy and conf_mode == "sampled") else 0)
 
 
 def device_info(device=None):
@@ -90,7 +95,8 @@ def prologue_fwd(guidance, confidence, feat_init, feat_fix, gamma, K, affinity="
 
 
 def forward(guidance, confidence, feat_init, feat_fix, gamma, K, T, affinity="TGASS",
-            preserve_input=True, always_clip=False, keep_src=True, use_offset=True):
+            preserve_input=True, always_clip=False, keep_src=True, use_offset=True,
+            conf_mode="premul", blend="post", legacy=False):
     """Fused prologue + T iterations (group-major).
     -> (offset | None, aff, conf_fixed | None, src [S,B,1,H,W], list_feat [T,B,1,H,W]).
     use_offset=False: fixed-local propagation (nlspnmodel.py:209-224), guidance is [B,N,H,W]."""
@@ -104,16 +110,23 @@ def forward(guidance, confidence, feat_init, feat_fix, gamma, K, T, affinity="TG
     preserve = bool(preserve_input and feat_fix is not None)
     dev = feat_init.device
     opt = dict(device=dev, dtype=torch.float32)
+    if conf_mode == "none":
+        confidence = None
+    if conf_mode == "sampled" and confidence is None:
+        raise RuntimeError("conf_mode='sampled' needs a confidence map")
     offset = torch.empty((B, 2 * K * K, H, W), **opt) if use_offset else None
     aff = torch.empty((B, K * K, H, W), **opt)
-    conf_fixed = torch.empty((B, 1, H, W), **opt) if confidence is not None else None
-    S = 1 if confidence is None else (T if keep_src else min(T, 2))
+    premul = confidence is not None and conf_mode == "premul"
+    conf_fixed = torch.empty((B, 1, H, W), **opt) if premul else None
+    use_src = premul or blend == "pre"            # the gather source differs from list_feat
+    S = 1 if not use_src else (T if keep_src else min(T, 2))
     src = torch.empty((S, B, 1, H, W), **opt)
     list_feat = torch.empty((T, B, 1, H, W), **opt)
     gam = _gamma(gamma, dev)
     with torch.cuda.device(dev):
         rc = lib.nlspn_forward(_ptr(guidance), _ptr(confidence), _ptr(feat_init), _ptr(feat_fix),
-                               _ptr(gam), _lib.AFFINITY[affinity], _flags(preserve, always_clip, use_offset),
+                               _ptr(gam), _lib.AFFINITY[affinity],
+                               _flags(preserve, always_clip, use_offset, conf_mode, blend, legacy),
                                B, H, W, K, T, _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(src), S,
                                _ptr(list_feat), _stream(dev))
     _lib.check(rc, "nlspn_forward")
@@ -144,7 +157,8 @@ def propagate_fwd(offset, aff, conf_fixed, feat_fix, src, list_feat, K, T,
 
 def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_feat, g_list,
              gamma, K, T, affinity="TGASS", preserve_input=True, always_clip=False,
-             g_offset_ext=None, g_aff_ext=None, per_iteration=False, use_offset=True):
+             g_offset_ext=None, g_aff_ext=None, per_iteration=False, use_offset=True,
+             conf_mode="premul", blend="post", legacy=False, confidence=None):
     """g_list: sequence of T tensors [B,1,H,W] or None.  -> (g_init, g_guidance, g_conf, g_gamma)."""
     lib = _lib.load()
     B, _, H, W = feat_init.shape
@@ -162,17 +176,21 @@ def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_f
     g_aff_ext = _chk("g_aff_ext", g_aff_ext, (B, K * K, H, W), optional=True)
     g_init = torch.empty((B, 1, H, W), **opt)
     g_guid = torch.empty((B, (3 if use_offset else 1) * N, H, W), **opt)
-    g_conf = torch.empty((B, 1, H, W), **opt) if conf_fixed is not None else None
+    sampled = conf_mode == "sampled"
+    confidence = _chk("confidence", confidence, (B, 1, H, W), optional=not sampled)
+    g_conf = torch.empty((B, 1, H, W), **opt) if (conf_fixed is not None or sampled) else None
     g_gamma = torch.empty((1,), device=dev, dtype=torch.float64)
     nbytes = lib.nlspn_backward_workspace_bytes(B, H, W, K, T)
     ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
     gam = _gamma(gamma, dev)
     with torch.cuda.device(dev):
         rc = lib.nlspn_backward(_ptr(guidance.contiguous()), _ptr(feat_init.contiguous()), _ptr(feat_fix),
+                                _ptr(confidence if sampled else None),
                                 _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(src), S, _ptr(list_feat),
                                 ptrs, _ptr(g_offset_ext), _ptr(g_aff_ext), _ptr(gam),
                                 _lib.AFFINITY[affinity],
-                                _flags(preserve, always_clip, use_offset) | (_lib.FLAG_BWD_PER_ITERATION if per_iteration else 0),
+                                _flags(preserve, always_clip, use_offset, conf_mode, blend, legacy)
+                                | (_lib.FLAG_BWD_PER_ITERATION if per_iteration else 0),
                                 B, H, W, K, T, _ptr(g_init), _ptr(g_guid), _ptr(g_conf), _ptr(g_gamma), _ptr(ws),
                                 nbytes, _stream(dev))
     _lib.check(rc, "nlspn_backward")

@@ -27,7 +27,7 @@ class NLSPNFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat_init, guidance, confidence, feat_fix, gamma, K, T, affinity,
-                preserve_input, always_clip, use_offset=True):
+                preserve_input, always_clip, use_offset=True, conf_mode="premul", blend="post", legacy=False):
         need_grad = any(t is not None and t.requires_grad for t in (feat_init, guidance, confidence, gamma))
         gamma_val = gamma.detach() if torch.is_tensor(gamma) else float(gamma)   # stays on the device
         feat_init_c = feat_init.detach().contiguous()
@@ -37,9 +37,12 @@ class NLSPNFunction(torch.autograd.Function):
         preserve = bool(preserve_input and fix_c is not None)
         offset, aff, conf_fixed, src, list_feat = F_.forward(
             guidance_c, conf_c, feat_init_c, fix_c, gamma_val, K, T, affinity, preserve, always_clip,
-            keep_src=need_grad, use_offset=use_offset)
+            keep_src=need_grad, use_offset=use_offset, conf_mode=conf_mode, blend=blend, legacy=legacy)
         ctx.cfg = (K, T, affinity, preserve, always_clip, gamma_val)
         ctx.use_offset = bool(use_offset)
+        ctx.mode = (conf_mode, blend, bool(legacy))
+        ctx.conf_raw = conf_c if (conf_mode == "sampled" and conf_c is not None) else None
+        ctx.conf_grad = conf_c is not None and conf_mode != "none"
         ctx.has_conf = conf_fixed is not None
         ctx.gamma_is_tensor = torch.is_tensor(gamma)
         ctx.save_for_backward(feat_init_c, guidance_c, fix_c, offset, aff, conf_fixed, src, list_feat)
@@ -65,25 +68,29 @@ class NLSPNFunction(torch.autograd.Function):
             g_off_ext = grads[i]
             i += 1
         g_cf_ext = grads[i] if ctx.has_conf else None
+        conf_mode, blend, legacy = ctx.mode
         g_init, g_guid, g_conf, g_gamma = F_.backward(
             guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_feat, g_list, gamma_val,
-            K, T, affinity, preserve, always_clip, g_off_ext, g_aff_ext, use_offset=ctx.use_offset)
+            K, T, affinity, preserve, always_clip, g_off_ext, g_aff_ext, use_offset=ctx.use_offset,
+            conf_mode=conf_mode, blend=blend, legacy=legacy, confidence=ctx.conf_raw)
         if g_cf_ext is not None:
             # conf_fixed = (1-m)*confidence + m, nlspnmodel.py:334
             m = (feat_fix > 0).to(g_cf_ext.dtype) if preserve else 0.0
             g_conf = g_conf + (1.0 - m) * g_cf_ext
         g_gam = g_gamma.to(torch.float32) if ctx.gamma_is_tensor else None
-        return g_init, g_guid, (g_conf if ctx.has_conf else None), None, g_gam, \
-            None, None, None, None, None, None
+        return g_init, g_guid, (g_conf if ctx.conf_grad else None), None, g_gam, \
+            None, None, None, None, None, None, None, None, None
 
 
 def nlspn_propagate(feat_init, guidance, confidence, feat_fix, gamma, prop_kernel=3, prop_time=18,
-                    affinity="TGASS", preserve_input=True, always_clip=False, use_offset=True):
+                    affinity="TGASS", preserve_input=True, always_clip=False, use_offset=True,
+                    conf_mode="premul", blend="post", legacy=False):
     """Functional form.  -> (feat_result, list_feat, offset|None, aff, conf_fixed|None).
     use_offset=False selects the fork's fixed-local propagation (nlspnmodel.py:209-224); guidance
     then holds the N raw affinities only and `offset` is None (as in nlspnmodel.py:306-308)."""
     outs = NLSPNFunction.apply(feat_init, guidance, confidence, feat_fix, gamma, prop_kernel,
-                               prop_time, affinity, preserve_input, always_clip, use_offset)
+                               prop_time, affinity, preserve_input, always_clip, use_offset,
+                               conf_mode if confidence is not None else "none", blend, legacy)
     T = prop_time
     list_feat = list(outs[:T])
     aff = outs[T]
@@ -121,6 +128,12 @@ class NLSPN(nn.Module):
         # args.offset: deformable gather (True; the north-star path) or the fork's fixed-local 3x3
         # propagation (False; the fork's command-line default, src/config.py:272-275)
         self.offset = bool(opt("offset", True))
+        # Fork semantics (the parity target) are the defaults.  conf_mode='sampled' + blend='pre'
+        # (+ legacy) select the UPSTREAM semantics the north-star prose describes;
+        # those are parity-unpinned: checked only against oracle/torchvision_port.py's restatement.
+        self.conf_mode = str(opt("conf_mode", "premul"))
+        self.blend = str(opt("blend", "post"))
+        self.legacy = bool(opt("legacy", False))
         assert (self.prop_kernel % 2) == 1, \
             'only odd kernel is supported but k_f = {}'.format(self.prop_kernel)   # nlspnmodel.py:29-30
         if self.prop_kernel not in (3, 5, 7):
@@ -158,5 +171,6 @@ class NLSPN(nn.Module):
             feat_fix = None
         feat_result, list_feat, offset, aff, _ = nlspn_propagate(
             feat_init, guidance, confidence, feat_fix, self.aff_scale_const, self.prop_kernel,
-            self.prop_time, self.affinity, self.preserve_input, self.always_clip, self.offset)
+            self.prop_time, self.affinity, self.preserve_input, self.always_clip, self.offset,
+            self.conf_mode, self.blend, self.legacy)
         return feat_result, list_feat, offset, aff, self.aff_scale_const.data

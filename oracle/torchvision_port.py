@@ -96,6 +96,86 @@ def fixed_local_step(x, aff):
     return (torch.cat(cols, 1) * aff).sum(1, keepdim=True)
 
 
+class DeformStep1x1(torch.autograd.Function):
+    """1x1 modulated deformable gather, pad 0 (the upstream conf_prop sampling call)."""
+
+    @staticmethod
+    def forward(ctx, x, offset, mask, weight, bias):
+        out = torch.ops.torchvision.deform_conv2d(x, weight, offset, mask, bias, 1, 1, 0, 0, 1, 1, 1, 1, True)
+        ctx.save_for_backward(x, offset, mask, weight, bias)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, offset, mask, weight, bias = ctx.saved_tensors
+        gi, gw, go, gm, gb = torch.ops.torchvision._deform_conv2d_backward(
+            g.contiguous(), x, weight, offset, mask, bias, 1, 1, 0, 0, 1, 1, 1, 1, True)
+        return gi, None, None, None, None          # offsets are detached upstream; mask/w/b are constants
+
+
+def upstream_affinity(aff_raw, offset, confidence, gamma, K, affinity, legacy):
+    """UPSTREAM (zzangjinsun/NLSPN_ECCV20) affinity path -- *parity unpinned*: that repository is
+    not under /root/reference; this restates BASELINE.json's north-star prose ("conf_prop confidence
+    bilinear sampling at the predicted offsets", SURVEY 0.2 right-hand column) from the public
+    upstream code as recalled: tanh/gamma, multiply each neighbour's affinity by the confidence
+    sampled with a 1x1 deformable gather at that neighbour's (detached) offset -- the tap
+    displacement is added to the offset only with --legacy -- then abs-sum normalisation."""
+    N = K * K - 1
+    if affinity == "TC":
+        aff = torch.tanh(aff_raw) / gamma
+    elif affinity == "TGASS":
+        aff = torch.tanh(aff_raw) / (gamma + 1e-8)
+    else:
+        aff = aff_raw
+    if confidence is not None:
+        B, _, H, W = aff.shape
+        ones = torch.ones(B, 1, H, W, dtype=aff.dtype)
+        w1 = torch.ones(1, 1, 1, 1, dtype=aff.dtype)
+        b0 = torch.zeros(1, dtype=aff.dtype)
+        confs = []
+        pad = (K - 1) // 2
+        for t in range(K * K):
+            hh, ww = divmod(t, K)
+            if hh == pad and ww == pad:
+                continue
+            off = offset[:, 2 * t:2 * t + 2].detach().clone()
+            if legacy:
+                off[:, 0] = off[:, 0] + (hh - pad)
+                off[:, 1] = off[:, 1] + (ww - pad)
+            confs.append(DeformStep1x1.apply(confidence, off.contiguous(), ones, w1, b0))
+        aff = aff * torch.cat(confs, 1)
+    abs_sum = aff.abs().sum(1, keepdim=True) + 1e-4
+    if affinity in ("ASS", "TGASS"):
+        abs_sum = torch.where(abs_sum < 1.0, torch.ones_like(abs_sum), abs_sum)
+    if affinity in ("AS", "ASS", "TGASS"):
+        aff = aff / abs_sum
+    ref = 1.0 - aff.sum(1, keepdim=True)
+    return torch.cat([aff[:, :N // 2], ref, aff[:, N // 2:]], 1)
+
+
+def propagate_upstream(feat_init, guidance, confidence, feat_fix, gamma, K, T, affinity="TGASS",
+                       preserve_input=True, legacy=False):
+    """Upstream loop: blend BEFORE every iteration only, no confidence pre-multiply, last output not
+    blended.  -> dict(feat_result, list_feat, offset, aff)."""
+    N = K * K - 1
+    offset = insert_center_offset(guidance[:, :2 * N], K)
+    aff = upstream_affinity(guidance[:, 2 * N:], offset, confidence, gamma, K, affinity, legacy)
+    preserve = preserve_input and feat_fix is not None
+    if preserve:
+        m = (feat_fix > 0).to(feat_init.dtype)
+    w = torch.ones(1, 1, K, K, dtype=feat_init.dtype)
+    b = torch.zeros(1, dtype=feat_init.dtype)
+    x = feat_init
+    out = []
+    for _ in range(T):
+        if preserve:
+            x = (1.0 - m) * x + m * feat_fix
+        x = DeformStep.apply(x, offset, aff, w, b, K)
+        out.append(x)
+    return dict(feat_result=x, list_feat=out, offset=offset, aff=aff, confidence=None)
+
+
 def propagate(feat_init, guidance, confidence, feat_fix, gamma, K, T, affinity="TGASS",
               preserve_input=True, always_clip=False, use_offset=True):
     """-> dict(feat_result, list_feat (list of T), offset, aff, confidence)."""

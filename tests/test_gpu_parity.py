@@ -401,3 +401,43 @@ def test_persistent_forward_equals_per_iteration_forward(dev, monkeypatch):
     fi2 = inp["feat_init"].clone().requires_grad_(True)
     mod(fi2, inp["guidance"], inp["confidence"], inp["feat_fix"])[0].sum().backward()
     assert float((g1 - fi2.grad).abs().max()) <= 1e-5 * float(g1.abs().max())
+
+
+@pytest.mark.parametrize("K,T,legacy,B,H,W", [(3, 6, False, 2, 28, 36), (3, 4, True, 1, 21, 27), (5, 3, False, 1, 24, 32)])
+def test_upstream_semantics_against_torchvision_restatement(dev, K, T, legacy, B, H, W):
+    """conf_mode='sampled' + blend='pre' (+legacy): the UPSTREAM semantics of the north-star prose.
+    PARITY UNPINNED -- no upstream code is in the reference tree; the referee is the restatement in
+    oracle/torchvision_port.py (CPU, autograd).  Forward 1e-4 m, gradients 1e-4 relative."""
+    from nlspn_eccv20_b200 import NLSPN
+    from nlspn_eccv20_b200.synth import make_inputs
+    from oracle import torchvision_port as TP
+    inp = make_inputs(B, H, W, K, seed=900 + K + T, conf_mean=1.0)
+    gamma = 0.5 * (K * K - 1)
+    # CPU referee
+    fi = inp["feat_init"].clone().requires_grad_(True)
+    gd = inp["guidance"].clone().requires_grad_(True)
+    cf = inp["confidence"].clone().requires_grad_(True)
+    gam = torch.tensor([gamma], requires_grad=True)
+    ref = TP.propagate_upstream(fi, gd, cf, inp["feat_fix"], gam, K, T, legacy=legacy)
+    gen = torch.Generator().manual_seed(1)
+    g_last = torch.randn(B, 1, H, W, generator=gen)
+    g_mid = torch.randn(B, 1, H, W, generator=gen)
+    torch.autograd.backward([ref["list_feat"][-1], ref["list_feat"][T // 2]], [g_last, g_mid])
+    # GPU
+    mod = NLSPN(prop_kernel=K, prop_time=T, conf_mode="sampled", blend="pre", legacy=legacy).to(dev)
+    fi2 = inp["feat_init"].to(dev).requires_grad_(True)
+    gd2 = inp["guidance"].to(dev).requires_grad_(True)
+    cf2 = inp["confidence"].to(dev).requires_grad_(True)
+    feat_result, list_feat, offset, aff, _ = mod(fi2, gd2, cf2, inp["feat_fix"].to(dev))
+    lf = torch.stack(list_feat, 0).detach().cpu()
+    assert float((lf - torch.stack(ref["list_feat"], 0).detach()).abs().max()) <= 1e-4
+    assert float((aff.detach().cpu() - ref["aff"].detach()).abs().max()) <= 2e-6
+    torch.autograd.backward([list_feat[-1], list_feat[T // 2]], [g_last.to(dev), g_mid.to(dev)])
+    N = K * K - 1
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+    assert rel(fi2.grad.cpu(), fi.grad) < 1e-4
+    assert rel(cf2.grad.cpu(), cf.grad) < 1e-4
+    assert rel(gd2.grad.cpu()[:, 2 * N:], gd.grad[:, 2 * N:]) < 2e-4
+    assert abs(float(mod.aff_scale_const.grad) - float(gam.grad)) <= 2e-4 * abs(float(gam.grad))
+    d = (gd2.grad.cpu()[:, :2 * N] - gd.grad[:, :2 * N]).abs()
+    assert float((d > 1e-4 * gd.grad[:, :2 * N].abs().max()).float().mean()) < 1e-3
