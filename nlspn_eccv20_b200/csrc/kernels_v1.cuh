@@ -302,7 +302,7 @@ iter_bwd_kernel(const float *__restrict__ src_prev, const float *__restrict__ of
 // backward of the prologue (formulas: SURVEY 3.2, derived from nlspnmodel.py:185-197,262-267).
 // g_guidance's offset part already holds the accumulated offset gradients.
 // ======================================================================================
-template <int K, bool BLOCKED>
+template <int K, bool BLOCKED, bool SAMPLED = false>
 __global__ void __launch_bounds__(kBlock)
 final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ init,
                  const float *__restrict__ dep, const float *__restrict__ conf,
@@ -373,7 +373,7 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         // all N affinities, and a gradient tolerates the last-bit difference of x * (1/d) vs x / d
         // (the FORWARD prologue keeps true divisions: its outputs are API-visible values).
         const float inv_g = 1.0f / g;
-        const bool sampled = (flags & kConfSampled) != 0;
+        constexpr bool sampled = SAMPLED;   // compile-time: the common (fork) path carries none of this
         const int ph = r / W, pw = r - ph * W;
         float a[G::N], th[G::N], Gh[G::N];
         float s0 = 0.f;

@@ -280,13 +280,14 @@ static int fwd_tile_h()
 {
     if (const char *e = getenv("NLSPN_FWD_TH")) {
         const int v = atoi(e);
-        if (v == 4 || v == 8 || v == 16 || v == 32) return v;
+        if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) return v;
     }
     return kFwdTH;
 }
 
 #define DISPATCH_TH(TH_, ...)                                  \
     switch (TH_) {                                             \
+    case 2: { constexpr int THC = 2; __VA_ARGS__; } break;     \
     case 8: { constexpr int THC = 8; __VA_ARGS__; } break;     \
     case 32: { constexpr int THC = 32; __VA_ARGS__; } break;   \
     case 16: { constexpr int THC = 16; __VA_ARGS__; } break;   \
@@ -314,7 +315,7 @@ static int param_tile_h()
 {
     if (const char *e = getenv("NLSPN_PARAM_TH")) {
         const int v = atoi(e);
-        if (v == 4 || v == 8 || v == 16) return v;
+        if (v == 2 || v == 4 || v == 8 || v == 16) return v;
     }
     return kParamTH;
 }
@@ -799,12 +800,21 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(g_confidence)");
         }
         ProfScope prof__(kProfFinalBwd, st);
-        DISPATCH_K(K, (final_bwd_kernel<KC, true><<<grid_for(P, nb), kBlock, 0, st>>>(
-                          guidance + o1 * 3 * N, feat_init + o1, fx, cf, s_last, g_aff_acc, g_conf_acc,
-                          g_offset_ext ? g_offset_ext + o1 * 2 * KK : nullptr,
-                          g_aff_ext ? g_aff_ext + o1 * KK : nullptr, gamma, affinity, flags, H, W,
-                          g_feat_init + o1, g_guidance + o1 * 3 * N, g_confidence ? g_confidence + o1 : nullptr,
-                          gamma_slots, sampled ? confidence + o1 : nullptr)));
+        if (sampled) {
+            DISPATCH_K(K, (final_bwd_kernel<KC, true, true><<<grid_for(P, nb), kBlock, 0, st>>>(
+                              guidance + o1 * 3 * N, feat_init + o1, fx, cf, s_last, g_aff_acc, g_conf_acc,
+                              g_offset_ext ? g_offset_ext + o1 * 2 * KK : nullptr,
+                              g_aff_ext ? g_aff_ext + o1 * KK : nullptr, gamma, affinity, flags, H, W,
+                              g_feat_init + o1, g_guidance + o1 * 3 * N, g_confidence + o1, gamma_slots,
+                              confidence + o1)));
+        } else {
+            DISPATCH_K(K, (final_bwd_kernel<KC, true, false><<<grid_for(P, nb), kBlock, 0, st>>>(
+                              guidance + o1 * 3 * N, feat_init + o1, fx, cf, s_last, g_aff_acc, g_conf_acc,
+                              g_offset_ext ? g_offset_ext + o1 * 2 * KK : nullptr,
+                              g_aff_ext ? g_aff_ext + o1 * KK : nullptr, gamma, affinity, flags, H, W,
+                              g_feat_init + o1, g_guidance + o1 * 3 * N, g_confidence ? g_confidence + o1 : nullptr,
+                              gamma_slots, nullptr)));
+        }
         NLSPN_CHECK_LAUNCH("final_bwd_kernel");
     }
     gamma_reduce.armed = true;
