@@ -1,0 +1,113 @@
+"""GPU (B200): our kernels against the reference's OWN CUDA kernels, run side by side on the same
+device and inputs (oracle/_ref/DCN_ref.so = the reference's modulated_deform_conv_cuda.cu compiled
+for sm_100a by oracle/build_ref_cuda.py; SURVEY 8c "patched build").
+
+Tolerances: forward depth 1e-4 m absolute after 18 iterations on the stable set (north_star);
+gradients relative 1e-4 of the tensor's max, offset gradients by outlier fraction (a floor() that
+flips between two fp32 evaluation orders changes one corner).  The reference's own atomics make its
+grad_input order-dependent too, so bit equality is not expected.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/DCN_ref.so not built (python oracle/build_ref_cuda.py)")
+    ref_cuda.load()
+    from nlspn_eccv20_b200 import _lib
+    _lib.load()
+    return ref_cuda
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("K,T,shape", [(3, 18, (2, 228, 304)), (5, 6, (1, 97, 131)), (7, 3, (1, 40, 53))])
+def test_module_matches_reference_cuda_kernels(ref, K, T, shape):
+    from nlspn_eccv20_b200 import NLSPN
+    from nlspn_eccv20_b200.synth import make_inputs, rmse_mae
+    dev = torch.device("cuda:0")
+    B, H, W = shape
+    d = make_inputs(B, H, W, K, max_depth=10.0, seed=11 + K, conf_mean=3.0, num_sample=500, device=dev)
+    N = K * K - 1
+    mod = NLSPN(prop_kernel=K, prop_time=T).to(dev)
+    gamma0 = float(mod.aff_scale_const)
+
+    fi, gd, cf = (d[k].clone().requires_grad_(True) for k in ("feat_init", "guidance", "confidence"))
+    feat_result, list_feat, offset, aff, _ = mod(fi, gd, cf, d["feat_fix"])
+    g_out = torch.randn(T, B, 1, H, W, generator=torch.Generator().manual_seed(3)).to(dev) / T
+    torch.autograd.backward(list_feat, [g_out[t] for t in range(T)])
+
+    fi2, gd2, cf2 = (d[k].clone().requires_grad_(True) for k in ("feat_init", "guidance", "confidence"))
+    gam = torch.tensor([gamma0], device=dev, requires_grad=True)
+    r = ref.propagate(fi2, gd2, cf2, d["feat_fix"], gam, K, T)
+    torch.autograd.backward(r["list_feat"], [g_out[t] for t in range(T)])
+
+    assert torch.equal(offset, r["offset"])                                   # offsets / indexing exact
+    assert (aff - r["aff"]).abs().max() <= 2e-6
+    lf, lr = torch.stack(list_feat), torch.stack(r["list_feat"])
+    assert (lf - lr).abs().max() <= 1e-4                                      # 1e-4 m after T iterations
+    a = rmse_mae(feat_result.detach().clamp(min=0).cpu(), d["gt"].cpu())
+    b = rmse_mae(r["feat_result"].detach().clamp(min=0).cpu(), d["gt"].cpu())
+    assert abs(a[0] - b[0]) <= 1e-5 and abs(a[1] - b[1]) <= 1e-5              # RMSE / MAE to 1e-5
+
+    assert _rel(fi.grad, fi2.grad) < 1e-4
+    assert _rel(cf.grad, cf2.grad) < 1e-4
+    assert _rel(gd.grad[:, 2 * N:], gd2.grad[:, 2 * N:]) < 2e-4
+    ref_g = float(gam.grad)
+    assert abs(float(mod.aff_scale_const.grad) - ref_g) <= 2e-4 * max(abs(ref_g), 1e-6)
+    dd = (gd.grad[:, :2 * N] - gd2.grad[:, :2 * N]).abs()
+    s = gd2.grad[:, :2 * N].abs().max()
+    assert float((dd > 1e-4 * s).float().mean()) < 1e-3
+
+
+def test_single_step_dropin_matches_reference_cuda_kernels(ref):
+    """Boundary B1, one call: border-planted and far-out-of-range offsets, signed mask, w and b non-trivial."""
+    from nlspn_eccv20_b200.dcn import ModulatedDeformConvFunction
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    for K in (3, 5):
+        B, H, W = 2, 37, 45
+        KK = K * K
+        x = torch.randn(B, 1, H, W, generator=g)
+        off = 3.0 * torch.randn(B, 2 * KK, H, W, generator=g)
+        off[:, :, :3] = torch.round(off[:, :, :3])          # exact-integer coordinates (incl. -1 and H)
+        off[:, :, -2:] *= 10.0                              # far out of range
+        msk = torch.randn(B, KK, H, W, generator=g)
+        w = torch.randn(1, 1, K, K, generator=g)
+        b = torch.randn(1, generator=g)
+        gout = torch.randn(B, 1, H, W, generator=g).to(dev)
+        ours = [t.to(dev).requires_grad_(True) for t in (x, off, msk, w, b)]
+        theirs = [t.to(dev).requires_grad_(True) for t in (x, off, msk, w, b)]
+        y = ModulatedDeformConvFunction.apply(*ours, 1, (K - 1) // 2, 1, 1, 1, 64)
+        yr = ref.RefDeformStep.apply(*theirs, K)
+        assert (y - yr).abs().max() <= 2e-5
+        y.backward(gout)
+        yr.backward(gout)
+        assert (ours[0].grad - theirs[0].grad).abs().max() <= 5e-5           # grad_input (atomics on both sides)
+        assert (ours[2].grad - theirs[2].grad).abs().max() <= 2e-5           # grad_mask
+        assert (ours[1].grad - theirs[1].grad).abs().max() <= 2e-4           # grad_offset
+
+
+def test_full_size_kitti_forward_against_reference_cuda_kernels(ref):
+    """BASELINE config 3's shape (one KITTI frame pair), forward only: every intermediate state."""
+    from nlspn_eccv20_b200 import NLSPN
+    from nlspn_eccv20_b200.synth import workload
+    dev = torch.device("cuda:0")
+    d = workload("kitti", 2, 3, seed=7240, conf_mean=3.0, device=dev)
+    mod = NLSPN(prop_kernel=3, prop_time=18).to(dev)
+    with torch.no_grad():
+        feat_result, list_feat, offset, aff, _ = mod(d["feat_init"], d["guidance"], d["confidence"], d["feat_fix"])
+        r = ref.propagate(d["feat_init"], d["guidance"], d["confidence"], d["feat_fix"],
+                          mod.aff_scale_const.detach(), 3, 18)
+    assert torch.equal(offset, r["offset"])
+    assert (torch.stack(list_feat) - torch.stack(r["list_feat"])).abs().max() <= 1e-4
