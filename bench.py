@@ -404,6 +404,17 @@ def main():
             "kernels": kernels,
             "roofline_step": {"alg_bytes_per_pix_iter": alg_bytes(K, T, args.mode), "achieved": step_gbs,
                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": step_gbs / peaks["hbm_gbs"]}}
+    # second roofline level: when the step's inputs are L2-resident the same algorithmic
+    # bytes are also quoted against the measured L2 copy bandwidth (tools/l2_bench.cu -> profiles/l2_peak.json)
+    try:
+        with open(os.path.join(ROOT, "profiles", "l2_peak.json")) as f:
+            l2 = json.load(f)
+        if guid_mb <= 126.0:
+            line["roofline_step_l2"] = {"achieved": step_gbs, "peak": l2["l2_copy_gbs"], "unit": "GB/s",
+                                        "frac": step_gbs / l2["l2_copy_gbs"],
+                                        "peak_source": "tools/l2_bench.cu, L2-resident copy (read+write), profiles/l2_peak.json"}
+    except Exception:
+        pass
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_img = args.cpu_images or min(os.cpu_count() or 1, 32)
