@@ -6,7 +6,7 @@
 All arithmetic runs in ``lib/libnlspn_b200.so`` (hand-written CUDA behind a C ABI, see
 include/nlspn_b200.h).  There is no CPU or PyTorch fallback: a missing library raises.
 """
-from .nlspn import NLSPN, NLSPNFunction, nlspn_propagate  # noqa: F401
+from .nlspn import NLSPN, NLSPNFunction, nlspn_propagate, GraphedNLSPN  # noqa: F401
 from . import dcn, functional  # noqa: F401
 
 __version__ = "0.1.0"

@@ -441,3 +441,26 @@ def test_upstream_semantics_against_torchvision_restatement(dev, K, T, legacy, B
     assert abs(float(mod.aff_scale_const.grad) - float(gam.grad)) <= 2e-4 * abs(float(gam.grad))
     d = (gd2.grad.cpu()[:, :2 * N] - gd.grad[:, :2 * N]).abs()
     assert float((d > 1e-4 * gd.grad[:, :2 * N].abs().max()).float().mean()) < 1e-3
+
+
+@pytest.mark.parametrize("shape,K", [((1, 228, 304), 3), ((2, 352, 1216), 3), ((1, 61, 84), 5)])
+def test_cuda_graph_replay_is_bit_identical_to_eager(dev, shape, K):
+    """GraphedNLSPN: one capture, replays with new inputs; persistent (one NYU frame), tiled (KITTI) and
+    the K=5 paths.  The forward has no atomics, so replay == eager bit for bit."""
+    from nlspn_eccv20_b200 import NLSPN
+    from nlspn_eccv20_b200.synth import make_inputs
+    B, H, W = shape
+    mod = NLSPN(prop_kernel=K, prop_time=18).to(dev)
+    a = make_inputs(B, H, W, K, seed=1, conf_mean=3.0, device=dev)
+    b = make_inputs(B, H, W, K, seed=2, conf_mean=3.0, device=dev)
+    args = lambda d: (d["feat_init"], d["guidance"], d["confidence"], d["feat_fix"])
+    g = mod.graphed(*args(a))
+    for d in (a, b, a):
+        with torch.no_grad():
+            eager = mod(*args(d))
+        out = g(*args(d))
+        assert torch.equal(out[0], eager[0])
+        assert all(torch.equal(x, y) for x, y in zip(out[1], eager[1]))
+        assert torch.equal(out[2], eager[2]) and torch.equal(out[3], eager[3])
+    with pytest.raises(RuntimeError):
+        g(a["feat_init"][:, :, :-1], a["guidance"][:, :, :-1], a["confidence"][:, :, :-1], a["feat_fix"][:, :, :-1])

@@ -5,6 +5,7 @@ out=${1:-gpurun_out/configs_r01.jsonl}
 run() { echo "# $1" >> $out; shift; python bench.py --no-cpu-baseline "$@" 2>/dev/null | tail -1 >> $out; }
 run "config1 NYU B=1 fwd (L2 flushed)"            --workload nyu --batch 1 --mode fwd --steps 20
 run "config1 NYU B=1 fwd (unflushed)"             --workload nyu --batch 1 --mode fwd --steps 20 --flush-l2 off
+run "config1 NYU B=1 fwd, CUDA graph replay (L2 flushed)" --workload nyu --batch 1 --mode fwd --steps 20 --cuda-graph
 run "config2 NYU B=12 fwd+bwd (L2 flushed)"       --workload nyu --batch 12
 run "config2 NYU B=12 fwd+bwd (unflushed)"        --workload nyu --batch 12 --flush-l2 off
 run "config3 KITTI B=16 fwd (1 GPU)"              --workload kitti --batch 16 --mode fwd
