@@ -189,6 +189,23 @@ NLSPN_API int nlspn_dcn_backward(const float *input, const float *weight, const 
                        float *grad_input, float *grad_offset, float *grad_mask,
                        float *grad_weight, float *grad_bias, void *stream);
 
+/* Double-precision variants of the single-step operator: the reference dispatches this op over
+ * float and double (AT_DISPATCH_FLOATING_TYPES, modulated_deform_conv_cuda.cu:93,224) and its
+ * tests run gradcheck in double (src/model/deformconv/test.py).  Same domain, argument order and
+ * error behaviour as the fp32 entries; simple (untuned) kernels. */
+NLSPN_API int nlspn_dcn_forward_f64(const double *input, const double *weight, const double *bias,
+                      const double *offset, const double *mask,
+                      int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                      int dilation_h, int dilation_w, int group, int deformable_group,
+                      int im2col_step, int B, int C, int H, int W, double *output, void *stream);
+NLSPN_API int nlspn_dcn_backward_f64(const double *input, const double *weight, const double *bias,
+                       const double *offset, const double *mask, const double *grad_output,
+                       int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                       int dilation_h, int dilation_w, int group, int deformable_group,
+                       int im2col_step, int B, int C, int H, int W,
+                       double *grad_input, double *grad_offset, double *grad_mask,
+                       double *grad_weight, double *grad_bias, void *stream);
+
 /* ---- debug: integer corners chosen for every tap (exact-index parity test) -------------
  * idx [B,KK,3,H,W] int32: floor(h_im), floor(w_im), valid (validity test of cuh:180),
  * with h_im = (float)(h - pad + i) + offset_h formed exactly as cuh:178-179. */

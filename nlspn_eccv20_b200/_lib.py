@@ -43,6 +43,8 @@ SIGNATURES = {
                                   _fp, _fp, _fp, _fp, _fp, _c.c_size_t, _fp]),
     "nlspn_dcn_forward": (_c.c_int, [_fp] * 5 + [_c.c_int] * 15 + [_fp, _fp]),
     "nlspn_dcn_backward": (_c.c_int, [_fp] * 6 + [_c.c_int] * 15 + [_fp] * 6),
+    "nlspn_dcn_forward_f64": (_c.c_int, [_fp] * 5 + [_c.c_int] * 15 + [_fp, _fp]),
+    "nlspn_dcn_backward_f64": (_c.c_int, [_fp] * 6 + [_c.c_int] * 15 + [_fp] * 6),
     "nlspn_debug_indices": (_c.c_int, [_fp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _fp, _fp]),
 }
 

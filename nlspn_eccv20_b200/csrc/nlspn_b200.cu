@@ -12,6 +12,7 @@
 #include "kernels_fixed.cuh"
 #include "kernels_persist.cuh"
 #include "kernels_tiled.cuh"
+#include "kernels_f64.cuh"
 
 using namespace nlspn;
 
@@ -895,6 +896,61 @@ int nlspn_dcn_backward(const float *input, const float *weight, const float *bia
     DISPATCH_K(kernel_h, (dcn_wb_grad_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
                              input, offset, mask, grad_output, H, W, grad_weight, grad_bias)));
     NLSPN_CHECK_LAUNCH("dcn_wb_grad_kernel");
+    return 0;
+}
+
+int nlspn_dcn_forward_f64(const double *input, const double *weight, const double *bias,
+                          const double *offset, const double *mask,
+                          int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                          int dilation_h, int dilation_w, int group, int deformable_group,
+                          int im2col_step, int B, int C, int H, int W, double *output, void *stream)
+{
+    (void)im2col_step;
+    if (int rc = check_dcn_domain(kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h,
+                                  dilation_w, group, deformable_group, C))
+        return rc;
+    if (int rc = check_shape(B, H, W, kernel_h, 1)) return rc;
+    if (!input || !weight || !bias || !offset || !mask || !output)
+        return fail(NLSPN_ERR_NULL, "dcn_forward_f64: a required pointer is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    { ProfScope prof__(kProfDcnFwd, st);
+    DISPATCH_K(kernel_h, (dcn_fwd_f64_kernel<KC><<<grid_for(H * W, B), kBlock, 0, st>>>(
+                             input, offset, mask, weight, bias, H, W, output))); }
+    NLSPN_CHECK_LAUNCH("dcn_fwd_f64_kernel");
+    return 0;
+}
+
+int nlspn_dcn_backward_f64(const double *input, const double *weight, const double *bias,
+                           const double *offset, const double *mask, const double *grad_output,
+                           int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                           int dilation_h, int dilation_w, int group, int deformable_group,
+                           int im2col_step, int B, int C, int H, int W,
+                           double *grad_input, double *grad_offset, double *grad_mask,
+                           double *grad_weight, double *grad_bias, void *stream)
+{
+    (void)im2col_step;
+    (void)bias;
+    if (int rc = check_dcn_domain(kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h,
+                                  dilation_w, group, deformable_group, C))
+        return rc;
+    if (int rc = check_shape(B, H, W, kernel_h, 1)) return rc;
+    if (!input || !weight || !offset || !mask || !grad_output || !grad_input || !grad_offset ||
+        !grad_mask || !grad_weight || !grad_bias)
+        return fail(NLSPN_ERR_NULL, "dcn_backward_f64: a required pointer is NULL");
+    const long BP = (long)B * H * W;
+    const int KK = kernel_h * kernel_h;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(grad_input, 0, sizeof(double) * BP, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_input)");
+    e = cudaMemsetAsync(grad_weight, 0, sizeof(double) * KK, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_weight)");
+    e = cudaMemsetAsync(grad_bias, 0, sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_bias)");
+    { ProfScope prof__(kProfDcnBwd, st);
+    DISPATCH_K(kernel_h, (dcn_bwd_f64_kernel<KC><<<grid_for(H * W, B), kBlock, 0, st>>>(
+                             input, offset, mask, weight, grad_output, H, W, grad_input, grad_offset,
+                             grad_mask, grad_weight, grad_bias))); }
+    NLSPN_CHECK_LAUNCH("dcn_bwd_f64_kernel");
     return 0;
 }
 

@@ -20,15 +20,15 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def _chk(name, t, shape=None, optional=False):
+def _chk(name, t, shape=None, optional=False, dtype=torch.float32):
     if t is None:
         if optional:
             return None
         raise RuntimeError("%s is required" % name)
     if not t.is_cuda:
         raise RuntimeError("%s must be a CUDA tensor (nlspn_eccv20_b200 has no CPU path)" % name)
-    if t.dtype != torch.float32:
-        raise RuntimeError("%s must be float32 (got %s)" % (name, t.dtype))
+    if t.dtype != dtype:
+        raise RuntimeError("%s must be %s (got %s)" % (name, str(dtype).replace("torch.", ""), t.dtype))
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise RuntimeError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
     return t.contiguous()
@@ -201,22 +201,33 @@ _DCN_INTS = ("kernel_h", "kernel_w", "stride_h", "stride_w", "pad_h", "pad_w", "
              "dilation_w", "group", "deformable_group", "im2col_step")
 
 
+def _dcn_dtype(input):
+    """The single-step operator serves float32 (tuned kernels) and float64 (the reference dispatches
+    both, modulated_deform_conv_cuda.cu:93,224); anything else raises."""
+    if input.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("DCN: float32 or float64 tensors only (got %s)" % input.dtype)
+    return input.dtype
+
+
 def dcn_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride_h, stride_w,
                 pad_h, pad_w, dilation_h, dilation_w, group, deformable_group, im2col_step):
     lib = _lib.load()
-    input = _chk("input", input)
+    dt = _dcn_dtype(input)
+    input = _chk("input", input, dtype=dt)
     B, C, H, W = input.shape
-    weight, bias, offset, mask = _chk("weight", weight), _chk("bias", bias), _chk("offset", offset), _chk("mask", mask)
+    weight, bias, offset, mask = (_chk(n, t, dtype=dt) for n, t in
+                                  (("weight", weight), ("bias", bias), ("offset", offset), ("mask", mask)))
     KK = kernel_h * kernel_w
     if tuple(offset.shape) != (B, 2 * KK, H, W) or tuple(mask.shape) != (B, KK, H, W):
         raise RuntimeError("offset/mask shape does not match input and kernel size")
     out = torch.empty_like(input)
     dev = input.device
     with torch.cuda.device(dev):
-        rc = lib.nlspn_dcn_forward(_ptr(input), _ptr(weight), _ptr(bias), _ptr(offset), _ptr(mask),
-                                   kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h,
-                                   dilation_w, group, deformable_group, im2col_step, B, C, H, W,
-                                   _ptr(out), _stream(dev))
+        fn = lib.nlspn_dcn_forward if dt == torch.float32 else lib.nlspn_dcn_forward_f64
+        rc = fn(_ptr(input), _ptr(weight), _ptr(bias), _ptr(offset), _ptr(mask),
+                kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h,
+                dilation_w, group, deformable_group, im2col_step, B, C, H, W,
+                _ptr(out), _stream(dev))
     _lib.check(rc, "nlspn_dcn_forward")
     return out
 
@@ -224,19 +235,22 @@ def dcn_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride_h,
 def dcn_backward(input, weight, bias, offset, mask, grad_output, kernel_h, kernel_w, stride_h,
                  stride_w, pad_h, pad_w, dilation_h, dilation_w, group, deformable_group, im2col_step):
     lib = _lib.load()
-    input = _chk("input", input)
+    dt = _dcn_dtype(input)
+    input = _chk("input", input, dtype=dt)
     B, C, H, W = input.shape
-    weight, bias, offset, mask = _chk("weight", weight), _chk("bias", bias), _chk("offset", offset), _chk("mask", mask)
-    grad_output = _chk("grad_output", grad_output, (B, C, H, W))
+    weight, bias, offset, mask = (_chk(n, t, dtype=dt) for n, t in
+                                  (("weight", weight), ("bias", bias), ("offset", offset), ("mask", mask)))
+    grad_output = _chk("grad_output", grad_output, (B, C, H, W), dtype=dt)
     gi, go, gm = torch.empty_like(input), torch.empty_like(offset), torch.empty_like(mask)
     gw, gb = torch.empty_like(weight), torch.empty_like(bias)
     dev = input.device
     with torch.cuda.device(dev):
-        rc = lib.nlspn_dcn_backward(_ptr(input), _ptr(weight), _ptr(bias), _ptr(offset), _ptr(mask),
-                                    _ptr(grad_output), kernel_h, kernel_w, stride_h, stride_w, pad_h,
-                                    pad_w, dilation_h, dilation_w, group, deformable_group, im2col_step,
-                                    B, C, H, W, _ptr(gi), _ptr(go), _ptr(gm), _ptr(gw), _ptr(gb),
-                                    _stream(dev))
+        fn = lib.nlspn_dcn_backward if dt == torch.float32 else lib.nlspn_dcn_backward_f64
+        rc = fn(_ptr(input), _ptr(weight), _ptr(bias), _ptr(offset), _ptr(mask),
+                _ptr(grad_output), kernel_h, kernel_w, stride_h, stride_w, pad_h,
+                pad_w, dilation_h, dilation_w, group, deformable_group, im2col_step,
+                B, C, H, W, _ptr(gi), _ptr(go), _ptr(gm), _ptr(gw), _ptr(gb),
+                _stream(dev))
     _lib.check(rc, "nlspn_dcn_backward")
     return gi, go, gm, gw, gb
 

@@ -25,7 +25,8 @@ def test_header_declares_the_expected_surface():
     syms = declared_symbols()
     for s in ["nlspn_abi_version", "nlspn_last_error", "nlspn_prologue_fwd", "nlspn_propagate_fwd",
               "nlspn_backward", "nlspn_backward_workspace_bytes", "nlspn_dcn_forward",
-              "nlspn_dcn_backward", "nlspn_debug_indices", "nlspn_device_info"]:
+              "nlspn_dcn_backward", "nlspn_dcn_forward_f64", "nlspn_dcn_backward_f64", "nlspn_debug_indices",
+              "nlspn_device_info"]:
         assert s in syms
 
 
