@@ -196,7 +196,7 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
 //   SKIP  invalid (cuh:308-311: contributes nothing)
 // A warp whose lanes are all-FAST runs a branch-free loop.
 // ======================================================================================
-template <int K, int C, int TH>
+template <int K, int C, int TH, int NS = 2>
 __global__ void __launch_bounds__(kTileW * TH, (TH >= 16 ? 1 : 16 / TH))   // <= 128 registers
 bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
                        const __grid_constant__ CUtensorMap list_map, int Bsrc, int b0,
@@ -210,16 +210,17 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
     constexpr int kHalo = TG::R;
     constexpr int kBoxW = TG::BoxW;
     constexpr int NCH = (G::KK + C - 1) / C;
-    __shared__ __align__(128) float box[2][TG::BoxFloats];
-    __shared__ __align__(8) uint64_t bar[2];
+    // NS-deep TMA pipeline: the boxes of iterations t-1 .. t-(NS-1) are in flight while plane t is consumed
+    __shared__ __align__(128) float box[NS][TG::BoxFloats];
+    __shared__ __align__(8) uint64_t bar[NS];
     const int P = H * W;
     const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * TH;
     const int b = NCH == 1 ? (int)blockIdx.z : (int)blockIdx.z / NCH;
     const int k0 = NCH == 1 ? 0 : ((int)blockIdx.z % NCH) * C;
     const int tid = threadIdx.y * kTileW + threadIdx.x;
     if (tid == 0) {
-        tma::mbar_init(&bar[0], 1);
-        tma::mbar_init(&bar[1], 1);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) tma::mbar_init(&bar[i], 1);
         tma::fence_barrier_init();
     }
     __syncthreads();
@@ -230,7 +231,11 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
         const int z = use_src ? (has_conf ? (t - 1) * Bsrc : 0) + b0 + b : (t - 2) * Bsrc + b0 + b;
         tma::load_3d(box[buf], use_src ? &src_map : &list_map, &bar[buf], x0 - kHalo, y0 - kHalo, z);
     };
-    if (tid == 0) issue(T, 0);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NS - 1; ++i)
+            if (T - i >= 1) issue(T - i, i);
+    }
 
     const int w = x0 + threadIdx.x, h = y0 + threadIdx.y;
     const bool inside = w < W && h < H;
@@ -286,11 +291,13 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
     float gy_n1 = inside ? __ldg(gy_all + (long)(T - 1) * GP + q) : 0.f;
     float gy_n2 = (inside && T > 1) ? __ldg(gy_all + (long)(T - 2) * GP + q) : 0.f;
     uint32_t phase_bits = 0u;   // bit i = parity the next wait on bar[i] expects
+    int cur = NS - 1;
     for (int t = T; t >= 1; --t) {
-        const int cur = (T - t) & 1;
-        // everyone is done reading box[cur^1] (consumed in the previous trip): refill it
+        const int freed = cur;                    // the box consumed in the previous trip
+        cur = cur + 1 == NS ? 0 : cur + 1;
+        // everyone is done reading box[freed]: refill it with the plane NS-1 iterations ahead
         __syncthreads();
-        if (tid == 0 && t > 1) issue(t - 1, cur ^ 1);
+        if (tid == 0 && t - (NS - 1) >= 1) issue(t - (NS - 1), freed);
         const float gy = gy_n1;
         gy_n1 = gy_n2;
         if (t > 2) gy_n2 = inside ? __ldg(gy_all + (long)(t - 3) * GP + q) : 0.f;

@@ -310,6 +310,7 @@ static int make_geometry_map(CUtensorMap *map, const float *base, int B, int C, 
 }
 
 constexpr int kStateTH = 4;   // pass-A TMA tile: 32 x 4 pixels
+constexpr int kParamStages = 2;   // pass-B TMA pipeline depth
 constexpr int kParamTH = 4;   // default pass-B tile: 32 x 4 pixels (B200 sweep: TH 4: 1.02, 8: 1.10, 16: 1.27 ms)
 
 static int param_tile_h()
@@ -784,10 +785,21 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                 dim3 tgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + pth - 1) / pth),
                            (unsigned)(nb * nch));
                 dim3 tblock(kTileW, pth);
-                DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, THC><<<tgrid, tblock, 0, st>>>(
-                                  src_map, list_map, B, b0, offset + o1 * 2 * KK, aff + o1 * KK, src + o1,
-                                  list_feat + o1, gy_all, use_src ? 1 : 0, H, W, T, BP, GP,
-                                  g_guidance + o1 * 3 * N, g_aff_acc))));
+#define PARAM_ARGS                                                                                          \
+    src_map, list_map, B, b0, offset + o1 * 2 * KK, aff + o1 * KK, src + o1, list_feat + o1, gy_all,          \
+        use_src ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc
+#define PARAM_LAUNCH(TH_, NS_)                                                                               \
+    DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, TH_, NS_><<<tgrid, tblock, 0, st>>>(PARAM_ARGS)))
+                // depth of pass B's TMA pipeline (boxes in flight + the one being consumed); deep pipelines
+                // only for the small tiles (static shared memory)
+                const int stages = getenv("NLSPN_PARAM_STAGES") ? atoi(getenv("NLSPN_PARAM_STAGES")) : kParamStages;
+                if (stages >= 4 && pth == 4) { PARAM_LAUNCH(4, 4); }
+                else if (stages == 3 && pth == 4) { PARAM_LAUNCH(4, 3); }
+                else if (stages >= 4 && pth == 8) { PARAM_LAUNCH(8, 4); }
+                else if (stages == 3 && pth == 8) { PARAM_LAUNCH(8, 3); }
+                else { DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, THC, 2><<<tgrid, tblock, 0, st>>>(PARAM_ARGS)))); }
+#undef PARAM_ARGS
+#undef PARAM_LAUNCH
                 NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
             } else {
                 DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
