@@ -111,3 +111,56 @@ def test_full_size_kitti_forward_against_reference_cuda_kernels(ref):
                           mod.aff_scale_const.detach(), 3, 18)
     assert torch.equal(offset, r["offset"])
     assert (torch.stack(list_feat) - torch.stack(r["list_feat"])).abs().max() <= 1e-4
+
+
+def test_randomized_sweep_against_reference_cuda_kernels(ref):
+    """24 seeded random configurations -- ragged sizes (W % 4 != 0 takes the non-TMA kernels, H not a
+    multiple of the tile), K in {3,5,7}, every affinity mode, confidence / preserve_input / always_clip on
+    and off, large offsets (footprints leaving the TMA box) -- forward states and all gradients against the
+    reference's own CUDA kernels."""
+    import random
+    from nlspn_eccv20_b200 import NLSPN
+    from nlspn_eccv20_b200.synth import make_inputs
+    dev = torch.device("cuda:0")
+    rnd = random.Random(20201018)
+    for case in range(24):
+        K = rnd.choice([3, 3, 3, 5, 5, 7])
+        T = rnd.randint(1, 8) if K < 7 else rnd.randint(1, 3)
+        B = rnd.randint(1, 3)
+        H, W = rnd.randint(9, 70), rnd.randint(9, 150)
+        if case % 3 == 0:
+            W = (W // 4) * 4 + 4                       # TMA-tiled path
+        affinity = rnd.choice(["TGASS", "TGASS", "ASS", "AS", "TC"])
+        use_conf, preserve, clip = rnd.random() < 0.7, rnd.random() < 0.7, rnd.random() < 0.3
+        sigma = rnd.choice([0.5, 2.0, 2.0, 6.0])
+        d = make_inputs(B, H, W, K, max_depth=10.0, seed=1000 + case, conf_mean=3.0, off_sigma=sigma,
+                        num_sample=max(1, H * W // 40), device=dev)
+        N = K * K - 1
+        mod = NLSPN(prop_kernel=K, prop_time=T, affinity=affinity, conf_prop=use_conf,
+                    preserve_input=preserve, always_clip=clip).to(dev)
+        g_out = torch.randn(T, B, 1, H, W, generator=torch.Generator().manual_seed(case)).to(dev)
+        leaves = lambda: [d[k].clone().requires_grad_(True) for k in ("feat_init", "guidance", "confidence")]
+        fi, gd, cf = leaves()
+        out = mod(fi, gd, cf if use_conf else None, d["feat_fix"] if preserve else None)
+        torch.autograd.backward(out[1], [g_out[t] for t in range(T)])
+        fi2, gd2, cf2 = leaves()
+        gam = mod.aff_scale_const.detach().clone().requires_grad_(affinity == "TGASS")
+        r = ref.propagate(fi2, gd2, cf2 if use_conf else None, d["feat_fix"] if preserve else None, gam, K, T,
+                          affinity=affinity, preserve_input=preserve, always_clip=clip)
+        torch.autograd.backward(r["list_feat"], [g_out[t] for t in range(T)])
+        tag = "case %d: K=%d T=%d B=%d %dx%d %s conf=%s preserve=%s clip=%s sigma=%.1f" % (
+            case, K, T, B, H, W, affinity, use_conf, preserve, clip, sigma)
+        assert torch.equal(out[2], r["offset"]), tag
+        lf, lr = torch.stack(out[1]), torch.stack(r["list_feat"])
+        scale = float(lr.abs().max().clamp_min(1.0))
+        assert float((lf - lr).abs().max()) <= 1e-5 * scale, tag
+        assert _rel(fi.grad, fi2.grad) < 1e-4, tag
+        if use_conf:
+            assert _rel(cf.grad, cf2.grad) < 1e-4, tag
+        assert _rel(gd.grad[:, 2 * N:], gd2.grad[:, 2 * N:]) < 2e-4, tag
+        if affinity == "TGASS":
+            rg = float(gam.grad)
+            assert abs(float(mod.aff_scale_const.grad) - rg) <= 2e-4 * max(abs(rg), 1e-6), tag
+        dd = (gd.grad[:, :2 * N] - gd2.grad[:, :2 * N]).abs()
+        s = gd2.grad[:, :2 * N].abs().max().clamp_min(1e-30)
+        assert float((dd > 1e-4 * s).float().mean()) < 2e-3, tag
