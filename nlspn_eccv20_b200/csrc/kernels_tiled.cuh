@@ -394,7 +394,7 @@ bwd_state_tma_kernel(const __grid_constant__ CUtensorMap off_map, const __grid_c
                      int b0, const float *__restrict__ conf, const float *__restrict__ dep,
                      const float *__restrict__ x_t, const float *__restrict__ g_ext, float *__restrict__ s_in,
                      float *__restrict__ s_out, float *__restrict__ gy_out, float *__restrict__ g_conf_acc,
-                     unsigned flags, int H, int W)
+                     unsigned flags, int H, int W, float *__restrict__ s_zero)
 {
     using G = Geo<K>;
     __shared__ __align__(128) float s_off[2 * G::KK][TH][kTileW];
@@ -442,6 +442,10 @@ bwd_state_tma_kernel(const __grid_constant__ CUtensorMap off_map, const __grid_c
         }
         if (si && conf) gca = g_conf_acc[q];
     }
+    if (s_zero)   // three-set rotation: clear the set iteration t+1 consumed, linearly (see zero_set_linear)
+        zero_set_linear(s_zero + (long)b * sg.image, sg.image / 4,
+                        ((long)blockIdx.y * gridDim.x + blockIdx.x) * (kTileW * TH) + tid,
+                        (long)gridDim.x * gridDim.y * (kTileW * TH));
     tma::mbar_wait(&bar, 0);
     if (!inside) return;
 
@@ -455,11 +459,11 @@ bwd_state_tma_kernel(const __grid_constant__ CUtensorMap off_map, const __grid_c
         if (flags & kPreserve) Gx = (1.0f - (dp > 0.f ? 1.f : 0.f)) * Gx;
     }
     const float gy = Gx;
-    if (si) {
+    if (si && !s_zero) {
 #pragma unroll
         for (int ph = 0; ph < 4; ++ph) si[cell[ph]] = 0.f;
-        if (conf) g_conf_acc[q] = gca + xt * gs;
     }
+    if (si && conf) g_conf_acc[q] = gca + xt * gs;
     gy_out[q] = gy;
     if (gy == 0.f) return;
 

@@ -44,22 +44,39 @@ __device__ __forceinline__ float ld_geo(const float *p)
     return STREAM ? __ldcs(p) : __ldg(p);
 }
 
+// Zeroing of the scatter planes.  Two sets (s_zero == nullptr): every thread clears the four cells it just
+// read -- four 4-byte stores that fill half of each 32-byte sector they touch (1 sector per pixel on the
+// SM->L2 write port, which is the port the REDs saturate).  Three sets (s_zero != nullptr): the set that
+// iteration t+1 consumed is cleared LINEARLY with one 16-byte store per thread (0.5 sector per pixel)
+// while this iteration reads the second set and scatters into the third.
+__device__ __forceinline__ void zero_set_linear(float *__restrict__ set_img, long n4, long i0, long stride)
+{
+    float4 *p = reinterpret_cast<float4 *>(set_img);
+    for (long i = i0; i < n4; i += stride) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 template <int K, bool STREAM, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff,
                  const float *__restrict__ conf, const float *__restrict__ dep,
                  const float *__restrict__ x_t, const float *__restrict__ g_ext,
                  float *__restrict__ s_in, float *__restrict__ s_out, float *__restrict__ gy_out,
-                 float *__restrict__ g_conf_acc, unsigned flags, int H, int W)
+                 float *__restrict__ g_conf_acc, unsigned flags, int H, int W, float *__restrict__ s_zero)
 {
     using G = Geo<K>;
     const int P = H * W;
     const int r = blockIdx.x * kBlock + threadIdx.x;
-    if (r >= P) return;
     const long b = blockIdx.y;
+    const ScatterGeo sg = scatter_geo(H, W);
+    if (r >= P) {   // tail threads only help clearing the third set
+        if (s_zero) {
+            tma::grid_dependency_wait();
+            zero_set_linear(s_zero + b * sg.image, sg.image / 4, r, (long)gridDim.x * kBlock);
+        }
+        return;
+    }
     const long q = b * P + r;
     const int h = r / W, w = r - h * W;
-    const ScatterGeo sg = scatter_geo(H, W);
 
     // ---- stage 1: issue EVERY load before the first store, so one memory round trip covers
     // the streamed geometry, the four scatter cells and the per-pixel planes.
@@ -106,11 +123,13 @@ bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff
     const float gy = Gx;
 
     // ---- stage 3: plain stores
-    if (si) {
+    if (s_zero) {
+        zero_set_linear(s_zero + b * sg.image, sg.image / 4, r, (long)gridDim.x * kBlock);
+    } else if (si) {
 #pragma unroll
         for (int ph = 0; ph < 4; ++ph) si[cell[ph]] = 0.f;
-        if (conf) g_conf_acc[q] = gca + xt * gs;
     }
+    if (si && conf) g_conf_acc[q] = gca + xt * gs;
     gy_out[q] = gy;
     if (gy == 0.f) return; // fixed pixels (and exact zeros) contribute nothing to the scatter
 

@@ -573,9 +573,9 @@ static size_t ws_bytes_v2(int B, int H, int W, int K, int T)
 {
     const size_t BP = (size_t)B * H * W;
     const ScatterGeo sg = scatter_geo(H, W);
-    // two sets of four phase planes + confidence-gradient accumulator + gy for every iteration
-    // + raw affinity-gradient accumulator (sized for the whole batch; a group uses a prefix)
-    return sizeof(float) * (2 * (size_t)B * sg.image + BP + (size_t)T * BP + (size_t)K * K * BP);
+    // three sets of four phase planes (read / scatter / being cleared) + confidence-gradient accumulator
+    // + gy for every iteration + raw affinity-gradient accumulator (whole batch; a group uses a prefix)
+    return sizeof(float) * (3 * (size_t)B * sg.image + BP + (size_t)T * BP + (size_t)K * K * BP);
 }
 
 size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T)
@@ -723,21 +723,28 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         if (int rc = make_geometry_map(&off_map, offset, B, 2 * KK, H, W, kStateTH)) return rc;
         if (int rc = make_geometry_map(&aff_map, aff, B, KK, H, W, kStateTH)) return rc;
     }
-    float *setA = ws, *setB = setA + (long)G * sg.image;
-    float *g_conf_acc = setB + (long)G * sg.image;
+    // scatter-plane sets rotate over three buffers so that clearing is a linear 16-byte-per-thread job
+    // (NLSPN_STATE_ZERO3=0: two sets, every thread clears the four cells it read)
+    const bool zero3 = !(getenv("NLSPN_STATE_ZERO3") && atoi(getenv("NLSPN_STATE_ZERO3")) == 0);
+    float *sets[3] = {ws, ws + (long)G * sg.image, ws + 2 * (long)G * sg.image};
+    float *g_conf_acc = sets[2] + (long)G * sg.image;
     float *gy_all = g_conf_acc + (long)G * P;          // [T, G, P]
     float *g_aff_acc = gy_all + (long)T * G * P;       // [G, KK, P]
     for (int b0 = 0; b0 < B; b0 += G) {
         const int nb = B - b0 < G ? B - b0 : G;
         const long o1 = (long)b0 * P;
         const long GP = (long)nb * P;                   // gy planes of this group are [T, nb, P]
-        e = cudaMemsetAsync(setA, 0, sizeof(float) * (2 * (size_t)G * sg.image + (size_t)G * P), st);
+        e = cudaMemsetAsync(sets[0], 0, sizeof(float) * (3 * (size_t)G * sg.image + (size_t)G * P), st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
         const float *cf = conf_fixed ? conf_fixed + o1 : nullptr;
         const float *fx = feat_fix ? feat_fix + o1 : nullptr;
+        const int nset = zero3 ? 3 : 2;
         for (int t = T; t >= 1; --t) {
-            float *s_out = ((T - t) % 2 == 0) ? setA : setB;
-            float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? setB : setA);
+            const int io = (T - t) % nset;
+            float *s_out = sets[io];
+            float *s_in = t == T ? nullptr : sets[(io + nset - 1) % nset];
+            // the set iteration t+1 read becomes iteration t-1's target: this launch clears it
+            float *s_zero = (zero3 && t < T && t > 1) ? sets[(io + 1) % 3] : nullptr;
             ProfScope prof__(kProfBwdState, st);
             const float *xt = list_feat + (long)(t - 1) * BP + o1;
             const float *ge = g_list[t - 1] ? g_list[t - 1] + o1 : nullptr;
@@ -745,15 +752,15 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
 #define STATE_LAUNCH(SH_, MB_)                                                                          \
     DISPATCH_K(K, (launch_pdl(bwd_state_kernel<KC, SH_, MB_>, grid_for(P, nb), dim3(kBlock), st,           \
                               offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, xt, ge, s_in, s_out, gyo,       \
-                              g_conf_acc, flags, H, W)))
+                              g_conf_acc, flags, H, W, s_zero)))
             if (state_tma) {
                 dim3 sgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + kStateTH - 1) / kStateTH), (unsigned)nb);
                 if (K == 3) {
                     e = launch_pdl(bwd_state_tma_kernel<3, kStateTH>, sgrid, dim3(kTileW, kStateTH), st, off_map,
-                                   aff_map, b0, cf, fx, xt, ge, s_in, s_out, gyo, g_conf_acc, flags, H, W);
+                                   aff_map, b0, cf, fx, xt, ge, s_in, s_out, gyo, g_conf_acc, flags, H, W, s_zero);
                 } else {
                     e = launch_pdl(bwd_state_tma_kernel<5, kStateTH>, sgrid, dim3(kTileW, kStateTH), st, off_map,
-                                   aff_map, b0, cf, fx, xt, ge, s_in, s_out, gyo, g_conf_acc, flags, H, W);
+                                   aff_map, b0, cf, fx, xt, ge, s_in, s_out, gyo, g_conf_acc, flags, H, W, s_zero);
                 }
                 if (e != cudaSuccess) return cuda_fail(e, "bwd_state_tma_kernel");
             } else if (stream_hint) {
@@ -774,7 +781,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
 #undef STATE_LAUNCH
             NLSPN_CHECK_LAUNCH("bwd_state_kernel");
         }
-        const float *s_last = ((T - 1) % 2 == 0) ? setA : setB;
+        const float *s_last = sets[(T - 1) % nset];
         {
             constexpr int C = 9;
             const int nch = (KK + C - 1) / C;
