@@ -13,7 +13,7 @@ does not, so the two thin Python layers above them are restated here:
                           oracle/torchvision_port.py (pinned against the unmodified reference by
                           tests/test_oracle_golden.py), device-aware.
 
-Only tests/ and tools/ref_cuda_bench.py may import this; the product never does.
+Only tests/ and tests/perf_reference_cuda.py may import this; the product never does.
 """
 from __future__ import annotations
 

@@ -3,8 +3,8 @@
 random-init, NYUv2 228x304, batch 12 per GPU, stock DDP + SyncBatchNorm over NCCL (the reference
 uses apex DDP + apex SyncBN at opt level O0 = fp32, main.py:133-153), Adam (utility.py:50-73).
 
-    python tools/config4_train_step.py                       # 1 GPU
-    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/config4_train_step.py
+    python tests/perf_config4_train_step.py                       # 1 GPU
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/perf_config4_train_step.py
 
 Prints one JSON line (rank 0): step time (CUDA events, max over ranks), images/s, and the
 propagation's share of the step, for `--prop ours` (fused op) and -- when oracle/_ref/DCN_ref.so is
@@ -16,7 +16,7 @@ import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402

@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """GPU-vs-GPU: the reference propagation (its own DCNv2 CUDA kernels, oracle/_ref/DCN_ref.so, under
 the reference's Python op chain restated in oracle/ref_cuda.py) timed on the same B200 next to
-ours, same inputs, same metric.  Test/measurement infrastructure, not the product and not bench.py's
+ours, same inputs, same metric.  Test/measurement infrastructure (lives under tests/ because it executes oracle/), not the product and not bench.py's
 contract arm (that one is the CPU implementation).
 
-    python tools/ref_cuda_bench.py [--workload kitti|nyu] [--batch B] [--kernel K] [--iters T] [--mode fwdbwd|fwd]
+    python tests/perf_reference_cuda.py [--workload kitti|nyu] [--batch B] [--kernel K] [--iters T] [--mode fwdbwd|fwd]
 prints one JSON line.
 """
 import argparse
@@ -12,7 +12,7 @@ import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 

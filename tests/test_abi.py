@@ -108,3 +108,19 @@ def test_cpu_tensors_are_rejected():
     assert list(m.state_dict().keys()) == ["aff_scale_const", "w", "b", "w_conf"]
     assert float(m.aff_scale_const) == 4.0 and m.aff_scale_const.requires_grad
     assert not m.w.requires_grad and tuple(m.w.shape) == (1, 1, 3, 3)
+
+
+def test_only_test_infrastructure_touches_the_oracle():
+    """tests/, __graft_entry__.py (build + smoke) and bench.py's CPU-baseline legs are the only places that
+    may import or execute oracle/ (the product, tools/ and everything else must not)."""
+    allowed = {os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")}
+    bad = []
+    for dp, dns, fs in os.walk(ROOT):
+        dns[:] = [d for d in dns if d not in (".git", "tests", "oracle", "gpurun_out", "__pycache__", "baseline", ".pytest_cache")]
+        for f in fs:
+            p = os.path.join(dp, f)
+            if f.endswith((".py", ".sh", ".cu", ".cuh", ".h")) and p not in allowed:
+                txt = open(p, errors="ignore").read()
+                if "import oracle" in txt or "from oracle" in txt or "liboracle" in txt or "oracle/_ref" in txt:
+                    bad.append(os.path.relpath(p, ROOT))
+    assert not bad, bad
