@@ -56,7 +56,7 @@ def parse():
                    help="forward-only runs: replay the module's forward from a CUDA graph (GraphedNLSPN)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-images", type=int, default=None, help="frames in the CPU sample (default: min(cores, 8))")
-    p.add_argument("--cpu-rows", type=int, default=48,
+    p.add_argument("--cpu-rows", type=int, default=176,
                    help="rows of each frame in the CPU sample (full width; bounds the CPU leg's run time)")
     return p.parse_args()
 
