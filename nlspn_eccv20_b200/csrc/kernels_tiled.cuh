@@ -196,8 +196,11 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
 //   SKIP  invalid (cuh:308-311: contributes nothing)
 // A warp whose lanes are all-FAST runs a branch-free loop.
 // ======================================================================================
+#ifndef NLSPN_PARAM_WARPS_PER_SM
+#define NLSPN_PARAM_WARPS_PER_SM 24   // 24 warps/SM -> <= 85 registers per thread (was 16 warps / 128 registers)
+#endif
 template <int K, int C, int TH, int NS = 2>
-__global__ void __launch_bounds__(kTileW * TH, (TH >= 16 ? 1 : 16 / TH))   // <= 128 registers
+__global__ void __launch_bounds__(kTileW * TH, (TH >= NLSPN_PARAM_WARPS_PER_SM ? 1 : NLSPN_PARAM_WARPS_PER_SM / TH))
 bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
                        const __grid_constant__ CUtensorMap list_map, int Bsrc, int b0,
                        const float *__restrict__ offset, const float *__restrict__ aff,
@@ -243,9 +246,11 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
     const long q = (long)b * P + r;
 
     // ---- per-tap geometry, computed once
+    // Register diet (24 warps per SM instead of 16): the coordinate weights (hl+1)-h and (wl+1)-w of
+    // cuh:101-122 are taken as 1-lh and 1-lw (identical up to one rounding of 2^-25), and the affinity
+    // factor of the offset gradients is applied once at the end (acc_h, acc_w sum gy*dh, gy*dw).
     int idx[C];                         // box index of the footprint's top-left corner (FAST taps)
-    float lh[C], lw[C], hl1[C], wl1[C]; // hl0 == lh, wl0 == lw (same expressions as cuh:101-122)
-    float av[C];
+    float lh[C], lw[C];
     float acc_h[C], acc_w[C], acc_a[C];
     unsigned slow_bits = 0u, skip_bits = 0u;
     constexpr int kCenterIdx = 0;
@@ -253,13 +258,12 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
     for (int c = 0; c < C; ++c) {
         const int k = k0 + c;
         idx[c] = kCenterIdx;
-        lh[c] = lw[c] = hl1[c] = wl1[c] = av[c] = 0.f;
+        lh[c] = lw[c] = 0.f;
         acc_h[c] = acc_w[c] = acc_a[c] = 0.f;
         if (!inside || k >= G::KK) {
             skip_bits |= 1u << c;
             continue;
         }
-        av[c] = __ldg(aff + ((long)b * G::KK + k) * P + r);
         if (k == G::REF) {
             idx[c] = (threadIdx.y + kHalo) * kBoxW + threadIdx.x + kHalo;
             continue;
@@ -276,8 +280,6 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
         const int hl = (int)hf, wl = (int)wf;
         lh[c] = h_im - hf;                       // == h_im - (float)hl
         lw[c] = w_im - wf;
-        hl1[c] = (float)(hl + 1) - h_im;
-        wl1[c] = (float)(wl + 1) - w_im;
         const int ty = hl - (y0 - kHalo), tx = wl - (x0 - kHalo);
         if ((unsigned)ty < (unsigned)(TG::BoxH - 1) && (unsigned)tx < (unsigned)(kBoxW - 1)) {
             idx[c] = ty * kBoxW + tx;
@@ -317,11 +319,10 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
                 const float hh = 1.f - lh[c], hw = 1.f - lw[c];
                 const float bil = (hh * hw) * v1 + (hh * lw[c]) * v2 + (lh[c] * hw) * v3 + (lh[c] * lw[c]) * v4;
                 acc_a[c] += gy * bil;                                            // cuh:314-315
-                const float top = gy * av[c];
-                const float dh = -1.f * wl1[c] * v1 + -1.f * lw[c] * v2 + wl1[c] * v3 + lw[c] * v4;
-                const float dw = -1.f * hl1[c] * v1 + hl1[c] * v2 + -1.f * lh[c] * v3 + lh[c] * v4;
-                acc_h[c] += dh * top;
-                acc_w[c] += dw * top;
+                const float dh = -1.f * hw * v1 + -1.f * lw[c] * v2 + hw * v3 + lw[c] * v4;
+                const float dw = -1.f * hh * v1 + hh * v2 + -1.f * lh[c] * v3 + lh[c] * v4;
+                acc_h[c] += dh * gy;
+                acc_w[c] += dw * gy;
             }
         } else if (gy != 0.f) {
             const float *im;
@@ -354,11 +355,10 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
                 const float hh = 1.f - lh[c], hw = 1.f - lw[c];
                 const float bil = (hh * hw) * v1 + (hh * lw[c]) * v2 + (lh[c] * hw) * v3 + (lh[c] * lw[c]) * v4;
                 acc_a[c] += gy * bil;
-                const float top = gy * av[c];
-                const float dh = -1.f * wl1[c] * v1 + -1.f * lw[c] * v2 + wl1[c] * v3 + lw[c] * v4;
-                const float dw = -1.f * hl1[c] * v1 + hl1[c] * v2 + -1.f * lh[c] * v3 + lh[c] * v4;
-                acc_h[c] += dh * top;
-                acc_w[c] += dw * top;
+                const float dh = -1.f * hw * v1 + -1.f * lw[c] * v2 + hw * v3 + lw[c] * v4;
+                const float dw = -1.f * hh * v1 + hh * v2 + -1.f * lh[c] * v3 + lh[c] * v4;
+                acc_h[c] += dh * gy;
+                acc_w[c] += dw * gy;
             }
         }
     }
@@ -372,8 +372,9 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
         gab[(long)k * P] = acc_a[c];
         if (k != G::REF) {
             const int n = k < G::REF ? k : k - 1;
-            ggb[(long)(2 * n) * P] = acc_h[c];
-            ggb[(long)(2 * n + 1) * P] = acc_w[c];
+            const float a = __ldg(aff + ((long)b * G::KK + k) * P + r);   // d/d offset carries the affinity
+            ggb[(long)(2 * n) * P] = acc_h[c] * a;
+            ggb[(long)(2 * n + 1) * P] = acc_w[c] * a;
         }
     }
 }
