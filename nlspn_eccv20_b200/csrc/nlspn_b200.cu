@@ -765,6 +765,8 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                 if (e != cudaSuccess) return cuda_fail(e, "bwd_state_tma_kernel");
             } else if (stream_hint) {
                 switch (state_minb) {
+                case 2: STATE_LAUNCH(true, 2); break;
+                case 3: STATE_LAUNCH(true, 3); break;
                 case 5: STATE_LAUNCH(true, 5); break;
                 case 6: STATE_LAUNCH(true, 6); break;
                 case 8: STATE_LAUNCH(true, 8); break;
@@ -772,6 +774,8 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                 }
             } else {
                 switch (state_minb) {
+                case 2: STATE_LAUNCH(false, 2); break;
+                case 3: STATE_LAUNCH(false, 3); break;
                 case 5: STATE_LAUNCH(false, 5); break;
                 case 6: STATE_LAUNCH(false, 6); break;
                 case 8: STATE_LAUNCH(false, 8); break;
