@@ -311,8 +311,12 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
                  const float *__restrict__ g_aff_ext, const float *__restrict__ gamma_ptr, int affinity,
                  unsigned flags, int H, int W, float *__restrict__ g_init, float *__restrict__ g_guidance,
                  float *__restrict__ g_conf, double *__restrict__ g_gamma,
-                 const float *__restrict__ conf_raw = nullptr)
+                 const float *__restrict__ conf_raw = nullptr, const float *__restrict__ gy_first = nullptr,
+                 const float *__restrict__ aff_norm = nullptr, const float *__restrict__ f_last = nullptr)
 {
+    // gy_first / aff_norm / f_last: the gather-form pass A (kernels_gather.cuh) keeps the centre tap and
+    // the overflowing taps out of the blocked planes; the consumer of the last planes adds
+    // gy_1[p] * aff_ref[p] and the overflow plane here.
     // conf_raw: only for kConfSampled (upstream conf_prop): the raw confidence the prologue sampled;
     // its gradient is SCATTERED into g_conf (zeroed by the host) with the bilinear corner weights.
     using G = Geo<K>;
@@ -336,6 +340,8 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         } else {
             gs = __ldg(s_in + q);
         }
+        if (f_last) gs += __ldg(f_last + q);
+        if (gy_first) gs += __ldg(gy_first + q) * __ldg(aff_norm + (b * G::KK + G::REF) * P + r);
         float x0 = __ldg(init + q);
         if (preserve) x0 = blend_fix(x0, d);
         const bool clipped = (flags & kAlwaysClip) && x0 < 0.f;

@@ -13,6 +13,7 @@
 #include "kernels_persist.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_f64.cuh"
+#include "kernels_gather.cuh"
 
 using namespace nlspn;
 
@@ -23,10 +24,11 @@ std::atomic<unsigned long long> g_launches{0};
 
 // ---- optional per-kernel-class timing (bench.py's roofline): CUDA events around every launch
 enum ProfClass { kProfPrologue = 0, kProfIterFwd, kProfBwdState, kProfBwdParam, kProfFinalBwd,
-                 kProfIterBwdV1, kProfDcnFwd, kProfDcnBwd, kProfClasses };
+                 kProfIterBwdV1, kProfDcnFwd, kProfDcnBwd, kProfBwdTable, kProfBwdGather, kProfClasses };
 const char *const kProfNames[kProfClasses] = {"prologue_fwd_kernel", "iter_fwd_kernel", "bwd_state_kernel",
                                               "bwd_param_kernel", "final_bwd_kernel", "iter_bwd_kernel",
-                                              "dcn_forward", "dcn_backward"};
+                                              "dcn_forward", "dcn_backward", "table_build_kernel",
+                                              "bwd_gather_kernel"};
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
 std::mutex g_prof_mu;
 std::atomic<int> g_prof_on{0};
@@ -310,6 +312,8 @@ static int make_geometry_map(CUtensorMap *map, const float *base, int B, int C, 
 }
 
 constexpr int kStateTH = 4;   // pass-A TMA tile: 32 x 4 pixels
+constexpr int kGatherMinT = 8;
+constexpr int kGatherMinK = 5;   // pass A: RED scatter for K = 3, tabulated gather for K >= 5 (measured, kernels_gather.cuh)
 constexpr int kParamStages = 2;   // pass-B TMA pipeline depth
 constexpr int kParamTH = 4;   // default pass-B tile: 32 x 4 pixels (B200 sweep: TH 4: 1.02, 8: 1.10, 16: 1.27 ms)
 
@@ -575,7 +579,13 @@ static size_t ws_bytes_v2(int B, int H, int W, int K, int T)
     const ScatterGeo sg = scatter_geo(H, W);
     // three sets of four phase planes (read / scatter / being cleared) + confidence-gradient accumulator
     // + gy for every iteration + raw affinity-gradient accumulator (whole batch; a group uses a prefix)
-    return sizeof(float) * (3 * (size_t)B * sg.image + BP + (size_t)T * BP + (size_t)K * K * BP);
+    const size_t red_form = sizeof(float) * (3 * (size_t)B * sg.image + BP + (size_t)T * BP + (size_t)K * K * BP);
+    // gather form (kernels_gather.cuh): entry table [cap][blocks] of 16 B + one set of planes + two overflow
+    // planes + block counters + per-pixel overflow masks (8 B reserved) + the accumulators above
+    const size_t NB = (size_t)B * sg.plane;
+    const size_t gather_form = 16 * (size_t)gather_cap(K) * 32 * (size_t)B * (size_t)table_groups(sg.plane) + sizeof(float) * ((size_t)B * sg.image + 2 * BP) +
+                               sizeof(int) * NB + 8 * BP + sizeof(float) * (BP + (size_t)T * BP + (size_t)K * K * BP) + 64;
+    return red_form > gather_form ? red_form : gather_form;
 }
 
 size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T)
@@ -723,6 +733,115 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         if (int rc = make_geometry_map(&off_map, offset, B, 2 * KK, H, W, kStateTH)) return rc;
         if (int rc = make_geometry_map(&aff_map, aff, B, KK, H, W, kStateTH)) return rc;
     }
+    // ---- pass A in gather form (kernels_gather.cuh): table built once, then per iteration an elementwise gy
+    // kernel and a gather-reduce kernel with plain stores.  Default for K >= 5; NLSPN_STATE_GATHER=0/1 overrides.
+    bool gather = K >= kGatherMinK && T >= kGatherMinT;   // the table build (once per call) must amortise
+    if (const char *ev = getenv("NLSPN_STATE_GATHER")) gather = atoi(ev) != 0;
+    if (H > 65535 || W > 65535) gather = false;      // table entries pack the source pixel as row << 16 | col
+    if (gather) {
+        const long NB = sg.plane;                       // blocks per image
+        const int cap = gather_cap(K);
+        float4 *entries = reinterpret_cast<float4 *>(ws);                     // [G][groups of 32 blocks][cap][32]
+        float *planes = reinterpret_cast<float *>(entries + (size_t)G * table_groups(NB) * cap * 32);   // [G][sg.image]
+        void *ovf = planes + (size_t)G * sg.image;                            // [G][P] masks, 8 B reserved each
+        int *count = reinterpret_cast<int *>(static_cast<char *>(ovf) + 8 * (size_t)G * P);   // [G][NB]
+        float *f0 = reinterpret_cast<float *>(count + (size_t)G * NB), *f1 = f0 + (size_t)G * P;
+        float *g_conf_acc = f1 + (size_t)G * P;
+        float *gy_all = g_conf_acc + (size_t)G * P;         // [T, G, P]
+        float *g_aff_acc = gy_all + (size_t)T * G * P;      // [G, KK, P]
+        for (int b0 = 0; b0 < B; b0 += G) {
+            const int nb = B - b0 < G ? B - b0 : G;
+            const long o1 = (long)b0 * P;
+            const long GP = (long)nb * P;
+            e = cudaMemsetAsync(f0, 0, sizeof(float) * 3 * (size_t)G * P, st);            // f0, f1, g_conf_acc
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+            e = cudaMemsetAsync(count, 0, sizeof(int) * (size_t)G * NB, st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(block counters)");
+            const float *cf = conf_fixed ? conf_fixed + o1 : nullptr;
+            const float *fx = feat_fix ? feat_fix + o1 : nullptr;
+            const float *off_g = offset + o1 * 2 * KK, *aff_g = aff + o1 * KK;
+            {
+                ProfScope prof__(kProfBwdTable, st);
+                DISPATCH_K(K, (table_build_kernel<KC><<<grid_for(P, nb), kBlock, 0, st>>>(
+                                  off_g, aff_g, H, W, count, entries,
+                                  static_cast<typename OvfMask<KC>::type *>(ovf))));
+                NLSPN_CHECK_LAUNCH("table_build_kernel");
+            }
+            const dim3 ggrid((unsigned)((NB + kBlock - 1) / kBlock), (unsigned)nb, 1);
+            for (int t = T; t >= 1; --t) {
+                const float *xt = list_feat + (long)(t - 1) * BP + o1;
+                const float *ge = g_list[t - 1] ? g_list[t - 1] + o1 : nullptr;
+                float *gyo = gy_all + (long)(t - 1) * GP;
+                const float *gyn = t < T ? gy_all + (long)t * GP : nullptr;
+                float *f_out = ((T - t) % 2 == 0) ? f0 : f1;
+                float *f_in = ((T - t) % 2 == 0) ? f1 : f0;
+                {
+                    ProfScope prof__(kProfBwdState, st);
+                    DISPATCH_K(K, (e = launch_pdl(bwd_gy_kernel<KC>, grid_for(P, nb), dim3(kBlock), st, off_g, aff_g, cf,
+                                                  fx, xt, ge, t < T ? (const float *)planes : (const float *)nullptr,
+                                                  f_in, f_out, gyn,
+                                                  static_cast<const typename OvfMask<KC>::type *>(ovf), gyo,
+                                                  g_conf_acc, flags, H, W)));
+                    if (e != cudaSuccess) return cuda_fail(e, "bwd_gy_kernel");
+                    NLSPN_CHECK_LAUNCH("bwd_gy_kernel");
+                }
+                {
+                    ProfScope prof__(kProfBwdGather, st);
+                    DISPATCH_K(K, (e = launch_pdl(bwd_gather_kernel<KC>, ggrid, dim3(kBlock), st, (const int *)count,
+                                                  (const float4 *)entries, (const float *)gyo, H, W,
+                                                  reinterpret_cast<float4 *>(planes))));
+                    if (e != cudaSuccess) return cuda_fail(e, "bwd_gather_kernel");
+                    NLSPN_CHECK_LAUNCH("bwd_gather_kernel");
+                }
+            }
+            const float *f_last = ((T - 1) % 2 == 0) ? f0 : f1;
+            {
+                constexpr int C = 9;
+                const int nch = (KK + C - 1) / C;
+                dim3 grid((unsigned)((P + kParamBlock - 1) / kParamBlock), (unsigned)nb, (unsigned)nch);
+                ProfScope prof__(kProfBwdParam, st);
+                if (use_tiled) {
+                    const int pth = param_tile_h();
+                    dim3 tgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + pth - 1) / pth),
+                               (unsigned)(nb * nch));
+                    dim3 tblock(kTileW, pth);
+                    DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, THC, 2><<<tgrid, tblock, 0, st>>>(
+                                      src_map, list_map, B, b0, off_g, aff_g, src + o1, list_feat + o1, gy_all,
+                                      use_src ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc))));
+                    NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
+                } else {
+                    DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
+                                      off_g, aff_g, src + o1, list_feat + o1, gy_all, use_src ? 1 : 0, H, W, T, BP, GP,
+                                      g_guidance + o1 * 3 * N, g_aff_acc)));
+                    NLSPN_CHECK_LAUNCH("bwd_param_kernel");
+                }
+            }
+            if (sampled) {
+                e = cudaMemsetAsync(g_confidence + o1, 0, sizeof(float) * (size_t)nb * P, st);
+                if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(g_confidence)");
+            }
+            ProfScope prof__(kProfFinalBwd, st);
+            if (sampled) {
+                DISPATCH_K(K, (final_bwd_kernel<KC, true, true><<<grid_for(P, nb), kBlock, 0, st>>>(
+                                  guidance + o1 * 3 * N, feat_init + o1, fx, cf, planes, g_aff_acc, g_conf_acc,
+                                  g_offset_ext ? g_offset_ext + o1 * 2 * KK : nullptr,
+                                  g_aff_ext ? g_aff_ext + o1 * KK : nullptr, gamma, affinity, flags, H, W,
+                                  g_feat_init + o1, g_guidance + o1 * 3 * N, g_confidence + o1, gamma_slots,
+                                  confidence + o1, gy_all, aff_g, f_last)));
+            } else {
+                DISPATCH_K(K, (final_bwd_kernel<KC, true, false><<<grid_for(P, nb), kBlock, 0, st>>>(
+                                  guidance + o1 * 3 * N, feat_init + o1, fx, cf, planes, g_aff_acc, g_conf_acc,
+                                  g_offset_ext ? g_offset_ext + o1 * 2 * KK : nullptr,
+                                  g_aff_ext ? g_aff_ext + o1 * KK : nullptr, gamma, affinity, flags, H, W,
+                                  g_feat_init + o1, g_guidance + o1 * 3 * N, g_confidence ? g_confidence + o1 : nullptr,
+                                  gamma_slots, nullptr, gy_all, aff_g, f_last)));
+            }
+            NLSPN_CHECK_LAUNCH("final_bwd_kernel");
+        }
+        gamma_reduce.armed = true;
+        return 0;
+    }
+
     // scatter-plane sets rotate over three buffers so that clearing is a linear 16-byte-per-thread job
     // (NLSPN_STATE_ZERO3=0: two sets, every thread clears the four cells it read)
     const bool zero3 = !(getenv("NLSPN_STATE_ZERO3") && atoi(getenv("NLSPN_STATE_ZERO3")) == 0);

@@ -281,11 +281,14 @@ def test_fused_path_equals_unfused_reference_statements(dev):
 
 
 @pytest.mark.parametrize("K,T,use_conf", [(3, 6, True), (5, 3, True), (3, 4, False), (7, 2, True)])
-def test_two_pass_backward_equals_per_iteration_backward(dev, K, T, use_conf):
-    """The default backward (pass A with REDx4 scatter + pass B in registers) against the
+@pytest.mark.parametrize("form", ["red", "gather"])
+def test_two_pass_backward_equals_per_iteration_backward(dev, monkeypatch, K, T, use_conf, form):
+    """Both forms of pass A -- the REDx4 scatter (kernels_v2.cuh; default for K = 3) and the tabulated
+    gather (kernels_gather.cuh; default for K >= 5) -- with pass B in registers, against the
     per-iteration formulation (accumulator RMW + scalar atomics) on the same saved tensors."""
     from nlspn_eccv20_b200 import functional as F_
     from nlspn_eccv20_b200.synth import make_inputs
+    monkeypatch.setenv("NLSPN_STATE_GATHER", "1" if form == "gather" else "0")
     B, H, W = 2, 38, 45
     inp = make_inputs(B, H, W, K, seed=77 + K, device=dev, conf_mean=2.0)
     gamma = 0.5 * (K * K - 1)
@@ -464,3 +467,37 @@ def test_cuda_graph_replay_is_bit_identical_to_eager(dev, shape, K):
         assert torch.equal(out[2], eager[2]) and torch.equal(out[3], eager[3])
     with pytest.raises(RuntimeError):
         g(a["feat_init"][:, :, :-1], a["guidance"][:, :, :-1], a["confidence"][:, :, :-1], a["feat_fix"][:, :, :-1])
+
+
+def test_gather_form_overflowing_blocks(dev, monkeypatch):
+    """Gather-form pass A with many footprints converging on the same 2x2 block (all taps of a whole region
+    point at one pixel: far more than CAP entries per block, so the overflow path carries most of the
+    gradient) against the RED-form pass A and the per-iteration backward."""
+    from nlspn_eccv20_b200 import functional as F_
+    from nlspn_eccv20_b200.synth import make_inputs
+    K, T, B, H, W = 3, 4, 1, 24, 32
+    inp = make_inputs(B, H, W, K, seed=5, device=dev, conf_mean=2.0)
+    gd = inp["guidance"].clone()
+    hh = torch.arange(H, device=dev).view(1, 1, H, 1).float()
+    ww = torch.arange(W, device=dev).view(1, 1, 1, W).float()
+    N = K * K - 1
+    for n in range(N):          # every tap of every pixel samples around pixel (10.3, 17.6)
+        t = n if n < N // 2 else n + 1
+        gd[:, 2 * n] = 10.3 - (hh - 1 + t // K)
+        gd[:, 2 * n + 1] = 17.6 - (ww - 1 + t % K)
+    gamma = 0.5 * N
+    offset, aff, cfx, src0 = F_.prologue_fwd(gd, inp["confidence"], inp["feat_init"], inp["feat_fix"], gamma, K)
+    src = torch.empty((T, B, 1, H, W), device=dev)
+    src[0].copy_(src0)
+    lf = torch.empty((T, B, 1, H, W), device=dev)
+    F_.propagate_fwd(offset, aff, cfx, inp["feat_fix"], src, lf, K, T)
+    g = torch.Generator().manual_seed(2)
+    g_list = [torch.randn(B, 1, H, W, generator=g).to(dev) for _ in range(T)]
+    args = (gd, inp["feat_init"], inp["feat_fix"], offset, aff, cfx, src, lf, g_list, gamma, K, T)
+    ref = F_.backward(*args, per_iteration=True)
+    for form in ("0", "1"):
+        monkeypatch.setenv("NLSPN_STATE_GATHER", form)
+        out = F_.backward(*args)
+        for x, y, name in zip(out, ref, ["g_init", "g_guidance", "g_conf", "g_gamma"]):
+            s = float(y.abs().max())
+            assert float((x - y).abs().max()) <= 5e-5 * max(s, 1e-20), (form, name)
