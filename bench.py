@@ -374,13 +374,19 @@ def main():
            "bwd_state_kernel": 12 * N + 40,
            "bwd_param_kernel": 8 * T + 24 * N + 8,
            "final_bwd_kernel": 8 * N + 4 * (N + 1) + 16 + 24,
-           "iter_bwd_kernel": 36 * N + 36}
+           "iter_bwd_kernel": 36 * N + 36,
+           # pass A in gather form (K >= 5): table entries 16 B x N + counter + one 16-byte block store;
+           # the gy kernel then moves ~53 B/px (bwd_state_kernel's class); table build once per step
+           "bwd_gather_kernel": 16 * N + 20,
+           "table_build_kernel": 12 * N + 16 * N + 4}
+    if "bwd_gather_kernel" in prof:
+        alg["bwd_state_kernel"] = 53
     fwd_names = ("prologue_fwd_kernel", "iter_fwd_kernel")
     phase_prof = {"forward": sum(prof[k][0] for k in prof if k in fwd_names),
                   "backward": sum(prof[k][0] for k in prof if k not in fwd_names)}
     kernels = {}
     nprof = max(1, min(args.steps, 3))
-    per_iter = ("iter_fwd_kernel", "bwd_state_kernel", "iter_bwd_kernel")
+    per_iter = ("iter_fwd_kernel", "bwd_state_kernel", "iter_bwd_kernel", "bwd_gather_kernel")
     for name, (ms, cnt) in prof.items():
         ph = "forward" if name in fwd_names else "backward"
         share = ms / phase_prof[ph] if phase_prof[ph] > 0 else 0.0
