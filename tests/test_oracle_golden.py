@@ -129,3 +129,52 @@ def test_torchvision_port_matches_reference(name):
             np.testing.assert_allclose(cf.grad.numpy(), g["out_g_confidence"], rtol=1e-5, atol=1e-7)
         if "out_g_gamma" in g and gam.grad is not None:
             np.testing.assert_allclose(gam.grad.numpy().reshape(-1), np.asarray(g["out_g_gamma"]).reshape(-1), rtol=1e-4)
+
+
+def test_torchvision_differs_from_the_reference_only_at_coordinate_minus_one(oracle):
+    """the reference returns a ZERO offset gradient when a sampling coordinate is <= -1
+    (modulated_deform_im2col_cuda.cuh:88-92,308-311); torchvision's CPU kernel uses a one-sided derivative at
+    exactly -1.  The C oracle follows the reference; the stand-in is corrected by the keep-mask of
+    oracle/torchvision_port.py.  This test pins both facts: the raw stand-in differs at exactly those
+    entries and nowhere else."""
+    import torch
+    import torchvision  # noqa: F401
+    from oracle import torchvision_port as TP
+    g = torch.Generator().manual_seed(4)
+    B, K, H, W = 2, 3, 7, 9
+    KK, pad = K * K, 1
+    x = torch.randn(B, 1, H, W, generator=g, dtype=torch.float64)
+    off = torch.round(3.0 * torch.randn(B, 2 * KK, H, W, generator=g, dtype=torch.float64))   # integer coordinates
+    off[:, :, 3:] += 0.37                                                                        # ... on the first rows only
+    msk = torch.randn(B, KK, H, W, generator=g, dtype=torch.float64)
+    w = torch.ones(1, 1, K, K, dtype=torch.float64)
+    b = torch.zeros(1, dtype=torch.float64)
+    gout = torch.randn(B, 1, H, W, generator=g, dtype=torch.float64)
+    _, _, go_raw, _, _ = torch.ops.torchvision._deform_conv2d_backward(gout, x, w, off, msk, b, 1, 1, pad, pad, 1, 1, 1, 1, True)
+    _, go_ref, _, _, _ = oracle.dcn_step_bwd(x.numpy(), off.numpy(), msk.numpy(), gout.numpy(), w.numpy(), want_wb=False)
+    keep = TP._keep_mask(off, K, pad).numpy()
+    diff = np.abs(go_raw.numpy() - go_ref) > 1e-12
+    assert diff.any(), "expected the stand-in to differ somewhere (coordinates of exactly -1 were planted)"
+    assert not (diff & (keep == 1)).any()                       # differences only where the reference zeroes
+    np.testing.assert_allclose(go_raw.numpy() * keep, go_ref, rtol=0, atol=1e-12)
+
+
+def test_oracle_known_answers_of_the_reference_dcn_test(oracle):
+    """deformconv/test.py:69-110 (zero offset, unit mask == plain convolution) and :142-181 (identity kernel,
+    zero offset == input) on the C oracle."""
+    import torch
+    g = torch.Generator().manual_seed(6)
+    for K in (3, 5):
+        x = torch.randn(2, 1, 11, 13, generator=g)
+        KK = K * K
+        off = torch.zeros(2, 2 * KK, 11, 13)
+        msk = torch.ones(2, KK, 11, 13)
+        w = torch.randn(1, 1, K, K, generator=g)
+        b = torch.randn(1, generator=g)
+        y = oracle.dcn_step_fwd(x.numpy(), off.numpy(), msk.numpy(), w.numpy(), b.numpy())
+        ref = torch.nn.functional.conv2d(x, w, b, padding=(K - 1) // 2).numpy()
+        np.testing.assert_allclose(y, ref, rtol=0, atol=2e-6)
+        ident = torch.zeros(1, 1, K, K)
+        ident[0, 0, K // 2, K // 2] = 1.0
+        y = oracle.dcn_step_fwd(x.numpy(), off.numpy(), msk.numpy(), ident.numpy(), np.zeros(1, np.float32))
+        assert np.array_equal(y, x.numpy())
