@@ -156,7 +156,11 @@ NLSPN_API int nlspn_forward(const float *guidance, const float *confidence, cons
  * `src` must be the S = T array written by the forward (S = 1 without confidence).
  * Gradient wrt feat_fix is not produced (mask_fix is detached, nlspnmodel.py:330).
  * The scatter uses fp32 atomics: summation order, hence the last bits, vary run to run,
- * as in the reference (deformconv/test.py:627-631). */
+ * as in the reference (deformconv/test.py:627-631).
+ * Workspace: query with the same (B, H, W, K, T) -- and the same environment -- as the call.  The size
+ * depends on the form the state-gradient pass takes: RED scatter (K = 3, or T < 8): three sets of blocked
+ * planes, ~0.55 GB at KITTI B = 8, K = 3, T = 18; tabulated gather (K >= 5 and T >= 8): a table of
+ * 16 B x CAP(K) x blocks, ~3.2 GB at K = 5 and ~4.9 GB at K = 7 for the same batch. */
 NLSPN_API size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T);
 NLSPN_API int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
                    const float *confidence, const float *offset, const float *aff, const float *conf_fixed,

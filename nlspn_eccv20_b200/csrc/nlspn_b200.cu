@@ -312,8 +312,6 @@ static int make_geometry_map(CUtensorMap *map, const float *base, int B, int C, 
 }
 
 constexpr int kStateTH = 4;   // pass-A TMA tile: 32 x 4 pixels
-constexpr int kGatherMinT = 8;
-constexpr int kGatherMinK = 5;   // pass A: RED scatter for K = 3, tabulated gather for K >= 5 (measured, kernels_gather.cuh)
 constexpr int kParamStages = 2;   // pass-B TMA pipeline depth
 constexpr int kParamTH = 4;   // default pass-B tile: 32 x 4 pixels (B200 sweep: TH 4: 1.02, 8: 1.10, 16: 1.27 ms)
 
@@ -573,6 +571,18 @@ static size_t ws_bytes_v1(int B, int H, int W, int K)
     return sizeof(float) * (3 * BP + (size_t)K * K * BP);
 }
 
+constexpr int kGatherMinT = 8;
+constexpr int kGatherMinK = 5;   // pass A: RED scatter for K = 3, tabulated gather for K >= 5 (measured, kernels_gather.cuh)
+
+// Which form of pass A a backward call with this shape takes (the workspace query must agree with the call).
+static bool gather_form_selected(int H, int W, int K, int T)
+{
+    bool gather = K >= kGatherMinK && T >= kGatherMinT;   // the table build (once per call) must amortise
+    if (const char *ev = getenv("NLSPN_STATE_GATHER")) gather = atoi(ev) != 0;
+    if (H > 65535 || W > 65535) gather = false;           // table entries pack the source pixel as row << 16 | col
+    return gather;
+}
+
 static size_t ws_bytes_v2(int B, int H, int W, int K, int T)
 {
     const size_t BP = (size_t)B * H * W;
@@ -585,7 +595,7 @@ static size_t ws_bytes_v2(int B, int H, int W, int K, int T)
     const size_t NB = (size_t)B * sg.plane;
     const size_t gather_form = 16 * (size_t)gather_cap(K) * 32 * (size_t)B * (size_t)table_groups(sg.plane) + sizeof(float) * ((size_t)B * sg.image + 2 * BP) +
                                sizeof(int) * NB + 8 * BP + sizeof(float) * (BP + (size_t)T * BP + (size_t)K * K * BP) + 64;
-    return red_form > gather_form ? red_form : gather_form;
+    return gather_form_selected(H, W, K, T) ? gather_form : red_form;
 }
 
 size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T)
@@ -735,9 +745,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     }
     // ---- pass A in gather form (kernels_gather.cuh): table built once, then per iteration an elementwise gy
     // kernel and a gather-reduce kernel with plain stores.  Default for K >= 5; NLSPN_STATE_GATHER=0/1 overrides.
-    bool gather = K >= kGatherMinK && T >= kGatherMinT;   // the table build (once per call) must amortise
-    if (const char *ev = getenv("NLSPN_STATE_GATHER")) gather = atoi(ev) != 0;
-    if (H > 65535 || W > 65535) gather = false;      // table entries pack the source pixel as row << 16 | col
+    const bool gather = gather_form_selected(H, W, K, T);
     if (gather) {
         const long NB = sg.plane;                       // blocks per image
         const int cap = gather_cap(K);
