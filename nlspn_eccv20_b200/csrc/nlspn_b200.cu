@@ -571,6 +571,9 @@ static size_t ws_bytes_v1(int B, int H, int W, int K)
     return sizeof(float) * (3 * BP + (size_t)K * K * BP);
 }
 
+// taps per pass-B chunk: K = 3 one chunk of 9; K = 5 five chunks of 5 (B200, KITTI B=8, T=36: C = 5 / 7 / 9 / 13
+// -> 5.01 / 5.69 / 5.30 / 6.86 ms); K = 7 six chunks of 9
+constexpr int param_chunk(int K) { return K == 5 ? 5 : 9; }
 constexpr int kGatherMinT = 8;
 constexpr int kGatherMinK = 5;   // pass A: RED scatter for K = 3, tabulated gather for K >= 5 (measured, kernels_gather.cuh)
 
@@ -804,8 +807,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             }
             const float *f_last = ((T - 1) % 2 == 0) ? f0 : f1;
             {
-                constexpr int C = 9;
-                const int nch = (KK + C - 1) / C;
+                const int nch = (KK + param_chunk(K) - 1) / param_chunk(K);
                 dim3 grid((unsigned)((P + kParamBlock - 1) / kParamBlock), (unsigned)nb, (unsigned)nch);
                 ProfScope prof__(kProfBwdParam, st);
                 if (use_tiled) {
@@ -813,12 +815,12 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                     dim3 tgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + pth - 1) / pth),
                                (unsigned)(nb * nch));
                     dim3 tblock(kTileW, pth);
-                    DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, THC, 2><<<tgrid, tblock, 0, st>>>(
+                    DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, param_chunk(KC), THC, 2><<<tgrid, tblock, 0, st>>>(
                                       src_map, list_map, B, b0, off_g, aff_g, src + o1, list_feat + o1, gy_all,
                                       use_src ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc))));
                     NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
                 } else {
-                    DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
+                    DISPATCH_K(K, (bwd_param_kernel<KC, param_chunk(KC)><<<grid, kParamBlock, 0, st>>>(
                                       off_g, aff_g, src + o1, list_feat + o1, gy_all, use_src ? 1 : 0, H, W, T, BP, GP,
                                       g_guidance + o1 * 3 * N, g_aff_acc)));
                     NLSPN_CHECK_LAUNCH("bwd_param_kernel");
@@ -914,8 +916,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         }
         const float *s_last = sets[(T - 1) % nset];
         {
-            constexpr int C = 9;
-            const int nch = (KK + C - 1) / C;
+            const int nch = (KK + param_chunk(K) - 1) / param_chunk(K);
             dim3 grid((unsigned)((P + kParamBlock - 1) / kParamBlock), (unsigned)nb, (unsigned)nch);
             ProfScope prof__(kProfBwdParam, st);
             if (use_tiled) {
@@ -927,7 +928,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     src_map, list_map, B, b0, offset + o1 * 2 * KK, aff + o1 * KK, src + o1, list_feat + o1, gy_all,          \
         use_src ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc
 #define PARAM_LAUNCH(TH_, NS_)                                                                               \
-    DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, TH_, NS_><<<tgrid, tblock, 0, st>>>(PARAM_ARGS)))
+    DISPATCH_K(K, (bwd_param_tiled_kernel<KC, param_chunk(KC), TH_, NS_><<<tgrid, tblock, 0, st>>>(PARAM_ARGS)))
                 // depth of pass B's TMA pipeline (boxes in flight + the one being consumed); deep pipelines
                 // only for the small tiles (static shared memory)
                 const int stages = getenv("NLSPN_PARAM_STAGES") ? atoi(getenv("NLSPN_PARAM_STAGES")) : kParamStages;
@@ -935,12 +936,12 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                 else if (stages == 3 && pth == 4) { PARAM_LAUNCH(4, 3); }
                 else if (stages >= 4 && pth == 8) { PARAM_LAUNCH(8, 4); }
                 else if (stages == 3 && pth == 8) { PARAM_LAUNCH(8, 3); }
-                else { DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, C, THC, 2><<<tgrid, tblock, 0, st>>>(PARAM_ARGS)))); }
+                else { DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, param_chunk(KC), THC, 2><<<tgrid, tblock, 0, st>>>(PARAM_ARGS)))); }
 #undef PARAM_ARGS
 #undef PARAM_LAUNCH
                 NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
             } else {
-                DISPATCH_K(K, (bwd_param_kernel<KC, C><<<grid, kParamBlock, 0, st>>>(
+                DISPATCH_K(K, (bwd_param_kernel<KC, param_chunk(KC)><<<grid, kParamBlock, 0, st>>>(
                                   offset + o1 * 2 * KK, aff + o1 * KK, src + o1, list_feat + o1, gy_all,
                                   use_src ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc)));
                 NLSPN_CHECK_LAUNCH("bwd_param_kernel");
