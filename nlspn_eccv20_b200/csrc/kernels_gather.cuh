@@ -80,7 +80,7 @@ table_build_kernel(const float *__restrict__ offset, const float *__restrict__ a
     const int blocks_per_phase = sg.Hb * sg.Wb;
     const float *ob = offset + b * 2 * G::KK * P + r;
     const float *ab = aff + b * G::KK * P + r;
-    int *cnt = count + b * NB;
+    int *cnt = count + b * table_groups(NB) * 32;          // counters are padded to whole groups
     float4 *ent = entries + b * table_groups(NB) * CAP * 32;
     M mask = 0;
 #pragma unroll
@@ -107,6 +107,52 @@ table_build_kernel(const float *__restrict__ offset, const float *__restrict__ a
             mask |= (M)1 << n;
     }
     ovf[b * P + r] = mask;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Table compaction: one warp per group of 32 blocks, once per call, after the build.
+// Past the mean occupancy a table row is only partly used, and which of its 32 columns are used is
+// random, so the readers touch most 64-byte DRAM chunks of a row for half the bytes.  Here the group's
+// columns are permuted by descending entry count: every row's live entries become a PREFIX of the row.
+// count[] is rewritten in column order and owner[] maps a column back to its block (-1: padding).
+//   grid = (ceil(groups / 8), nb), block = 256 (8 warps).
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+table_compact_kernel(int H, int W, int *__restrict__ count, float4 *__restrict__ entries, int *__restrict__ owner)
+{
+    constexpr int CAP = gather_cap(K);
+    const ScatterGeo sg = scatter_geo(H, W);
+    const long NB = sg.plane;
+    const long groups = table_groups(NB);
+    const long g = (long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    if (g >= groups) return;
+    const int lane = threadIdx.x & 31;
+    const long b = blockIdx.y;
+    const long blk = g * 32 + lane;
+    int *cnt = count + b * groups * 32 + g * 32;
+    int n = cnt[lane];
+    n = n < CAP ? n : CAP;
+    if (blk >= NB) n = 0;
+    // rank of this column in descending count order (stable)
+    int r = 0, nmax = 0;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        const int v = __shfl_sync(0xffffffffu, n, o);
+        r += (v > n || (v == n && o < lane)) ? 1 : 0;
+        nmax = v > nmax ? v : nmax;
+    }
+    float4 *ent = entries + (b * groups + g) * CAP * 32;
+    for (int j = 0; j < nmax; ++j) {
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < n) e = ent[j * 32 + lane];
+        __syncwarp();
+        if (j < n) ent[j * 32 + r] = e;
+        __syncwarp();
+    }
+    __syncwarp();
+    cnt[r] = n;
+    owner[b * groups * 32 + g * 32 + r] = blk < NB ? (int)blk : -1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,23 +247,28 @@ bwd_gy_kernel(const float *__restrict__ offset, const float *__restrict__ aff,
 // ---------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(kBlock)
-bwd_gather_kernel(const int *__restrict__ count, const float4 *__restrict__ entries,
-                  const float *__restrict__ gy, int H, int W, float4 *__restrict__ s_out)
+bwd_gather_kernel(const int *__restrict__ count, const int *__restrict__ owner,
+                  const float4 *__restrict__ entries, const float *__restrict__ gy, int H, int W,
+                  float4 *__restrict__ s_out)
 {
     constexpr int CAP = gather_cap(K);
     constexpr int U = NLSPN_GATHER_U;         // entries in flight per thread and trip
     const int P = H * W;
     const ScatterGeo sg = scatter_geo(H, W);
     const long NB = sg.plane;
+    const long NBpad = table_groups(NB) * 32;      // thread i serves COLUMN i of the compacted table
     const long i = (long)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= NB) return;
+    if (i >= NBpad) return;
     const long b = blockIdx.y;
     tma::grid_launch_dependents();
+    // owner == nullptr: the table was not compacted (short runs), column i is block i
+    const int blk = owner ? __ldg(owner + b * NBpad + i) : (i < NB ? (int)i : -1);
+    if (blk < 0) return;
     // The table does not depend on the previous launch: its first U slots are fetched before waiting for gy.
     // (Fetching them unconditionally, in parallel with the counter, was measured and is slower: the kernel is
     // bound by table bytes, and slots past the counter are wasted traffic.)
     const float4 *ent = entries + b * table_groups(NB) * CAP * 32 + table_index<CAP>(i, 0);
-    int n = __ldg(count + b * NB + i);
+    int n = __ldg(count + b * NBpad + i);
     n = n < CAP ? n : CAP;
     float4 e[U];
 #pragma unroll
@@ -252,7 +303,7 @@ bwd_gather_kernel(const int *__restrict__ count, const float4 *__restrict__ entr
 #pragma unroll
         for (int u = 0; u < U; ++u) e[u] = nx[u];
     }
-    s_out[b * NB + i] = acc;
+    s_out[b * NB + blk] = acc;
 }
 
 } // namespace nlspn

@@ -575,6 +575,7 @@ static size_t ws_bytes_v1(int B, int H, int W, int K)
 // -> 5.01 / 5.69 / 5.30 / 6.86 ms); K = 7 six chunks of 9
 constexpr int param_chunk(int K) { return K == 5 ? 5 : 9; }
 constexpr int kGatherMinT = 8;
+constexpr int kCompactMinT = 24;   // table compaction pays off from about two dozen iterations
 constexpr int kGatherMinK = 5;   // pass A: RED scatter for K = 3, tabulated gather for K >= 5 (measured, kernels_gather.cuh)
 
 // Which form of pass A a backward call with this shape takes (the workspace query must agree with the call).
@@ -597,7 +598,8 @@ static size_t ws_bytes_v2(int B, int H, int W, int K, int T)
     // planes + block counters + per-pixel overflow masks (8 B reserved) + the accumulators above
     const size_t NB = (size_t)B * sg.plane;
     const size_t gather_form = 16 * (size_t)gather_cap(K) * 32 * (size_t)B * (size_t)table_groups(sg.plane) + sizeof(float) * ((size_t)B * sg.image + 2 * BP) +
-                               sizeof(int) * NB + 8 * BP + sizeof(float) * (BP + (size_t)T * BP + (size_t)K * K * BP) + 64;
+                               2 * sizeof(int) * 32 * (size_t)B * (size_t)table_groups(sg.plane) + 8 * BP +
+                               sizeof(float) * (BP + (size_t)T * BP + (size_t)K * K * BP) + 64;
     return gather_form_selected(H, W, K, T) ? gather_form : red_form;
 }
 
@@ -755,8 +757,11 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         float4 *entries = reinterpret_cast<float4 *>(ws);                     // [G][groups of 32 blocks][cap][32]
         float *planes = reinterpret_cast<float *>(entries + (size_t)G * table_groups(NB) * cap * 32);   // [G][sg.image]
         void *ovf = planes + (size_t)G * sg.image;                            // [G][P] masks, 8 B reserved each
-        int *count = reinterpret_cast<int *>(static_cast<char *>(ovf) + 8 * (size_t)G * P);   // [G][NB]
-        float *f0 = reinterpret_cast<float *>(count + (size_t)G * NB), *f1 = f0 + (size_t)G * P;
+        const long NBpad = table_groups(NB) * 32;
+        const bool compact = getenv("NLSPN_GATHER_COMPACT") ? atoi(getenv("NLSPN_GATHER_COMPACT")) != 0 : T >= kCompactMinT;
+        int *count = reinterpret_cast<int *>(static_cast<char *>(ovf) + 8 * (size_t)G * P);   // [G][NBpad]
+        int *owner = count + (size_t)G * NBpad;                                               // [G][NBpad]
+        float *f0 = reinterpret_cast<float *>(owner + (size_t)G * NBpad), *f1 = f0 + (size_t)G * P;
         float *g_conf_acc = f1 + (size_t)G * P;
         float *gy_all = g_conf_acc + (size_t)G * P;         // [T, G, P]
         float *g_aff_acc = gy_all + (size_t)T * G * P;      // [G, KK, P]
@@ -766,7 +771,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             const long GP = (long)nb * P;
             e = cudaMemsetAsync(f0, 0, sizeof(float) * 3 * (size_t)G * P, st);            // f0, f1, g_conf_acc
             if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
-            e = cudaMemsetAsync(count, 0, sizeof(int) * (size_t)G * NB, st);
+            e = cudaMemsetAsync(count, 0, sizeof(int) * (size_t)G * NBpad, st);
             if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(block counters)");
             const float *cf = conf_fixed ? conf_fixed + o1 : nullptr;
             const float *fx = feat_fix ? feat_fix + o1 : nullptr;
@@ -777,8 +782,15 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                                   off_g, aff_g, H, W, count, entries,
                                   static_cast<typename OvfMask<KC>::type *>(ovf))));
                 NLSPN_CHECK_LAUNCH("table_build_kernel");
+                // compaction (columns of a group sorted by entry count) costs about a third of the build and saves
+                // ~11 % of every gather launch: worth it for long runs (K=5, T=36: 26.6 -> 25.9 ms; K=7, T=12: loses)
+                if (compact) {
+                    const dim3 cgrid((unsigned)((table_groups(NB) + kBlock / 32 - 1) / (kBlock / 32)), (unsigned)nb, 1);
+                    DISPATCH_K(K, (table_compact_kernel<KC><<<cgrid, kBlock, 0, st>>>(H, W, count, entries, owner)));
+                    NLSPN_CHECK_LAUNCH("table_compact_kernel");
+                }
             }
-            const dim3 ggrid((unsigned)((NB + kBlock - 1) / kBlock), (unsigned)nb, 1);
+            const dim3 ggrid((unsigned)((NBpad + kBlock - 1) / kBlock), (unsigned)nb, 1);
             for (int t = T; t >= 1; --t) {
                 const float *xt = list_feat + (long)(t - 1) * BP + o1;
                 const float *ge = g_list[t - 1] ? g_list[t - 1] + o1 : nullptr;
@@ -799,6 +811,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                 {
                     ProfScope prof__(kProfBwdGather, st);
                     DISPATCH_K(K, (e = launch_pdl(bwd_gather_kernel<KC>, ggrid, dim3(kBlock), st, (const int *)count,
+                                                  compact ? (const int *)owner : (const int *)nullptr,
                                                   (const float4 *)entries, (const float *)gyo, H, W,
                                                   reinterpret_cast<float4 *>(planes))));
                     if (e != cudaSuccess) return cuda_fail(e, "bwd_gather_kernel");

@@ -281,14 +281,15 @@ def test_fused_path_equals_unfused_reference_statements(dev):
 
 
 @pytest.mark.parametrize("K,T,use_conf", [(3, 6, True), (5, 3, True), (3, 4, False), (7, 2, True)])
-@pytest.mark.parametrize("form", ["red", "gather"])
+@pytest.mark.parametrize("form", ["red", "gather", "gather-compact"])
 def test_two_pass_backward_equals_per_iteration_backward(dev, monkeypatch, K, T, use_conf, form):
     """Both forms of pass A -- the REDx4 scatter (kernels_v2.cuh; default for K = 3) and the tabulated
     gather (kernels_gather.cuh; default for K >= 5) -- with pass B in registers, against the
     per-iteration formulation (accumulator RMW + scalar atomics) on the same saved tensors."""
     from nlspn_eccv20_b200 import functional as F_
     from nlspn_eccv20_b200.synth import make_inputs
-    monkeypatch.setenv("NLSPN_STATE_GATHER", "1" if form == "gather" else "0")
+    monkeypatch.setenv("NLSPN_STATE_GATHER", "0" if form == "red" else "1")
+    monkeypatch.setenv("NLSPN_GATHER_COMPACT", "1" if form == "gather-compact" else "0")
     B, H, W = 2, 38, 45
     inp = make_inputs(B, H, W, K, seed=77 + K, device=dev, conf_mean=2.0)
     gamma = 0.5 * (K * K - 1)
@@ -495,8 +496,9 @@ def test_gather_form_overflowing_blocks(dev, monkeypatch):
     g_list = [torch.randn(B, 1, H, W, generator=g).to(dev) for _ in range(T)]
     args = (gd, inp["feat_init"], inp["feat_fix"], offset, aff, cfx, src, lf, g_list, gamma, K, T)
     ref = F_.backward(*args, per_iteration=True)
-    for form in ("0", "1"):
+    for form, compact in (("0", "0"), ("1", "0"), ("1", "1")):
         monkeypatch.setenv("NLSPN_STATE_GATHER", form)
+        monkeypatch.setenv("NLSPN_GATHER_COMPACT", compact)
         out = F_.backward(*args)
         for x, y, name in zip(out, ref, ["g_init", "g_guidance", "g_conf", "g_gamma"]):
             s = float(y.abs().max())

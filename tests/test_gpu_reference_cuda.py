@@ -31,13 +31,14 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("form", ["default", "red", "gather"])
+@pytest.mark.parametrize("form", ["default", "red", "gather", "gather-compact"])
 @pytest.mark.parametrize("K,T,shape", [(3, 18, (2, 228, 304)), (5, 6, (1, 97, 131)), (5, 12, (2, 64, 96)), (7, 3, (1, 40, 53))])
 def test_module_matches_reference_cuda_kernels(ref, monkeypatch, K, T, shape, form):
     """`form` selects pass A of the backward: the library's default for this K and T, the RED scatter, or the
     tabulated gather (kernels_gather.cuh)."""
     if form != "default":
-        monkeypatch.setenv("NLSPN_STATE_GATHER", "1" if form == "gather" else "0")
+        monkeypatch.setenv("NLSPN_STATE_GATHER", "0" if form == "red" else "1")
+        monkeypatch.setenv("NLSPN_GATHER_COMPACT", "1" if form == "gather-compact" else "0")
     from nlspn_eccv20_b200 import NLSPN
     from nlspn_eccv20_b200.synth import make_inputs, rmse_mae
     dev = torch.device("cuda:0")
