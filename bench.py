@@ -13,9 +13,12 @@ metric  Gpix*iter/s = (GPUs * B * H * W * T) / seconds, forward+backward.
 value   device-timed (CUDA events, max over ranks), inputs resident in HBM.
 e2e     same metric through the public module with PINNED HOST inputs: H2D of the step's
         inputs and D2H of the step's loss inside the timed region.
-roofline  dominant kernel = the backward iteration kernel; achieved = algorithmic bytes per
-        launch (36N+36 B/px) / average launch duration from CUDA events around
-        the backward phase of every timed step; peak = MEASURED_PEAKS.json hbm_gbs.
+roofline  dominant kernel = the one with the largest share of the step (K=3: pass A of the backward,
+        bwd_state_kernel, 12N+40 B/px per launch; K>=5: bwd_gather_kernel, 16N+20 B/px; DESIGN.md 3, 9);
+        achieved = its algorithmic bytes per launch / its average launch duration (CUDA-event time of
+        its phase in the timed region x its share of that phase from an event-bracketed pass);
+        peak = MEASURED_PEAKS.json hbm_gbs; traffic = measured DRAM bytes per launch (profiles/ncu_traffic.json).
+        roofline_step = SURVEY 8d's algorithmic bytes of the whole step against the same peak.
 cpu_baseline  the reference path restated over torchvision.ops.deform_conv2d (north_star's CPU
         stand-in; oracle/torchvision_port.py, pinned against the unmodified reference), one image
         per host thread, on a bounded sample of the same workload.  Rank 0, N=1 only.
