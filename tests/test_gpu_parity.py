@@ -79,8 +79,14 @@ def test_forward_matches_reference_golden(dev, name):
     assert abs(a[0] - b[0]) <= 1e-5 and abs(a[1] - b[1]) <= 1e-5
 
 
+@pytest.mark.parametrize("form", ["default", "gather"])
 @pytest.mark.parametrize("name", [n for n in PATHS if "fullmodel" not in n])
-def test_backward_matches_reference_autograd(dev, name):
+def test_backward_matches_reference_autograd(dev, monkeypatch, name, form):
+    """`form`: pass A of the backward as the library chooses it, or forced to the tabulated gather
+    (kernels_gather.cuh) -- every mode of the golden set (affinity modes, no confidence, no preserve_input,
+    always_clip, K = 5) goes through both."""
+    if form == "gather":
+        monkeypatch.setenv("NLSPN_STATE_GATHER", "1")
     g = load_golden(name)
     mod, (fi, gd, cf), (feat_result, list_feat, offset, aff, _), m = _run_module(g, dev, grad=True)
     gl = torch.from_numpy(g["out_g_list"]).to(dev)
@@ -407,14 +413,16 @@ def test_persistent_forward_equals_per_iteration_forward(dev, monkeypatch):
     assert float((g1 - fi2.grad).abs().max()) <= 1e-5 * float(g1.abs().max())
 
 
+@pytest.mark.parametrize("form", ["red", "gather"])
 @pytest.mark.parametrize("K,T,legacy,B,H,W", [(3, 6, False, 2, 28, 36), (3, 4, True, 1, 21, 27), (5, 3, False, 1, 24, 32)])
-def test_upstream_semantics_against_torchvision_restatement(dev, K, T, legacy, B, H, W):
+def test_upstream_semantics_against_torchvision_restatement(dev, monkeypatch, K, T, legacy, B, H, W, form):
     """conf_mode='sampled' + blend='pre' (+legacy): the UPSTREAM semantics of the north-star prose.
     PARITY UNPINNED -- no upstream code is in the reference tree; the referee is the restatement in
     oracle/torchvision_port.py (CPU, autograd).  Forward 1e-4 m, gradients 1e-4 relative."""
     from nlspn_eccv20_b200 import NLSPN
     from nlspn_eccv20_b200.synth import make_inputs
     from oracle import torchvision_port as TP
+    monkeypatch.setenv("NLSPN_STATE_GATHER", "1" if form == "gather" else "0")     # both forms of pass A
     inp = make_inputs(B, H, W, K, seed=900 + K + T, conf_mean=1.0)
     gamma = 0.5 * (K * K - 1)
     # CPU referee
