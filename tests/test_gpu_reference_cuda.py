@@ -124,12 +124,13 @@ def test_randomized_sweep_against_reference_cuda_kernels(ref):
     multiple of the tile), K in {3,5,7}, every affinity mode, confidence / preserve_input / always_clip on
     and off, large offsets (footprints leaving the TMA box) -- forward states and all gradients against the
     reference's own CUDA kernels."""
+    import os
     import random
     from nlspn_eccv20_b200 import NLSPN
     from nlspn_eccv20_b200.synth import make_inputs
     dev = torch.device("cuda:0")
     rnd = random.Random(20201018)
-    for case in range(24):
+    for case in range(int(os.environ.get("NLSPN_SWEEP_CASES", "24"))):    # soak runs: NLSPN_SWEEP_CASES=400
         K = rnd.choice([3, 3, 3, 5, 5, 7])
         T = rnd.randint(1, 8) if K < 7 else rnd.randint(1, 3)
         B = rnd.randint(1, 3)
