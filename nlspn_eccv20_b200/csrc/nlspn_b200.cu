@@ -283,17 +283,16 @@ static int fwd_tile_h()
 {
     if (const char *e = getenv("NLSPN_FWD_TH")) {
         const int v = atoi(e);
-        if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) return v;
+        if (v == 4 || v == 8) return v;
     }
     return kFwdTH;
 }
 
+// Tile heights: the B200 sweeps settled on 4 rows; 8 is kept as the one alternative.  (2, 16 and
+// 32 were measured in round 1 and are no longer instantiated: they only cost compile time.)
 #define DISPATCH_TH(TH_, ...)                                  \
     switch (TH_) {                                             \
-    case 2: { constexpr int THC = 2; __VA_ARGS__; } break;     \
     case 8: { constexpr int THC = 8; __VA_ARGS__; } break;     \
-    case 32: { constexpr int THC = 32; __VA_ARGS__; } break;   \
-    case 16: { constexpr int THC = 16; __VA_ARGS__; } break;   \
     default: { constexpr int THC = 4; __VA_ARGS__; } break;    \
     }
 // [B, C, H, W] fp32 tensor viewed 4-D; box = {32 px, box_h rows, all C channels, 1 image}
@@ -319,7 +318,7 @@ static int param_tile_h()
 {
     if (const char *e = getenv("NLSPN_PARAM_TH")) {
         const int v = atoi(e);
-        if (v == 2 || v == 4 || v == 8 || v == 16) return v;
+        if (v == 4 || v == 8) return v;
     }
     return kParamTH;
 }
@@ -942,14 +941,8 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         use_src ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc
 #define PARAM_LAUNCH(TH_, NS_)                                                                               \
     DISPATCH_K(K, (bwd_param_tiled_kernel<KC, param_chunk(KC), TH_, NS_><<<tgrid, tblock, 0, st>>>(PARAM_ARGS)))
-                // depth of pass B's TMA pipeline (boxes in flight + the one being consumed); deep pipelines
-                // only for the small tiles (static shared memory)
-                const int stages = getenv("NLSPN_PARAM_STAGES") ? atoi(getenv("NLSPN_PARAM_STAGES")) : kParamStages;
-                if (stages >= 4 && pth == 4) { PARAM_LAUNCH(4, 4); }
-                else if (stages == 3 && pth == 4) { PARAM_LAUNCH(4, 3); }
-                else if (stages >= 4 && pth == 8) { PARAM_LAUNCH(8, 4); }
-                else if (stages == 3 && pth == 8) { PARAM_LAUNCH(8, 3); }
-                else { DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, param_chunk(KC), THC, 2><<<tgrid, tblock, 0, st>>>(PARAM_ARGS)))); }
+                // (a deeper TMA pipeline -- 3 or 4 boxes in flight -- was measured in round 1: no gain)
+                DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, param_chunk(KC), THC, 2><<<tgrid, tblock, 0, st>>>(PARAM_ARGS))));
 #undef PARAM_ARGS
 #undef PARAM_LAUNCH
                 NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
