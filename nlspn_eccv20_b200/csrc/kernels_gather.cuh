@@ -9,10 +9,12 @@
 //                        phase-shifted blocked planes as the RED path, so consumers are unchanged)
 //                        gets an entry {source pixel (row << 16 | col), aff, th, lw} (16 B; th, lw = the top-row /
 //                        left-column bilinear weights) in the next free
-//                        slot of that block (one ATOMG per tap, once per step).  Layout is
-//                        slot-major, entries[slot][block], so the readers below are coalesced.
+//                        slot of that block (one ATOMG per tap, once per step).  Blocks are grouped
+//                        by 32; inside a group the layout is slot-major, so the readers are coalesced.
 //                        Taps that overflow a block's CAP slots are flagged per pixel and keep
 //                        the scatter form (scalar REDs into a plain "overflow" plane).
+//   table_compact_kernel (long runs) sorts each group's 32 columns by entry count, so that the live entries
+//                        of every row form a prefix: the readers then stream exactly the table's bytes.
 //   bwd_gy_kernel        per iteration, per pixel: gs = 4 phase cells + overflow plane, then
 //                        G, gy exactly as bwd_state_kernel's stages 1-3 (nlspnmodel.py:351,357,361);
 //                        stores gy, accumulates the confidence gradient.
@@ -22,10 +24,10 @@
 //                        store per thread; reads 16 B per entry, coalesced.
 //
 // Per pixel and iteration this moves ~16 B x N entries + ~60 B through HBM on the READ side instead of N
-// RED sectors through the write port.  Measured on B200 (KITTI, B = 8): the table rows are sparsely
-// filled past the mean occupancy, so the gather kernel streams ~1.4x the ideal bytes at ~5 TB/s:
-//   K = 3, T = 18: gy 0.72 + gather 2.50 + table 0.61 = 3.83 ms  vs  3.17 ms for the RED scatter  -> RED stays
-//   K = 5, T = 36: gy 1.45 + gather 10.6 + table 1.97 = 14.0 ms  vs  16.1 ms                       -> gather form
+// RED sectors through the write port.  Measured on B200 (KITTI, B = 8), uncompacted / compacted table:
+//   K = 3, T = 18: gy 0.72 + gather 2.50 / 2.25 + table 0.61 / 0.85 = 3.83 ms  vs  3.17 ms RED scatter -> RED stays
+//   K = 5, T = 36: gy 1.45 + gather 10.3 / 9.2  + table 1.97 / 2.60 = 13.7 / 13.3 ms  vs  16.1 ms     -> gather form
+// ncu, K = 5, compacted: 1.48 GB of DRAM reads in 260 us = 5.7 TB/s, 87 % of the measured HBM peak.
 // (RED cost grows with 32-byte sectors per tap, the table with 16 bytes per tap).  Also measured: a
 // TMA-delivered gy box for the gy[src] gathers (no gain: the kernel is bound by table bytes), 8 instead
 // of 4 entries in flight per thread (slower), fetching the first slots in parallel with the counter
