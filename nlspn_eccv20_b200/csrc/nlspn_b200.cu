@@ -311,7 +311,6 @@ static int make_geometry_map(CUtensorMap *map, const float *base, int B, int C, 
 }
 
 constexpr int kStateTH = 4;   // pass-A TMA tile: 32 x 4 pixels
-constexpr int kParamStages = 2;   // pass-B TMA pipeline depth
 constexpr int kParamTH = 4;   // default pass-B tile: 32 x 4 pixels (B200 sweep: TH 4: 1.02, 8: 1.10, 16: 1.27 ms)
 
 static int param_tile_h()
@@ -939,12 +938,9 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
 #define PARAM_ARGS                                                                                          \
     src_map, list_map, B, b0, offset + o1 * 2 * KK, aff + o1 * KK, src + o1, list_feat + o1, gy_all,          \
         use_src ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc
-#define PARAM_LAUNCH(TH_, NS_)                                                                               \
-    DISPATCH_K(K, (bwd_param_tiled_kernel<KC, param_chunk(KC), TH_, NS_><<<tgrid, tblock, 0, st>>>(PARAM_ARGS)))
                 // (a deeper TMA pipeline -- 3 or 4 boxes in flight -- was measured in round 1: no gain)
                 DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, param_chunk(KC), THC, 2><<<tgrid, tblock, 0, st>>>(PARAM_ARGS))));
 #undef PARAM_ARGS
-#undef PARAM_LAUNCH
                 NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
             } else {
                 DISPATCH_K(K, (bwd_param_kernel<KC, param_chunk(KC)><<<grid, kParamBlock, 0, st>>>(
