@@ -97,6 +97,16 @@ NLSPN_API const char *nlspn_last_error(void);
  * bench.py to report gpu_launches). */
 NLSPN_API unsigned long long nlspn_launch_count(void);
 
+/* Tuning options.  The NLSPN_<NAME> environment variables seed the defaults ONCE, when the
+ * library is loaded; nothing on the call path reads the environment.  Names: tiled, persist, pdl, fwd_th,
+ * param_th, state_tma, state_gather, gather_compact, state_zero3, state_minb, group_images, stream_hint,
+ * state_ahead, param_pair, persist_bwd, dcn_blocked.  value -1 = auto where the default depends on the shape.
+ * Options that select the form of the backward (state_gather) change nlspn_backward_workspace_bytes: query
+ * after setting them (a too-small workspace is always refused, never overrun). */
+NLSPN_API int nlspn_set_option(const char *name, int value);
+NLSPN_API int nlspn_get_option(const char *name, int *value);
+NLSPN_API int nlspn_reset_options(void);
+
 /* Optional per-kernel timing for bench.py's roofline.  While enabled, every kernel launch of
  * this library is bracketed by CUDA events on the caller's stream (this perturbs throughput a
  * little: never enable it inside a timed region whose `value` is reported).
@@ -192,6 +202,44 @@ NLSPN_API int nlspn_dcn_backward(const float *input, const float *weight, const 
                        int im2col_step, int B, int C, int H, int W,
                        float *grad_input, float *grad_offset, float *grad_mask,
                        float *grad_weight, float *grad_bias, void *stream);
+
+/* Same operator with a caller-owned workspace (nlspn_dcn_backward_workspace_bytes): grad_input is scattered with
+ * ONE vector reduction per tap into four phase-shifted 2x2-blocked copies of the plane and collected afterwards,
+ * and the gather source travels as TMA boxes -- the form nlspn_eccv20_b200.dcn uses.  Falls back to the scalar
+ * form of nlspn_dcn_backward when W % 4 != 0 or the workspace is NULL / too small. */
+NLSPN_API size_t nlspn_dcn_backward_workspace_bytes(int B, int H, int W, int K);
+NLSPN_API int nlspn_dcn_backward_ws(const float *input, const float *weight, const float *bias,
+                       const float *offset, const float *mask, const float *grad_output,
+                       int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                       int dilation_h, int dilation_w, int group, int deformable_group,
+                       int im2col_step, int B, int C, int H, int W,
+                       float *grad_input, float *grad_offset, float *grad_mask,
+                       float *grad_weight, float *grad_bias, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
+/* ---- ONE fused iteration of the loop body (SURVEY 8b nlspn_step_fwd/_bwd; row f2) -----------------------
+ * For callers whose affinities change between iterations -- the fork's GRU mode, nlspnmodel.py:365-373 --
+ * and therefore cannot use the T-iteration entries.  Replaces, per call, nlspnmodel.py:350-361:
+ *   out      = clamp(blend(G(src_prev; offset, aff)))       G = ModulatedDeformConvFunction with w = 1, b = 0
+ *              (:205-208) or, under NO_OFFSET / offset == NULL, the fixed-local 3x3 sum (:209-224)
+ *   src_next = out * conf_fixed                              (the next call's src_prev; NULL without confidence,
+ *              the next call then reads `out`)
+ * src_prev [B,1,H,W] is the PRE-MULTIPLIED state (x * conf_fixed); offset [B,2KK,H,W] with the zero centre pair
+ * (nlspnmodel.py:252-259); aff [B,KK,H,W] normalised, centre included (:261-269).
+ * flags: PRESERVE_INPUT (needs feat_fix), ALWAYS_CLIP, NO_OFFSET.
+ * Backward: g_out / g_src_next are the upstream gradients of the two outputs (either may be NULL = zero);
+ * `out` is the forward's result (read when g_src_next or ALWAYS_CLIP is given).  Overwrites g_src_prev [B,1,H,W],
+ * g_offset [B,2KK,H,W] (centre pair zero; NULL under NO_OFFSET), g_aff [B,KK,H,W], g_conf [B,1,H,W] (NULL iff
+ * conf_fixed is NULL; gradient wrt conf_fixed of THIS step only). */
+NLSPN_API int nlspn_step_fwd(const float *src_prev, const float *offset, const float *aff, const float *conf_fixed,
+                             const float *feat_fix, unsigned flags, int B, int H, int W, int K,
+                             float *out, float *src_next, void *stream);
+NLSPN_API size_t nlspn_step_bwd_workspace_bytes(int B, int H, int W, int K, unsigned flags);
+NLSPN_API int nlspn_step_bwd(const float *src_prev, const float *offset, const float *aff, const float *conf_fixed,
+                             const float *feat_fix, const float *out, const float *g_out, const float *g_src_next,
+                             unsigned flags, int B, int H, int W, int K,
+                             float *g_src_prev, float *g_offset, float *g_aff, float *g_conf,
+                             void *workspace, size_t workspace_bytes, void *stream);
 
 /* Double-precision variants of the single-step operator: the reference dispatches this op over
  * float and double (AT_DISPATCH_FLOATING_TYPES, modulated_deform_conv_cuda.cu:93,224) and its

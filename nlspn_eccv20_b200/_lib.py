@@ -22,6 +22,9 @@ SIGNATURES = {
     "nlspn_abi_version": (_c.c_int, []),
     "nlspn_last_error": (_c.c_char_p, []),
     "nlspn_launch_count": (_c.c_ulonglong, []),
+    "nlspn_set_option": (_c.c_int, [_c.c_char_p, _c.c_int]),
+    "nlspn_get_option": (_c.c_int, [_c.c_char_p, _c.POINTER(_c.c_int)]),
+    "nlspn_reset_options": (_c.c_int, []),
     "nlspn_profile_enable": (_c.c_int, [_c.c_int]),
     "nlspn_profile_classes": (_c.c_int, []),
     "nlspn_profile_class_name": (_c.c_char_p, [_c.c_int]),
@@ -43,6 +46,11 @@ SIGNATURES = {
                                   _fp, _fp, _fp, _fp, _fp, _c.c_size_t, _fp]),
     "nlspn_dcn_forward": (_c.c_int, [_fp] * 5 + [_c.c_int] * 15 + [_fp, _fp]),
     "nlspn_dcn_backward": (_c.c_int, [_fp] * 6 + [_c.c_int] * 15 + [_fp] * 6),
+    "nlspn_dcn_backward_workspace_bytes": (_c.c_size_t, [_c.c_int] * 4),
+    "nlspn_dcn_backward_ws": (_c.c_int, [_fp] * 6 + [_c.c_int] * 15 + [_fp] * 5 + [_fp, _c.c_size_t, _fp]),
+    "nlspn_step_fwd": (_c.c_int, [_fp] * 5 + [_c.c_uint] + [_c.c_int] * 4 + [_fp, _fp, _fp]),
+    "nlspn_step_bwd_workspace_bytes": (_c.c_size_t, [_c.c_int] * 4 + [_c.c_uint]),
+    "nlspn_step_bwd": (_c.c_int, [_fp] * 8 + [_c.c_uint] + [_c.c_int] * 4 + [_fp] * 4 + [_fp, _c.c_size_t, _fp]),
     "nlspn_dcn_forward_f64": (_c.c_int, [_fp] * 5 + [_c.c_int] * 15 + [_fp, _fp]),
     "nlspn_dcn_backward_f64": (_c.c_int, [_fp] * 6 + [_c.c_int] * 15 + [_fp] * 6),
     "nlspn_debug_indices": (_c.c_int, [_fp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _fp, _fp]),
@@ -89,6 +97,36 @@ def check(rc: int, what: str):
         msg = load().nlspn_last_error().decode("utf-8", "replace")
         kind = "validation error" if rc < 0 else "CUDA error"
         raise RuntimeError("%s failed: %s %d: %s" % (what, kind, rc, msg))
+
+
+def set_option(name: str, value: int):
+    """Tuning knob of the library; -1 = auto where the default depends on the shape.  The
+    NLSPN_<NAME> environment variables only seed the defaults when the library is loaded."""
+    check(load().nlspn_set_option(name.encode(), int(value)), "nlspn_set_option(%s)" % name)
+
+
+def get_option(name: str) -> int:
+    v = _c.c_int(0)
+    check(load().nlspn_get_option(name.encode(), _c.byref(v)), "nlspn_get_option(%s)" % name)
+    return v.value
+
+
+class options:
+    """``with _lib.options(state_gather=1, gather_compact=0): ...`` -- set, then restore."""
+
+    def __init__(self, **kw):
+        self.kw, self.old = kw, {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.old[k] = get_option(k)
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
+        return False
 
 
 def profile_read():

@@ -87,6 +87,16 @@ __device__ __forceinline__ float blend_fix(float v, float dep)
     return (1.f - m) * v + m * dep;
 }
 
+// always_clip (nlspnmodel.py:346-348,359-361): torch.clamp(x, min=0) passes the gradient where x >= 0, i.e. also at
+// x == 0 exactly.  The forward therefore stores a clipped value as -0.0f and everything else with a + sign on
+// zero; the backward recognises "was clipped" by that bit pattern alone (no extra plane).  -0.0f compares equal
+// to 0 and multiplies/adds like 0, so the forward arithmetic is unchanged.
+__device__ __forceinline__ float clip_keep_sign(float v)
+{
+    return v < 0.f ? __int_as_float((int)0x80000000u) : v + 0.f;
+}
+__device__ __forceinline__ bool was_clipped(float stored) { return __float_as_uint(stored) == 0x80000000u; }
+
 // geometry of the blocked scatter planes of one image
 struct ScatterGeo {
     int Hb, Wb;          // blocks per column / row

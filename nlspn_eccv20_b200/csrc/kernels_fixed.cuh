@@ -40,7 +40,7 @@ fixed_fwd_kernel(const float *__restrict__ src_prev, const float *__restrict__ a
         acc += __ldg(im + hh * W + ww) * av[t];          // feat * aff, summed over dim 1 (:223-224)
     }
     if (flags & kPreserve) acc = blend_fix(acc, dp);
-    if (flags & kAlwaysClip) acc = fmaxf(acc, 0.f);
+    if (flags & kAlwaysClip) acc = clip_keep_sign(acc);
     out[q] = acc;
     if (src_next) src_next[q] = conf ? acc * cf : acc;
 }
@@ -77,7 +77,7 @@ fixed_state_kernel(const float *__restrict__ aff, const float *__restrict__ conf
     }
     float Gx = gext;
     if (s_in) Gx += conf ? cf * gs : gs;
-    if ((flags & kAlwaysClip) && !(xt > 0.f)) Gx = 0.f;
+    if ((flags & kAlwaysClip) && was_clipped(xt)) Gx = 0.f;
     if (flags & kPreserve) Gx = (1.0f - (dp > 0.f ? 1.f : 0.f)) * Gx;
     if (s_in) {
         s_in[q] = 0.f;

@@ -137,7 +137,7 @@ persist_fwd_kernel(const float *__restrict__ offset, const float *__restrict__ a
                 acc += v * av[k];
             }
             if (flags & kPreserve) acc = blend_fix(acc, dp);
-            if (flags & kAlwaysClip) acc = fmaxf(acc, 0.f);
+            if (flags & kAlwaysClip) acc = clip_keep_sign(acc);
             list_feat[(long)(t - 1) * BP + q] = acc;
             if (src_next) src_next[q] = acc * cf;
         }

@@ -177,7 +177,7 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
         return;
     }
     if (flags & kPreserve) acc = blend_fix(acc, dp);
-    if (flags & kAlwaysClip) acc = fmaxf(acc, 0.f);
+    if (flags & kAlwaysClip) acc = clip_keep_sign(acc);
     out[q] = acc;
     if (src_next) src_next[q] = conf ? acc * cf : acc;
 }
@@ -456,7 +456,7 @@ bwd_state_tma_kernel(const __grid_constant__ CUtensorMap off_map, const __grid_c
         if (si) Gx += (flags & kPreserve) ? (1.0f - (dp > 0.f ? 1.f : 0.f)) * gs : gs;
     } else {
         if (si) Gx += conf ? cf * gs : gs;
-        if ((flags & kAlwaysClip) && !(xt > 0.f)) Gx = 0.f;
+        if ((flags & kAlwaysClip) && was_clipped(xt)) Gx = 0.f;
         if (flags & kPreserve) Gx = (1.0f - (dp > 0.f ? 1.f : 0.f)) * Gx;
     }
     const float gy = Gx;

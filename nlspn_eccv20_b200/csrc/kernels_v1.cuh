@@ -179,7 +179,7 @@ iter_fwd_kernel(const float *__restrict__ src_prev, const float *__restrict__ of
             if (src_next) src_next[q] = (flags & kPreserve) ? blend_fix(acc, __ldg(dep + q)) : acc;
         } else {
             if (flags & kPreserve) acc = blend_fix(acc, __ldg(dep + q));
-            if (flags & kAlwaysClip) acc = fmaxf(acc, 0.f);
+            if (flags & kAlwaysClip) acc = clip_keep_sign(acc);
             out[q] = acc;
             if (src_next) src_next[q] = conf ? acc * __ldg(conf + q) : acc;
         }
@@ -231,7 +231,7 @@ iter_bwd_kernel(const float *__restrict__ src_prev, const float *__restrict__ of
         }
     }
     if (CENTER_ZERO) {
-        if ((flags & kAlwaysClip) && !(__ldg(x_t + q) > 0.f)) Gx = 0.f;
+        if ((flags & kAlwaysClip) && was_clipped(__ldg(x_t + q))) Gx = 0.f;
         if (flags & kPreserve) Gx = (1.0f - (__ldg(dep + q) > 0.f ? 1.f : 0.f)) * Gx;
     }
     const float gy = Gx;

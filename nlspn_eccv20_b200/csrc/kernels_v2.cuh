@@ -117,7 +117,7 @@ bwd_state_kernel(const float *__restrict__ offset, const float *__restrict__ aff
         if (si) Gx += (flags & kPreserve) ? (1.0f - (dp > 0.f ? 1.f : 0.f)) * gs : gs;
     } else {
         if (si) Gx += conf ? cf * gs : gs;
-        if ((flags & kAlwaysClip) && !(xt > 0.f)) Gx = 0.f;
+        if ((flags & kAlwaysClip) && was_clipped(xt)) Gx = 0.f;
         if (flags & kPreserve) Gx = (1.0f - (dp > 0.f ? 1.f : 0.f)) * Gx;
     }
     const float gy = Gx;

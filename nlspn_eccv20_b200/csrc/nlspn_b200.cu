@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "kernels_tiled.cuh"
 #include "kernels_f64.cuh"
 #include "kernels_gather.cuh"
+#include "kernels_step.cuh"
 
 using namespace nlspn;
 
@@ -21,6 +23,42 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+
+// ---- tuning options.  Read ONCE from the environment when the library is loaded; afterwards only
+// nlspn_set_option changes them (tests, tools).  Nothing on the call path touches getenv.
+// -1 = "auto" where a default depends on the shape.
+enum Opt { kOptTiled = 0, kOptPersist, kOptPdl, kOptFwdTH, kOptParamTH, kOptStateTma, kOptStateGather,
+           kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint, kOptStateAhead,
+           kOptParamPair, kOptPersistBwd, kOptDcnBlocked, kOptCount };
+struct OptDef { const char *name; const char *env; int def; };
+const OptDef kOptDefs[kOptCount] = {
+    {"tiled", "NLSPN_TILED", 1},
+    {"persist", "NLSPN_PERSIST", -1},
+    {"pdl", "NLSPN_PDL", 1},
+    {"fwd_th", "NLSPN_FWD_TH", 4},
+    {"param_th", "NLSPN_PARAM_TH", 4},
+    {"state_tma", "NLSPN_STATE_TMA", -1},
+    {"state_gather", "NLSPN_STATE_GATHER", -1},
+    {"gather_compact", "NLSPN_GATHER_COMPACT", -1},
+    {"state_zero3", "NLSPN_STATE_ZERO3", 1},
+    {"state_minb", "NLSPN_STATE_MINB", 4},
+    {"group_images", "NLSPN_GROUP_IMAGES", 0},
+    {"stream_hint", "NLSPN_STREAM_HINT", -1},
+    {"state_ahead", "NLSPN_STATE_AHEAD", -1},
+    {"param_pair", "NLSPN_PARAM_PAIR", 1},
+    {"persist_bwd", "NLSPN_PERSIST_BWD", -1},
+    {"dcn_blocked", "NLSPN_DCN_BLOCKED", 1},
+};
+std::atomic<int> g_opt[kOptCount];
+const bool g_opt_init = []() {
+    for (int i = 0; i < kOptCount; ++i) {
+        int v = kOptDefs[i].def;
+        if (const char *e = getenv(kOptDefs[i].env)) v = atoi(e);
+        g_opt[i].store(v, std::memory_order_relaxed);
+    }
+    return true;
+}();
+inline int opt(Opt o) { return g_opt[o].load(std::memory_order_relaxed); }
 
 // ---- optional per-kernel-class timing (bench.py's roofline): CUDA events around every launch
 enum ProfClass { kProfPrologue = 0, kProfIterFwd, kProfBwdState, kProfBwdParam, kProfFinalBwd,
@@ -124,6 +162,34 @@ const char *nlspn_last_error(void) { return g_err; }
 
 unsigned long long nlspn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int nlspn_set_option(const char *name, int value)
+{
+    if (!name) return fail(NLSPN_ERR_NULL, "set_option: NULL name");
+    for (int i = 0; i < kOptCount; ++i)
+        if (strcmp(name, kOptDefs[i].name) == 0) {
+            g_opt[i].store(value, std::memory_order_relaxed);
+            return 0;
+        }
+    return fail(NLSPN_ERR_DOMAIN, "set_option: unknown option '%s'", name);
+}
+
+int nlspn_get_option(const char *name, int *value)
+{
+    if (!name || !value) return fail(NLSPN_ERR_NULL, "get_option: NULL argument");
+    for (int i = 0; i < kOptCount; ++i)
+        if (strcmp(name, kOptDefs[i].name) == 0) {
+            *value = g_opt[i].load(std::memory_order_relaxed);
+            return 0;
+        }
+    return fail(NLSPN_ERR_DOMAIN, "get_option: unknown option '%s'", name);
+}
+
+int nlspn_reset_options(void)
+{
+    for (int i = 0; i < kOptCount; ++i) g_opt[i].store(kOptDefs[i].def, std::memory_order_relaxed);
+    return 0;
+}
+
 int nlspn_profile_enable(int on)
 {
     std::lock_guard<std::mutex> lock(g_prof_mu);
@@ -159,21 +225,28 @@ int nlspn_profile_read(double *ms, long long *launches, int n)
 
 int nlspn_device_info(int device, int *sm_count, int *l2_bytes)
 {
+    // one slot per device, filled once (DataParallel worker threads each drive their own device)
+    constexpr int kMaxDev = 64;
+    struct Slot { std::atomic<int> ready{0}; int sm = 0, l2 = 0, coop = 0; };
+    static Slot slots[kMaxDev];
     static std::mutex mu;
-    static int cached_dev = -1, cached_sm = 0, cached_l2 = 0;
-    std::lock_guard<std::mutex> lock(mu);
-    if (cached_dev != device) {
-        int sm = 0, l2 = 0;
-        cudaError_t e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(SM count)");
-        e = cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(L2 size)");
-        cached_dev = device;
-        cached_sm = sm;
-        cached_l2 = l2;
+    if (device < 0 || device >= kMaxDev) return fail(NLSPN_ERR_SHAPE, "device index %d out of range", device);
+    Slot &s = slots[device];
+    if (!s.ready.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!s.ready.load(std::memory_order_relaxed)) {
+            int sm = 0, l2 = 0;
+            cudaError_t e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(SM count)");
+            e = cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(L2 size)");
+            s.sm = sm;
+            s.l2 = l2;
+            s.ready.store(1, std::memory_order_release);
+        }
     }
-    if (sm_count) *sm_count = cached_sm;
-    if (l2_bytes) *l2_bytes = cached_l2;
+    if (sm_count) *sm_count = s.sm;
+    if (l2_bytes) *l2_bytes = s.l2;
     return 0;
 }
 
@@ -187,8 +260,8 @@ int nlspn_device_info(int device, int *sm_count, int *l2_bytes)
 // every unit < 20 % busy; see profiles/).
 static int group_images(int B, int H, int W, int K, bool backward)
 {
-    if (const char *e = getenv("NLSPN_GROUP_IMAGES")) {
-        const int g = atoi(e);
+    {
+        const int g = opt(kOptGroupImages);
         if (g > 0) return g < B ? g : B;
     }
     // Measured on B200 (KITTI, B=8, K=3, T=18; profiles/): once every load of a thread is issued
@@ -221,11 +294,7 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-static bool tiled_enabled()
-{
-    const char *e = getenv("NLSPN_TILED");
-    return !(e && atoi(e) == 0);
-}
+static bool tiled_enabled() { return opt(kOptTiled) != 0; }
 
 // true when the tiled (TMA) kernels can serve this shape
 static bool tiled_ok(const void *base, int W)
@@ -233,8 +302,55 @@ static bool tiled_ok(const void *base, int W)
     return tiled_enabled() && (W % 4) == 0 && aligned16(base) && encode_tiled_fn() != nullptr;
 }
 
+// A tensor map only encodes (address, extents, box), so it can be cached by value: the torch caching
+// allocator hands the same addresses back step after step, and cuTensorMapEncodeTiled (a driver call, 2-4 per
+// API call) disappears from the steady-state launch path.  Small LRU, thread-safe.
+struct MapKey {
+    const void *base;
+    long d2, d3;
+    int H, W, box_w, box_h, box_c, rank;
+    bool operator==(const MapKey &o) const
+    {
+        return base == o.base && d2 == o.d2 && d3 == o.d3 && H == o.H && W == o.W && box_w == o.box_w &&
+               box_h == o.box_h && box_c == o.box_c && rank == o.rank;
+    }
+};
+struct MapSlot { MapKey key; CUtensorMap map; unsigned long long stamp; bool used; };
+constexpr int kMapSlots = 32;
+static MapSlot g_maps[kMapSlots];
+static std::mutex g_maps_mu;
+static unsigned long long g_maps_clock = 0;
+
+static bool map_cache_get(const MapKey &k, CUtensorMap *out)
+{
+    std::lock_guard<std::mutex> lock(g_maps_mu);
+    for (int i = 0; i < kMapSlots; ++i)
+        if (g_maps[i].used && g_maps[i].key == k) {
+            g_maps[i].stamp = ++g_maps_clock;
+            *out = g_maps[i].map;
+            return true;
+        }
+    return false;
+}
+
+static void map_cache_put(const MapKey &k, const CUtensorMap &m)
+{
+    std::lock_guard<std::mutex> lock(g_maps_mu);
+    int victim = 0;
+    for (int i = 0; i < kMapSlots; ++i) {
+        if (!g_maps[i].used) { victim = i; break; }
+        if (g_maps[i].stamp < g_maps[victim].stamp) victim = i;
+    }
+    g_maps[victim].key = k;
+    g_maps[victim].map = m;
+    g_maps[victim].stamp = ++g_maps_clock;
+    g_maps[victim].used = true;
+}
+
 static int make_plane_map(CUtensorMap *map, const float *base, long planes, int H, int W, int box_w, int box_h)
 {
+    const MapKey key{base, planes, 0, H, W, box_w, box_h, 1, 3};
+    if (map_cache_get(key, map)) return 0;
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
@@ -244,22 +360,24 @@ static int make_plane_map(CUtensorMap *map, const float *base, long planes, int 
                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(NLSPN_ERR_SHAPE, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    map_cache_put(key, *map);
     return 0;
 }
 
 // Launch with programmatic stream serialisation (PDL): the grid may become resident while the
 // previous kernel in the stream is still draining; the kernel itself orders its dependent
 // accesses with griddepcontrol.wait (tma::grid_dependency_wait).
-static bool pdl_enabled()
-{
-    const char *e = getenv("NLSPN_PDL");
-    return !(e && atoi(e) == 0);
-}
+static bool pdl_enabled() { return opt(kOptPdl) != 0; }
 
 } // extern "C" (templates need C++ linkage)
 
+// `chained` = the previous kernel in the stream is one of OUR PDL-aware kernels AND everything this kernel reads
+// before its griddepcontrol.wait is older than that kernel.  The first launch after a plain producer (prologue,
+// table build, a memset, the caller's own kernels) is launched without the attribute: the PDL contract only
+// makes the producer's writes visible after the wait, and the early loads prefetch geometry.
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args)
+static cudaError_t launch_pdl(bool chained, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st,
+                              Args... args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -268,7 +386,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (chained && pdl_enabled()) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
@@ -281,11 +399,8 @@ constexpr int kFwdTH = 4;     // default forward tile: 32 x 4 pixels (B200 sweep
 // forward tile height: 8, 16 or 32 rows (NLSPN_FWD_TH overrides the default; tuning knob)
 static int fwd_tile_h()
 {
-    if (const char *e = getenv("NLSPN_FWD_TH")) {
-        const int v = atoi(e);
-        if (v == 4 || v == 8) return v;
-    }
-    return kFwdTH;
+    const int v = opt(kOptFwdTH);
+    return (v == 4 || v == 8) ? v : kFwdTH;
 }
 
 // Tile heights: the B200 sweeps settled on 4 rows; 8 is kept as the one alternative.  (2, 16 and
@@ -298,6 +413,8 @@ static int fwd_tile_h()
 // [B, C, H, W] fp32 tensor viewed 4-D; box = {32 px, box_h rows, all C channels, 1 image}
 static int make_geometry_map(CUtensorMap *map, const float *base, int B, int C, int H, int W, int box_h)
 {
+    const MapKey key{base, C, B, H, W, kTileW, box_h, C, 4};
+    if (map_cache_get(key, map)) return 0;
     const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
     const cuuint32_t box[4] = {(cuuint32_t)kTileW, (cuuint32_t)box_h, (cuuint32_t)C, 1};
@@ -307,6 +424,7 @@ static int make_geometry_map(CUtensorMap *map, const float *base, int B, int C, 
                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(NLSPN_ERR_SHAPE, "cuTensorMapEncodeTiled(4d) failed (CUresult %d)", (int)r);
+    map_cache_put(key, *map);
     return 0;
 }
 
@@ -315,16 +433,13 @@ constexpr int kParamTH = 4;   // default pass-B tile: 32 x 4 pixels (B200 sweep:
 
 static int param_tile_h()
 {
-    if (const char *e = getenv("NLSPN_PARAM_TH")) {
-        const int v = atoi(e);
-        if (v == 4 || v == 8) return v;
-    }
-    return kParamTH;
+    const int v = opt(kOptParamTH);
+    return (v == 4 || v == 8) ? v : kParamTH;
 }
 
 static bool stream_hint_for(int B, int H, int W, int K)
 {
-    if (const char *e = getenv("NLSPN_STREAM_HINT")) return atoi(e) != 0;
+    if (opt(kOptStreamHint) >= 0) return opt(kOptStreamHint) != 0;
     int dev = 0, l2 = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, nullptr, &l2) != 0) return true;
     return (double)B * H * W * 4.0 * 3.0 * K * K > 0.5 * (double)l2;   // geometry does not fit L2
@@ -386,10 +501,10 @@ static int launch_iter_fwd(const FwdCall &c, int b0, int nb, int t, const CUtens
     if (c.flags & NLSPN_FLAG_NO_OFFSET) {
         cudaError_t e;
         if (stream)
-            e = launch_pdl(fixed_fwd_kernel<true>, grid_for(P, nb), dim3(kBlock), c.st, src_prev,
+            e = launch_pdl(t > 1, fixed_fwd_kernel<true>, grid_for(P, nb), dim3(kBlock), c.st, src_prev,
                            c.aff + o1 * KK, cf, fx, c.flags, c.H, c.W, out, src_next);
         else
-            e = launch_pdl(fixed_fwd_kernel<false>, grid_for(P, nb), dim3(kBlock), c.st, src_prev,
+            e = launch_pdl(t > 1, fixed_fwd_kernel<false>, grid_for(P, nb), dim3(kBlock), c.st, src_prev,
                            c.aff + o1 * KK, cf, fx, c.flags, c.H, c.W, out, src_next);
         if (e != cudaSuccess) return cuda_fail(e, "fixed_fwd_kernel");
         NLSPN_CHECK_LAUNCH("fixed_fwd_kernel");
@@ -400,11 +515,11 @@ static int launch_iter_fwd(const FwdCall &c, int b0, int nb, int t, const CUtens
         dim3 grid((unsigned)((c.W + kTileW - 1) / kTileW), (unsigned)((c.H + th - 1) / th), (unsigned)nb);
         dim3 block(kTileW, th);
         if (stream) {
-            DISPATCH_TH(th, DISPATCH_K(c.K, (launch_pdl(iter_fwd_tiled_kernel<KC, THC, true>, grid, block, c.st,
+            DISPATCH_TH(th, DISPATCH_K(c.K, (launch_pdl(t > 1, iter_fwd_tiled_kernel<KC, THC, true>, grid, block, c.st,
                                 *map, plane_z, src_prev, c.offset + o1 * 2 * KK, c.aff + o1 * KK, cf, fx,
                                 c.flags, c.H, c.W, out, src_next))));
         } else {
-            DISPATCH_TH(th, DISPATCH_K(c.K, (launch_pdl(iter_fwd_tiled_kernel<KC, THC, false>, grid, block, c.st,
+            DISPATCH_TH(th, DISPATCH_K(c.K, (launch_pdl(t > 1, iter_fwd_tiled_kernel<KC, THC, false>, grid, block, c.st,
                                 *map, plane_z, src_prev, c.offset + o1 * 2 * KK, c.aff + o1 * KK, cf, fx,
                                 c.flags, c.H, c.W, out, src_next))));
         }
@@ -435,8 +550,7 @@ static int try_persistent_forward(const FwdCall &c, bool prologue, int *tried)
     *tried = 0;
     if (c.K != 3) return 0;   // 24 / 48 taps of geometry do not fit the register file
     if (c.flags & NLSPN_FLAG_BLEND_PRE) return 0;   // upstream ordering: per-iteration kernels only
-    if (const char *e = getenv("NLSPN_PERSIST"))
-        if (atoi(e) == 0) return 0;
+    if (opt(kOptPersist) == 0) return 0;
     int dev = 0, sms = 0, coop = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, &sms, nullptr) != 0) return 0;
     if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) return 0;
@@ -580,8 +694,8 @@ constexpr int kGatherMinK = 5;   // pass A: RED scatter for K = 3, tabulated gat
 static bool gather_form_selected(int H, int W, int K, int T)
 {
     bool gather = K >= kGatherMinK && T >= kGatherMinT;   // the table build (once per call) must amortise
-    if (const char *ev = getenv("NLSPN_STATE_GATHER")) gather = atoi(ev) != 0;
-    if (H > 65535 || W > 65535) gather = false;           // table entries pack the source pixel as row << 16 | col
+    if (opt(kOptStateGather) >= 0) gather = opt(kOptStateGather) != 0;
+    if (H > 32767 || W > 65535) gather = false;           // table entries pack the source pixel as row << 16 | col (signed int)
     return gather;
 }
 
@@ -667,11 +781,11 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             float *s_in = t == T ? nullptr : (((T - t) % 2 == 0) ? planeB : planeA);
             ProfScope prof__(kProfBwdState, st);
             if (sh)
-                e = launch_pdl(fixed_state_kernel<true>, grid_for(P, B), dim3(kBlock), st, aff, conf_fixed,
+                e = launch_pdl(t < T, fixed_state_kernel<true>, grid_for(P, B), dim3(kBlock), st, aff, conf_fixed,
                                feat_fix, list_feat + (long)(t - 1) * BP, g_list[t - 1], s_in, s_out,
                                gy_all + (long)(t - 1) * BP, g_conf_acc, flags, H, W);
             else
-                e = launch_pdl(fixed_state_kernel<false>, grid_for(P, B), dim3(kBlock), st, aff, conf_fixed,
+                e = launch_pdl(t < T, fixed_state_kernel<false>, grid_for(P, B), dim3(kBlock), st, aff, conf_fixed,
                                feat_fix, list_feat + (long)(t - 1) * BP, g_list[t - 1], s_in, s_out,
                                gy_all + (long)(t - 1) * BP, g_conf_acc, flags, H, W);
             if (e != cudaSuccess) return cuda_fail(e, "fixed_state_kernel");
@@ -727,7 +841,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     const ScatterGeo sg = scatter_geo(H, W);
     const int G = group_images(B, H, W, K, true);
     const bool stream_hint = stream_hint_for(G, H, W, K);
-    const int state_minb = getenv("NLSPN_STATE_MINB") ? atoi(getenv("NLSPN_STATE_MINB")) : 4;
+    const int state_minb = opt(kOptStateMinB);
     CUtensorMap src_map, list_map;
     const bool use_tiled = tiled_ok(src, W) && aligned16(list_feat);
     if (use_tiled) {
@@ -740,8 +854,8 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     // K=5 only; NLSPN_STATE_TMA=1/0 forces it on (K<=5; K=7 would need 75 KB of smem per CTA) / off.
     CUtensorMap off_map, aff_map;
     bool state_tma = use_tiled && K == 5 && aligned16(offset) && aligned16(aff);
-    if (const char *ev = getenv("NLSPN_STATE_TMA"))
-        state_tma = use_tiled && K <= 5 && aligned16(offset) && aligned16(aff) && atoi(ev) != 0;
+    if (opt(kOptStateTma) >= 0)
+        state_tma = use_tiled && K <= 5 && aligned16(offset) && aligned16(aff) && opt(kOptStateTma) != 0;
     if (state_tma) {
         if (int rc = make_geometry_map(&off_map, offset, B, 2 * KK, H, W, kStateTH)) return rc;
         if (int rc = make_geometry_map(&aff_map, aff, B, KK, H, W, kStateTH)) return rc;
@@ -756,7 +870,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         float *planes = reinterpret_cast<float *>(entries + (size_t)G * table_groups(NB) * cap * 32);   // [G][sg.image]
         void *ovf = planes + (size_t)G * sg.image;                            // [G][P] masks, 8 B reserved each
         const long NBpad = table_groups(NB) * 32;
-        const bool compact = getenv("NLSPN_GATHER_COMPACT") ? atoi(getenv("NLSPN_GATHER_COMPACT")) != 0 : T >= kCompactMinT;
+        const bool compact = opt(kOptGatherCompact) >= 0 ? opt(kOptGatherCompact) != 0 : T >= kCompactMinT;
         int *count = reinterpret_cast<int *>(static_cast<char *>(ovf) + 8 * (size_t)G * P);   // [G][NBpad]
         int *owner = count + (size_t)G * NBpad;                                               // [G][NBpad]
         float *f0 = reinterpret_cast<float *>(owner + (size_t)G * NBpad), *f1 = f0 + (size_t)G * P;
@@ -798,7 +912,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                 float *f_in = ((T - t) % 2 == 0) ? f1 : f0;
                 {
                     ProfScope prof__(kProfBwdState, st);
-                    DISPATCH_K(K, (e = launch_pdl(bwd_gy_kernel<KC>, grid_for(P, nb), dim3(kBlock), st, off_g, aff_g, cf,
+                    DISPATCH_K(K, (e = launch_pdl(t < T, bwd_gy_kernel<KC>, grid_for(P, nb), dim3(kBlock), st, off_g, aff_g, cf,
                                                   fx, xt, ge, t < T ? (const float *)planes : (const float *)nullptr,
                                                   f_in, f_out, gyn,
                                                   static_cast<const typename OvfMask<KC>::type *>(ovf), gyo,
@@ -808,7 +922,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                 }
                 {
                     ProfScope prof__(kProfBwdGather, st);
-                    DISPATCH_K(K, (e = launch_pdl(bwd_gather_kernel<KC>, ggrid, dim3(kBlock), st, (const int *)count,
+                    DISPATCH_K(K, (e = launch_pdl(true, bwd_gather_kernel<KC>, ggrid, dim3(kBlock), st, (const int *)count,
                                                   compact ? (const int *)owner : (const int *)nullptr,
                                                   (const float4 *)entries, (const float *)gyo, H, W,
                                                   reinterpret_cast<float4 *>(planes))));
@@ -865,7 +979,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
 
     // scatter-plane sets rotate over three buffers so that clearing is a linear 16-byte-per-thread job
     // (NLSPN_STATE_ZERO3=0: two sets, every thread clears the four cells it read)
-    const bool zero3 = !(getenv("NLSPN_STATE_ZERO3") && atoi(getenv("NLSPN_STATE_ZERO3")) == 0);
+    const bool zero3 = opt(kOptStateZero3) != 0;
     float *sets[3] = {ws, ws + (long)G * sg.image, ws + 2 * (long)G * sg.image};
     float *g_conf_acc = sets[2] + (long)G * sg.image;
     float *gy_all = g_conf_acc + (long)G * P;          // [T, G, P]
@@ -890,16 +1004,16 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             const float *ge = g_list[t - 1] ? g_list[t - 1] + o1 : nullptr;
             float *gyo = gy_all + (long)(t - 1) * GP;
 #define STATE_LAUNCH(SH_, MB_)                                                                          \
-    DISPATCH_K(K, (launch_pdl(bwd_state_kernel<KC, SH_, MB_>, grid_for(P, nb), dim3(kBlock), st,           \
+    DISPATCH_K(K, (launch_pdl(t < T, bwd_state_kernel<KC, SH_, MB_>, grid_for(P, nb), dim3(kBlock), st,           \
                               offset + o1 * 2 * KK, aff + o1 * KK, cf, fx, xt, ge, s_in, s_out, gyo,       \
                               g_conf_acc, flags, H, W, s_zero)))
             if (state_tma) {
                 dim3 sgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + kStateTH - 1) / kStateTH), (unsigned)nb);
                 if (K == 3) {
-                    e = launch_pdl(bwd_state_tma_kernel<3, kStateTH>, sgrid, dim3(kTileW, kStateTH), st, off_map,
+                    e = launch_pdl(t < T, bwd_state_tma_kernel<3, kStateTH>, sgrid, dim3(kTileW, kStateTH), st, off_map,
                                    aff_map, b0, cf, fx, xt, ge, s_in, s_out, gyo, g_conf_acc, flags, H, W, s_zero);
                 } else {
-                    e = launch_pdl(bwd_state_tma_kernel<5, kStateTH>, sgrid, dim3(kTileW, kStateTH), st, off_map,
+                    e = launch_pdl(t < T, bwd_state_tma_kernel<5, kStateTH>, sgrid, dim3(kTileW, kStateTH), st, off_map,
                                    aff_map, b0, cf, fx, xt, ge, s_in, s_out, gyo, g_conf_acc, flags, H, W, s_zero);
                 }
                 if (e != cudaSuccess) return cuda_fail(e, "bwd_state_tma_kernel");
@@ -1005,6 +1119,16 @@ int nlspn_dcn_forward(const float *input, const float *weight, const float *bias
         return fail(NLSPN_ERR_NULL, "dcn_forward: a required pointer is NULL");
     const int P = H * W;
     cudaStream_t st = (cudaStream_t)stream;
+    if (tiled_ok(input, W)) {   // gather source delivered as TMA boxes (kernels_step.cuh)
+        CUtensorMap in_map;
+        if (int rc = make_plane_map(&in_map, input, B, H, W, kTileW + 2 * halo_for(kernel_h), kFwdTH + 2 * halo_for(kernel_h))) return rc;
+        dim3 grid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + kFwdTH - 1) / kFwdTH), (unsigned)B);
+        ProfScope prof__(kProfDcnFwd, st);
+        DISPATCH_K(kernel_h, (dcn_fwd_tiled_kernel<KC, kFwdTH><<<grid, dim3(kTileW, kFwdTH), 0, st>>>(
+                                 in_map, input, offset, mask, weight, bias, H, W, output)));
+        NLSPN_CHECK_LAUNCH("dcn_fwd_tiled_kernel");
+        return 0;
+    }
     { ProfScope prof__(kProfDcnFwd, st);
     DISPATCH_K(kernel_h, (iter_fwd_kernel<KC, false><<<grid_for(P, B), kBlock, 0, st>>>(
                              input, offset, mask, nullptr, nullptr, weight, bias, 0u, H, W, output,
@@ -1046,6 +1170,172 @@ int nlspn_dcn_backward(const float *input, const float *weight, const float *bia
                              nullptr, grad_input, grad_offset, (long)2 * KK * P, grad_mask, nullptr,
                              0u, 1, H, W))); }
     NLSPN_CHECK_LAUNCH("iter_bwd_kernel<dcn>");
+    DISPATCH_K(kernel_h, (dcn_wb_grad_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
+                             input, offset, mask, grad_output, H, W, grad_weight, grad_bias)));
+    NLSPN_CHECK_LAUNCH("dcn_wb_grad_kernel");
+    return 0;
+}
+
+// ---- single fused iteration (kernels_step.cuh) --------------------------------------------------------
+static int check_step(const float *src_prev, const float *offset, const float *aff, const float *feat_fix,
+                      unsigned flags, int B, int H, int W, int K)
+{
+    if (int rc = check_shape(B, H, W, K, 1)) return rc;
+    if (flags & ~(NLSPN_FLAG_PRESERVE_INPUT | NLSPN_FLAG_ALWAYS_CLIP | NLSPN_FLAG_NO_OFFSET))
+        return fail(NLSPN_ERR_DOMAIN, "step: only PRESERVE_INPUT, ALWAYS_CLIP and NO_OFFSET apply to a single step");
+    const bool no_off = (flags & NLSPN_FLAG_NO_OFFSET) != 0;
+    if (no_off && K != 3) return fail(NLSPN_ERR_KERNEL, "fixed-local propagation (NO_OFFSET) is 3x3 only (got K=%d)", K);
+    if (!src_prev || !aff || (!offset && !no_off)) return fail(NLSPN_ERR_NULL, "step: src_prev, aff (and offset) are required");
+    if ((flags & NLSPN_FLAG_PRESERVE_INPUT) && !feat_fix) return fail(NLSPN_ERR_NULL, "step: PRESERVE_INPUT needs feat_fix");
+    return 0;
+}
+
+int nlspn_step_fwd(const float *src_prev, const float *offset, const float *aff, const float *conf_fixed,
+                   const float *feat_fix, unsigned flags, int B, int H, int W, int K,
+                   float *out, float *src_next, void *stream)
+{
+    if (int rc = check_step(src_prev, offset, aff, feat_fix, flags, B, H, W, K)) return rc;
+    if (!out) return fail(NLSPN_ERR_NULL, "step_fwd: out is required");
+    if (conf_fixed && !src_next) return fail(NLSPN_ERR_NULL, "step_fwd: src_next is required with a confidence");
+    const int P = H * W, KK = K * K;
+    (void)KK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof__(kProfIterFwd, st);
+    if (flags & NLSPN_FLAG_NO_OFFSET) {
+        cudaError_t e = launch_pdl(false, fixed_fwd_kernel<false>, grid_for(P, B), dim3(kBlock), st, src_prev, aff,
+                                   conf_fixed, feat_fix, flags, H, W, out, src_next);
+        if (e != cudaSuccess) return cuda_fail(e, "fixed_fwd_kernel");
+        NLSPN_CHECK_LAUNCH("fixed_fwd_kernel");
+        return 0;
+    }
+    if (tiled_ok(src_prev, W)) {
+        CUtensorMap map;
+        const int th = fwd_tile_h();
+        if (int rc = make_plane_map(&map, src_prev, B, H, W, kTileW + 2 * halo_for(K), th + 2 * halo_for(K))) return rc;
+        dim3 grid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + th - 1) / th), (unsigned)B);
+        dim3 block(kTileW, th);
+        DISPATCH_TH(th, DISPATCH_K(K, (launch_pdl(false, iter_fwd_tiled_kernel<KC, THC, false>, grid, block, st, map, 0,
+                                                 src_prev, offset, aff, conf_fixed, feat_fix, flags, H, W, out,
+                                                 src_next))));
+        NLSPN_CHECK_LAUNCH("iter_fwd_tiled_kernel");
+        return 0;
+    }
+    DISPATCH_K(K, (iter_fwd_kernel<KC, true><<<grid_for(P, B), kBlock, 0, st>>>(
+                      src_prev, offset, aff, conf_fixed, feat_fix, nullptr, nullptr, flags, H, W, out, src_next)));
+    NLSPN_CHECK_LAUNCH("iter_fwd_kernel");
+    return 0;
+}
+
+size_t nlspn_step_bwd_workspace_bytes(int B, int H, int W, int K, unsigned flags)
+{
+    if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+    if (flags & NLSPN_FLAG_NO_OFFSET) return 16;
+    return sizeof(float) * (size_t)B * (size_t)scatter_geo(H, W).image + 16;   // four phase-shifted blocked planes
+}
+
+} // extern "C" (templates need C++ linkage)
+
+// shared by nlspn_step_bwd (DCN = false) and nlspn_dcn_backward_ws (DCN = true)
+template <bool DCN>
+static int run_step_bwd(const float *src_prev, const float *offset, const float *aff, const float *conf_fixed,
+                        const float *feat_fix, const float *out, const float *g_out, const float *g_src_next,
+                        const float *weight, unsigned flags, int B, int H, int W, int K, float *g_src_prev,
+                        float *g_offset, float *g_aff, float *g_conf, void *workspace, size_t workspace_bytes,
+                        cudaStream_t st)
+{
+    const int P = H * W;
+    const long BP = (long)B * P;
+    const bool blocked = opt(kOptDcnBlocked) != 0 && tiled_ok(src_prev, W) && workspace && aligned16(workspace) &&
+                         workspace_bytes >= nlspn_step_bwd_workspace_bytes(B, H, W, K, 0);
+    ProfScope prof__(DCN ? kProfDcnBwd : kProfIterBwdV1, st);
+    if (blocked) {
+        const ScatterGeo sg = scatter_geo(H, W);
+        float *planes = static_cast<float *>(workspace);
+        cudaError_t e = cudaMemsetAsync(planes, 0, sizeof(float) * (size_t)B * sg.image, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(scatter planes)");
+        CUtensorMap map;
+        if (int rc = make_plane_map(&map, src_prev, B, H, W, kTileW + 2 * halo_for(K), kFwdTH + 2 * halo_for(K))) return rc;
+        dim3 grid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + kFwdTH - 1) / kFwdTH), (unsigned)B);
+        DISPATCH_K(K, (step_bwd_tiled_kernel<KC, kFwdTH, DCN><<<grid, dim3(kTileW, kFwdTH), 0, st>>>(
+                          map, src_prev, offset, aff, conf_fixed, feat_fix, out, g_out, g_src_next, weight, flags, H, W,
+                          planes, g_offset, g_aff, g_conf)));
+        NLSPN_CHECK_LAUNCH("step_bwd_tiled_kernel");
+        scatter_collect_kernel<<<grid_for(P, B), kBlock, 0, st>>>(planes, H, W, g_src_prev);
+        NLSPN_CHECK_LAUNCH("scatter_collect_kernel");
+        return 0;
+    }
+    cudaError_t e = cudaMemsetAsync(g_src_prev, 0, sizeof(float) * BP, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(g_src_prev)");
+    DISPATCH_K(K, (step_bwd_direct_kernel<KC, DCN><<<grid_for(P, B), kBlock, 0, st>>>(
+                      src_prev, offset, aff, conf_fixed, feat_fix, out, g_out, g_src_next, weight, flags, H, W,
+                      g_src_prev, g_offset, g_aff, g_conf)));
+    NLSPN_CHECK_LAUNCH("step_bwd_direct_kernel");
+    return 0;
+}
+
+extern "C" {
+
+int nlspn_step_bwd(const float *src_prev, const float *offset, const float *aff, const float *conf_fixed,
+                   const float *feat_fix, const float *out, const float *g_out, const float *g_src_next,
+                   unsigned flags, int B, int H, int W, int K,
+                   float *g_src_prev, float *g_offset, float *g_aff, float *g_conf,
+                   void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (int rc = check_step(src_prev, offset, aff, feat_fix, flags, B, H, W, K)) return rc;
+    const bool no_off = (flags & NLSPN_FLAG_NO_OFFSET) != 0;
+    if (!g_src_prev || !g_aff || (!g_offset && !no_off)) return fail(NLSPN_ERR_NULL, "step_bwd: gradient outputs are required");
+    if (!out && (g_src_next || (flags & NLSPN_FLAG_ALWAYS_CLIP)))
+        return fail(NLSPN_ERR_NULL, "step_bwd: `out` (the forward's result) is required with g_src_next or ALWAYS_CLIP");
+    if (conf_fixed && !g_conf) return fail(NLSPN_ERR_NULL, "step_bwd: g_conf is required with a confidence");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (no_off) {
+        const int P = H * W;
+        cudaError_t e = cudaMemsetAsync(g_src_prev, 0, sizeof(float) * (size_t)B * P, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(g_src_prev)");
+        ProfScope prof__(kProfIterBwdV1, st);
+        fixed_step_bwd_kernel<<<grid_for(P, B), kBlock, 0, st>>>(src_prev, aff, conf_fixed, feat_fix, out, g_out,
+                                                                 g_src_next, flags, H, W, g_src_prev, g_aff, g_conf);
+        NLSPN_CHECK_LAUNCH("fixed_step_bwd_kernel");
+        return 0;
+    }
+    return run_step_bwd<false>(src_prev, offset, aff, conf_fixed, feat_fix, out, g_out, g_src_next, nullptr, flags, B, H,
+                               W, K, g_src_prev, g_offset, g_aff, g_conf, workspace, workspace_bytes, st);
+}
+
+size_t nlspn_dcn_backward_workspace_bytes(int B, int H, int W, int K)
+{
+    return nlspn_step_bwd_workspace_bytes(B, H, W, K, 0);
+}
+
+int nlspn_dcn_backward_ws(const float *input, const float *weight, const float *bias,
+                          const float *offset, const float *mask, const float *grad_output,
+                          int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                          int dilation_h, int dilation_w, int group, int deformable_group,
+                          int im2col_step, int B, int C, int H, int W,
+                          float *grad_input, float *grad_offset, float *grad_mask,
+                          float *grad_weight, float *grad_bias, void *workspace, size_t workspace_bytes,
+                          void *stream)
+{
+    (void)im2col_step;
+    (void)bias;
+    if (int rc = check_dcn_domain(kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h,
+                                  dilation_w, group, deformable_group, C))
+        return rc;
+    if (int rc = check_shape(B, H, W, kernel_h, 1)) return rc;
+    if (!input || !weight || !offset || !mask || !grad_output || !grad_input || !grad_offset ||
+        !grad_mask || !grad_weight || !grad_bias)
+        return fail(NLSPN_ERR_NULL, "dcn_backward: a required pointer is NULL");
+    const int P = H * W;
+    const int KK = kernel_h * kernel_h;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(grad_weight, 0, sizeof(float) * KK, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_weight)");
+    e = cudaMemsetAsync(grad_bias, 0, sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_bias)");
+    if (int rc = run_step_bwd<true>(input, offset, mask, nullptr, nullptr, nullptr, grad_output, nullptr, weight, 0u, B, H,
+                                    W, kernel_h, grad_input, grad_offset, grad_mask, nullptr, workspace,
+                                    workspace_bytes, st))
+        return rc;
     DISPATCH_K(kernel_h, (dcn_wb_grad_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
                              input, offset, mask, grad_output, H, W, grad_weight, grad_bias)));
     NLSPN_CHECK_LAUNCH("dcn_wb_grad_kernel");

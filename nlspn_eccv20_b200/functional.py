@@ -13,7 +13,7 @@ import torch
 from . import _lib
 
 __all__ = ["forward", "prologue_fwd", "propagate_fwd", "backward", "dcn_forward", "dcn_backward",
-           "debug_indices", "device_info"]
+           "step_fwd", "step_bwd", "debug_indices", "device_info"]
 
 
 def _ptr(t):
@@ -245,14 +245,68 @@ def dcn_backward(input, weight, bias, offset, mask, grad_output, kernel_h, kerne
     gw, gb = torch.empty_like(weight), torch.empty_like(bias)
     dev = input.device
     with torch.cuda.device(dev):
-        fn = lib.nlspn_dcn_backward if dt == torch.float32 else lib.nlspn_dcn_backward_f64
-        rc = fn(_ptr(input), _ptr(weight), _ptr(bias), _ptr(offset), _ptr(mask),
-                _ptr(grad_output), kernel_h, kernel_w, stride_h, stride_w, pad_h,
-                pad_w, dilation_h, dilation_w, group, deformable_group, im2col_step,
-                B, C, H, W, _ptr(gi), _ptr(go), _ptr(gm), _ptr(gw), _ptr(gb),
-                _stream(dev))
+        if dt == torch.float32:
+            # vector-RED scatter into blocked planes + TMA-delivered gather source (kernels_step.cuh)
+            nbytes = lib.nlspn_dcn_backward_workspace_bytes(B, H, W, kernel_h)
+            ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+            rc = lib.nlspn_dcn_backward_ws(_ptr(input), _ptr(weight), _ptr(bias), _ptr(offset), _ptr(mask),
+                                           _ptr(grad_output), kernel_h, kernel_w, stride_h, stride_w, pad_h,
+                                           pad_w, dilation_h, dilation_w, group, deformable_group, im2col_step,
+                                           B, C, H, W, _ptr(gi), _ptr(go), _ptr(gm), _ptr(gw), _ptr(gb),
+                                           _ptr(ws), nbytes, _stream(dev))
+        else:
+            rc = lib.nlspn_dcn_backward_f64(_ptr(input), _ptr(weight), _ptr(bias), _ptr(offset), _ptr(mask),
+                                            _ptr(grad_output), kernel_h, kernel_w, stride_h, stride_w, pad_h,
+                                            pad_w, dilation_h, dilation_w, group, deformable_group, im2col_step,
+                                            B, C, H, W, _ptr(gi), _ptr(go), _ptr(gm), _ptr(gw), _ptr(gb),
+                                            _stream(dev))
     _lib.check(rc, "nlspn_dcn_backward")
     return gi, go, gm, gw, gb
+
+
+def step_fwd(src_prev, offset, aff, conf_fixed, feat_fix, K, preserve_input=True, always_clip=False):
+    """One fused iteration (nlspnmodel.py:350-361).  -> (out, src_next | None).  offset=None: fixed-local."""
+    lib = _lib.load()
+    src_prev = _chk("src_prev", src_prev)
+    B, _, H, W = src_prev.shape
+    offset = _chk("offset", offset, (B, 2 * K * K, H, W), optional=True)
+    aff = _chk("aff", aff, (B, K * K, H, W))
+    conf_fixed = _chk("conf_fixed", conf_fixed, (B, 1, H, W), optional=True)
+    feat_fix = _chk("feat_fix", feat_fix, (B, 1, H, W), optional=True)
+    preserve = bool(preserve_input and feat_fix is not None)
+    out = torch.empty_like(src_prev)
+    src_next = torch.empty_like(src_prev) if conf_fixed is not None else None
+    dev = src_prev.device
+    with torch.cuda.device(dev):
+        rc = lib.nlspn_step_fwd(_ptr(src_prev), _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(feat_fix),
+                                _flags(preserve, always_clip, offset is not None), B, H, W, K, _ptr(out),
+                                _ptr(src_next), _stream(dev))
+    _lib.check(rc, "nlspn_step_fwd")
+    return out, src_next
+
+
+def step_bwd(src_prev, offset, aff, conf_fixed, feat_fix, out, g_out, g_src_next, K,
+             preserve_input=True, always_clip=False):
+    """-> (g_src_prev, g_offset | None, g_aff, g_conf | None)."""
+    lib = _lib.load()
+    B, _, H, W = src_prev.shape
+    dev = src_prev.device
+    g_out = _chk("g_out", g_out, (B, 1, H, W), optional=True)
+    g_src_next = _chk("g_src_next", g_src_next, (B, 1, H, W), optional=True)
+    preserve = bool(preserve_input and feat_fix is not None)
+    flags = _flags(preserve, always_clip, offset is not None)
+    g_src_prev = torch.empty_like(src_prev)
+    g_off = torch.empty_like(offset) if offset is not None else None
+    g_aff = torch.empty_like(aff)
+    g_conf = torch.empty_like(conf_fixed) if conf_fixed is not None else None
+    nbytes = lib.nlspn_step_bwd_workspace_bytes(B, H, W, K, flags)
+    ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        rc = lib.nlspn_step_bwd(_ptr(src_prev), _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(feat_fix), _ptr(out),
+                                _ptr(g_out), _ptr(g_src_next), flags, B, H, W, K, _ptr(g_src_prev), _ptr(g_off),
+                                _ptr(g_aff), _ptr(g_conf), _ptr(ws), nbytes, _stream(dev))
+    _lib.check(rc, "nlspn_step_bwd")
+    return g_src_prev, g_off, g_aff, g_conf
 
 
 def debug_indices(offset, K):

@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import functional as F_
 
-__all__ = ["NLSPN", "NLSPNFunction", "nlspn_propagate", "GraphedNLSPN"]
+__all__ = ["NLSPN", "NLSPNFunction", "nlspn_propagate", "NLSPNStepFunction", "nlspn_step", "GraphedNLSPN"]
 
 
 class NLSPNFunction(torch.autograd.Function):
@@ -27,8 +27,10 @@ class NLSPNFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat_init, guidance, confidence, feat_fix, gamma, K, T, affinity,
-                preserve_input, always_clip, use_offset=True, conf_mode="premul", blend="post", legacy=False):
-        need_grad = any(t is not None and t.requires_grad for t in (feat_init, guidance, confidence, gamma))
+                preserve_input, always_clip, use_offset=True, conf_mode="premul", blend="post", legacy=False,
+                need_grad=None):
+        if need_grad is None:   # direct .apply() callers: grad mode is already off in here, so only the inputs count
+            need_grad = any(torch.is_tensor(t) and t.requires_grad for t in (feat_init, guidance, confidence, gamma))
         gamma_val = gamma.detach() if torch.is_tensor(gamma) else float(gamma)   # stays on the device
         feat_init_c = feat_init.detach().contiguous()
         guidance_c = guidance.detach().contiguous()
@@ -38,14 +40,16 @@ class NLSPNFunction(torch.autograd.Function):
         offset, aff, conf_fixed, src, list_feat = F_.forward(
             guidance_c, conf_c, feat_init_c, fix_c, gamma_val, K, T, affinity, preserve, always_clip,
             keep_src=need_grad, use_offset=use_offset, conf_mode=conf_mode, blend=blend, legacy=legacy)
-        ctx.cfg = (K, T, affinity, preserve, always_clip, gamma_val)
+        ctx.cfg = (K, T, affinity, preserve, always_clip, None if torch.is_tensor(gamma_val) else gamma_val)
         ctx.use_offset = bool(use_offset)
         ctx.mode = (conf_mode, blend, bool(legacy))
         ctx.conf_raw = conf_c if (conf_mode == "sampled" and conf_c is not None) else None
         ctx.conf_grad = conf_c is not None and conf_mode != "none"
         ctx.has_conf = conf_fixed is not None
         ctx.gamma_is_tensor = torch.is_tensor(gamma)
-        ctx.save_for_backward(feat_init_c, guidance_c, fix_c, offset, aff, conf_fixed, src, list_feat)
+        # gamma goes through save_for_backward so that an in-place update between forward and backward is caught
+        ctx.save_for_backward(feat_init_c, guidance_c, fix_c, offset, aff, conf_fixed, src, list_feat,
+                              gamma_val if torch.is_tensor(gamma_val) else None)
         ctx.set_materialize_grads(False)
         # outputs: T states, aff, [offset], [conf_fixed]
         outs = tuple(list_feat[t] for t in range(T)) + (aff,)
@@ -59,7 +63,9 @@ class NLSPNFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, *grads):
         K, T, affinity, preserve, always_clip, gamma_val = ctx.cfg
-        feat_init, guidance, feat_fix, offset, aff, conf_fixed, src, list_feat = ctx.saved_tensors
+        feat_init, guidance, feat_fix, offset, aff, conf_fixed, src, list_feat, gamma_t = ctx.saved_tensors
+        if gamma_t is not None:
+            gamma_val = gamma_t
         g_list = list(grads[:T])
         g_aff_ext = grads[T]
         i = T + 1
@@ -79,7 +85,43 @@ class NLSPNFunction(torch.autograd.Function):
             g_conf = g_conf + (1.0 - m) * g_cf_ext
         g_gam = g_gamma.to(torch.float32) if ctx.gamma_is_tensor else None
         return g_init, g_guid, (g_conf if ctx.conf_grad else None), None, g_gam, \
-            None, None, None, None, None, None, None, None, None
+            None, None, None, None, None, None, None, None, None, None
+
+
+class NLSPNStepFunction(torch.autograd.Function):
+    """ONE fused iteration of the loop body nlspnmodel.py:350-361 (nlspn_step_fwd / nlspn_step_bwd):
+    (src_prev, offset|None, aff, conf_fixed|None, feat_fix|None) -> out [, src_next = out * conf_fixed]."""
+
+    @staticmethod
+    def forward(ctx, src_prev, offset, aff, conf_fixed, feat_fix, K, preserve_input, always_clip):
+        src_c = src_prev.detach().contiguous()
+        off_c = offset.detach().contiguous() if offset is not None else None
+        aff_c = aff.detach().contiguous()
+        conf_c = conf_fixed.detach().contiguous() if conf_fixed is not None else None
+        fix_c = feat_fix.detach().contiguous() if feat_fix is not None else None
+        preserve = bool(preserve_input and fix_c is not None)
+        out, src_next = F_.step_fwd(src_c, off_c, aff_c, conf_c, fix_c, K, preserve, always_clip)
+        ctx.cfg = (K, preserve, bool(always_clip))
+        ctx.save_for_backward(src_c, off_c, aff_c, conf_c, fix_c, out)
+        ctx.set_materialize_grads(False)
+        return out if src_next is None else (out, src_next)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out, g_src_next=None):
+        K, preserve, always_clip = ctx.cfg
+        src, off, aff, conf, fix, out = ctx.saved_tensors
+        g_src, g_off, g_aff, g_conf = F_.step_bwd(src, off, aff, conf, fix, out, g_out, g_src_next, K,
+                                                  preserve, always_clip)
+        return g_src, g_off, g_aff, g_conf, None, None, None, None
+
+
+def nlspn_step(src_prev, offset, aff, conf_fixed, feat_fix, prop_kernel=3, preserve_input=True, always_clip=False):
+    """One propagation iteration on the PRE-MULTIPLIED state: -> (out, src_next | None).
+    ``offset`` [B,2K^2,H,W] incl. the zero centre pair, or None for the fork's fixed-local propagation;
+    ``aff`` [B,K^2,H,W] normalised incl. the centre weight.  Differentiable in src_prev, offset, aff, conf_fixed."""
+    r = NLSPNStepFunction.apply(src_prev, offset, aff, conf_fixed, feat_fix, prop_kernel, preserve_input, always_clip)
+    return r if isinstance(r, tuple) else (r, None)
 
 
 def nlspn_propagate(feat_init, guidance, confidence, feat_fix, gamma, prop_kernel=3, prop_time=18,
@@ -88,9 +130,12 @@ def nlspn_propagate(feat_init, guidance, confidence, feat_fix, gamma, prop_kerne
     """Functional form.  -> (feat_result, list_feat, offset|None, aff, conf_fixed|None).
     use_offset=False selects the fork's fixed-local propagation (nlspnmodel.py:209-224); guidance
     then holds the N raw affinities only and `offset` is None (as in nlspnmodel.py:306-308)."""
+    # a backward can only follow when autograd is recording (eval / no_grad / graph capture keep two src planes)
+    need_grad = torch.is_grad_enabled() and any(
+        torch.is_tensor(t) and t.requires_grad for t in (feat_init, guidance, confidence, gamma))
     outs = NLSPNFunction.apply(feat_init, guidance, confidence, feat_fix, gamma, prop_kernel,
                                prop_time, affinity, preserve_input, always_clip, use_offset,
-                               conf_mode if confidence is not None else "none", blend, legacy)
+                               conf_mode if confidence is not None else "none", blend, legacy, need_grad)
     T = prop_time
     list_feat = list(outs[:T])
     aff = outs[T]

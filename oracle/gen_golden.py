@@ -16,6 +16,8 @@ autograd for a fixed loss.  Cases:
                 (ref_harness.reference_propagate) on designed inputs (stable set,
                 signed set, edge set, K=5, no-confidence, other affinity modes).
   dcn_*         single ModulatedDeformConvFunction.apply calls (boundary B1).
+  gru_*         a real ``NLSPNModel(use_GRU=True, use_S2D=True)`` forward + backward (the fork's default
+                configuration; affinities re-estimated between iterations), with and without offsets.
 """
 from __future__ import annotations
 
@@ -184,6 +186,8 @@ def case_paths():
         ("path_ASS_k3_t4", 1, 12, 16, 3, 4, dict(), dict(affinity="ASS"), True),
         ("path_TC_k3_t4", 1, 12, 16, 3, 4, dict(), dict(affinity="TC"), True),
         ("path_clip_k3_t4", 1, 12, 16, 3, 4, dict(signed=True), dict(always_clip=True), True),
+        # always_clip with EXACT zeros in the state: torch.clamp(min=0) passes the gradient at x == 0
+        ("path_clipzero_k3_t4", 1, 16, 24, 3, 4, dict(signed=True, off_sigma=1.0), dict(always_clip=True), True),
         # the fork's default: no offsets -> fixed-local 3x3 propagation (nlspnmodel.py:209-224)
         ("path_fixedlocal_k3_t6", 2, 14, 20, 3, 6, dict(), dict(offset=False), True),
         ("path_fixedlocal_noconf_k3_t3", 1, 9, 13, 3, 3, dict(signed=True), dict(offset=False, conf_prop=False), False),
@@ -201,6 +205,11 @@ def case_paths():
             o[0, 12, H - 1, :] = 0.0  # tap 6 (after insert tap 7) dh: row H-1 -> h_im = H
             o[1, 2, 3, :] = 1.0
             o[1, 4:6, 7, :] = 40.0   # far out of range
+        if name.startswith("path_clipzero"):
+            # a block of exact zeros wider than T iterations can reach across (ReLU head output, no sparse depth)
+            inp["feat_init"][:, :, :, :14] = 0.0
+            inp["feat_fix"][:, :, :, :14] = 0.0
+            inp["guidance"][:, :2 * (K * K - 1)].clamp_(-1.5, 1.5)
         with_grad = True
         rec = run_path(model, inp, with_grad=with_grad, use_conf=use_conf)
         a = model.args
@@ -248,9 +257,67 @@ def case_dcn():
         print("wrote %-40s %7.1f KB" % (name + ".npz", os.path.getsize(path) / 1024))
 
 
+GRU_MODULES = ("GRU", "encode_aff", "encode_dep", "decode_aff")
+
+
+def case_gru():
+    """The fork's GRU mode (nlspnmodel.py:365-373; its DEFAULT configuration, src/config.py:225-232): a real
+    ``NLSPNModel(use_GRU=True, use_S2D=True).forward`` + backward.  Stored: the three head outputs (captured by
+    hooks), the small GRU-side sub-modules' parameters, every intermediate prediction, the last re-estimated
+    affinities, and the reference's autograd gradients wrt the head outputs, gamma and the GRU-side parameters."""
+    for name, offset in (("gru_offset_k3_t4", True), ("gru_fixedlocal_k3_t4", False)):
+        torch.manual_seed(SEED + len(name))
+        B, H, W, K, T = 1, 24, 32, 3, 4
+        model = RH.build_reference_model(network="resnet18", prop_kernel=K, prop_time=T, offset=offset,
+                                         use_GRU=True, use_S2D=True, patch_height=H, patch_width=W)
+        model.train(False)
+        with torch.no_grad():
+            model.off_aff_dec0[0].weight.mul_(40.0)       # fresh heads give tiny guidance: make offsets matter
+        cap = {}
+
+        def grab(key):
+            def hook(m, i, o):
+                o.retain_grad()
+                cap[key] = o
+            return hook
+        hooks = [model.id_dec0.register_forward_hook(grab("feat_init")),
+                 model.off_aff_dec0.register_forward_hook(grab("guidance")),
+                 model.cf_dec0.register_forward_hook(grab("confidence"))]
+        g = torch.Generator().manual_seed(SEED + 5)
+        gt = smooth_field(g, B, H, W, 0.5, 10.0)
+        dep = gt * (torch.rand(B, 1, H, W, generator=g) < 0.1).float()
+        rgb = torch.randn(B, 3, H, W, generator=g)
+        out = model({"rgb": rgb, "dep": dep})
+        for h in hooks:
+            h.remove()
+        loss = loss_fn(out, gt)
+        loss.backward()
+        d = {"in_feat_init": cap["feat_init"], "in_guidance": cap["guidance"], "in_confidence": cap["confidence"],
+             "in_feat_fix": dep, "in_gt": gt,
+             "out_pred": out["pred"], "out_list_feat": torch.stack(out["pred_inter"], 0), "out_aff": out["aff"],
+             "out_conf_fixed": out["confidence"], "out_loss": loss,
+             "out_g_feat_init": cap["feat_init"].grad, "out_g_guidance": cap["guidance"].grad,
+             "out_g_confidence": cap["confidence"].grad, "out_g_gamma": model.aff_scale_const.grad}
+        if offset:
+            d["out_offset"] = out["offset"]
+        for k, v in model.state_dict().items():
+            if k.split(".")[0] in GRU_MODULES:
+                d["param_" + k] = v
+        for k, v in model.named_parameters():
+            if k.split(".")[0] in GRU_MODULES:
+                d["pgrad_" + k] = v.grad
+        meta = dict(K=K, T=T, affinity="TGASS", preserve=1, use_conf=1, always_clip=0, use_offset=int(offset),
+                    gamma=float(model.aff_scale_const.detach()), max_depth=float(model.args.max_depth))
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **{k: v.detach().numpy() for k, v in d.items()},
+                            **{"meta_" + k: np.asarray(v) for k, v in meta.items()})
+        print("wrote %-40s %7.1f KB" % (name + ".npz", os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
-    case_fullmodel()
-    case_paths()
-    case_dcn()
+    only = sys.argv[1:]          # optional: names of the case groups to (re)generate
+    for fn in (case_fullmodel, case_paths, case_dcn, case_gru):
+        if not only or fn.__name__ in only:
+            fn()

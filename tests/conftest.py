@@ -33,3 +33,18 @@ def oracle():
     from oracle import nlspn_oracle
     nlspn_oracle.build()
     return nlspn_oracle
+
+
+@pytest.fixture
+def nlspn_opt():
+    """Sets tuning options of libnlspn_b200.so for one test (nlspn_set_option) and restores them afterwards."""
+    from nlspn_eccv20_b200 import _lib
+    old = {}
+
+    def set_(**kw):
+        for k, v in kw.items():
+            old.setdefault(k, _lib.get_option(k))
+            _lib.set_option(k, int(v))
+    yield set_
+    for k, v in old.items():
+        _lib.set_option(k, v)

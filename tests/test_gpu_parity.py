@@ -81,12 +81,12 @@ def test_forward_matches_reference_golden(dev, name):
 
 @pytest.mark.parametrize("form", ["default", "gather"])
 @pytest.mark.parametrize("name", [n for n in PATHS if "fullmodel" not in n])
-def test_backward_matches_reference_autograd(dev, monkeypatch, name, form):
+def test_backward_matches_reference_autograd(dev, nlspn_opt, name, form):
     """`form`: pass A of the backward as the library chooses it, or forced to the tabulated gather
     (kernels_gather.cuh) -- every mode of the golden set (affinity modes, no confidence, no preserve_input,
     always_clip, K = 5) goes through both."""
     if form == "gather":
-        monkeypatch.setenv("NLSPN_STATE_GATHER", "1")
+        nlspn_opt(state_gather=1)
     g = load_golden(name)
     mod, (fi, gd, cf), (feat_result, list_feat, offset, aff, _), m = _run_module(g, dev, grad=True)
     gl = torch.from_numpy(g["out_g_list"]).to(dev)
@@ -288,14 +288,13 @@ def test_fused_path_equals_unfused_reference_statements(dev):
 
 @pytest.mark.parametrize("K,T,use_conf", [(3, 6, True), (5, 3, True), (3, 4, False), (7, 2, True)])
 @pytest.mark.parametrize("form", ["red", "gather", "gather-compact"])
-def test_two_pass_backward_equals_per_iteration_backward(dev, monkeypatch, K, T, use_conf, form):
+def test_two_pass_backward_equals_per_iteration_backward(dev, nlspn_opt, K, T, use_conf, form):
     """Both forms of pass A -- the REDx4 scatter (kernels_v2.cuh; default for K = 3) and the tabulated
     gather (kernels_gather.cuh; default for K >= 5) -- with pass B in registers, against the
     per-iteration formulation (accumulator RMW + scalar atomics) on the same saved tensors."""
     from nlspn_eccv20_b200 import functional as F_
     from nlspn_eccv20_b200.synth import make_inputs
-    monkeypatch.setenv("NLSPN_STATE_GATHER", "0" if form == "red" else "1")
-    monkeypatch.setenv("NLSPN_GATHER_COMPACT", "1" if form == "gather-compact" else "0")
+    nlspn_opt(state_gather=0 if form == "red" else 1, gather_compact=1 if form == "gather-compact" else 0)
     B, H, W = 2, 38, 45
     inp = make_inputs(B, H, W, K, seed=77 + K, device=dev, conf_mean=2.0)
     gamma = 0.5 * (K * K - 1)
@@ -388,7 +387,7 @@ def test_unusual_inputs(dev):
         mod(inp["feat_init"].double(), inp["guidance"], inp["confidence"], inp["feat_fix"])
 
 
-def test_persistent_forward_equals_per_iteration_forward(dev, monkeypatch):
+def test_persistent_forward_equals_per_iteration_forward(dev, nlspn_opt):
     """One NYU-sized frame takes the persistent cooperative kernel (geometry in registers, grid
     barrier per iteration); NLSPN_PERSIST=0 forces the per-iteration kernels.  Same arithmetic."""
     from nlspn_eccv20_b200 import NLSPN
@@ -397,17 +396,17 @@ def test_persistent_forward_equals_per_iteration_forward(dev, monkeypatch):
     mod = NLSPN(prop_kernel=3, prop_time=18).to(dev)
     with torch.no_grad():
         a = mod(inp["feat_init"], inp["guidance"], inp["confidence"], inp["feat_fix"])
-        monkeypatch.setenv("NLSPN_PERSIST", "0")
+        nlspn_opt(persist=0)
         b = mod(inp["feat_init"], inp["guidance"], inp["confidence"], inp["feat_fix"])
     for x, y in zip(a[1], b[1]):
         assert float((x - y).abs().max()) <= 2e-6
     # and with gradients (all src planes kept): backward consumes what the persistent kernel saved
-    monkeypatch.delenv("NLSPN_PERSIST")
+    nlspn_opt(persist=-1)
     fi = inp["feat_init"].clone().requires_grad_(True)
     out = mod(fi, inp["guidance"], inp["confidence"], inp["feat_fix"])
     out[0].sum().backward()
     g1 = fi.grad.clone()
-    monkeypatch.setenv("NLSPN_PERSIST", "0")
+    nlspn_opt(persist=0)
     fi2 = inp["feat_init"].clone().requires_grad_(True)
     mod(fi2, inp["guidance"], inp["confidence"], inp["feat_fix"])[0].sum().backward()
     assert float((g1 - fi2.grad).abs().max()) <= 1e-5 * float(g1.abs().max())
@@ -415,14 +414,14 @@ def test_persistent_forward_equals_per_iteration_forward(dev, monkeypatch):
 
 @pytest.mark.parametrize("form", ["red", "gather"])
 @pytest.mark.parametrize("K,T,legacy,B,H,W", [(3, 6, False, 2, 28, 36), (3, 4, True, 1, 21, 27), (5, 3, False, 1, 24, 32)])
-def test_upstream_semantics_against_torchvision_restatement(dev, monkeypatch, K, T, legacy, B, H, W, form):
+def test_upstream_semantics_against_torchvision_restatement(dev, nlspn_opt, K, T, legacy, B, H, W, form):
     """conf_mode='sampled' + blend='pre' (+legacy): the UPSTREAM semantics of the north-star prose.
     PARITY UNPINNED -- no upstream code is in the reference tree; the referee is the restatement in
     oracle/torchvision_port.py (CPU, autograd).  Forward 1e-4 m, gradients 1e-4 relative."""
     from nlspn_eccv20_b200 import NLSPN
     from nlspn_eccv20_b200.synth import make_inputs
     from oracle import torchvision_port as TP
-    monkeypatch.setenv("NLSPN_STATE_GATHER", "1" if form == "gather" else "0")     # both forms of pass A
+    nlspn_opt(state_gather=1 if form == "gather" else 0)     # both forms of pass A
     inp = make_inputs(B, H, W, K, seed=900 + K + T, conf_mean=1.0)
     gamma = 0.5 * (K * K - 1)
     # CPU referee
@@ -478,7 +477,7 @@ def test_cuda_graph_replay_is_bit_identical_to_eager(dev, shape, K):
         g(a["feat_init"][:, :, :-1], a["guidance"][:, :, :-1], a["confidence"][:, :, :-1], a["feat_fix"][:, :, :-1])
 
 
-def test_gather_form_overflowing_blocks(dev, monkeypatch):
+def test_gather_form_overflowing_blocks(dev, nlspn_opt):
     """Gather-form pass A with many footprints converging on the same 2x2 block (all taps of a whole region
     point at one pixel: far more than CAP entries per block, so the overflow path carries most of the
     gradient) against the RED-form pass A and the per-iteration backward."""
@@ -505,8 +504,7 @@ def test_gather_form_overflowing_blocks(dev, monkeypatch):
     args = (gd, inp["feat_init"], inp["feat_fix"], offset, aff, cfx, src, lf, g_list, gamma, K, T)
     ref = F_.backward(*args, per_iteration=True)
     for form, compact in (("0", "0"), ("1", "0"), ("1", "1")):
-        monkeypatch.setenv("NLSPN_STATE_GATHER", form)
-        monkeypatch.setenv("NLSPN_GATHER_COMPACT", compact)
+        nlspn_opt(state_gather=int(form), gather_compact=int(compact))
         out = F_.backward(*args)
         for x, y, name in zip(out, ref, ["g_init", "g_guidance", "g_conf", "g_gamma"]):
             s = float(y.abs().max())
