@@ -269,8 +269,9 @@ def test_deviation_denormal_gradients_are_flushed(ref):
 def test_deviation_nan_offsets(ref):
     """A NaN offset: both sides drop that tap from the forward gather and from grad_input (the validity test of
     cuh:180 is false for NaN).  The reference's coordinate-gradient kernel then computes with the NaN coordinate
-    (cuh:308-311 only catches <= -1 / >= H) and returns NaN for that tap's grad_offset; ours returns 0 for an
-    invalid tap.  Everything else agrees."""
+    (cuh:308-311 only catches <= -1 / >= H) and returns NaN for that tap's grad_offset and grad_mask, which the
+    normalisation backward spreads over that pixel's guidance channels; ours returns 0 for an invalid tap, so
+    every gradient stays finite.  Everything outside the planted pixels agrees."""
     from nlspn_eccv20_b200 import NLSPN
     from nlspn_eccv20_b200.synth import make_inputs
     dev = torch.device("cuda:0")
@@ -295,7 +296,13 @@ def test_deviation_nan_offsets(ref):
     for n, y, x in planted:
         assert float(gd.grad[0, 2 * n, y, x]) == 0.0 and float(gd.grad[0, 2 * n + 1, y, x]) == 0.0
     ok = torch.isfinite(gd2.grad)
-    assert int((~ok).sum()) <= 2 * len(planted)                        # the reference: NaN only at the planted taps
+    # the reference: NaN only at the planted PIXELS -- the tap's two offset channels, and (its grad_mask being
+    # NaN too, cuh:312-316) whatever the normalisation backward couples to it at that pixel
+    at_planted = torch.zeros(H, W, dtype=torch.bool, device=dev)
+    for n, y, x in planted:
+        at_planted[y, x] = True
+    assert not bool(((~ok) & ~at_planted[None, None]).any())
+    assert int((~ok).sum()) <= 3 * N * len(planted)
     dd = (gd.grad - torch.where(ok, gd2.grad, gd.grad)).abs()
     assert float((dd[:, :2 * N] > 1e-4 * gd2.grad[ok].abs().max()).float().mean()) < 2e-3
     assert float(dd[:, 2 * N:].max()) <= 2e-4 * float(gd2.grad[:, 2 * N:][ok[:, 2 * N:]].abs().max())
@@ -327,4 +334,6 @@ def test_always_clip_passes_gradient_at_exact_zero(ref):
     assert _rel(cf.grad, cf2.grad) < 1e-4
     N = K * K - 1
     assert _rel(gd.grad[:, 2 * N:], gd2.grad[:, 2 * N:]) < 2e-4
-    assert (torch.stack(out[1]) - torch.stack(r["list_feat"])).abs().max() <= 1e-4
+    # signed (non-convex) inputs: the relative bound of SURVEY 8c, max|d| / max|x| <= 1e-5
+    ref_states = torch.stack(r["list_feat"]).detach()
+    assert (torch.stack(out[1]).detach() - ref_states).abs().max() <= 1e-5 * max(1.0, float(ref_states.abs().max()))
