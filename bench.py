@@ -11,22 +11,29 @@ no collective on the data path -- SURVEY 8e).
 
 metric  Gpix*iter/s = (GPUs * B * H * W * T) / seconds, forward+backward.
 value   device-timed (CUDA events, max over ranks), inputs resident in HBM.
-e2e     same metric through the public module with PINNED HOST inputs: H2D of the step's
-        inputs and D2H of the step's loss inside the timed region.
+e2e     same metric through the public module with PINNED HOST inputs: every step uploads its inputs
+        (H2D) and reads back the loss AND the step's result feat_result (D2H into pinned memory) inside the
+        timed region.  e2e_variants also reports the round-1 definition (loss only) and the strictest one
+        (all input gradients copied back as well).
 roofline  dominant kernel = the one with the largest share of the step (K=3: pass A of the backward,
         bwd_state_kernel, 12N+40 B/px per launch; K>=5: bwd_gather_kernel, 16N+20 B/px; DESIGN.md 3, 9);
         achieved = its algorithmic bytes per launch / its average launch duration (CUDA-event time of
         its phase in the timed region x its share of that phase from an event-bracketed pass);
         peak = MEASURED_PEAKS.json hbm_gbs; traffic = measured DRAM bytes per launch (profiles/ncu_traffic.json).
-        roofline_step = SURVEY 8d's algorithmic bytes of the whole step against the same peak.
+        roofline_step = SURVEY 8d's algorithmic bytes of the whole step against the same peak;
+        roofline_step_dram = the DRAM bytes the kernels really move (ncu) against the same peak.
+ref_cuda  (N=1, when oracle/_ref/DCN_ref.so travelled with the repo) the reference's OWN CUDA kernels compiled
+        for sm_100a, under the reference's per-iteration op chain, timed on the same GPU and inputs.
 cpu_baseline  the reference path restated over torchvision.ops.deform_conv2d (north_star's CPU
-        stand-in; oracle/torchvision_port.py, pinned against the unmodified reference), one image
-        per host thread, on a bounded sample of the same workload.  Rank 0, N=1 only.
+        stand-in; oracle/torchvision_port.py, pinned against the unmodified reference), one full frame
+        per host thread.  Rank 0, N=1 only.
+other_configs  (N=1) BASELINE.json's configs 1, 2, 3 and 5 on this GPU, a few steps each.
 --impl reference  times that CPU implementation alone (rank 0), same metric/config.
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import sys
@@ -38,7 +45,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "nlspn_propagation_fwd_bwd_gpix_iter_per_s"
+METRIC_FWD = "nlspn_propagation_fwd_gpix_iter_per_s"
 UNIT = "Gpix*iter/s"
+L2_MB = 126.0
 
 
 def parse():
@@ -58,9 +67,11 @@ def parse():
     p.add_argument("--cuda-graph", action="store_true",
                    help="forward-only runs: replay the module's forward from a CUDA graph (GraphedNLSPN)")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-images", type=int, default=None, help="frames in the CPU sample (default: min(cores, 8))")
-    p.add_argument("--cpu-rows", type=int, default=176,
-                   help="rows of each frame in the CPU sample (full width; bounds the CPU leg's run time)")
+    p.add_argument("--no-ref-cuda", action="store_true")
+    p.add_argument("--no-other-configs", action="store_true")
+    p.add_argument("--cpu-images", type=int, default=None, help="frames in the CPU sample (default: host cores, <= 32)")
+    p.add_argument("--cpu-rows", type=int, default=0,
+                   help="rows of each frame in the CPU sample (0 = full height; full width always)")
     return p.parse_args()
 
 
@@ -75,12 +86,48 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def l2_peak():
+    try:
+        with open(os.path.join(ROOT, "profiles", "l2_peak.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def alg_bytes(K, T, mode):
     """Algorithmic bytes per pixel*iteration (fork semantics, fp32)."""
     N = K * K - 1
     fwd = 12 * N + 20 + (24 * N + 28) / T
     bwd = 36 * N + 36 + (28 * N + 12) / T
     return fwd if mode == "fwd" else fwd + bwd
+
+
+def bind_host(local, world):
+    """Multi-rank runs: spread the ranks' host threads -- and with them the first-touch placement of their
+    pinned staging buffers -- over the box's NUMA nodes, so that N ranks' H2D streams do not all pull from one
+    node's DRAM.  Returns what was done (reported in the JSON line)."""
+    info = {"numa_nodes": 1, "bound_to_node": None}
+    try:
+        nodes = sorted(glob.glob("/sys/devices/system/node/node[0-9]*"), key=lambda p: int(p.rsplit("node", 1)[1]))
+        info["numa_nodes"] = max(1, len(nodes))
+        if world > 1 and len(nodes) > 1:
+            node = nodes[(local * len(nodes)) // world]
+            cpus = set()
+            for part in open(os.path.join(node, "cpulist")).read().strip().split(","):
+                if "-" in part:
+                    a, b = part.split("-")
+                    cpus.update(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.add(int(part))
+            allowed = os.sched_getaffinity(0)
+            cpus = cpus & allowed if cpus & allowed else cpus
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound_to_node"] = int(node.rsplit("node", 1)[1])
+                info["cpus"] = len(cpus)
+    except Exception as e:       # never fatal: this is placement, not correctness
+        info["error"] = str(e)[:80]
+    return info
 
 
 class ClockSampler:
@@ -135,8 +182,9 @@ class ClockSampler:
 
 def cpu_reference_run(args, H, W, md, n_images, steps, warmup):
     """Times oracle/torchvision_port.py (the reference path over torchvision) on host cores.
-    Sample: n_images frames of min(H, --cpu-rows) rows x full width, one frame per host thread."""
-    H = min(H, args.cpu_rows)
+    Sample: n_images full frames (--cpu-rows R > 0: full-width strips of R rows), one frame per host thread."""
+    if args.cpu_rows and args.cpu_rows > 0:
+        H = min(H, args.cpu_rows)
     import torch
     from nlspn_eccv20_b200.synth import make_inputs
     from oracle import torchvision_port as TP
@@ -163,6 +211,294 @@ def cpu_reference_run(args, H, W, md, n_images, steps, warmup):
                 host_cores=cores, n_images=n_images, rows=H)
 
 
+def cpu_sample_text(r, H, W, train):
+    shape = ("full %dx%d frames" % (H, W)) if r["rows"] == H else \
+        ("%d-row x %d-col full-width strips of the %dx%d frame" % (r["rows"], W, H, W))
+    return ("%d %s per step, one frame per host thread, fwd%s, torchvision deform_conv2d stand-in "
+            "(oracle/torchvision_port.py), %d host cores, %.1f s per pass (mean; best pass = %.5f %s)"
+            % (r["n_images"], shape, "+bwd" if train else "", r["host_cores"], r["seconds"], r["best"], UNIT))
+
+
+class GpuRun:
+    """One workload on one GPU: resident-input timing, optional per-kernel split, optional end-to-end legs."""
+
+    def __init__(self, torch, dev, lib, workload_name, B, K, T, mode, seed, smooth=False, pin=False):
+        from nlspn_eccv20_b200 import NLSPN
+        from nlspn_eccv20_b200.synth import SHAPES, workload
+        self.torch, self.dev, self.lib = torch, dev, lib
+        self.H, self.W, self.md = SHAPES[workload_name]
+        self.B, self.K, self.T, self.mode = B, K, T, mode
+        self.train = mode == "fwdbwd"
+        self.host = workload(workload_name, B, K, seed=seed, smooth_offsets=smooth, pin=pin)
+        self.names = ["feat_init", "guidance", "confidence", "feat_fix"]
+        self.dev_in = {k: self.host[k].to(dev) for k in self.names}
+        self.gt = self.host["gt"].to(dev)
+        self.mod = NLSPN(prop_kernel=K, prop_time=T).to(dev)
+        self.graphed = None
+        self.guid_mb = B * 3 * (K * K - 1) * self.H * self.W * 4 / 1e6
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def use_graph(self):
+        d = self.dev_in
+        self.graphed = self.mod.graphed(d["feat_init"], d["guidance"], d["confidence"], d["feat_fix"])
+
+    def step(self, inp, rec=None):
+        torch, mod, train = self.torch, self.mod, self.train
+        fi, gd, cf = inp["feat_init"], inp["guidance"], inp["confidence"]
+        if train:
+            fi, gd, cf = (t.detach().requires_grad_(True) for t in (fi, gd, cf))
+            mod.aff_scale_const.grad = None
+        e0, e1, e2 = (self.ev(), self.ev(), self.ev()) if rec is not None else (None, None, None)
+        if rec is not None:
+            e0.record()
+        with torch.set_grad_enabled(train):
+            if self.graphed is not None and inp is self.dev_in:      # resident inputs ARE the graph's static buffers
+                feat_result = self.graphed(*self.graphed.inputs)[0]
+            else:
+                feat_result = (self.graphed or mod)(fi, gd, cf, inp["feat_fix"])[0]
+            pred = torch.clamp(feat_result, min=0)
+            loss = (pred - self.gt).abs().sum()      # L1 surrogate of the reference loss (l1loss.py:27-42)
+        if rec is not None:
+            e1.record()
+        if train:
+            loss.backward()
+        if rec is not None:
+            e2.record()
+            rec.append((e0, e1, e2))
+        return loss
+
+    def timed(self, steps, warmup, flush, sync_all):
+        """-> total_ms, fwd_ms, bwd_ms (per step), launches."""
+        torch, lib = self.torch, self.lib
+        for _ in range(warmup):
+            self.step(self.dev_in)
+        sync_all()
+        rec = []
+        n0 = lib.nlspn_launch_count()
+        t_start, t_end = self.ev(), self.ev()
+        flush_buf = torch.empty(64 * 1024 * 1024, device=self.dev, dtype=torch.float32) if flush else None
+        t_start.record()
+        for _ in range(steps):
+            if flush:
+                flush_buf.fill_(1.0)           # evicts L2; excluded from the step time below
+            self.step(self.dev_in, rec)
+        t_end.record()
+        sync_all()
+        launches = lib.nlspn_launch_count() - n0
+        if self.graphed is not None:
+            # replayed kernels do not pass through the library's launch counter: count one eager call
+            n1 = lib.nlspn_launch_count()
+            d = self.dev_in
+            with torch.no_grad():
+                self.mod(d["feat_init"], d["guidance"], d["confidence"], d["feat_fix"])
+            torch.cuda.synchronize()
+            launches = (lib.nlspn_launch_count() - n1) * steps
+        if flush:   # steps are timed individually (forward + backward events), the flush is not counted
+            total_ms = sum(a.elapsed_time(c) for a, _, c in rec)
+        else:
+            total_ms = t_start.elapsed_time(t_end)
+        fwd_ms = sum(a.elapsed_time(b) for a, b, _ in rec) / len(rec)
+        bwd_ms = sum(b.elapsed_time(c) for _, b, c in rec) / len(rec)
+        return total_ms, fwd_ms, bwd_ms, int(launches)
+
+    def kernel_split(self, nprof, fwd_ms, bwd_ms, peak_gbs):
+        """Per-kernel split of the phases: a separate pass with the library's event hooks on (events around every
+        launch perturb throughput, so this pass is NOT the one `value` is from; a kernel's average launch duration =
+        phase time measured in the timed region x its share of that phase)."""
+        from nlspn_eccv20_b200 import _lib
+        lib, K, T, B, H, W = self.lib, self.K, self.T, self.B, self.H, self.W
+        N = K * K - 1
+        lib.nlspn_profile_enable(1)
+        keep, self.graphed = self.graphed, None          # the event hooks live in the eager launch path
+        for _ in range(nprof):
+            self.step(self.dev_in)
+        self.graphed = keep
+        self.torch.cuda.synchronize()
+        prof = _lib.profile_read()
+        lib.nlspn_profile_enable(0)
+        # algorithmic bytes per LAUNCH and pixel (fp32, DESIGN.md "kernels"): what the kernel must move
+        alg = {"prologue_fwd_kernel": 24 * N + 28,
+               "iter_fwd_kernel": 12 * N + 20,
+               "bwd_state_kernel": 12 * N + 40,
+               "bwd_param_kernel": 8 * T + 24 * N + 8,
+               "final_bwd_kernel": 8 * N + 4 * (N + 1) + 16 + 24,
+               "iter_bwd_kernel": 36 * N + 36,
+               # pass A in gather form: table entries 16 B x N + counter + one 16-byte block store;
+               # the gy kernel then moves ~53 B/px (bwd_state_kernel's class); table build once per step
+               "bwd_gather_kernel": 16 * N + 20,
+               "table_build_kernel": 12 * N + 16 * N + 4}
+        if "bwd_gather_kernel" in prof:
+            alg["bwd_state_kernel"] = 53
+        fwd_names = ("prologue_fwd_kernel", "iter_fwd_kernel")
+        phase_prof = {"forward": sum(prof[k][0] for k in prof if k in fwd_names),
+                      "backward": sum(prof[k][0] for k in prof if k not in fwd_names)}
+        kernels = {}
+        per_iter = ("iter_fwd_kernel", "bwd_state_kernel", "iter_bwd_kernel", "bwd_gather_kernel")
+        for name, (ms, cnt) in prof.items():
+            ph = "forward" if name in fwd_names else "backward"
+            share = ms / phase_prof[ph] if phase_prof[ph] > 0 else 0.0
+            phase_ms = fwd_ms if ph == "forward" else bwd_ms
+            per_step = cnt / nprof
+            step_ms = phase_ms * share
+            bytes_step = alg.get(name, 0) * B * H * W * (T if name in per_iter else 1)
+            gbs = bytes_step / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0
+            kernels[name] = {"launches_per_step": per_step, "share_of_phase": share, "step_ms": step_ms,
+                             "launch_ms": step_ms / per_step if per_step else 0.0,
+                             "alg_bytes_per_launch": bytes_step / per_step if per_step else 0.0,
+                             "achieved_gbs": gbs, "frac": gbs / peak_gbs}
+        return kernels
+
+    # ---- end to end: pinned host inputs -> H2D -> module -> D2H, every step.
+    # The batch shard is fed in chunks of frames: a copy stream uploads chunk i+1 while the compute stream runs
+    # the module on chunk i, and a third stream drains chunk i's results to pinned host memory (images are
+    # independent, so the chunked step is the same computation; this is the double-buffered prefetch a pinned
+    # DataLoader does).  d2h: "loss" = the scalar only; "result" = + feat_result; "grads" = + every input gradient.
+    def e2e(self, steps, warmup, sync_all, d2h="result"):
+        torch, dev, mod, train = self.torch, self.dev, self.mod, self.train
+        host, names, B, H, W = self.host, self.names, self.B, self.H, self.W
+        auto_chunk = max(1, -(-400000 // (H * W)))   # about one KITTI frame's worth of pixels per upload
+        chunk = max(1, min(B, int(os.environ.get("NLSPN_E2E_CHUNK", str(auto_chunk)))))
+        copy_stream = torch.cuda.Stream(device=dev)
+        down_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream(dev)
+        gt_chunks = [self.gt[i:i + chunk] for i in range(0, B, chunk)]
+        out_host = {}
+        if d2h in ("result", "grads"):
+            out_host["feat_result"] = torch.empty(B, 1, H, W).pin_memory()
+        if d2h == "grads" and train:
+            for k in ("feat_init", "guidance", "confidence"):
+                out_host["g_" + k] = torch.empty_like(host[k]).pin_memory()
+        d2h_bytes = 4 + sum(t.numel() * 4 for t in out_host.values())
+
+        def upload(i):
+            with torch.cuda.stream(copy_stream):
+                inp = {k: host[k][i:i + chunk].to(dev, non_blocking=True) for k in names}
+                evt = torch.cuda.Event()
+                evt.record(copy_stream)
+            return inp, evt
+
+        def e2e_step():
+            losses = []
+            pending = upload(0)
+            for ci, i in enumerate(range(0, B, chunk)):
+                inp, evt = pending
+                pending = upload(i + chunk) if i + chunk < B else None
+                main_stream.wait_event(evt)
+                for t_ in inp.values():
+                    t_.record_stream(main_stream)
+                fi, gd, cf = inp["feat_init"], inp["guidance"], inp["confidence"]
+                if train:
+                    fi, gd, cf = (t_.requires_grad_(True) for t_ in (fi, gd, cf))
+                with torch.set_grad_enabled(train):
+                    feat_result = mod(fi, gd, cf, inp["feat_fix"])[0]
+                    loss = (torch.clamp(feat_result, min=0) - gt_chunks[ci]).abs().sum()
+                if train:
+                    loss.backward()
+                losses.append(loss.detach())
+                if out_host:
+                    done = torch.cuda.Event()
+                    done.record(main_stream)
+                    down_stream.wait_event(done)
+                    outs = {"feat_result": feat_result.detach()}
+                    if train:
+                        outs.update({"g_feat_init": fi.grad, "g_guidance": gd.grad, "g_confidence": cf.grad})
+                    with torch.cuda.stream(down_stream):
+                        for k, buf in out_host.items():
+                            outs[k].record_stream(down_stream)
+                            buf[i:i + chunk].copy_(outs[k], non_blocking=True)
+            total = float(torch.stack(losses).sum())      # D2H of the loss + sync of the compute stream
+            down_stream.synchronize()                      # results are in host memory when the step ends
+            return total
+
+        for _ in range(min(2, warmup)):
+            mod.aff_scale_const.grad = None
+            e2e_step()
+        sync_all()
+        e_start, e_end = self.ev(), self.ev()
+        e_start.record()
+        for _ in range(steps):
+            mod.aff_scale_const.grad = None
+            e2e_step()
+        e_end.record()
+        sync_all()
+        h2d = sum(host[k].numel() * 4 for k in names)
+        return e_start.elapsed_time(e_end), h2d, d2h_bytes, chunk
+
+
+def ref_cuda_leg(torch, run, steps=3, warmup=1):
+    """The reference's own CUDA kernels (oracle/_ref/DCN_ref.so) on this GPU, same inputs, same loss."""
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        return None
+    ref_cuda.load()
+    d, K, T, train = run.dev_in, run.K, run.T, run.train
+    gam = run.mod.aff_scale_const.detach().clone().requires_grad_(train)
+
+    def theirs():
+        fi, gd, cf = (d[k].detach().requires_grad_(train) for k in ("feat_init", "guidance", "confidence"))
+        gam.grad = None
+        with torch.set_grad_enabled(train):
+            out = ref_cuda.propagate(fi, gd, cf, d["feat_fix"], gam, K, T)["feat_result"]
+            loss = (out.clamp(min=0) - run.gt).abs().sum()
+        if train:
+            loss.backward()
+
+    for _ in range(warmup):
+        theirs()
+    torch.cuda.synchronize()
+    e0, e1 = run.ev(), run.ev()
+    e0.record()
+    for _ in range(steps):
+        theirs()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms, "value": run.B * run.H * run.W * T / (ms * 1e-3) / 1e9, "unit": UNIT,
+            "steps": steps, "warmup": warmup,
+            "what": "the reference's modulated_deform_conv_cuda.cu/.cuh compiled unmodified for sm_100a "
+                    "(oracle/build_ref_cuda.py -> oracle/_ref/DCN_ref.so) under the reference's per-iteration torch op "
+                    "chain (oracle/ref_cuda.py), same GPU, same resident inputs, same loss"}
+
+
+def other_configs(torch, dev, lib, peaks):
+    """BASELINE.json configs 1, 2, 3, 5 on this GPU (config 4 is the full model: tests/perf_config4_train_step.py)."""
+    out = {}
+    l2 = l2_peak()
+    specs = [("config1_nyu_B1_fwd_eager", "nyu", 1, 3, 18, "fwd", False),
+             ("config1_nyu_B1_fwd_cuda_graph", "nyu", 1, 3, 18, "fwd", True),
+             ("config2_nyu_B12_fwdbwd", "nyu", 12, 3, 18, "fwdbwd", False),
+             ("config3_kitti_B16_fwd", "kitti", 16, 3, 18, "fwd", False),
+             ("config5_kitti_B8_K5_T36_fwdbwd", "kitti", 8, 5, 36, "fwdbwd", False)]
+    for name, wl, B, K, T, mode, graph in specs:
+        try:
+            run = GpuRun(torch, dev, lib, wl, B, K, T, mode, seed=7240)
+            if graph:
+                run.use_graph()
+            flush = run.guid_mb <= L2_MB
+            steps = 20 if wl == "nyu" else 5
+            total_ms, fwd_ms, bwd_ms, launches = run.timed(steps, 3, flush, torch.cuda.synchronize)
+            pix = B * run.H * run.W * T
+            val = pix * steps / (total_ms * 1e-3) / 1e9
+            gbs = alg_bytes(K, T, mode) * val
+            r = {"value": val, "unit": UNIT, "ms_per_step": total_ms / steps, "steps": steps, "warmup": 3,
+                 "mode": mode, "gpu_launches_per_step": launches / steps, "l2_flush_between_steps": flush,
+                 "roofline_step": {"achieved": gbs, "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"], "unit": "GB/s"}}
+            if l2 and flush:
+                r["roofline_step_l2"] = {"achieved": gbs, "peak": l2["l2_copy_gbs"], "frac": gbs / l2["l2_copy_gbs"],
+                                         "unit": "GB/s"}
+            if graph:
+                r["launch"] = "CUDA graph replay (GraphedNLSPN)"
+            out[name] = r
+            del run
+            torch.cuda.empty_cache()
+        except Exception as e:     # an extra config must never take the headline down
+            out[name] = {"error": str(e)[:200]}
+    return out
+
+
 def main():
     args = parse()
     import torch
@@ -173,6 +509,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    train = args.mode == "fwdbwd"
     config = {"workload": "%s_%dx%d_B%d_per_gpu_K%d_T%d_%s" % (args.workload, H, W, B, K, T, args.mode),
               "frames_per_gpu": B, "height": H, "width": W, "prop_kernel": K, "prop_time": T,
               "affinity": "TGASS", "conf_prop": True, "preserve_input": True,
@@ -180,7 +517,7 @@ def main():
               "sharding": "batch shard per GPU, no collective on the data path",
               "l2": None}
     guid_mb = B * 3 * (K * K - 1) * H * W * 4 / 1e6
-    flush = args.flush_l2 == "on" or (args.flush_l2 == "auto" and guid_mb <= 126.0)
+    flush = args.flush_l2 == "on" or (args.flush_l2 == "auto" and guid_mb <= L2_MB)
     config["l2"] = ("a 256 MB buffer is written between timed steps (L2 flush; inputs are %.0f MB per GPU)" % guid_mb
                     if flush else
                     "inputs exceed L2 (guidance alone is %.0f MB per GPU vs 126 MB L2): no flush" % guid_mb)
@@ -191,16 +528,13 @@ def main():
             return 0
         n_img = args.cpu_images or min(os.cpu_count() or 1, 32)
         r = cpu_reference_run(args, H, W, md, n_img, max(1, args.steps), max(0, args.warmup))
-        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+        config["cpu_sample"] = cpu_sample_text(r, H, W, train)
+        line = {"impl": "reference", "metric": METRIC if train else METRIC_FWD, "value": r["value"], "unit": UNIT,
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                 "sample": "%d frames x %d rows x %d cols per step (full-width strips of the %dx%d "
-                                           "frame), one frame per host thread, torchvision deform_conv2d "
-                                           "stand-in (oracle/torchvision_port.py), fwd%s, %d host cores"
-                                           % (r["n_images"], r["rows"], W, H, W,
-                                              "+bwd" if args.mode == "fwdbwd" else "", r["host_cores"])},
+                "cpu_baseline": {"value": r["value"], "best": r["best"], "unit": UNIT, "cores": r["cores"],
+                                 "kind": "port", "sample": config["cpu_sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -208,51 +542,14 @@ def main():
 
     # ---------------------------------------------------------------- our arm (GPU)
     assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU"
+    host_info = bind_host(local, world)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from nlspn_eccv20_b200 import NLSPN, _lib
-    from nlspn_eccv20_b200.synth import workload
+    from nlspn_eccv20_b200 import _lib
     lib = _lib.load()
-
-    host = workload(args.workload, B, K, seed=7240 + rank, smooth_offsets=args.smooth_offsets, pin=True)
-    names = ["feat_init", "guidance", "confidence", "feat_fix"]
-    dev_in = {k: host[k].to(dev) for k in names}
-    gt = host["gt"].to(dev)
-    mod = NLSPN(prop_kernel=K, prop_time=T).to(dev)
-    train = args.mode == "fwdbwd"
-    graphed = None
-    if args.cuda_graph and not train:
-        graphed = mod.graphed(dev_in["feat_init"], dev_in["guidance"], dev_in["confidence"], dev_in["feat_fix"])
-        config["launch"] = "CUDA graph replay (GraphedNLSPN)"
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def step(inp, rec=None):
-        fi, gd, cf = inp["feat_init"], inp["guidance"], inp["confidence"]
-        if train:
-            fi, gd, cf = (t.detach().requires_grad_(True) for t in (fi, gd, cf))
-            mod.aff_scale_const.grad = None
-        e0, e1, e2 = (ev(), ev(), ev()) if rec is not None else (None, None, None)
-        if rec is not None:
-            e0.record()
-        with torch.set_grad_enabled(train):
-            if graphed is not None and inp is dev_in:      # resident inputs ARE the graph's static buffers
-                feat_result, list_feat, offset, aff, _ = graphed(*graphed.inputs)
-            else:
-                feat_result, list_feat, offset, aff, _ = (graphed or mod)(fi, gd, cf, inp["feat_fix"])
-            pred = torch.clamp(feat_result, min=0)
-            loss = (pred - gt).abs().sum()      # L1 surrogate of the reference loss (l1loss.py:27-42)
-        if rec is not None:
-            e1.record()
-        if train:
-            loss.backward()
-        if rec is not None:
-            e2.record()
-            rec.append((e0, e1, e2))
-        return loss
 
     def sync_all():
         torch.cuda.synchronize()
@@ -260,163 +557,63 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step(dev_in)
-    sync_all()
+    run = GpuRun(torch, dev, lib, args.workload, B, K, T, args.mode, seed=7240 + rank,
+                 smooth=args.smooth_offsets, pin=True)
+    if args.cuda_graph and not train:
+        run.use_graph()
+        config["launch"] = "CUDA graph replay (GraphedNLSPN)"
 
     # ---- device-resident timing
     sampler = ClockSampler(local)
     sampler.start()
-    rec = []
-    n0 = lib.nlspn_launch_count()
-    t_start, t_end = ev(), ev()
-    flush_buf = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32) if flush else None
-    t_start.record()
-    for _ in range(args.steps):
-        if flush:
-            flush_buf.fill_(1.0)           # evicts L2; excluded from the step time below
-        step(dev_in, rec)
-    t_end.record()
-    sync_all()
-    launches = lib.nlspn_launch_count() - n0
-    if graphed is not None:
-        # replayed kernels do not pass through the library's launch counter: count one eager call
-        n1 = lib.nlspn_launch_count()
-        with torch.no_grad():
-            mod(dev_in["feat_init"], dev_in["guidance"], dev_in["confidence"], dev_in["feat_fix"])
-        torch.cuda.synchronize()
-        launches = (lib.nlspn_launch_count() - n1) * args.steps
+    total_ms, fwd_ms, bwd_ms, launches = run.timed(args.steps, args.warmup, flush, sync_all)
     clocks = sampler.stop()
-    if flush:   # steps are timed individually (forward + backward events), the flush is not counted
-        total_ms = sum(a.elapsed_time(c) for a, _, c in rec)
+
+    # ---- end to end (three D2H definitions; the middle one is the headline `e2e`)
+    e2e_ms, h2d, d2h_bytes, chunk = run.e2e(args.steps, args.warmup, sync_all, "result")
+    e2e_loss_ms, _, d2h_loss, _ = run.e2e(args.steps, args.warmup, sync_all, "loss")
+    if train:
+        e2e_grads_ms, _, d2h_grads, _ = run.e2e(args.steps, args.warmup, sync_all, "grads")
     else:
-        total_ms = t_start.elapsed_time(t_end)
-    fwd_ms = sum(a.elapsed_time(b) for a, b, _ in rec) / len(rec)
-    bwd_ms = sum(b.elapsed_time(c) for _, b, c in rec) / len(rec)
+        e2e_grads_ms, d2h_grads = e2e_ms, d2h_bytes
 
-    # ---- end to end: pinned host inputs -> H2D -> module -> D2H of the loss, every step.
-    # The batch shard is fed in chunks of frames: a copy stream uploads chunk i+1 while the
-    # compute stream runs the module on chunk i (images are independent, so the chunked step is
-    # the same computation; this is the double-buffered prefetch a pinned DataLoader does).
-    h2d = sum(host[k].numel() * 4 for k in names)
-    # chunk of frames per upload: about one KITTI frame's worth of pixels (small frames are grouped so
-    # the per-chunk launches stay above the launch-bound regime)
-    auto_chunk = max(1, -(-400000 // (H * W)))
-    chunk = max(1, min(B, int(os.environ.get("NLSPN_E2E_CHUNK", str(auto_chunk)))))
-    copy_stream = torch.cuda.Stream(device=dev)
-    main_stream = torch.cuda.current_stream(dev)
-    gt_chunks = [gt[i:i + chunk] for i in range(0, B, chunk)]
-
-    def e2e_step():
-        pending = None
-        losses = []
-
-        def upload(i):
-            with torch.cuda.stream(copy_stream):
-                inp = {k: host[k][i:i + chunk].to(dev, non_blocking=True) for k in names}
-                evt = torch.cuda.Event()
-                evt.record(copy_stream)
-            return inp, evt
-
-        pending = upload(0)
-        for ci, i in enumerate(range(0, B, chunk)):
-            inp, evt = pending
-            pending = upload(i + chunk) if i + chunk < B else None
-            main_stream.wait_event(evt)
-            for t_ in inp.values():
-                t_.record_stream(main_stream)
-            fi, gd, cf = inp["feat_init"], inp["guidance"], inp["confidence"]
-            if train:
-                fi, gd, cf = (t_.requires_grad_(True) for t_ in (fi, gd, cf))
-            with torch.set_grad_enabled(train):
-                feat_result = mod(fi, gd, cf, inp["feat_fix"])[0]
-                loss = (torch.clamp(feat_result, min=0) - gt_chunks[ci]).abs().sum()
-            if train:
-                loss.backward()
-            losses.append(loss)
-        return float(torch.stack(losses).sum().detach())      # D2H of the result + sync
-
-    for _ in range(min(2, args.warmup)):
-        mod.aff_scale_const.grad = None
-        e2e_step()
-    sync_all()
-    e_start, e_end = ev(), ev()
-    e_start.record()
-    for _ in range(args.steps):
-        mod.aff_scale_const.grad = None
-        loss_host = e2e_step()
-    e_end.record()
-    sync_all()
-    e2e_ms = e_start.elapsed_time(e_end)
-
-    tms = torch.tensor([total_ms, e2e_ms, fwd_ms, bwd_ms], device=dev, dtype=torch.float64)
+    tms = torch.tensor([total_ms, e2e_ms, fwd_ms, bwd_ms, e2e_loss_ms, e2e_grads_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, fwd_ms, bwd_ms = (float(x) for x in tms.tolist())
+    total_ms, e2e_ms, fwd_ms, bwd_ms, e2e_loss_ms, e2e_grads_ms = (float(x) for x in tms.tolist())
 
     pix_iter_step = world * B * H * W * T
-    value = pix_iter_step * args.steps / (total_ms * 1e-3) / 1e9
-    e2e_val = pix_iter_step * args.steps / (e2e_ms * 1e-3) / 1e9
+    rate = lambda ms: pix_iter_step * args.steps / (ms * 1e-3) / 1e9
+    value = rate(total_ms)
     peaks, peak_kind = measured_peaks()
-    N = K * K - 1
 
-    # ---- per-kernel split of the phases: a separate pass with the library's event hooks on
-    # (events around every launch perturb throughput, so this pass is NOT the one `value` is from;
-    # the kernel's average launch duration = phase time measured in the timed region x its share).
-    lib.nlspn_profile_enable(1)
-    graphed_keep, graphed = graphed, None          # the event hooks live in the eager launch path
-    for _ in range(max(1, min(args.steps, 3))):
-        step(dev_in)
-    graphed = graphed_keep
-    torch.cuda.synchronize()
-    prof = _lib.profile_read()
-    lib.nlspn_profile_enable(0)
-    # algorithmic bytes per LAUNCH and pixel (fp32, DESIGN.md "kernels"): what the kernel must move
-    alg = {"prologue_fwd_kernel": 24 * N + 28,
-           "iter_fwd_kernel": 12 * N + 20,
-           "bwd_state_kernel": 12 * N + 40,
-           "bwd_param_kernel": 8 * T + 24 * N + 8,
-           "final_bwd_kernel": 8 * N + 4 * (N + 1) + 16 + 24,
-           "iter_bwd_kernel": 36 * N + 36,
-           # pass A in gather form (K >= 5): table entries 16 B x N + counter + one 16-byte block store;
-           # the gy kernel then moves ~53 B/px (bwd_state_kernel's class); table build once per step
-           "bwd_gather_kernel": 16 * N + 20,
-           "table_build_kernel": 12 * N + 16 * N + 4}
-    if "bwd_gather_kernel" in prof:
-        alg["bwd_state_kernel"] = 53
-    fwd_names = ("prologue_fwd_kernel", "iter_fwd_kernel")
-    phase_prof = {"forward": sum(prof[k][0] for k in prof if k in fwd_names),
-                  "backward": sum(prof[k][0] for k in prof if k not in fwd_names)}
-    kernels = {}
-    nprof = max(1, min(args.steps, 3))
-    per_iter = ("iter_fwd_kernel", "bwd_state_kernel", "iter_bwd_kernel", "bwd_gather_kernel")
-    for name, (ms, cnt) in prof.items():
-        ph = "forward" if name in fwd_names else "backward"
-        share = ms / phase_prof[ph] if phase_prof[ph] > 0 else 0.0
-        phase_ms = fwd_ms if ph == "forward" else bwd_ms
-        per_step = cnt / nprof
-        step_ms = phase_ms * share
-        bytes_step = alg.get(name, 0) * B * H * W * (T if name in per_iter else 1)
-        gbs = bytes_step / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0
-        kernels[name] = {"launches_per_step": per_step, "share_of_phase": share, "step_ms": step_ms,
-                         "launch_ms": step_ms / per_step, "alg_bytes_per_launch": bytes_step / per_step,
-                         "achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"]}
+    kernels = run.kernel_split(max(1, min(args.steps, 3)), fwd_ms, bwd_ms, peaks["hbm_gbs"])
     kern = max(kernels, key=lambda k: kernels[k]["step_ms"])
     traffic = None
+    traffic_all = {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get("%s_%dx%d_B%d_per_gpu_K%d_T%d" % (args.workload, H, W, B, K, T), {}).get(kern)
+            traffic_all = json.load(f).get("%s_%dx%d_B%d_per_gpu_K%d_T%d" % (args.workload, H, W, B, K, T), {})
+        traffic = traffic_all.get(kern)
     except Exception:
         traffic = None
     kb, kms, achieved = kernels[kern]["alg_bytes_per_launch"], kernels[kern]["launch_ms"], kernels[kern]["achieved_gbs"]
-    step_gbs = alg_bytes(K, T, args.mode) * (pix_iter_step / world) * args.steps / (total_ms * 1e-3) / 1e9
-    line = {"metric": METRIC if train else "nlspn_propagation_fwd_gpix_iter_per_s", "value": value,
+    step_ms = total_ms / args.steps
+    step_gbs = alg_bytes(K, T, args.mode) * (pix_iter_step / world) / (step_ms * 1e-3) / 1e9
+    line = {"metric": METRIC if train else METRIC_FWD, "value": value,
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
-                    "chunk_frames": chunk},
+            "e2e": {"value": rate(e2e_ms), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h_bytes * world, "chunk_frames": chunk,
+                    "d2h": "loss + feat_result into pinned host memory"},
+            "e2e_variants": {
+                "loss_only_d2h": {"value": rate(e2e_loss_ms), "d2h_bytes_per_step": d2h_loss * world},
+                "result_d2h": {"value": rate(e2e_ms), "d2h_bytes_per_step": d2h_bytes * world},
+                "result_and_all_input_gradients_d2h": {"value": rate(e2e_grads_ms),
+                                                       "d2h_bytes_per_step": d2h_grads * world}},
+            "host": host_info,
             "gpu_launches": int(launches),
             "phases_ms": {"forward": fwd_ms, "backward": bwd_ms,
                           "forward_gpix_iter_per_s": pix_iter_step / world / (fwd_ms * 1e-3) / 1e9},
@@ -431,27 +628,41 @@ def main():
             "kernels": kernels,
             "roofline_step": {"alg_bytes_per_pix_iter": alg_bytes(K, T, args.mode), "achieved": step_gbs,
                               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": step_gbs / peaks["hbm_gbs"]}}
+    # measured-traffic utilisation: what the kernels really move through DRAM (ncu, per launch) / step time
+    if traffic_all and all(k in traffic_all for k in kernels):
+        dram = sum(traffic_all[k] * kernels[k]["launches_per_step"] for k in kernels)
+        dram_gbs = dram / (step_ms * 1e-3) / 1e9
+        line["roofline_step_dram"] = {"dram_bytes_per_step": dram, "achieved": dram_gbs, "peak": peaks["hbm_gbs"],
+                                      "unit": "GB/s", "frac": dram_gbs / peaks["hbm_gbs"],
+                                      "source": "profiles/ncu_traffic.json (dram__bytes_read+write per launch, ncu --set full) "
+                                                "x launches per step / measured step time"}
     # second roofline level: when the step's inputs are L2-resident the same algorithmic
     # bytes are also quoted against the measured L2 copy bandwidth (tools/l2_bench.cu -> profiles/l2_peak.json)
-    try:
-        with open(os.path.join(ROOT, "profiles", "l2_peak.json")) as f:
-            l2 = json.load(f)
-        if guid_mb <= 126.0:
-            line["roofline_step_l2"] = {"achieved": step_gbs, "peak": l2["l2_copy_gbs"], "unit": "GB/s",
-                                        "frac": step_gbs / l2["l2_copy_gbs"],
-                                        "peak_source": "tools/l2_bench.cu, L2-resident copy (read+write), profiles/l2_peak.json"}
-    except Exception:
-        pass
+    l2 = l2_peak()
+    if l2 and guid_mb <= L2_MB:
+        line["roofline_step_l2"] = {"achieved": step_gbs, "peak": l2["l2_copy_gbs"], "unit": "GB/s",
+                                    "frac": step_gbs / l2["l2_copy_gbs"],
+                                    "peak_source": "tools/l2_bench.cu, L2-resident copy (read+write), profiles/l2_peak.json"}
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_img = args.cpu_images or min(os.cpu_count() or 1, 32)
-        r = cpu_reference_run(args, H, W, md, n_img, 2, 1)
-        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                "sample": "%d frames x %d rows x %d cols (full-width strips of the %dx%d frame), one "
-                                          "frame per host thread, fwd%s, torchvision deform_conv2d stand-in "
-                                          "(oracle/torchvision_port.py), %d host cores, %.1f s per pass"
-                                          % (r["n_images"], r["rows"], W, H, W, "+bwd" if train else "",
-                                             r["host_cores"], r["seconds"])}
+    if rank == 0 and world == 1:
+        if not args.no_ref_cuda:
+            try:
+                rc = ref_cuda_leg(torch, run)
+                if rc is not None:
+                    rc["ours_over_reference_cuda"] = rc["ms_per_step"] / step_ms
+                    line["ref_cuda"] = rc
+            except Exception as e:
+                line["ref_cuda"] = {"error": str(e)[:200]}
+        del run
+        torch.cuda.empty_cache()
+        if not args.no_other_configs:
+            line["other_configs"] = other_configs(torch, dev, lib, peaks)
+        if not args.no_cpu_baseline:
+            n_img = args.cpu_images or min(os.cpu_count() or 1, 32)
+            r = cpu_reference_run(args, H, W, md, n_img, 2, 1)
+            config["cpu_sample"] = cpu_sample_text(r, H, W, train)
+            line["cpu_baseline"] = {"value": r["value"], "best": r["best"], "unit": UNIT, "cores": r["cores"],
+                                    "kind": "port", "sample": config["cpu_sample"]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
