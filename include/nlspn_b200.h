@@ -100,7 +100,7 @@ NLSPN_API unsigned long long nlspn_launch_count(void);
 /* Tuning options.  The NLSPN_<NAME> environment variables seed the defaults ONCE, when the
  * library is loaded; nothing on the call path reads the environment.  Names: tiled, persist, pdl, fwd_th,
  * param_th, state_tma, state_gather, gather_compact, state_zero3, state_minb, group_images, stream_hint,
- * state_ahead, param_pair, persist_bwd, dcn_blocked.  value -1 = auto where the default depends on the shape.
+ * state_ahead, param_factored, persist_bwd, dcn_blocked.  value -1 = auto where the default depends on the shape.
  * Options that select the form of the backward (state_gather) change nlspn_backward_workspace_bytes: query
  * after setting them (a too-small workspace is always refused, never overrun). */
 NLSPN_API int nlspn_set_option(const char *name, int value);

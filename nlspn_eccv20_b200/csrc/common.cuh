@@ -45,6 +45,15 @@ __device__ __forceinline__ void floor_small(float x, float &xf, int &xi)
     xi = ri;
 }
 
+// float part only (same precondition)
+__device__ __forceinline__ float floor_small_f(float x)
+{
+    const float t = x + 12582912.f;
+    float rf = t - 12582912.f;
+    if (rf > x) rf -= 1.f;
+    return rf;
+}
+
 // The four corner values of a zero-padded bilinear sample read straight from global memory
 // with the per-corner guards of cuh:37-48.  Precondition: tap_valid().
 struct Quad {

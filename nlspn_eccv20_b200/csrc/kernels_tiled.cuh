@@ -199,7 +199,14 @@ iter_fwd_tiled_kernel(const __grid_constant__ CUtensorMap src_map, int plane_z,
 #ifndef NLSPN_PARAM_WARPS_PER_SM
 #define NLSPN_PARAM_WARPS_PER_SM 24   // 24 warps/SM -> <= 85 registers per thread (was 16 warps / 128 registers)
 #endif
-template <int K, int C, int TH, int NS = 2>
+// FACTORED = true (default): the bilinear value and its two coordinate derivatives are evaluated in factored form
+// (11 FP instructions per tap and iteration instead of ~23; the round-1 kernel issued at 65 % next to an LSU at 85 %):
+//     d1 = v2 - v1, d2 = v4 - v3, top = v1 + lw d1, bot = v3 + lw d2,
+//     d/dh = bot - top, value = top + lh (bot - top), d/dw = d1 + lh (d2 - d1)
+// (algebraically the expressions of cuh:50-52,101-122).  Measured and dropped: a second copy of every box shifted
+// by one column, so that the row pair (p[0], p[1]) of any footprint is one aligned LDS.64 -- cp.async.bulk.tensor
+// traps (error 715) on a start coordinate that is not 16-byte aligned, for loads as for stores.
+template <int K, int C, int TH, int NS = 2, bool FACTORED = true>
 __global__ void __launch_bounds__(kTileW * TH, (TH >= NLSPN_PARAM_WARPS_PER_SM ? 1 : NLSPN_PARAM_WARPS_PER_SM / TH))
 bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
                        const __grid_constant__ CUtensorMap list_map, int Bsrc, int b0,
@@ -315,6 +322,16 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
                     acc_a[c] += gy * p[0];
                     continue;
                 }
+                if (FACTORED) {
+                    const float v1 = p[0], v2 = p[1], v3 = p[kBoxW], v4 = p[kBoxW + 1];
+                    const float d1 = v2 - v1, d2 = v4 - v3;
+                    const float top = fmaf(lw[c], d1, v1), bot = fmaf(lw[c], d2, v3);
+                    const float dh = bot - top;
+                    acc_a[c] = fmaf(gy, fmaf(lh[c], dh, top), acc_a[c]);             // cuh:314-315
+                    acc_h[c] = fmaf(gy, dh, acc_h[c]);
+                    acc_w[c] = fmaf(gy, fmaf(lh[c], d2 - d1, d1), acc_w[c]);
+                    continue;
+                }
                 const float v1 = p[0], v2 = p[1], v3 = p[kBoxW], v4 = p[kBoxW + 1];
                 const float hh = 1.f - lh[c], hw = 1.f - lw[c];
                 const float bil = (hh * hw) * v1 + (hh * lw[c]) * v2 + (lh[c] * hw) * v3 + (lh[c] * lw[c]) * v4;
@@ -351,6 +368,15 @@ bwd_param_tiled_kernel(const __grid_constant__ CUtensorMap src_map,
                 } else {
                     const float *p = bx + idx[c];
                     v1 = p[0]; v2 = p[1]; v3 = p[kBoxW]; v4 = p[kBoxW + 1];
+                }
+                if (FACTORED) {
+                    const float d1 = v2 - v1, d2 = v4 - v3;
+                    const float top = fmaf(lw[c], d1, v1), bot = fmaf(lw[c], d2, v3);
+                    const float dh = bot - top;
+                    acc_a[c] = fmaf(gy, fmaf(lh[c], dh, top), acc_a[c]);
+                    acc_h[c] = fmaf(gy, dh, acc_h[c]);
+                    acc_w[c] = fmaf(gy, fmaf(lh[c], d2 - d1, d1), acc_w[c]);
+                    continue;
                 }
                 const float hh = 1.f - lh[c], hw = 1.f - lw[c];
                 const float bil = (hh * hw) * v1 + (hh * lw[c]) * v2 + (lh[c] * hw) * v3 + (lh[c] * lw[c]) * v4;

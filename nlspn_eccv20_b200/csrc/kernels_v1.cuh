@@ -302,7 +302,9 @@ iter_bwd_kernel(const float *__restrict__ src_prev, const float *__restrict__ of
 // backward of the prologue (formulas: SURVEY 3.2, derived from nlspnmodel.py:185-197,262-267).
 // g_guidance's offset part already holds the accumulated offset gradients.
 // ======================================================================================
-template <int K, bool BLOCKED, bool SAMPLED = false>
+// LAYOUT of s_in: 0 = plain [B,H,W] plane, 1 = four phase copies of the 2x2-blocked plane (kernels_v2.cuh),
+// 2 = one plane padded by `pad` cells on every side with row pitch `pitch` (kernels_local.cuh)
+template <int K, int LAYOUT, bool SAMPLED = false>
 __global__ void __launch_bounds__(kBlock)
 final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ init,
                  const float *__restrict__ dep, const float *__restrict__ conf,
@@ -312,7 +314,8 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
                  unsigned flags, int H, int W, float *__restrict__ g_init, float *__restrict__ g_guidance,
                  float *__restrict__ g_conf, double *__restrict__ g_gamma,
                  const float *__restrict__ conf_raw = nullptr, const float *__restrict__ gy_first = nullptr,
-                 const float *__restrict__ aff_norm = nullptr, const float *__restrict__ f_last = nullptr)
+                 const float *__restrict__ aff_norm = nullptr, const float *__restrict__ f_last = nullptr,
+                 int pad = 0, int pitch = 0, long pad_plane = 0)
 {
     // gy_first / aff_norm / f_last: the gather-form pass A (kernels_gather.cuh) keeps the centre tap and
     // the overflowing taps out of the blocked planes; the consumer of the last planes adds
@@ -330,7 +333,10 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         const float d = preserve ? __ldg(dep + q) : 0.f;
         const float m = d > 0.f ? 1.f : 0.f;
         float gs;
-        if (BLOCKED) {   // four phase copies of the 2x2-blocked scatter plane (kernels_v2.cuh)
+        if (LAYOUT == 2) {
+            const int hh = r / W, ww = r - hh * W;
+            gs = __ldg(s_in + b * pad_plane + (long)(hh + pad) * pitch + (ww + pad));
+        } else if (LAYOUT == 1) {   // four phase copies of the 2x2-blocked scatter plane (kernels_v2.cuh)
             const ScatterGeo sg = scatter_geo(H, W);
             const float *sl = s_in + b * sg.image;
             const int hh = r / W, ww = r - hh * W;

@@ -16,6 +16,7 @@
 #include "kernels_f64.cuh"
 #include "kernels_gather.cuh"
 #include "kernels_step.cuh"
+#include "kernels_local.cuh"
 
 using namespace nlspn;
 
@@ -29,7 +30,7 @@ std::atomic<unsigned long long> g_launches{0};
 // -1 = "auto" where a default depends on the shape.
 enum Opt { kOptTiled = 0, kOptPersist, kOptPdl, kOptFwdTH, kOptParamTH, kOptStateTma, kOptStateGather,
            kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint, kOptStateAhead,
-           kOptParamPair, kOptPersistBwd, kOptDcnBlocked, kOptCount };
+           kOptParamFactored, kOptPersistBwd, kOptDcnBlocked, kOptStateLocal, kOptCount };
 struct OptDef { const char *name; const char *env; int def; };
 const OptDef kOptDefs[kOptCount] = {
     {"tiled", "NLSPN_TILED", 1},
@@ -45,9 +46,10 @@ const OptDef kOptDefs[kOptCount] = {
     {"group_images", "NLSPN_GROUP_IMAGES", 0},
     {"stream_hint", "NLSPN_STREAM_HINT", -1},
     {"state_ahead", "NLSPN_STATE_AHEAD", -1},
-    {"param_pair", "NLSPN_PARAM_PAIR", 1},
+    {"param_factored", "NLSPN_PARAM_FACTORED", 1},
     {"persist_bwd", "NLSPN_PERSIST_BWD", -1},
     {"dcn_blocked", "NLSPN_DCN_BLOCKED", 1},
+    {"state_local", "NLSPN_STATE_LOCAL", -1},
 };
 std::atomic<int> g_opt[kOptCount];
 const bool g_opt_init = []() {
@@ -376,6 +378,23 @@ static bool pdl_enabled() { return opt(kOptPdl) != 0; }
 // table build, a memset, the caller's own kernels) is launched without the attribute: the PDL contract only
 // makes the producer's writes visible after the wait, and the early loads prefetch geometry.
 template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_smem(bool chained, size_t smem, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                                   cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (chained && pdl_enabled()) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(bool chained, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st,
                               Args... args)
 {
@@ -699,8 +718,35 @@ static bool gather_form_selected(int H, int W, int K, int T)
     return gather;
 }
 
-static size_t ws_bytes_v2(int B, int H, int W, int K, int T)
+// Pass A as a CTA-local transpose through shared memory (kernels_local.cuh): K = 3, tiled shapes.
+static bool local_form_selected(int H, int W, int K, int T)
 {
+    (void)H;
+    if (K != 3 || (W % 4) != 0 || !tiled_enabled() || gather_form_selected(H, W, K, T)) return false;
+    return opt(kOptStateLocal) != 0;     // -1 (auto) and 1: on
+}
+
+static long local_tiles(int H, int W)
+{
+    using L = LocalGeo<3>;
+    return (long)((W + L::TW - 1) / L::TW) * ((H + L::TH - 1) / L::TH);
+}
+
+static size_t ws_bytes_local(int B, int H, int W, int K, int T)
+{
+    using L = LocalGeo<3>;
+    const size_t BP = (size_t)B * H * W;
+    const PadGeo pg = pad_geo(H, W, L::R);
+    const size_t tiles = (size_t)B * (size_t)local_tiles(H, W);
+    // two padded planes + confidence-gradient accumulator + gy of every iteration + raw affinity-gradient
+    // accumulator + the schedule (slots: 16 B per pixel slot of every tile; row starts: ROWS uint16 per tile)
+    return sizeof(float) * (2 * (size_t)B * pg.plane + BP + (size_t)T * BP + (size_t)K * K * BP) + 64 +
+           tiles * (L::NT * sizeof(uint4) + L::ROWS * sizeof(unsigned short)) + 64;
+}
+
+static size_t ws_bytes_v2(int B, int H, int W, int K, int T, bool allow_local = true)
+{
+    if (allow_local && local_form_selected(H, W, K, T)) return ws_bytes_local(B, H, W, K, T);
     const size_t BP = (size_t)B * H * W;
     const ScatterGeo sg = scatter_geo(H, W);
     // three sets of four phase planes (read / scatter / being cleared) + confidence-gradient accumulator
@@ -970,6 +1016,117 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                                   g_aff_ext ? g_aff_ext + o1 * KK : nullptr, gamma, affinity, flags, H, W,
                                   g_feat_init + o1, g_guidance + o1 * 3 * N, g_confidence ? g_confidence + o1 : nullptr,
                                   gamma_slots, nullptr, gy_all, aff_g, f_last)));
+            }
+            NLSPN_CHECK_LAUNCH("final_bwd_kernel");
+        }
+        gamma_reduce.armed = true;
+        return 0;
+    }
+
+    // ---- pass A as a CTA-local transpose (kernels_local.cuh): K = 3 default.  One schedule build per call, then per
+    // iteration ONE kernel whose only global scatter is a TMA tensor reduction of the tile's 48 x 24 region.
+    const bool local_form = local_form_selected(H, W, K, T) && use_tiled;
+    if (!local_form && local_form_selected(H, W, K, T) &&
+        workspace_bytes < ws_bytes_v2(B, H, W, K, T, false) + sizeof(double) * kGammaSlots)
+        return fail(NLSPN_ERR_WORKSPACE, "backward: tensors are not 16-byte aligned, so the scatter form is needed, "
+                                         "and the workspace is too small for it (%zu < %zu)",
+                    workspace_bytes, ws_bytes_v2(B, H, W, K, T, false) + sizeof(double) * kGammaSlots);
+    if (local_form) {
+        using L = LocalGeo<3>;
+        const PadGeo pg = pad_geo(H, W, L::R);
+        const long tiles = local_tiles(H, W);
+        float *planes = ws;                                              // [2][G][PH][PW]
+        float *g_conf_acc = planes + 2 * (size_t)G * pg.plane;           // [G][P]
+        float *gy_all = g_conf_acc + (size_t)G * P;                      // [T][G][P]
+        float *g_aff_acc = gy_all + (size_t)T * G * P;                   // [G][KK][P]
+        uintptr_t sp = reinterpret_cast<uintptr_t>(g_aff_acc + (size_t)G * KK * P);
+        sp = (sp + 15) & ~(uintptr_t)15;
+        uint4 *slots = reinterpret_cast<uint4 *>(sp);                    // [G][tiles][256]
+        unsigned short *sched_tab = reinterpret_cast<unsigned short *>(slots + (size_t)G * tiles * L::NT);
+        CUtensorMap plane_map;
+        if (int rc = make_plane_map(&plane_map, planes, 2L * G, pg.PH, pg.PW, L::RW, L::RH)) return rc;
+        static std::once_flag smem_once[2];
+        static cudaError_t smem_err[2] = {cudaSuccess, cudaSuccess};
+        std::call_once(smem_once[0], [] {
+            smem_err[0] = cudaFuncSetAttribute(bwd_state_local_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)LocalSmem<3>::bytes);
+        });
+        std::call_once(smem_once[1], [] {
+            smem_err[1] = cudaFuncSetAttribute(bwd_state_local_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)LocalSmem<3>::bytes);
+        });
+        if (smem_err[0] != cudaSuccess) return cuda_fail(smem_err[0], "cudaFuncSetAttribute(bwd_state_local_kernel)");
+        if (smem_err[1] != cudaSuccess) return cuda_fail(smem_err[1], "cudaFuncSetAttribute(bwd_state_local_kernel)");
+        for (int b0 = 0; b0 < B; b0 += G) {
+            const int nb = B - b0 < G ? B - b0 : G;
+            const long o1 = (long)b0 * P;
+            const long GP = (long)nb * P;
+            e = cudaMemsetAsync(planes, 0, sizeof(float) * (2 * (size_t)G * pg.plane + (size_t)G * P), st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+            const float *cf = conf_fixed ? conf_fixed + o1 : nullptr;
+            const float *fx = feat_fix ? feat_fix + o1 : nullptr;
+            const float *off_g = offset + o1 * 2 * KK, *aff_g = aff + o1 * KK;
+            const dim3 lgrid((unsigned)((W + L::TW - 1) / L::TW), (unsigned)((H + L::TH - 1) / L::TH), (unsigned)nb);
+            const dim3 lblock(L::TW, L::TH);
+            {
+                ProfScope prof__(kProfBwdTable, st);
+                sched_build_kernel<3><<<lgrid, lblock, 0, st>>>(off_g, H, W, slots, sched_tab);
+                NLSPN_CHECK_LAUNCH("sched_build_kernel");
+            }
+            for (int t = T; t >= 1; --t) {
+                const int io = (T - t) % 2;
+                float *s_out = planes + (size_t)io * G * pg.plane;
+                float *s_in = t == T ? nullptr : planes + (size_t)(1 - io) * G * pg.plane;
+                const float *xt = list_feat + (long)(t - 1) * BP + o1;
+                const float *ge = g_list[t - 1] ? g_list[t - 1] + o1 : nullptr;
+                float *gyo = gy_all + (long)(t - 1) * GP;
+                ProfScope prof__(kProfBwdState, st);
+                if (stream_hint)
+                    e = launch_pdl_smem(t < T, LocalSmem<3>::bytes, bwd_state_local_kernel<3, true>, lgrid, lblock, st,
+                                        plane_map, io * G, off_g, aff_g, cf, fx, xt, ge, s_in, s_out,
+                                        (const uint4 *)slots, (const unsigned short *)sched_tab, gyo, g_conf_acc, flags, H, W);
+                else
+                    e = launch_pdl_smem(t < T, LocalSmem<3>::bytes, bwd_state_local_kernel<3, false>, lgrid, lblock, st,
+                                        plane_map, io * G, off_g, aff_g, cf, fx, xt, ge, s_in, s_out,
+                                        (const uint4 *)slots, (const unsigned short *)sched_tab, gyo, g_conf_acc, flags, H, W);
+                if (e != cudaSuccess) return cuda_fail(e, "bwd_state_local_kernel");
+                NLSPN_CHECK_LAUNCH("bwd_state_local_kernel");
+            }
+            const float *s_last = planes + (size_t)((T - 1) % 2) * G * pg.plane;
+            {
+                ProfScope prof__(kProfBwdParam, st);
+                const int pth = param_tile_h();
+                dim3 tgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + pth - 1) / pth), (unsigned)nb);
+                dim3 tblock(kTileW, pth);
+                if (opt(kOptParamFactored) != 0) {
+                    DISPATCH_TH(pth, (bwd_param_tiled_kernel<3, 9, THC, 2, true><<<tgrid, tblock, 0, st>>>(
+                                         src_map, list_map, B, b0, off_g, aff_g, src + o1, list_feat + o1, gy_all,
+                                         use_src ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc)));
+                } else {   // round-1 form (4 scalar LDS per tap, literal expressions): kept for A/B measurements
+                    DISPATCH_TH(pth, (bwd_param_tiled_kernel<3, 9, THC, 2, false><<<tgrid, tblock, 0, st>>>(
+                                         src_map, list_map, B, b0, off_g, aff_g, src + o1, list_feat + o1, gy_all,
+                                         use_src ? 1 : 0, H, W, T, BP, GP, g_guidance + o1 * 3 * N, g_aff_acc)));
+                }
+                NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
+            }
+            if (sampled) {
+                e = cudaMemsetAsync(g_confidence + o1, 0, sizeof(float) * (size_t)nb * P, st);
+                if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(g_confidence)");
+            }
+            ProfScope prof__(kProfFinalBwd, st);
+            if (sampled) {
+                final_bwd_kernel<3, 2, true><<<grid_for(P, nb), kBlock, 0, st>>>(
+                    guidance + o1 * 3 * N, feat_init + o1, fx, cf, s_last, g_aff_acc, g_conf_acc,
+                    g_offset_ext ? g_offset_ext + o1 * 2 * KK : nullptr, g_aff_ext ? g_aff_ext + o1 * KK : nullptr,
+                    gamma, affinity, flags, H, W, g_feat_init + o1, g_guidance + o1 * 3 * N, g_confidence + o1,
+                    gamma_slots, confidence + o1, nullptr, nullptr, nullptr, L::R, pg.PW, pg.plane);
+            } else {
+                final_bwd_kernel<3, 2, false><<<grid_for(P, nb), kBlock, 0, st>>>(
+                    guidance + o1 * 3 * N, feat_init + o1, fx, cf, s_last, g_aff_acc, g_conf_acc,
+                    g_offset_ext ? g_offset_ext + o1 * 2 * KK : nullptr, g_aff_ext ? g_aff_ext + o1 * KK : nullptr,
+                    gamma, affinity, flags, H, W, g_feat_init + o1, g_guidance + o1 * 3 * N,
+                    g_confidence ? g_confidence + o1 : nullptr, gamma_slots, nullptr, nullptr, nullptr, nullptr,
+                    L::R, pg.PW, pg.plane);
             }
             NLSPN_CHECK_LAUNCH("final_bwd_kernel");
         }

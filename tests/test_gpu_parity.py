@@ -79,14 +79,16 @@ def test_forward_matches_reference_golden(dev, name):
     assert abs(a[0] - b[0]) <= 1e-5 and abs(a[1] - b[1]) <= 1e-5
 
 
-@pytest.mark.parametrize("form", ["default", "gather"])
+@pytest.mark.parametrize("form", ["default", "red", "gather"])
 @pytest.mark.parametrize("name", [n for n in PATHS if "fullmodel" not in n])
 def test_backward_matches_reference_autograd(dev, nlspn_opt, name, form):
-    """`form`: pass A of the backward as the library chooses it, or forced to the tabulated gather
-    (kernels_gather.cuh) -- every mode of the golden set (affinity modes, no confidence, no preserve_input,
-    always_clip, K = 5) goes through both."""
+    """`form`: pass A of the backward as the library chooses it (K = 3: the CTA-local transpose, kernels_local.cuh),
+    forced to the RED scatter (kernels_v2.cuh) or to the tabulated gather (kernels_gather.cuh) -- every mode of
+    the golden set (affinity modes, no confidence, no preserve_input, always_clip, K = 5) goes through all three."""
     if form == "gather":
         nlspn_opt(state_gather=1)
+    elif form == "red":
+        nlspn_opt(state_gather=0, state_local=0)
     g = load_golden(name)
     mod, (fi, gd, cf), (feat_result, list_feat, offset, aff, _), m = _run_module(g, dev, grad=True)
     gl = torch.from_numpy(g["out_g_list"]).to(dev)
@@ -287,15 +289,16 @@ def test_fused_path_equals_unfused_reference_statements(dev):
 
 
 @pytest.mark.parametrize("K,T,use_conf", [(3, 6, True), (5, 3, True), (3, 4, False), (7, 2, True)])
-@pytest.mark.parametrize("form", ["red", "gather", "gather-compact"])
+@pytest.mark.parametrize("form", ["red", "local", "gather", "gather-compact"])
 def test_two_pass_backward_equals_per_iteration_backward(dev, nlspn_opt, K, T, use_conf, form):
     """Both forms of pass A -- the REDx4 scatter (kernels_v2.cuh; default for K = 3) and the tabulated
     gather (kernels_gather.cuh; default for K >= 5) -- with pass B in registers, against the
     per-iteration formulation (accumulator RMW + scalar atomics) on the same saved tensors."""
     from nlspn_eccv20_b200 import functional as F_
     from nlspn_eccv20_b200.synth import make_inputs
-    nlspn_opt(state_gather=0 if form == "red" else 1, gather_compact=1 if form == "gather-compact" else 0)
-    B, H, W = 2, 38, 45
+    nlspn_opt(state_gather=0 if form in ("red", "local") else 1, gather_compact=1 if form == "gather-compact" else 0,
+              state_local=1 if form == "local" else 0)
+    B, H, W = (2, 38, 45) if form != "local" else (2, 38, 44)     # the local form needs W % 4 == 0 (TMA row pitch)
     inp = make_inputs(B, H, W, K, seed=77 + K, device=dev, conf_mean=2.0)
     gamma = 0.5 * (K * K - 1)
     conf = inp["confidence"] if use_conf else None

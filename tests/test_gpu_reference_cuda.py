@@ -31,13 +31,14 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("form", ["default", "red", "gather", "gather-compact"])
+@pytest.mark.parametrize("form", ["default", "red", "local", "gather", "gather-compact"])
 @pytest.mark.parametrize("K,T,shape", [(3, 18, (2, 228, 304)), (5, 6, (1, 97, 131)), (5, 12, (2, 64, 96)), (7, 3, (1, 40, 53))])
 def test_module_matches_reference_cuda_kernels(ref, nlspn_opt, K, T, shape, form):
     """`form` selects pass A of the backward: the library's default for this K and T, the RED scatter, or the
     tabulated gather (kernels_gather.cuh)."""
     if form != "default":
-        nlspn_opt(state_gather=0 if form == "red" else 1, gather_compact=1 if form == "gather-compact" else 0)
+        nlspn_opt(state_gather=0 if form in ("red", "local") else 1, gather_compact=1 if form == "gather-compact" else 0,
+                  state_local=1 if form == "local" else 0)
     from nlspn_eccv20_b200 import NLSPN
     from nlspn_eccv20_b200.synth import make_inputs, rmse_mae
     dev = torch.device("cuda:0")
@@ -222,6 +223,12 @@ def _compare_fwd_bwd(ref, workload_name, B, K, T, seed=7240, offset_outliers=1e-
 def test_kitti_k3_t18_forward_backward_against_reference_cuda_kernels(ref):
     """The HEADLINE benchmark shape (KITTI 352x1216, K=3, T=18; bench.py default), B=2: forward + all gradients
     incl. gamma.  Width 1216 is where fp32 coordinate arithmetic bites."""
+    _compare_fwd_bwd(ref, "kitti", 2, 3, 18)
+
+
+def test_kitti_k3_t18_red_scatter_form_against_reference_cuda_kernels(ref, nlspn_opt):
+    """Same shape with pass A forced to the RED scatter (bwd_state_kernel; the default until round 2)."""
+    nlspn_opt(state_local=0)
     _compare_fwd_bwd(ref, "kitti", 2, 3, 18)
 
 
