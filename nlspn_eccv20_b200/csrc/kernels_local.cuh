@@ -265,13 +265,17 @@ bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
 
     // ---- stage 1: gs, G, gy (nlspnmodel.py:351,357,361 backwards; identical to bwd_state_kernel)
     float gy = 0.f;
+    const long pc = b * pg.plane + (long)(h + L::R) * pg.PW + (w + L::R);
+    float gs = 0.f, gca = 0.f;
+    if (inside && s_in) {
+        gs = __ldcg(s_in + pc);
+        if (conf) gca = g_conf_acc[q];
+    }
+    // keep every use of the stage-0 loads BELOW the two loads above: otherwise the scheduler parks a use of `dp`
+    // in front of griddepcontrol.wait and the CTA pays two serialised memory round trips (ncu: 1167 + 806 stall
+    // samples on those two instructions)
+    asm volatile("" : "+f"(dp), "+f"(cf), "+f"(xt), "+f"(gext));
     if (inside) {
-        const long pc = b * pg.plane + (long)(h + L::R) * pg.PW + (w + L::R);
-        float gs = 0.f, gca = 0.f;
-        if (s_in) {
-            gs = __ldcg(s_in + pc);
-            if (conf) gca = g_conf_acc[q];
-        }
         float Gx = gext;
         if (flags & kBlendPre) {   // upstream order: the blend sits on the gather's INPUT
             if (s_in) Gx += (flags & kPreserve) ? (1.0f - (dp > 0.f ? 1.f : 0.f)) * gs : gs;
