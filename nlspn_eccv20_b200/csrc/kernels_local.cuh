@@ -17,7 +17,12 @@
 //       blocks by that count and lays the tile's <= 2048 footprints out as JAGGED DIAGONALS: the j-th footprint
 //       of the block at sorted position p lives in slot jd[j] + p.  Output: 8 x uint16 slots per pixel, the
 //       sorted block list and the diagonal starts (25 B per pixel).  Invalid taps (cuh:180) get kSlotSkip,
-//       footprints outside the region kSlotGlobal.
+//       footprints outside the region kSlotGlobal.  The same kernel re-packs everything the T iterations read
+//       per pixel and that does not change between them -- the slots, the 8 offset pairs, the 9 affinities, the
+//       fixed confidence and the input-preserving multiplier -- into ONE record of 8 x 16 bytes per pixel, laid
+//       out [tile][vector][thread]: an iteration then issues 8 coalesced 128-bit loads from one base address
+//       instead of 30 scalar loads with a 64-bit address chain each (ncu, first version: 248 of 982 instructions
+//       per warp and iteration were stage-0 address arithmetic).
 //
 //   bwd_state_local_kernel (one launch per iteration; same grid)
 //       stage 1  exactly bwd_state_kernel's: gs from the scatter plane (now ONE padded plane: one coalesced
@@ -57,12 +62,16 @@ template <> struct LocalGeo<3> {
     // per-tile table (uint16): sorted block list [NBLK] (block | length << 11), diagonal starts [32], nnz + padding [8]
     static constexpr int TAB_JD = NBLK, TAB_NNZ = NBLK + 32;
     static constexpr int ROWS = NBLK + 32 + 8;               // 1192 uint16 = 149 x 16 bytes
+    // packed per-pixel record, [tile][GEOV][NT] x 16 bytes: 0 slots | 1-4 offset pairs of taps (2i, 2i+1) as
+    // (dh, dw, dh, dw) | 5-6 affinities of the 8 neighbours | 7 (centre affinity, confidence, preserve factor, 0)
+    static constexpr int GEOV = 8;
 };
 
 template <int K> struct LocalSmem {
     using L = LocalGeo<K>;
-    static constexpr size_t bytes = sizeof(float4) * (L::NQUAD + L::NBLK) + sizeof(float) * L::NT +
-                                    sizeof(unsigned short) * L::ROWS;
+    // quads (32 KB; after stage 3a the same bytes hold the block sums and the flush tile) + centre taps + table
+    static constexpr size_t bytes = sizeof(float4) * L::NQUAD + sizeof(float) * L::NT + sizeof(unsigned short) * L::ROWS;
+    static_assert(sizeof(float4) * L::NBLK + sizeof(float) * L::NCELL <= sizeof(float4) * L::NQUAD, "block sums + flush tile alias the quads");
 };
 
 constexpr unsigned kSlotSkip = 0xFFFEu;      // invalid tap (cuh:180) or pixel outside the image
@@ -83,13 +92,14 @@ __host__ __device__ inline PadGeo pad_geo(int H, int W, int R)
 }
 
 // ======================================================================================
-// Schedule build.  grid = (ceil(W/32), ceil(H/8), nb), block = (32, 8).
-//   slots     [nb][tiles][256] uint4 = 8 x uint16 per pixel (tap n in bits 16*(n&1) of word n>>1)
+// Schedule build + geometry re-pack.  grid = (ceil(W/32), ceil(H/8), nb), block = (32, 8).
+//   geo       [nb][tiles][GEOV][256] x 16 B: the packed per-pixel record (LocalGeo::GEOV)
 //   table     [nb][tiles][ROWS] uint16: sorted blocks (block | length << 11), diagonal starts, nnz
 // ======================================================================================
 template <int K>
 __global__ void __launch_bounds__(LocalGeo<K>::NT)
-sched_build_kernel(const float *__restrict__ offset, int H, int W, uint4 *__restrict__ slots,
+sched_build_kernel(const float *__restrict__ offset, const float *__restrict__ aff, const float *__restrict__ conf,
+                   const float *__restrict__ dep, unsigned flags, int H, int W, uint4 *__restrict__ geo,
                    unsigned short *__restrict__ table_g)
 {
     using G = Geo<K>;
@@ -112,14 +122,18 @@ sched_build_kernel(const float *__restrict__ offset, int H, int W, uint4 *__rest
     const float *ob = offset + b * 2 * G::KK * P + r;
     int blk[L::NTAP];
     unsigned rank[L::NTAP];
+    float oh[L::NTAP], ow[L::NTAP];
 #pragma unroll
     for (int n = 0; n < L::NTAP; ++n) {
         const int t = n < G::REF ? n : n + 1;
         blk[n] = -1;
         rank[n] = 0u;
+        oh[n] = ow[n] = 0.f;
         if (!inside) continue;
-        const float h_im = (float)(h - G::PAD + t / K) + __ldg(ob + (long)(2 * t) * P);
-        const float w_im = (float)(w - G::PAD + t % K) + __ldg(ob + (long)(2 * t + 1) * P);
+        oh[n] = __ldg(ob + (long)(2 * t) * P);
+        ow[n] = __ldg(ob + (long)(2 * t + 1) * P);
+        const float h_im = (float)(h - G::PAD + t / K) + oh[n];
+        const float w_im = (float)(w - G::PAD + t % K) + ow[n];
         if (!tap_valid(h_im, w_im, H, W)) continue;
         float hf, wf;
         int hl, wl;
@@ -165,11 +179,10 @@ sched_build_kernel(const float *__restrict__ offset, int H, int W, uint4 *__rest
     // sorted positions: blocks of length l occupy [start[l], start[l] + hist[l])
     for (int i = tid; i < L::NBLK; i += L::NT) {
         const unsigned len = cnt[i] < (unsigned)L::MAXLEN ? cnt[i] : (unsigned)L::MAXLEN;
-        if (len) {
-            const unsigned p = start_s[len] + atomicAdd(&fill[len], 1u);
-            pos_s[i] = (unsigned short)p;
-            tab[p] = (unsigned short)(i | (len << 11));
-        }
+        // empty blocks (len 0) follow the nnz non-empty ones: start_s[0] = nnz, so the list covers all NBLK blocks
+        const unsigned p = start_s[len] + atomicAdd(&fill[len], 1u);
+        pos_s[i] = (unsigned short)p;
+        tab[p] = (unsigned short)(i | (len << 11));
     }
     __syncthreads();
     unsigned sl[L::NTAP];
@@ -181,8 +194,25 @@ sched_build_kernel(const float *__restrict__ offset, int H, int W, uint4 *__rest
             sl[n] = blk[n] == -2 ? kSlotGlobal : kSlotSkip;
     }
     const long tile = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    slots[tile * L::NT + tid] = make_uint4(sl[0] | (sl[1] << 16), sl[2] | (sl[3] << 16), sl[4] | (sl[5] << 16),
-                                           sl[6] | (sl[7] << 16));
+    // the packed record (pixels of the tile that lie outside the image: all taps skipped, zeros)
+    float av[G::KK];
+    float cf = 1.f, pm = 1.f;
+    const float *ab = aff + b * G::KK * P + r;
+#pragma unroll
+    for (int t = 0; t < G::KK; ++t) av[t] = inside ? __ldg(ab + (long)t * P) : 0.f;
+    if (inside) {
+        if (conf) cf = __ldg(conf + b * P + r);
+        if (flags & kPreserve) pm = 1.0f - (__ldg(dep + b * P + r) > 0.f ? 1.f : 0.f);   // nlspnmodel.py:357 backwards
+    }
+    uint4 *gp = geo + tile * (L::GEOV * L::NT) + tid;
+    gp[0] = make_uint4(sl[0] | (sl[1] << 16), sl[2] | (sl[3] << 16), sl[4] | (sl[5] << 16), sl[6] | (sl[7] << 16));
+    float4 *gf = reinterpret_cast<float4 *>(gp);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gf[(1 + i) * L::NT] = make_float4(oh[2 * i], ow[2 * i], oh[2 * i + 1], ow[2 * i + 1]);
+    // neighbour n = tap n (n < REF) or n + 1
+    gf[5 * L::NT] = make_float4(av[0], av[1], av[2], av[3]);
+    gf[6 * L::NT] = make_float4(av[5], av[6], av[7], av[8]);
+    gf[7 * L::NT] = make_float4(av[G::REF], cf, pm, 0.f);
     uint4 *tg = reinterpret_cast<uint4 *>(table_g + tile * L::ROWS);
     if (tid < L::ROWS / 8) tg[tid] = reinterpret_cast<const uint4 *>(tab)[tid];
 }
@@ -195,113 +225,139 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, const 
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void tma_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 16-byte store to a shared-memory address computed once per thread (the generic-pointer form makes the compiler
+// rebuild the CTA's shared window base in front of every store inside a divergent region: 3 instructions per tap)
+__device__ __forceinline__ void sts128(unsigned addr, const float4 &v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// the CTA may exit once the bulk reduction has READ its shared-memory source; the global side completes before the
+// grid does (same rule as every TMA-store epilogue)
+__device__ __forceinline__ void tma_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// pull `bytes` (multiple of 16, 16-byte aligned) into L2 without a destination
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 // ======================================================================================
 // One backward iteration of the state gradient, local-transpose form.
+//   geo    packed per-pixel records of sched_build_kernel
 //   s_in   padded planes [nb][PH][PW] written by iteration t+1 (nullptr at t = T): read, then cleared
 //   s_out  padded planes of this iteration (plane_map describes [planes][PH][PW]; z_out = plane of image 0)
 // grid = (ceil(W/32), ceil(H/8), nb), block = (32, 8).
 // ======================================================================================
-template <int K, bool STREAM>
-__global__ void __launch_bounds__(LocalGeo<K>::NT, 3)
-bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
-                       const float *__restrict__ offset, const float *__restrict__ aff,
-                       const float *__restrict__ conf, const float *__restrict__ dep,
-                       const float *__restrict__ x_t, const float *__restrict__ g_ext,
+template <int K, bool STREAM, int MINB>
+__global__ void __launch_bounds__(LocalGeo<K>::NT, MINB)
+bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out, const uint4 *__restrict__ geo,
+                       int has_conf, const float *__restrict__ x_t, const float *__restrict__ g_ext,
                        float *__restrict__ s_in, float *__restrict__ s_out,
-                       const uint4 *__restrict__ slots, const unsigned short *__restrict__ table_g,
-                       float *__restrict__ gy_out, float *__restrict__ g_conf_acc, unsigned flags, int H, int W)
+                       const unsigned short *__restrict__ table_g,
+                       float *__restrict__ gy_out, float *__restrict__ g_conf_acc, unsigned flags, int H, int W,
+                       int pf_dist)
 {
+    static_assert(K == 3, "the packed record holds 8 neighbours");
     using G = Geo<K>;
     using L = LocalGeo<K>;
     // dynamic shared memory (LocalSmem<K>::bytes > the 48 KB static limit)
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4 *quads = reinterpret_cast<float4 *>(smem_raw);                     // stage 2/3a; reused as the flush tile
-    float4 *blocksum = quads + L::NQUAD;
-    float *centre = reinterpret_cast<float *>(blocksum + L::NBLK);
+    float4 *quads = reinterpret_cast<float4 *>(smem_raw);                     // stage 2/3a
+    float4 *blocksum = quads;                                                 // stage 3a' / 3b: aliases the consumed quads
+    float *flush = reinterpret_cast<float *>(quads + L::NBLK);                // stage 3b / 4: behind the block sums
+    float *centre = reinterpret_cast<float *>(quads + L::NQUAD);
     unsigned short *tab = reinterpret_cast<unsigned short *>(centre + L::NT);   // sorted blocks, diagonal starts, nnz
     const int P = H * W;
     const int x0 = blockIdx.x * L::TW, y0 = blockIdx.y * L::TH;
-    const long b = blockIdx.z;
+    const int b = blockIdx.z;
     const int tid = threadIdx.y * L::TW + threadIdx.x;
     const int w = x0 + threadIdx.x, h = y0 + threadIdx.y;
     const bool inside = w < W && h < H;
     const int r = inside ? h * W + w : 0;
-    const long q = b * P + r;
     const PadGeo pg = pad_geo(H, W, L::R);
-    const long tile = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const long tile = ((long)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    // per-image bases are CTA-uniform 64-bit values; everything per thread is a 32-bit index on top of them
+    const float *xb = x_t + (long)b * P;
+    const float *geb = g_ext ? g_ext + (long)b * P : nullptr;
+    float *gyb = gy_out + (long)b * P;
+    float *gcb = g_conf_acc + (long)b * P;
+    float *sib = s_in ? s_in + (long)b * pg.plane : nullptr;
+    float *sob = s_out + (long)b * pg.plane;
 
     // ---- stage 0: everything that does not depend on the previous backward iteration
     tma::grid_launch_dependents();
+    if (tid == 0 && pf_dist > 0) {
+        // the CTA that will run `pf_dist` tiles from now (about one wave of resident CTAs) finds its record in L2:
+        // CTA lifetime here is ~8x its issue time, most of it the DRAM round trip of stage 0
+        const long nt = tile + pf_dist;
+        if (nt < (long)gridDim.x * gridDim.y * gridDim.z) {
+            bulk_prefetch_l2(geo + nt * (L::GEOV * L::NT), L::GEOV * L::NT * 16);
+            bulk_prefetch_l2(table_g + nt * L::ROWS, L::ROWS * 2);
+        }
+    }
     if (tid < L::ROWS / 8)
         reinterpret_cast<uint4 *>(tab)[tid] = __ldg(reinterpret_cast<const uint4 *>(table_g + tile * L::ROWS) + tid);
-    for (int k = tid; k < L::NBLK; k += L::NT) blocksum[k] = make_float4(0.f, 0.f, 0.f, 0.f);   // empty blocks stay zero
-    const uint4 sl4 = __ldg(slots + tile * L::NT + tid);
-    const float *ob = offset + b * 2 * G::KK * P + r;
-    const float *ab = aff + b * G::KK * P + r;
-    float oh[G::KK], ow[G::KK], av[G::KK];
-    float gext = 0.f, cf = 1.f, xt = 1.f, dp = 0.f;
-    const bool need_x = (s_in && conf) || (flags & kAlwaysClip);
+    const uint4 *gp = geo + tile * (L::GEOV * L::NT) + tid;
+    const float4 *gf = reinterpret_cast<const float4 *>(gp);
+    const uint4 sl4 = STREAM ? __ldcs(gp) : __ldg(gp);
+    float4 o4[4], a4[2], m4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o4[i] = STREAM ? __ldcs(gf + (1 + i) * L::NT) : __ldg(gf + (1 + i) * L::NT);
+    a4[0] = STREAM ? __ldcs(gf + 5 * L::NT) : __ldg(gf + 5 * L::NT);
+    a4[1] = STREAM ? __ldcs(gf + 6 * L::NT) : __ldg(gf + 6 * L::NT);
+    m4 = STREAM ? __ldcs(gf + 7 * L::NT) : __ldg(gf + 7 * L::NT);   // (centre affinity, confidence, preserve factor, -)
+    const bool need_x = (s_in && has_conf) || (flags & kAlwaysClip);
+    float gext = 0.f, xt = 1.f;
     if (inside) {
-#pragma unroll
-        for (int t = 0; t < G::KK; ++t) {
-            av[t] = ld_geo<STREAM>(ab + (long)t * P);
-            oh[t] = ow[t] = 0.f;
-            if (t != G::REF) {
-                oh[t] = ld_geo<STREAM>(ob + (long)(2 * t) * P);
-                ow[t] = ld_geo<STREAM>(ob + (long)(2 * t + 1) * P);
-            }
-        }
-        gext = g_ext ? __ldg(g_ext + q) : 0.f;
-        cf = conf ? __ldg(conf + q) : 1.f;
-        xt = need_x ? __ldg(x_t + q) : 1.f;
-        dp = (flags & kPreserve) ? __ldg(dep + q) : 0.f;
-    } else {
-#pragma unroll
-        for (int t = 0; t < G::KK; ++t) av[t] = oh[t] = ow[t] = 0.f;
+        gext = geb ? __ldg(geb + r) : 0.f;
+        xt = need_x ? __ldg(xb + r) : 1.f;
     }
     tma::grid_dependency_wait();   // s_in / s_out / g_conf_acc belong to the previous launch
 
     // ---- stage 1: gs, G, gy (nlspnmodel.py:351,357,361 backwards; identical to bwd_state_kernel)
     float gy = 0.f;
-    const long pc = b * pg.plane + (long)(h + L::R) * pg.PW + (w + L::R);
+    const int pc = (h + L::R) * pg.PW + (w + L::R);
     float gs = 0.f, gca = 0.f;
-    if (inside && s_in) {
-        gs = __ldcg(s_in + pc);
-        if (conf) gca = g_conf_acc[q];
+    if (inside && sib) {
+        gs = __ldcg(sib + pc);
+        if (has_conf) gca = gcb[r];
     }
-    // keep every use of the stage-0 loads BELOW the two loads above: otherwise the scheduler parks a use of `dp`
+    // keep every use of the stage-0 loads BELOW the two loads above: otherwise the scheduler parks a use of them
     // in front of griddepcontrol.wait and the CTA pays two serialised memory round trips (ncu: 1167 + 806 stall
     // samples on those two instructions)
-    asm volatile("" : "+f"(dp), "+f"(cf), "+f"(xt), "+f"(gext));
+    asm volatile("" : "+f"(m4.y), "+f"(m4.z), "+f"(xt), "+f"(gext));
+    const float cf = m4.y, pm = m4.z;
     if (inside) {
         float Gx = gext;
         if (flags & kBlendPre) {   // upstream order: the blend sits on the gather's INPUT
-            if (s_in) Gx += (flags & kPreserve) ? (1.0f - (dp > 0.f ? 1.f : 0.f)) * gs : gs;
+            if (sib) Gx += (flags & kPreserve) ? pm * gs : gs;
         } else {
-            if (s_in) Gx += conf ? cf * gs : gs;
+            if (sib) Gx += has_conf ? cf * gs : gs;
             if ((flags & kAlwaysClip) && was_clipped(xt)) Gx = 0.f;
-            if (flags & kPreserve) Gx = (1.0f - (dp > 0.f ? 1.f : 0.f)) * Gx;
+            if (flags & kPreserve) Gx = pm * Gx;
         }
         gy = Gx;
-        if (s_in) {
-            s_in[pc] = 0.f;                      // this plane is the target of iteration t-1
-            if (conf) g_conf_acc[q] = gca + xt * gs;
+        if (sib) {
+            sib[pc] = 0.f;                      // this plane is the target of iteration t-1
+            if (has_conf) gcb[r] = gca + xt * gs;
         }
-        gy_out[q] = gy;
+        gyb[r] = gy;
     }
 
     // ---- stage 2: weighted corner quads to their slots
     const unsigned slw[4] = {sl4.x, sl4.y, sl4.z, sl4.w};
+    unsigned quads_s = tma::smem_u32(quads);
+    asm volatile("" : "+r"(quads_s));            // opaque: computed once, not rebuilt in front of every store
+    const float ohv[8] = {o4[0].x, o4[0].z, o4[1].x, o4[1].z, o4[2].x, o4[2].z, o4[3].x, o4[3].z};
+    const float owv[8] = {o4[0].y, o4[0].w, o4[1].y, o4[1].w, o4[2].y, o4[2].w, o4[3].y, o4[3].w};
+    const float avv[8] = {a4[0].x, a4[0].y, a4[0].z, a4[0].w, a4[1].x, a4[1].y, a4[1].z, a4[1].w};
 #pragma unroll
     for (int n = 0; n < L::NTAP; ++n) {
         const int t = n < G::REF ? n : n + 1;
         const unsigned slot = (slw[n >> 1] >> (16 * (n & 1))) & 0xFFFFu;
         if (slot == kSlotSkip) continue;
-        const float top = gy * av[t];
-        const float h_im = (float)(h - G::PAD + t / K) + oh[t];
-        const float w_im = (float)(w - G::PAD + t % K) + ow[t];
+        const float top = gy * avv[n];
+        const float h_im = (float)(h - G::PAD + t / K) + ohv[n];
+        const float w_im = (float)(w - G::PAD + t % K) + owv[n];
         const float hf = floor_small_f(h_im), wf = floor_small_f(w_im);
         // mdmcn_get_gradient_weight, cuh:71-79 (expressions kept literal; (float)(hl+1) == hf + 1 exactly)
         const float h1 = hf + 1.f, w1 = wf + 1.f;
@@ -309,11 +365,11 @@ bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
         const float lw_ = w1 - w_im, rw = (w_im + 1.f) - w1;
         const float4 qd = make_float4(th * lw_ * top, th * rw * top, bh * lw_ * top, bh * rw * top);
         if (slot != kSlotGlobal) {
-            quads[slot] = qd;
+            sts128(quads_s + slot * 16u, qd);
         } else if (gy != 0.f) {
             // far footprint: guarded scalar REDs (cuh:229-252 with the guards of :37-48) into the padded plane
             const int hl = (int)hf, wl = (int)wf;
-            float *sp = s_out + b * pg.plane + (long)(hl + L::R) * pg.PW + (wl + L::R);
+            float *sp = sob + ((hl + L::R) * pg.PW + (wl + L::R));
             const bool topv = hl >= 0, botv = hl + 1 <= H - 1, lefv = wl >= 0, rigv = wl + 1 <= W - 1;
             if (topv && lefv) atomicAdd(sp, qd.x);
             if (topv && rigv) atomicAdd(sp + 1, qd.y);
@@ -321,32 +377,48 @@ bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
             if (botv && rigv) atomicAdd(sp + pg.PW + 1, qd.w);
         }
     }
-    centre[tid] = gy * av[G::REF];     // the centre tap has a structurally zero offset: lands on the pixel itself
+    centre[tid] = gy * m4.x;     // the centre tap has a structurally zero offset: lands on the pixel itself
     __syncthreads();
 
-    // ---- stage 3a: block sums over the jagged diagonals: thread p owns sorted block p, its j-th quad is slot jd[j] + p
+    // ---- stage 3a: block sums over the jagged diagonals.  Thread `tid` owns the sorted blocks p_k = tid + 256 k;
+    // the j-th quad of block p is slot jd[j] + p.  Blocks are sorted by descending length, so len(p_0) >= len(p_1)
+    // >= ...: at diagonal j the thread's active blocks are a prefix of k, and lanes of a warp agree on it except at
+    // one boundary.  One read of jd[j] serves all of them.  The sums stay in registers until every quad has been
+    // read; then they overwrite the quads (block sums and flush tile alias them: 36 KB per CTA instead of 55).
     {
-        const int nnz = tab[L::TAB_NNZ];
-        for (int p = tid; p < nnz; p += L::NT) {
-            const unsigned e = tab[p];
-            const int len = (int)(e >> 11);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int j = 0; j < len; ++j) {
-                const float4 v = quads[tab[L::TAB_JD + j] + p];
-                acc.x += v.x;
-                acc.y += v.y;
-                acc.z += v.z;
-                acc.w += v.w;
-            }
-            blocksum[e & 0x7FFu] = acc;
+        constexpr int NK = (L::NBLK + L::NT - 1) / L::NT;     // 5 (the last one half full)
+        unsigned e[NK];
+        int len[NK];
+        float4 acc[NK];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const int p = tid + k * L::NT;
+            e[k] = p < L::NBLK ? tab[p] : 0u;               // the list covers all NBLK blocks, empty ones last
+            len[k] = (int)(e[k] >> 11);
+            acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        for (int j = 0; j < len[0]; ++j) {
+            const float4 *qj = quads + tab[L::TAB_JD + j] + tid;
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                if (j >= len[k]) break;
+                const float4 v = qj[k * L::NT];
+                acc[k].x += v.x;
+                acc[k].y += v.y;
+                acc[k].z += v.z;
+                acc[k].w += v.w;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
+            if (tid + k * L::NT < L::NBLK) blocksum[e[k] & 0x7FFu] = acc[k];
     }
     __syncthreads();
 
     // ---- stage 3b: every aligned 2x2 cell group adds the four block phases that overlap it
     //   phase (sy, sx) block (by, bx) covers region rows 2*by + sy, +1 and columns 2*bx + sx, +1;
     //   components x y z w = (row0,col0) (row0,col1) (row1,col0) (row1,col1).
-    float *flush = reinterpret_cast<float *>(quads);           // all slots were consumed in stage 3a
     constexpr int PB = L::BH * L::BW;
     for (int k = tid; k < PB; k += L::NT) {
         const int cy = k / L::BW, cx = k - cy * L::BW;
@@ -382,8 +454,8 @@ bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
     // (y0 - R, x0 - R) = padded coordinates (y0, x0): never negative, x0 a multiple of 32 (16-byte aligned);
     // the part of the box beyond the plane's high edges is clipped by the TMA unit.
     if (tid == 0) {
-        tma_reduce_add_3d(&plane_map, flush, x0, y0, z_out + (int)b);
-        tma_bulk_wait_all();      // the reduction is performed before this CTA (and with it the grid) completes
+        tma_reduce_add_3d(&plane_map, flush, x0, y0, z_out + b);
+        tma_bulk_wait_read();     // shared memory must outlive the read; the grid completes after the global side
     }
 }
 

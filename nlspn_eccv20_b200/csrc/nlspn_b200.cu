@@ -30,7 +30,7 @@ std::atomic<unsigned long long> g_launches{0};
 // -1 = "auto" where a default depends on the shape.
 enum Opt { kOptTiled = 0, kOptPersist, kOptPdl, kOptFwdTH, kOptParamTH, kOptStateTma, kOptStateGather,
            kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint, kOptStateAhead,
-           kOptParamFactored, kOptPersistBwd, kOptDcnBlocked, kOptStateLocal, kOptCount };
+           kOptParamFactored, kOptPersistBwd, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptCount };
 struct OptDef { const char *name; const char *env; int def; };
 const OptDef kOptDefs[kOptCount] = {
     {"tiled", "NLSPN_TILED", 1},
@@ -50,6 +50,8 @@ const OptDef kOptDefs[kOptCount] = {
     {"persist_bwd", "NLSPN_PERSIST_BWD", -1},
     {"dcn_blocked", "NLSPN_DCN_BLOCKED", 1},
     {"state_local", "NLSPN_STATE_LOCAL", -1},
+    {"local_prefetch", "NLSPN_LOCAL_PREFETCH", 0},
+    {"local_minb", "NLSPN_LOCAL_MINB", 5},
 };
 std::atomic<int> g_opt[kOptCount];
 const bool g_opt_init = []() {
@@ -739,9 +741,10 @@ static size_t ws_bytes_local(int B, int H, int W, int K, int T)
     const PadGeo pg = pad_geo(H, W, L::R);
     const size_t tiles = (size_t)B * (size_t)local_tiles(H, W);
     // two padded planes + confidence-gradient accumulator + gy of every iteration + raw affinity-gradient
-    // accumulator + the schedule (slots: 16 B per pixel slot of every tile; row starts: ROWS uint16 per tile)
+    // accumulator + the schedule (packed per-pixel records: GEOV x 16 B per pixel slot of every tile; block lists:
+    // ROWS uint16 per tile)
     return sizeof(float) * (2 * (size_t)B * pg.plane + BP + (size_t)T * BP + (size_t)K * K * BP) + 64 +
-           tiles * (L::NT * sizeof(uint4) + L::ROWS * sizeof(unsigned short)) + 64;
+           tiles * (L::GEOV * L::NT * sizeof(uint4) + L::ROWS * sizeof(unsigned short)) + 64;
 }
 
 static size_t ws_bytes_v2(int B, int H, int W, int K, int T, bool allow_local = true)
@@ -1041,22 +1044,35 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         float *g_aff_acc = gy_all + (size_t)T * G * P;                   // [G][KK][P]
         uintptr_t sp = reinterpret_cast<uintptr_t>(g_aff_acc + (size_t)G * KK * P);
         sp = (sp + 15) & ~(uintptr_t)15;
-        uint4 *slots = reinterpret_cast<uint4 *>(sp);                    // [G][tiles][256]
-        unsigned short *sched_tab = reinterpret_cast<unsigned short *>(slots + (size_t)G * tiles * L::NT);
+        uint4 *geo = reinterpret_cast<uint4 *>(sp);                      // [G][tiles][GEOV][256]
+        unsigned short *sched_tab = reinterpret_cast<unsigned short *>(geo + (size_t)G * tiles * L::GEOV * L::NT);
         CUtensorMap plane_map;
         if (int rc = make_plane_map(&plane_map, planes, 2L * G, pg.PH, pg.PW, L::RW, L::RH)) return rc;
-        static std::once_flag smem_once[2];
-        static cudaError_t smem_err[2] = {cudaSuccess, cudaSuccess};
-        std::call_once(smem_once[0], [] {
-            smem_err[0] = cudaFuncSetAttribute(bwd_state_local_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)LocalSmem<3>::bytes);
+        static std::once_flag smem_once;
+        static cudaError_t smem_err = cudaSuccess;
+        std::call_once(smem_once, [] {
+            auto set = [](auto kernel) {
+                const cudaError_t e1 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                            (int)LocalSmem<3>::bytes);
+                if (e1 != cudaSuccess && smem_err == cudaSuccess) smem_err = e1;
+            };
+            set(bwd_state_local_kernel<3, true, 4>);
+            set(bwd_state_local_kernel<3, false, 4>);
+            set(bwd_state_local_kernel<3, true, 5>);
+            set(bwd_state_local_kernel<3, false, 5>);
+            set(bwd_state_local_kernel<3, true, 6>);
+            set(bwd_state_local_kernel<3, false, 6>);
         });
-        std::call_once(smem_once[1], [] {
-            smem_err[1] = cudaFuncSetAttribute(bwd_state_local_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)LocalSmem<3>::bytes);
-        });
-        if (smem_err[0] != cudaSuccess) return cuda_fail(smem_err[0], "cudaFuncSetAttribute(bwd_state_local_kernel)");
-        if (smem_err[1] != cudaSuccess) return cuda_fail(smem_err[1], "cudaFuncSetAttribute(bwd_state_local_kernel)");
+        if (smem_err != cudaSuccess) return cuda_fail(smem_err, "cudaFuncSetAttribute(bwd_state_local_kernel)");
+        const int local_minb = opt(kOptLocalMinB);
+        // L2 prefetch distance (in tiles) of the packed records; -1 = one wave of resident CTAs.  Measured on B200
+        // (KITTI B=8): no gain at 5 CTAs per SM (2.48 vs 2.46 ms of pass A per step), so the default is off.
+        int pf_dist = opt(kOptLocalPrefetch);
+        if (pf_dist < 0) {
+            int dev = 0, sms = 148;
+            if (cudaGetDevice(&dev) == cudaSuccess) nlspn_device_info(dev, &sms, nullptr);
+            pf_dist = 5 * sms;
+        }
         for (int b0 = 0; b0 < B; b0 += G) {
             const int nb = B - b0 < G ? B - b0 : G;
             const long o1 = (long)b0 * P;
@@ -1070,7 +1086,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             const dim3 lblock(L::TW, L::TH);
             {
                 ProfScope prof__(kProfBwdTable, st);
-                sched_build_kernel<3><<<lgrid, lblock, 0, st>>>(off_g, H, W, slots, sched_tab);
+                sched_build_kernel<3><<<lgrid, lblock, 0, st>>>(off_g, aff_g, cf, fx, flags, H, W, geo, sched_tab);
                 NLSPN_CHECK_LAUNCH("sched_build_kernel");
             }
             for (int t = T; t >= 1; --t) {
@@ -1081,14 +1097,20 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                 const float *ge = g_list[t - 1] ? g_list[t - 1] + o1 : nullptr;
                 float *gyo = gy_all + (long)(t - 1) * GP;
                 ProfScope prof__(kProfBwdState, st);
-                if (stream_hint)
-                    e = launch_pdl_smem(t < T, LocalSmem<3>::bytes, bwd_state_local_kernel<3, true>, lgrid, lblock, st,
-                                        plane_map, io * G, off_g, aff_g, cf, fx, xt, ge, s_in, s_out,
-                                        (const uint4 *)slots, (const unsigned short *)sched_tab, gyo, g_conf_acc, flags, H, W);
-                else
-                    e = launch_pdl_smem(t < T, LocalSmem<3>::bytes, bwd_state_local_kernel<3, false>, lgrid, lblock, st,
-                                        plane_map, io * G, off_g, aff_g, cf, fx, xt, ge, s_in, s_out,
-                                        (const uint4 *)slots, (const unsigned short *)sched_tab, gyo, g_conf_acc, flags, H, W);
+#define LOCAL_LAUNCH(SH_, MB_)                                                                                      \
+    e = launch_pdl_smem(t < T, LocalSmem<3>::bytes, bwd_state_local_kernel<3, SH_, MB_>, lgrid, lblock, st, plane_map, \
+                        io * G, (const uint4 *)geo, cf ? 1 : 0, xt, ge, s_in, s_out,                                \
+                        (const unsigned short *)sched_tab, gyo, g_conf_acc, flags, H, W, pf_dist)
+                if (stream_hint) {
+                    if (local_minb == 4) LOCAL_LAUNCH(true, 4);
+                    else if (local_minb == 6) LOCAL_LAUNCH(true, 6);
+                    else LOCAL_LAUNCH(true, 5);
+                } else {
+                    if (local_minb == 4) LOCAL_LAUNCH(false, 4);
+                    else if (local_minb == 6) LOCAL_LAUNCH(false, 6);
+                    else LOCAL_LAUNCH(false, 5);
+                }
+#undef LOCAL_LAUNCH
                 if (e != cudaSuccess) return cuda_fail(e, "bwd_state_local_kernel");
                 NLSPN_CHECK_LAUNCH("bwd_state_local_kernel");
             }
