@@ -18,7 +18,7 @@
 //       of the block at sorted position p lives in slot jd[j] + p.  Output: 8 x uint16 slots per pixel, the
 //       sorted block list and the diagonal starts (25 B per pixel).  Invalid taps (cuh:180) get kSlotSkip,
 //       footprints outside the region kSlotGlobal.  The same kernel re-packs everything the T iterations read
-//       per pixel and that does not change between them -- the slots, the 8 offset pairs, the 9 affinities, the
+//       per pixel and that does not change between them -- the slots, the 8 sampling coordinates, the 9 affinities, the
 //       fixed confidence and the input-preserving multiplier -- into ONE record of 8 x 16 bytes per pixel, laid
 //       out [tile][vector][thread]: an iteration then issues 8 coalesced 128-bit loads from one base address
 //       instead of 30 scalar loads with a 64-bit address chain each (ncu, first version: 248 of 982 instructions
@@ -48,27 +48,29 @@
 
 namespace nlspn {
 
-template <int K> struct LocalGeo;
-template <> struct LocalGeo<3> {
-    static constexpr int TW = 32, TH = 8, R = 8;
-    static constexpr int RW = TW + 2 * R, RH = TH + 2 * R;   // region: 48 x 24 cells
-    static constexpr int BW = RW / 2, BH = RH / 2;           // 24 x 12 blocks per phase
-    static constexpr int NBLK = 4 * BH * BW;                 // 1152 blocks
-    static constexpr int NCELL = RW * RH;                    // 1152 cells
-    static constexpr int NT = TW * TH;                       // 256 threads = pixels per tile
+template <int K, int TH_> struct LocalGeo;
+template <int TH_> struct LocalGeo<3, TH_> {
+    static_assert(TH_ == 8 || TH_ == 16, "tile height 8 or 16");
+    static constexpr int TW = 32, TH = TH_, R = 8;
+    static constexpr int RW = TW + 2 * R, RH = TH + 2 * R;   // region: 48 x 24 (48 x 32) cells
+    static constexpr int BW = RW / 2, BH = RH / 2;           // 24 x 12 (24 x 16) blocks per phase
+    static constexpr int NBLK = 4 * BH * BW;                 // 1152 (1536) blocks: 4.5 (3) per pixel
+    static constexpr int NCELL = RW * RH;                    // 1152 (1536) cells
+    static constexpr int NT = TW * TH;                       // 256 (512) threads = pixels per tile
     static constexpr int NTAP = 8;
-    static constexpr int NQUAD = NT * NTAP;                  // 2048 slots
+    static constexpr int NQUAD = NT * NTAP;                  // 2048 (4096) slots
     static constexpr int MAXLEN = 31;                        // footprints per block kept in the tile (more -> global REDs)
     // per-tile table (uint16): sorted block list [NBLK] (block | length << 11), diagonal starts [32], nnz + padding [8]
     static constexpr int TAB_JD = NBLK, TAB_NNZ = NBLK + 32;
-    static constexpr int ROWS = NBLK + 32 + 8;               // 1192 uint16 = 149 x 16 bytes
-    // packed per-pixel record, [tile][GEOV][NT] x 16 bytes: 0 slots | 1-4 offset pairs of taps (2i, 2i+1) as
-    // (dh, dw, dh, dw) | 5-6 affinities of the 8 neighbours | 7 (centre affinity, confidence, preserve factor, 0)
+    static constexpr int ROWS = NBLK + 32 + 8;               // 1192 (1576) uint16 = 149 (197) x 16 bytes
+    static_assert(NBLK <= 2048 && ROWS % 8 == 0 && ROWS / 8 <= NT, "table entry = block (11 bits) | length (5 bits)");
+    // packed per-pixel record, [tile][GEOV][NT] x 16 bytes: 0 slots | 1-4 sampling coordinates of taps (2i, 2i+1)
+    // as (h, w, h, w) | 5-6 affinities of the 8 neighbours | 7 (centre affinity, confidence, preserve factor, 0)
     static constexpr int GEOV = 8;
 };
 
-template <int K> struct LocalSmem {
-    using L = LocalGeo<K>;
+template <int K, int TH> struct LocalSmem {
+    using L = LocalGeo<K, TH>;
     // quads (32 KB; after stage 3a the same bytes hold the block sums and the flush tile) + centre taps + table
     static constexpr size_t bytes = sizeof(float4) * L::NQUAD + sizeof(float) * L::NT + sizeof(unsigned short) * L::ROWS;
     static_assert(sizeof(float4) * L::NBLK + sizeof(float) * L::NCELL <= sizeof(float4) * L::NQUAD, "block sums + flush tile alias the quads");
@@ -91,19 +93,41 @@ __host__ __device__ inline PadGeo pad_geo(int H, int W, int R)
     return g;
 }
 
+// ---- host side: tiles per image and workspace bytes of the local form
+template <int TH>
+inline long local_tiles(int H, int W)
+{
+    using L = LocalGeo<3, TH>;
+    return (long)((W + L::TW - 1) / L::TW) * ((H + L::TH - 1) / L::TH);
+}
+
+template <int TH>
+inline size_t ws_bytes_local_th(int B, int H, int W, int K, int T)
+{
+    using L = LocalGeo<3, TH>;
+    const size_t BP = (size_t)B * H * W;
+    const PadGeo pg = pad_geo(H, W, L::R);
+    const size_t tiles = (size_t)B * (size_t)local_tiles<TH>(H, W);
+    // two padded planes + confidence-gradient accumulator + gy of every iteration + raw affinity-gradient
+    // accumulator + the schedule (packed per-pixel records: GEOV x 16 B per pixel slot of every tile; block lists:
+    // ROWS uint16 per tile)
+    return sizeof(float) * (2 * (size_t)B * pg.plane + BP + (size_t)T * BP + (size_t)K * K * BP) + 64 +
+           tiles * (L::GEOV * L::NT * sizeof(uint4) + L::ROWS * sizeof(unsigned short)) + 64;
+}
+
 // ======================================================================================
 // Schedule build + geometry re-pack.  grid = (ceil(W/32), ceil(H/8), nb), block = (32, 8).
 //   geo       [nb][tiles][GEOV][256] x 16 B: the packed per-pixel record (LocalGeo::GEOV)
 //   table     [nb][tiles][ROWS] uint16: sorted blocks (block | length << 11), diagonal starts, nnz
 // ======================================================================================
-template <int K>
-__global__ void __launch_bounds__(LocalGeo<K>::NT)
+template <int K, int TH>
+__global__ void __launch_bounds__(LocalGeo<K, TH>::NT)
 sched_build_kernel(const float *__restrict__ offset, const float *__restrict__ aff, const float *__restrict__ conf,
                    const float *__restrict__ dep, unsigned flags, int H, int W, uint4 *__restrict__ geo,
                    unsigned short *__restrict__ table_g)
 {
     using G = Geo<K>;
-    using L = LocalGeo<K>;
+    using L = LocalGeo<K, TH>;
     __shared__ unsigned int cnt[L::NBLK];            // footprints per block
     __shared__ unsigned short pos_s[L::NBLK];        // sorted position of a block
     __shared__ __align__(16) unsigned short tab[L::ROWS];
@@ -130,10 +154,12 @@ sched_build_kernel(const float *__restrict__ offset, const float *__restrict__ a
         rank[n] = 0u;
         oh[n] = ow[n] = 0.f;
         if (!inside) continue;
-        oh[n] = __ldg(ob + (long)(2 * t) * P);
-        ow[n] = __ldg(ob + (long)(2 * t + 1) * P);
-        const float h_im = (float)(h - G::PAD + t / K) + oh[n];
-        const float w_im = (float)(w - G::PAD + t % K) + ow[n];
+        // the record keeps the sampling COORDINATE (integer part added first, one floating add: cuh:157-158), which
+        // is what every iteration would rebuild from the offset
+        const float h_im = (float)(h - G::PAD + t / K) + __ldg(ob + (long)(2 * t) * P);
+        const float w_im = (float)(w - G::PAD + t % K) + __ldg(ob + (long)(2 * t + 1) * P);
+        oh[n] = h_im;
+        ow[n] = w_im;
         if (!tap_valid(h_im, w_im, H, W)) continue;
         float hf, wf;
         int hl, wl;
@@ -247,8 +273,8 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes)
 //   s_out  padded planes of this iteration (plane_map describes [planes][PH][PW]; z_out = plane of image 0)
 // grid = (ceil(W/32), ceil(H/8), nb), block = (32, 8).
 // ======================================================================================
-template <int K, bool STREAM, int MINB>
-__global__ void __launch_bounds__(LocalGeo<K>::NT, MINB)
+template <int K, int TH, bool STREAM, int MINB>
+__global__ void __launch_bounds__(LocalGeo<K, TH>::NT, MINB)
 bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out, const uint4 *__restrict__ geo,
                        int has_conf, const float *__restrict__ x_t, const float *__restrict__ g_ext,
                        float *__restrict__ s_in, float *__restrict__ s_out,
@@ -258,7 +284,7 @@ bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
 {
     static_assert(K == 3, "the packed record holds 8 neighbours");
     using G = Geo<K>;
-    using L = LocalGeo<K>;
+    using L = LocalGeo<K, TH>;
     // dynamic shared memory (LocalSmem<K>::bytes > the 48 KB static limit)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *quads = reinterpret_cast<float4 *>(smem_raw);                     // stage 2/3a
@@ -294,8 +320,11 @@ bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
             bulk_prefetch_l2(table_g + nt * L::ROWS, L::ROWS * 2);
         }
     }
+    // the tile's block list goes global -> shared without a register round trip (first needed in stage 3a)
     if (tid < L::ROWS / 8)
-        reinterpret_cast<uint4 *>(tab)[tid] = __ldg(reinterpret_cast<const uint4 *>(table_g + tile * L::ROWS) + tid);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tma::smem_u32(tab) + tid * 16u),
+                     "l"(table_g + tile * L::ROWS + tid * 8) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
     const uint4 *gp = geo + tile * (L::GEOV * L::NT) + tid;
     const float4 *gf = reinterpret_cast<const float4 *>(gp);
     const uint4 sl4 = STREAM ? __ldcs(gp) : __ldg(gp);
@@ -352,12 +381,10 @@ bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
     const float avv[8] = {a4[0].x, a4[0].y, a4[0].z, a4[0].w, a4[1].x, a4[1].y, a4[1].z, a4[1].w};
 #pragma unroll
     for (int n = 0; n < L::NTAP; ++n) {
-        const int t = n < G::REF ? n : n + 1;
         const unsigned slot = (slw[n >> 1] >> (16 * (n & 1))) & 0xFFFFu;
         if (slot == kSlotSkip) continue;
         const float top = gy * avv[n];
-        const float h_im = (float)(h - G::PAD + t / K) + ohv[n];
-        const float w_im = (float)(w - G::PAD + t % K) + owv[n];
+        const float h_im = ohv[n], w_im = owv[n];
         const float hf = floor_small_f(h_im), wf = floor_small_f(w_im);
         // mdmcn_get_gradient_weight, cuh:71-79 (expressions kept literal; (float)(hl+1) == hf + 1 exactly)
         const float h1 = hf + 1.f, w1 = wf + 1.f;
@@ -378,6 +405,7 @@ bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
         }
     }
     centre[tid] = gy * m4.x;     // the centre tap has a structurally zero offset: lands on the pixel itself
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // ---- stage 3a: block sums over the jagged diagonals.  Thread `tid` owns the sorted blocks p_k = tid + 256 k;
@@ -419,21 +447,36 @@ bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
     // ---- stage 3b: every aligned 2x2 cell group adds the four block phases that overlap it
     //   phase (sy, sx) block (by, bx) covers region rows 2*by + sy, +1 and columns 2*bx + sx, +1;
     //   components x y z w = (row0,col0) (row0,col1) (row1,col0) (row1,col1).
+    //   Every lane reads the six blocks at its own column with full 16-byte loads (consecutive lanes, consecutive
+    //   blocks: no bank conflicts) and takes the three left-hand blocks' components from lane - 1 by shuffle; only
+    //   lane 0 of a warp fetches them itself.  (The first version read single components at a 16-byte lane stride:
+    //   4-way conflicts, 56 wavefronts per warp for 20 ideal.)
     constexpr int PB = L::BH * L::BW;
-    for (int k = tid; k < PB; k += L::NT) {
+    static_assert(PB % 32 == 0, "whole warps of cell groups");
+    for (int k = tid; k < PB; k += L::NT) {          // warp-uniform: PB is a multiple of 32
         const int cy = k / L::BW, cx = k - cy * L::BW;
         const bool up = cy > 0, lf = cx > 0;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 p00 = blocksum[k];
-        const float4 p01l = lf ? blocksum[PB + k - 1] : z4, p01r = blocksum[PB + k];
-        const float4 p10u = up ? blocksum[2 * PB + k - L::BW] : z4, p10d = blocksum[2 * PB + k];
-        const float4 p11ul = (up && lf) ? blocksum[3 * PB + k - L::BW - 1] : z4;
-        const float4 p11ur = up ? blocksum[3 * PB + k - L::BW] : z4;
-        const float4 p11dl = lf ? blocksum[3 * PB + k - 1] : z4;
+        const float4 p01r = blocksum[PB + k];
+        const float4 p10d = blocksum[2 * PB + k];
         const float4 p11dr = blocksum[3 * PB + k];
-        float a00 = ((p00.x + p01l.y) + p10u.z) + p11ul.w;
+        const float4 p10u = up ? blocksum[2 * PB + k - L::BW] : z4;
+        const float4 p11ur = up ? blocksum[3 * PB + k - L::BW] : z4;
+        // left neighbours = lane - 1's right-hand blocks (same row whenever cx > 0)
+        float p01l_y = __shfl_up_sync(0xffffffffu, p01r.y, 1), p01l_w = __shfl_up_sync(0xffffffffu, p01r.w, 1);
+        float p11dl_y = __shfl_up_sync(0xffffffffu, p11dr.y, 1), p11ul_w = __shfl_up_sync(0xffffffffu, p11ur.w, 1);
+        if ((tid & 31) == 0 && lf) {
+            const float4 a = blocksum[PB + k - 1];
+            p01l_y = a.y;
+            p01l_w = a.w;
+            p11dl_y = blocksum[3 * PB + k - 1].y;
+            p11ul_w = up ? blocksum[3 * PB + k - L::BW - 1].w : 0.f;
+        }
+        if (!lf) p01l_y = p01l_w = p11dl_y = p11ul_w = 0.f;
+        float a00 = ((p00.x + p01l_y) + p10u.z) + p11ul_w;
         float a01 = ((p00.y + p01r.x) + p10u.w) + p11ur.z;
-        float a10 = ((p00.z + p01l.w) + p10d.x) + p11dl.y;
+        float a10 = ((p00.z + p01l_w) + p10d.x) + p11dl_y;
         float a11 = ((p00.w + p01r.z) + p10d.y) + p11dr.x;
         const int ty = 2 * cy - L::R, tx = 2 * cx - L::R;       // tile coordinates of the group's first cell
         if ((unsigned)ty < (unsigned)L::TH && (unsigned)tx < (unsigned)L::TW) {

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <atomic>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/nlspn_b200.h"
@@ -51,7 +52,7 @@ const OptDef kOptDefs[kOptCount] = {
     {"dcn_blocked", "NLSPN_DCN_BLOCKED", 1},
     {"state_local", "NLSPN_STATE_LOCAL", -1},
     {"local_prefetch", "NLSPN_LOCAL_PREFETCH", 0},
-    {"local_minb", "NLSPN_LOCAL_MINB", 5},
+    {"local_minb", "NLSPN_LOCAL_MINB", 1},      // 0 / 1 / 2 = 4 / 5 / 6 CTAs per SM
 };
 std::atomic<int> g_opt[kOptCount];
 const bool g_opt_init = []() {
@@ -728,24 +729,7 @@ static bool local_form_selected(int H, int W, int K, int T)
     return opt(kOptStateLocal) != 0;     // -1 (auto) and 1: on
 }
 
-static long local_tiles(int H, int W)
-{
-    using L = LocalGeo<3>;
-    return (long)((W + L::TW - 1) / L::TW) * ((H + L::TH - 1) / L::TH);
-}
-
-static size_t ws_bytes_local(int B, int H, int W, int K, int T)
-{
-    using L = LocalGeo<3>;
-    const size_t BP = (size_t)B * H * W;
-    const PadGeo pg = pad_geo(H, W, L::R);
-    const size_t tiles = (size_t)B * (size_t)local_tiles(H, W);
-    // two padded planes + confidence-gradient accumulator + gy of every iteration + raw affinity-gradient
-    // accumulator + the schedule (packed per-pixel records: GEOV x 16 B per pixel slot of every tile; block lists:
-    // ROWS uint16 per tile)
-    return sizeof(float) * (2 * (size_t)B * pg.plane + BP + (size_t)T * BP + (size_t)K * K * BP) + 64 +
-           tiles * (L::GEOV * L::NT * sizeof(uint4) + L::ROWS * sizeof(unsigned short)) + 64;
-}
+static size_t ws_bytes_local(int B, int H, int W, int K, int T) { return ws_bytes_local_th<8>(B, H, W, K, T); }
 
 static size_t ws_bytes_v2(int B, int H, int W, int K, int T, bool allow_local = true)
 {
@@ -1034,10 +1018,12 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         return fail(NLSPN_ERR_WORKSPACE, "backward: tensors are not 16-byte aligned, so the scatter form is needed, "
                                          "and the workspace is too small for it (%zu < %zu)",
                     workspace_bytes, ws_bytes_v2(B, H, W, K, T, false) + sizeof(double) * kGammaSlots);
-    if (local_form) {
-        using L = LocalGeo<3>;
+    auto run_local = [&](auto th_tag) -> int {
+        constexpr int TH = decltype(th_tag)::value;
+        constexpr int MB_LO = TH == 8 ? 4 : 1, MB_MID = TH == 8 ? 5 : 2, MB_HI = TH == 8 ? 6 : 3;   // CTAs per SM
+        using L = LocalGeo<3, TH>;
         const PadGeo pg = pad_geo(H, W, L::R);
-        const long tiles = local_tiles(H, W);
+        const long tiles = local_tiles<TH>(H, W);
         float *planes = ws;                                              // [2][G][PH][PW]
         float *g_conf_acc = planes + 2 * (size_t)G * pg.plane;           // [G][P]
         float *gy_all = g_conf_acc + (size_t)G * P;                      // [T][G][P]
@@ -1053,15 +1039,15 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         std::call_once(smem_once, [] {
             auto set = [](auto kernel) {
                 const cudaError_t e1 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                            (int)LocalSmem<3>::bytes);
+                                                            (int)LocalSmem<3, TH>::bytes);
                 if (e1 != cudaSuccess && smem_err == cudaSuccess) smem_err = e1;
             };
-            set(bwd_state_local_kernel<3, true, 4>);
-            set(bwd_state_local_kernel<3, false, 4>);
-            set(bwd_state_local_kernel<3, true, 5>);
-            set(bwd_state_local_kernel<3, false, 5>);
-            set(bwd_state_local_kernel<3, true, 6>);
-            set(bwd_state_local_kernel<3, false, 6>);
+            set(bwd_state_local_kernel<3, TH, true, MB_LO>);
+            set(bwd_state_local_kernel<3, TH, false, MB_LO>);
+            set(bwd_state_local_kernel<3, TH, true, MB_MID>);
+            set(bwd_state_local_kernel<3, TH, false, MB_MID>);
+            set(bwd_state_local_kernel<3, TH, true, MB_HI>);
+            set(bwd_state_local_kernel<3, TH, false, MB_HI>);
         });
         if (smem_err != cudaSuccess) return cuda_fail(smem_err, "cudaFuncSetAttribute(bwd_state_local_kernel)");
         const int local_minb = opt(kOptLocalMinB);
@@ -1086,7 +1072,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             const dim3 lblock(L::TW, L::TH);
             {
                 ProfScope prof__(kProfBwdTable, st);
-                sched_build_kernel<3><<<lgrid, lblock, 0, st>>>(off_g, aff_g, cf, fx, flags, H, W, geo, sched_tab);
+                sched_build_kernel<3, TH><<<lgrid, lblock, 0, st>>>(off_g, aff_g, cf, fx, flags, H, W, geo, sched_tab);
                 NLSPN_CHECK_LAUNCH("sched_build_kernel");
             }
             for (int t = T; t >= 1; --t) {
@@ -1098,17 +1084,17 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
                 float *gyo = gy_all + (long)(t - 1) * GP;
                 ProfScope prof__(kProfBwdState, st);
 #define LOCAL_LAUNCH(SH_, MB_)                                                                                      \
-    e = launch_pdl_smem(t < T, LocalSmem<3>::bytes, bwd_state_local_kernel<3, SH_, MB_>, lgrid, lblock, st, plane_map, \
+    e = launch_pdl_smem(t < T, LocalSmem<3, TH>::bytes, bwd_state_local_kernel<3, TH, SH_, MB_>, lgrid, lblock, st, plane_map, \
                         io * G, (const uint4 *)geo, cf ? 1 : 0, xt, ge, s_in, s_out,                                \
                         (const unsigned short *)sched_tab, gyo, g_conf_acc, flags, H, W, pf_dist)
                 if (stream_hint) {
-                    if (local_minb == 4) LOCAL_LAUNCH(true, 4);
-                    else if (local_minb == 6) LOCAL_LAUNCH(true, 6);
-                    else LOCAL_LAUNCH(true, 5);
+                    if (local_minb == 0) LOCAL_LAUNCH(true, MB_LO);
+                    else if (local_minb == 2) LOCAL_LAUNCH(true, MB_HI);
+                    else LOCAL_LAUNCH(true, MB_MID);
                 } else {
-                    if (local_minb == 4) LOCAL_LAUNCH(false, 4);
-                    else if (local_minb == 6) LOCAL_LAUNCH(false, 6);
-                    else LOCAL_LAUNCH(false, 5);
+                    if (local_minb == 0) LOCAL_LAUNCH(false, MB_LO);
+                    else if (local_minb == 2) LOCAL_LAUNCH(false, MB_HI);
+                    else LOCAL_LAUNCH(false, MB_MID);
                 }
 #undef LOCAL_LAUNCH
                 if (e != cudaSuccess) return cuda_fail(e, "bwd_state_local_kernel");
@@ -1154,7 +1140,10 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         }
         gamma_reduce.armed = true;
         return 0;
-    }
+    };
+    // tile height 8 (256 threads).  32 x 16 tiles (3 instead of 4.5 region cells per pixel) were measured on B200 and
+    // lose: pass A 2.88 / 3.28 / 3.49 ms at 1 / 2 / 3 CTAs per SM vs 2.46 ms (16-warp barriers)
+    if (local_form) return run_local(std::integral_constant<int, 8>{});
 
     // scatter-plane sets rotate over three buffers so that clearing is a linear 16-byte-per-thread job
     // (NLSPN_STATE_ZERO3=0: two sets, every thread clears the four cells it read)
