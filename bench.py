@@ -463,6 +463,59 @@ def ref_cuda_leg(torch, run, steps=3, warmup=1):
                     "chain (oracle/ref_cuda.py), same GPU, same resident inputs, same loss"}
 
 
+def dcn_step_leg(torch, run, steps=10, warmup=3):
+    """Boundary B1 (the reference's own operator signature): ONE ModulatedDeformConvFunction forward + backward at
+    the headline shape through nlspn_eccv20_b200.dcn, and -- when oracle/_ref/DCN_ref.so travelled -- the reference's
+    kernels under the same autograd Function shape (oracle/ref_cuda.RefDeformStep)."""
+    from nlspn_eccv20_b200 import dcn
+    B, H, W, K = run.B, run.H, run.W, run.K
+    g = torch.Generator(device=run.dev).manual_seed(7240)
+    x = torch.rand(B, 1, H, W, device=run.dev, generator=g)
+    off = 2.0 * torch.randn(B, 2 * K * K, H, W, device=run.dev, generator=g)
+    msk = torch.rand(B, K * K, H, W, device=run.dev, generator=g)
+    w = torch.ones(1, 1, K, K, device=run.dev)
+    bias = torch.zeros(1, device=run.dev)
+    pad = (K - 1) // 2
+
+    def ours():
+        a, o, m = (t.detach().requires_grad_(True) for t in (x, off, msk))
+        y = dcn.ModulatedDeformConvFunction.apply(a, o, m, w, bias, 1, pad, 1, 1, 1, 64)
+        y.sum().backward()
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = run.ev(), run.ev()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    ms = timed(ours)
+    out = {"workload": "one DCN step fwd+bwd, %dx%d B=%d K=%d (offset, mask and input gradients)" % (H, W, B, K),
+           "ms_per_step": ms, "value": B * H * W / (ms * 1e-3) / 1e9, "unit": UNIT, "steps": steps, "warmup": warmup}
+    try:
+        from oracle import ref_cuda
+        if ref_cuda.available():
+            ref_cuda.load()
+
+            def theirs():
+                a, o, m = (t.detach().requires_grad_(True) for t in (x, off, msk))
+                y = ref_cuda.RefDeformStep.apply(a, o, m, w, bias, K)
+                y.sum().backward()
+
+            ms_ref = timed(theirs)
+            out["ref_cuda_ms_per_step"] = ms_ref
+            out["ours_over_reference_cuda"] = ms_ref / ms
+    except Exception as e:     # the referee is optional
+        out["ref_cuda_error"] = str(e)[:200]
+    torch.cuda.empty_cache()
+    return out
+
+
 def other_configs(torch, dev, lib, peaks):
     """BASELINE.json configs 1, 2, 3, 5 on this GPU (config 4 is the full model: tests/perf_config4_train_step.py)."""
     out = {}
@@ -653,6 +706,10 @@ def main():
                     line["ref_cuda"] = rc
             except Exception as e:
                 line["ref_cuda"] = {"error": str(e)[:200]}
+            try:
+                line["dcn_step"] = dcn_step_leg(torch, run)
+            except Exception as e:
+                line["dcn_step"] = {"error": str(e)[:200]}
         del run
         torch.cuda.empty_cache()
         if not args.no_other_configs:

@@ -89,6 +89,14 @@ enum nlspn_affinity { NLSPN_AFF_AS = 0, NLSPN_AFF_ASS = 1, NLSPN_AFF_TC = 2, NLS
  * gradient accumulators and scatter with scalar atomics (the reference's structure); results
  * agree with the default two-pass backward up to fp32 summation order. */
 #define NLSPN_FLAG_BWD_PER_ITERATION 0x100u
+/* nlspn_backward only: bit-identical gradients from run to run.  The default forms of the state-gradient pass
+ * (and the reference's col2im, modulated_deform_im2col_cuda.cuh:229-252; its own test admits the difference,
+ * deformconv/test.py:627-631) add floating-point contributions in scheduling order.  With this flag the
+ * transposed operator is tabulated exactly (CSR over destination pixels, rows sorted by source) and every sum
+ * runs in a fixed order; gamma's gradient uses a fixed-order tree.  Slower (about 2x on the state-gradient pass)
+ * and needs nlspn_backward_workspace_bytes_ex(..., flags) bytes of workspace.  Not combinable with NO_OFFSET,
+ * BWD_PER_ITERATION, CONF_SAMPLED.  Limits: H*W <= 2^24, 4*(K*K-1)*B*H*W < 2^32. */
+#define NLSPN_FLAG_DETERMINISTIC 0x200u
 
 NLSPN_API int nlspn_abi_version(void);
 NLSPN_API const char *nlspn_last_error(void);
@@ -172,6 +180,8 @@ NLSPN_API int nlspn_forward(const float *guidance, const float *confidence, cons
  * planes, ~0.55 GB at KITTI B = 8, K = 3, T = 18; tabulated gather (K >= 5 and T >= 8): a table of
  * 16 B x CAP(K) x blocks, ~3.2 GB at K = 5 and ~4.9 GB at K = 7 for the same batch. */
 NLSPN_API size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T);
+/* the same query for a call with `flags` (NLSPN_FLAG_DETERMINISTIC changes the workspace layout) */
+NLSPN_API size_t nlspn_backward_workspace_bytes_ex(int B, int H, int W, int K, int T, unsigned flags);
 NLSPN_API int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
                    const float *confidence, const float *offset, const float *aff, const float *conf_fixed,
                    const float *src, int S, const float *list_feat, const float *const *g_list,

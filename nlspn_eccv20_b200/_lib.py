@@ -40,6 +40,7 @@ SIGNATURES = {
                                  _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                  _fp, _fp, _fp, _fp, _c.c_int, _fp, _fp]),
     "nlspn_backward_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "nlspn_backward_workspace_bytes_ex": (_c.c_size_t, [_c.c_int] * 5 + [_c.c_uint]),
     "nlspn_backward": (_c.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _c.c_int, _fp,
                                   _c.POINTER(_c.c_void_p), _fp, _fp, _fp, _c.c_int, _c.c_uint,
                                   _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
@@ -64,6 +65,7 @@ FLAG_BLEND_PRE = 8
 FLAG_CONF_SAMPLED = 16
 FLAG_LEGACY = 32
 FLAG_BWD_PER_ITERATION = 0x100
+FLAG_DETERMINISTIC = 0x200
 
 
 def lib_path() -> str:

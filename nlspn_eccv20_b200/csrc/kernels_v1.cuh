@@ -10,7 +10,7 @@
 namespace nlspn {
 
 enum : unsigned { kPreserve = 1u, kAlwaysClip = 2u, kNoOffset = 4u, kBlendPre = 8u, kConfSampled = 16u,
-                  kLegacy = 32u };
+                  kLegacy = 32u, kDeterministic = 0x200u };
 enum : int { kAS = 0, kASS = 1, kTC = 2, kTGASS = 3 };
 constexpr int kGammaSlots = 64;   // partial sums of d loss / d gamma (final_bwd_kernel -> gamma_reduce_kernel)
 
@@ -468,8 +468,10 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
             double tot = 0.0;
 #pragma unroll
             for (int i = 0; i < kBlock / 32; ++i) tot += red[i];
-            // spread over kGammaSlots addresses: thousands of same-address fp64 atomics serialise in L2
-            if (tot != 0.0) atomicAdd(g_gamma + (blockIdx.x + blockIdx.y * gridDim.x) % kGammaSlots, tot);
+            // spread over kGammaSlots addresses: thousands of same-address fp64 atomics serialise in L2.
+            // Deterministic mode: g_gamma is a per-block array, summed in a fixed order by gamma_reduce_det_kernel.
+            if (flags & kDeterministic) g_gamma[blockIdx.x + blockIdx.y * gridDim.x] = tot;
+            else if (tot != 0.0) atomicAdd(g_gamma + (blockIdx.x + blockIdx.y * gridDim.x) % kGammaSlots, tot);
         }
     }
 }

@@ -18,6 +18,7 @@
 #include "kernels_gather.cuh"
 #include "kernels_step.cuh"
 #include "kernels_local.cuh"
+#include "kernels_det.cuh"
 
 using namespace nlspn;
 
@@ -607,6 +608,10 @@ static int check_mode_flags(unsigned flags)
                                       "ALWAYS_CLIP, NO_OFFSET or BWD_PER_ITERATION");
     if ((flags & NLSPN_FLAG_LEGACY) && !sampled)
         return fail(NLSPN_ERR_DOMAIN, "LEGACY only modifies CONF_SAMPLED");
+    if ((flags & NLSPN_FLAG_DETERMINISTIC) &&
+        (flags & (NLSPN_FLAG_NO_OFFSET | NLSPN_FLAG_BWD_PER_ITERATION | NLSPN_FLAG_CONF_SAMPLED)))
+        return fail(NLSPN_ERR_DOMAIN, "DETERMINISTIC cannot be combined with NO_OFFSET, BWD_PER_ITERATION or CONF_SAMPLED "
+                                      "(their scatters are atomic)");
     return 0;
 }
 
@@ -748,11 +753,27 @@ static size_t ws_bytes_v2(int B, int H, int W, int K, int T, bool allow_local = 
     return gather_form_selected(H, W, K, T) ? gather_form : red_form;
 }
 
-size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T)
+// deterministic form (kernels_det.cuh): per-block gamma partials, counts / row starts / scan tiles, the CSR entries
+// (worst case: every corner of every neighbour tap in the image), one plain plane, the accumulators
+static size_t ws_bytes_det(int B, int H, int W, int K, int T)
+{
+    const size_t P = (size_t)H * W, BP = (size_t)B * P, N = (size_t)K * K - 1;
+    const size_t nblk = ((P + kBlock - 1) / kBlock) * B, ntiles = (BP + kDetScanTile - 1) / kDetScanTile;
+    return sizeof(double) * nblk + sizeof(unsigned) * (2 * BP + 1 + ntiles) + 64 + sizeof(DetEntry) * 4 * N * BP +
+           sizeof(float) * (2 * BP + (size_t)T * BP + (size_t)K * K * BP) + 64;
+}
+
+size_t nlspn_backward_workspace_bytes_ex(int B, int H, int W, int K, int T, unsigned flags)
 {
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0 || T <= 0) return 0;
+    if (flags & NLSPN_FLAG_DETERMINISTIC) return ws_bytes_det(B, H, W, K, T) + sizeof(double) * kGammaSlots;
     const size_t a = ws_bytes_v1(B, H, W, K), b = ws_bytes_v2(B, H, W, K, T);
     return (a > b ? a : b) + sizeof(double) * kGammaSlots;
+}
+
+size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T)
+{
+    return nlspn_backward_workspace_bytes_ex(B, H, W, K, T, 0u);
 }
 
 int nlspn_backward(const float *guidance, const float *feat_init, const float *feat_fix,
@@ -783,9 +804,9 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         return fail(NLSPN_ERR_AFFINITY, "unknown affinity mode %d", affinity);
     if (use_src && S < T)
         return fail(NLSPN_ERR_SHAPE, "backward: src must keep all T planes (S=%d, T=%d)", S, T);
-    if (workspace_bytes < nlspn_backward_workspace_bytes(B, H, W, K, T) || !aligned16(workspace))
+    if (workspace_bytes < nlspn_backward_workspace_bytes_ex(B, H, W, K, T, flags) || !aligned16(workspace))
         return fail(NLSPN_ERR_WORKSPACE, "backward: workspace too small (%zu < %zu) or misaligned",
-                    workspace_bytes, nlspn_backward_workspace_bytes(B, H, W, K, T));
+                    workspace_bytes, nlspn_backward_workspace_bytes_ex(B, H, W, K, T, flags));
     const int P = H * W, KK = K * K;
     const long BP = (long)B * P;
     const int N = KK - 1;
@@ -893,6 +914,84 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         if (int rc = make_geometry_map(&off_map, offset, B, 2 * KK, H, W, kStateTH)) return rc;
         if (int rc = make_geometry_map(&aff_map, aff, B, KK, H, W, kStateTH)) return rc;
     }
+    // ---- deterministic form (NLSPN_FLAG_DETERMINISTIC, kernels_det.cuh): exact CSR table of the transposed
+    // operator, rows sorted by source; one gather kernel per iteration, no atomics in any floating-point sum
+    if (flags & NLSPN_FLAG_DETERMINISTIC) {
+        if ((size_t)P > ((size_t)1 << 24) || (size_t)4 * N * (size_t)BP >= ((size_t)1 << 32))
+            return fail(NLSPN_ERR_SHAPE, "DETERMINISTIC: H*W <= 2^24 and 4*(K*K-1)*B*H*W < 2^32 (split the batch)");
+        const size_t nblk = ((size_t)(P + kBlock - 1) / kBlock) * B;
+        const long ntiles = (BP + kDetScanTile - 1) / kDetScanTile;
+        double *gamma_part = reinterpret_cast<double *>(ws);                 // [nblk]
+        unsigned *count = reinterpret_cast<unsigned *>(gamma_part + nblk);   // [BP]   (then the fill cursor)
+        unsigned *start = count + BP;                                        // [BP + 1]
+        unsigned *tile_sum = start + BP + 1;                                 // [ntiles]
+        uintptr_t ep = reinterpret_cast<uintptr_t>(tile_sum + ntiles);
+        ep = (ep + 15) & ~(uintptr_t)15;
+        DetEntry *entries = reinterpret_cast<DetEntry *>(ep);                // [<= 4 N BP]
+        float *splane = reinterpret_cast<float *>(entries + (size_t)4 * N * BP);   // [BP]
+        float *g_conf_acc = splane + BP;                                     // [BP]
+        float *gy_all = g_conf_acc + BP;                                     // [T][BP]
+        float *g_aff_acc = gy_all + (size_t)T * BP;                          // [B][KK][P]
+        e = cudaMemsetAsync(gamma_part, 0, sizeof(double) * nblk + sizeof(unsigned) * (size_t)BP, st);   // + count
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(row counts)");
+        e = cudaMemsetAsync(g_conf_acc, 0, sizeof(float) * (size_t)BP, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(confidence gradient)");
+        {
+            ProfScope prof__(kProfBwdTable, st);
+            DISPATCH_K(K, (det_count_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(offset, H, W, count)));
+            NLSPN_CHECK_LAUNCH("det_count_kernel");
+            det_scan_tiles_kernel<<<(unsigned)ntiles, 256, 0, st>>>(count, BP, tile_sum);
+            NLSPN_CHECK_LAUNCH("det_scan_tiles_kernel");
+            det_scan_sums_kernel<<<1, 1024, 0, st>>>(tile_sum, ntiles);
+            NLSPN_CHECK_LAUNCH("det_scan_sums_kernel");
+            det_scan_apply_kernel<<<(unsigned)ntiles, 256, 0, st>>>(count, BP, tile_sum, start);
+            NLSPN_CHECK_LAUNCH("det_scan_apply_kernel");
+            DISPATCH_K(K, (det_fill_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(offset, aff, H, W, start, count, entries)));
+            NLSPN_CHECK_LAUNCH("det_fill_kernel");
+            det_sort_kernel<<<(unsigned)((BP + kBlock / 32 - 1) / (kBlock / 32)), kBlock, 0, st>>>(start, BP, entries);
+            NLSPN_CHECK_LAUNCH("det_sort_kernel");
+        }
+        for (int t = T; t >= 0; --t) {
+            // t >= 1: gy_t from gy_{t+1};  t == 0: only the gathered plane (gradient reaching x_0)
+            const float *gyn = t < T ? gy_all + (size_t)t * BP : nullptr;
+            float *gyo = t >= 1 ? gy_all + (size_t)(t - 1) * BP : nullptr;
+            const float *xt = t >= 1 ? list_feat + (long)(t - 1) * BP : nullptr;
+            const float *ge = t >= 1 ? g_list[t - 1] : nullptr;
+            ProfScope prof__(kProfBwdState, st);
+            DISPATCH_K(K, (det_state_kernel<KC><<<grid_for(P, B), kBlock, 0, st>>>(
+                              start, entries, aff, conf_fixed, feat_fix, xt, ge, gyn, gyo, splane, g_conf_acc, flags, H, W)));
+            NLSPN_CHECK_LAUNCH("det_state_kernel");
+        }
+        {
+            const int nch = (KK + param_chunk(K) - 1) / param_chunk(K);
+            ProfScope prof__(kProfBwdParam, st);
+            if (use_tiled) {
+                const int pth = param_tile_h();
+                dim3 tgrid((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + pth - 1) / pth), (unsigned)(B * nch));
+                dim3 tblock(kTileW, pth);
+                DISPATCH_TH(pth, DISPATCH_K(K, (bwd_param_tiled_kernel<KC, param_chunk(KC), THC, 2><<<tgrid, tblock, 0, st>>>(
+                                  src_map, list_map, B, 0, offset, aff, src, list_feat, gy_all, use_src ? 1 : 0, H, W, T,
+                                  BP, BP, g_guidance, g_aff_acc))));
+                NLSPN_CHECK_LAUNCH("bwd_param_tiled_kernel");
+            } else {
+                dim3 grid((unsigned)((P + kParamBlock - 1) / kParamBlock), (unsigned)B, (unsigned)nch);
+                DISPATCH_K(K, (bwd_param_kernel<KC, param_chunk(KC)><<<grid, kParamBlock, 0, st>>>(
+                                  offset, aff, src, list_feat, gy_all, use_src ? 1 : 0, H, W, T, BP, BP, g_guidance, g_aff_acc)));
+                NLSPN_CHECK_LAUNCH("bwd_param_kernel");
+            }
+        }
+        {
+            ProfScope prof__(kProfFinalBwd, st);
+            DISPATCH_K(K, (final_bwd_kernel<KC, 0, false><<<grid_for(P, B), kBlock, 0, st>>>(
+                              guidance, feat_init, feat_fix, conf_fixed, splane, g_aff_acc, g_conf_acc, g_offset_ext,
+                              g_aff_ext, gamma, affinity, flags, H, W, g_feat_init, g_guidance, g_confidence, gamma_part)));
+            NLSPN_CHECK_LAUNCH("final_bwd_kernel");
+            gamma_reduce_det_kernel<<<1, 256, 0, st>>>(gamma_part, (long)nblk, g_gamma);
+            NLSPN_CHECK_LAUNCH("gamma_reduce_det_kernel");
+        }
+        return 0;
+    }
+
     // ---- pass A in gather form (kernels_gather.cuh): table built once, then per iteration an elementwise gy
     // kernel and a gather-reduce kernel with plain stores.  Default for K >= 5; NLSPN_STATE_GATHER=0/1 overrides.
     const bool gather = gather_form_selected(H, W, K, T);

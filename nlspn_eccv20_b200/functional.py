@@ -158,8 +158,9 @@ def propagate_fwd(offset, aff, conf_fixed, feat_fix, src, list_feat, K, T,
 def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_feat, g_list,
              gamma, K, T, affinity="TGASS", preserve_input=True, always_clip=False,
              g_offset_ext=None, g_aff_ext=None, per_iteration=False, use_offset=True,
-             conf_mode="premul", blend="post", legacy=False, confidence=None):
-    """g_list: sequence of T tensors [B,1,H,W] or None.  -> (g_init, g_guidance, g_conf, g_gamma)."""
+             conf_mode="premul", blend="post", legacy=False, confidence=None, deterministic=False):
+    """g_list: sequence of T tensors [B,1,H,W] or None.  -> (g_init, g_guidance, g_conf, g_gamma).
+    deterministic: NLSPN_FLAG_DETERMINISTIC -- bit-identical gradients from run to run (slower)."""
     lib = _lib.load()
     B, _, H, W = feat_init.shape
     N = K * K - 1
@@ -180,7 +181,9 @@ def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_f
     confidence = _chk("confidence", confidence, (B, 1, H, W), optional=not sampled)
     g_conf = torch.empty((B, 1, H, W), **opt) if (conf_fixed is not None or sampled) else None
     g_gamma = torch.empty((1,), device=dev, dtype=torch.float64)
-    nbytes = lib.nlspn_backward_workspace_bytes(B, H, W, K, T)
+    flags = _flags(preserve, always_clip, use_offset, conf_mode, blend, legacy) \
+        | (_lib.FLAG_BWD_PER_ITERATION if per_iteration else 0) | (_lib.FLAG_DETERMINISTIC if deterministic else 0)
+    nbytes = lib.nlspn_backward_workspace_bytes_ex(B, H, W, K, T, flags)
     ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
     gam = _gamma(gamma, dev)
     with torch.cuda.device(dev):
@@ -188,9 +191,7 @@ def backward(guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_f
                                 _ptr(confidence if sampled else None),
                                 _ptr(offset), _ptr(aff), _ptr(conf_fixed), _ptr(src), S, _ptr(list_feat),
                                 ptrs, _ptr(g_offset_ext), _ptr(g_aff_ext), _ptr(gam),
-                                _lib.AFFINITY[affinity],
-                                _flags(preserve, always_clip, use_offset, conf_mode, blend, legacy)
-                                | (_lib.FLAG_BWD_PER_ITERATION if per_iteration else 0),
+                                _lib.AFFINITY[affinity], flags,
                                 B, H, W, K, T, _ptr(g_init), _ptr(g_guid), _ptr(g_conf), _ptr(g_gamma), _ptr(ws),
                                 nbytes, _stream(dev))
     _lib.check(rc, "nlspn_backward")

@@ -28,7 +28,7 @@ class NLSPNFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat_init, guidance, confidence, feat_fix, gamma, K, T, affinity,
                 preserve_input, always_clip, use_offset=True, conf_mode="premul", blend="post", legacy=False,
-                need_grad=None):
+                need_grad=None, deterministic=False):
         if need_grad is None:   # direct .apply() callers: grad mode is already off in here, so only the inputs count
             need_grad = any(torch.is_tensor(t) and t.requires_grad for t in (feat_init, guidance, confidence, gamma))
         gamma_val = gamma.detach() if torch.is_tensor(gamma) else float(gamma)   # stays on the device
@@ -43,6 +43,7 @@ class NLSPNFunction(torch.autograd.Function):
         ctx.cfg = (K, T, affinity, preserve, always_clip, None if torch.is_tensor(gamma_val) else gamma_val)
         ctx.use_offset = bool(use_offset)
         ctx.mode = (conf_mode, blend, bool(legacy))
+        ctx.deterministic = bool(deterministic)
         ctx.conf_raw = conf_c if (conf_mode == "sampled" and conf_c is not None) else None
         ctx.conf_grad = conf_c is not None and conf_mode != "none"
         ctx.has_conf = conf_fixed is not None
@@ -78,14 +79,15 @@ class NLSPNFunction(torch.autograd.Function):
         g_init, g_guid, g_conf, g_gamma = F_.backward(
             guidance, feat_init, feat_fix, offset, aff, conf_fixed, src, list_feat, g_list, gamma_val,
             K, T, affinity, preserve, always_clip, g_off_ext, g_aff_ext, use_offset=ctx.use_offset,
-            conf_mode=conf_mode, blend=blend, legacy=legacy, confidence=ctx.conf_raw)
+            conf_mode=conf_mode, blend=blend, legacy=legacy, confidence=ctx.conf_raw,
+            deterministic=ctx.deterministic)
         if g_cf_ext is not None:
             # conf_fixed = (1-m)*confidence + m, nlspnmodel.py:334
             m = (feat_fix > 0).to(g_cf_ext.dtype) if preserve else 0.0
             g_conf = g_conf + (1.0 - m) * g_cf_ext
         g_gam = g_gamma.to(torch.float32) if ctx.gamma_is_tensor else None
         return g_init, g_guid, (g_conf if ctx.conf_grad else None), None, g_gam, \
-            None, None, None, None, None, None, None, None, None, None
+            None, None, None, None, None, None, None, None, None, None, None
 
 
 class NLSPNStepFunction(torch.autograd.Function):
@@ -126,7 +128,7 @@ def nlspn_step(src_prev, offset, aff, conf_fixed, feat_fix, prop_kernel=3, prese
 
 def nlspn_propagate(feat_init, guidance, confidence, feat_fix, gamma, prop_kernel=3, prop_time=18,
                     affinity="TGASS", preserve_input=True, always_clip=False, use_offset=True,
-                    conf_mode="premul", blend="post", legacy=False):
+                    conf_mode="premul", blend="post", legacy=False, deterministic=False):
     """Functional form.  -> (feat_result, list_feat, offset|None, aff, conf_fixed|None).
     use_offset=False selects the fork's fixed-local propagation (nlspnmodel.py:209-224); guidance
     then holds the N raw affinities only and `offset` is None (as in nlspnmodel.py:306-308)."""
@@ -135,7 +137,8 @@ def nlspn_propagate(feat_init, guidance, confidence, feat_fix, gamma, prop_kerne
         torch.is_tensor(t) and t.requires_grad for t in (feat_init, guidance, confidence, gamma))
     outs = NLSPNFunction.apply(feat_init, guidance, confidence, feat_fix, gamma, prop_kernel,
                                prop_time, affinity, preserve_input, always_clip, use_offset,
-                               conf_mode if confidence is not None else "none", blend, legacy, need_grad)
+                               conf_mode if confidence is not None else "none", blend, legacy, need_grad,
+                               deterministic)
     T = prop_time
     list_feat = list(outs[:T])
     aff = outs[T]
@@ -179,6 +182,9 @@ class NLSPN(nn.Module):
         self.conf_mode = str(opt("conf_mode", "premul"))
         self.blend = str(opt("blend", "post"))
         self.legacy = bool(opt("legacy", False))
+        # bit-identical gradients from run to run (NLSPN_FLAG_DETERMINISTIC; the reference itself is not:
+        # deformconv/test.py:627-631); slower backward
+        self.deterministic = bool(opt("deterministic", False))
         assert (self.prop_kernel % 2) == 1, \
             'only odd kernel is supported but k_f = {}'.format(self.prop_kernel)   # nlspnmodel.py:29-30
         if self.prop_kernel not in (3, 5, 7):
@@ -217,7 +223,7 @@ class NLSPN(nn.Module):
         feat_result, list_feat, offset, aff, _ = nlspn_propagate(
             feat_init, guidance, confidence, feat_fix, self.aff_scale_const, self.prop_kernel,
             self.prop_time, self.affinity, self.preserve_input, self.always_clip, self.offset,
-            self.conf_mode, self.blend, self.legacy)
+            self.conf_mode, self.blend, self.legacy, self.deterministic)
         return feat_result, list_feat, offset, aff, self.aff_scale_const.data
 
     def graphed(self, feat_init, guidance, confidence=None, feat_fix=None, warmup=2):

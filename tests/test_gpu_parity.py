@@ -323,6 +323,65 @@ def test_two_pass_backward_equals_per_iteration_backward(dev, nlspn_opt, K, T, u
         assert float((x - y).abs().max()) <= 2e-5 * max(s, 1e-20), name
 
 
+@pytest.mark.parametrize("K,T,B,H,W,use_conf,always_clip", [(3, 8, 2, 64, 96, True, False), (5, 5, 2, 48, 61, True, False),
+                                                             (3, 4, 1, 37, 45, False, True), (7, 2, 1, 30, 41, True, False)])
+def test_deterministic_backward_is_bit_identical_and_matches_default(dev, K, T, B, H, W, use_conf, always_clip):
+    """NLSPN_FLAG_DETERMINISTIC (kernels_det.cuh): ten backward calls on the same saved tensors give bit-identical
+    gradients (the reference's own backward does not: deformconv/test.py:627-631), and they agree with the default
+    (atomic) form within the summation-order tolerance."""
+    from nlspn_eccv20_b200 import functional as F_
+    from nlspn_eccv20_b200.synth import make_inputs
+    inp = make_inputs(B, H, W, K, seed=900 + K, device=dev, conf_mean=2.0)
+    gamma = 0.5 * (K * K - 1)
+    conf = inp["confidence"] if use_conf else None
+    offset, aff, cfx, src0 = F_.prologue_fwd(inp["guidance"], conf, inp["feat_init"], inp["feat_fix"], gamma, K)
+    S = T if use_conf else 1
+    src = torch.empty((S, B, 1, H, W), device=dev)
+    src[0].copy_(src0)
+    lf = torch.empty((T, B, 1, H, W), device=dev)
+    F_.propagate_fwd(offset, aff, cfx, inp["feat_fix"], src, lf, K, T, always_clip=always_clip)
+    g = torch.Generator().manual_seed(2)
+    g_list = [torch.randn(B, 1, H, W, generator=g).to(dev) if t % 2 == 0 or t == T - 1 else None for t in range(T)]
+    goe = torch.randn(offset.shape, generator=g).to(dev)
+    gae = torch.randn(aff.shape, generator=g).to(dev)
+    args = (inp["guidance"], inp["feat_init"], inp["feat_fix"], offset, aff, cfx, src, lf, g_list, gamma, K, T)
+    kw = dict(g_offset_ext=goe, g_aff_ext=gae, always_clip=always_clip)
+    first = F_.backward(*args, deterministic=True, **kw)
+    for _ in range(9):
+        again = F_.backward(*args, deterministic=True, **kw)
+        for x, y, name in zip(first, again, ["g_init", "g_guidance", "g_conf", "g_gamma"]):
+            assert (x is None) == (y is None)
+            if x is not None:
+                assert torch.equal(x, y), name
+    ref = F_.backward(*args, **kw)
+    for x, y, name in zip(first, ref, ["g_init", "g_guidance", "g_conf", "g_gamma"]):
+        if x is None:
+            assert y is None
+            continue
+        s = float(y.abs().max())
+        assert float((x - y).abs().max()) <= 2e-5 * max(s, 1e-20), name
+
+
+def test_deterministic_module_backward_repeats_exactly(dev):
+    """The same through the module: NLSPN(deterministic=True), loss.backward() twice -> identical .grad tensors,
+    gamma's included."""
+    from nlspn_eccv20_b200 import NLSPN
+    from nlspn_eccv20_b200.synth import make_inputs
+    K, T = 3, 6
+    mod = NLSPN(prop_kernel=K, prop_time=T, deterministic=True).to(dev)
+    inp = make_inputs(2, 40, 52, K, seed=41, device=dev, conf_mean=2.0)
+    got = []
+    for _ in range(3):
+        fi, gd, cf = (inp[k].clone().requires_grad_(True) for k in ("feat_init", "guidance", "confidence"))
+        mod.aff_scale_const.grad = None
+        out = mod(fi, gd, cf, inp["feat_fix"])[0]
+        (out.clamp(min=0) - inp["gt"]).abs().sum().backward()
+        got.append([fi.grad.clone(), gd.grad.clone(), cf.grad.clone(), mod.aff_scale_const.grad.clone()])
+    for other in got[1:]:
+        for x, y in zip(got[0], other):
+            assert torch.equal(x, y)
+
+
 def test_non_default_stream_and_concurrent_threads(dev):
     """Boundary B1/B2 threading contract: work is enqueued on the caller's CURRENT
     stream, and two host threads (the reference's test() uses nn.DataParallel worker threads,

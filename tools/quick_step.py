@@ -19,6 +19,7 @@ def main():
     p.add_argument("--mode", default="fwdbwd")
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--opt", action="append", default=[])
+    p.add_argument("--deterministic", action="store_true")
     a = p.parse_args()
     from nlspn_eccv20_b200 import NLSPN, _lib
     from nlspn_eccv20_b200.synth import SHAPES, workload
@@ -29,7 +30,7 @@ def main():
     dev = torch.device("cuda:0")
     H, W, _ = SHAPES[a.workload]
     d = workload(a.workload, a.batch, a.kernel, seed=7240, device=dev)
-    mod = NLSPN(prop_kernel=a.kernel, prop_time=a.iters).to(dev)
+    mod = NLSPN(prop_kernel=a.kernel, prop_time=a.iters, deterministic=a.deterministic).to(dev)
     train = a.mode == "fwdbwd"
 
     def step():
@@ -57,7 +58,7 @@ def main():
     torch.cuda.synchronize()
     prof = _lib.profile_read()
     lib.nlspn_profile_enable(0)
-    print(json.dumps({"opts": a.opt, "ms_per_step": round(ms, 4),
+    print(json.dumps({"opts": a.opt + (["deterministic"] if a.deterministic else []), "ms_per_step": round(ms, 4),
                       "gpix_iter_s": round(a.batch * H * W * a.iters / ms / 1e6, 3),
                       "kernel_ms_per_step": {k: round(v[0] / 3, 4) for k, v in prof.items()}}))
 
