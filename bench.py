@@ -331,6 +331,10 @@ class GpuRun:
                "table_build_kernel": 12 * N + 16 * N + 4}
         if "bwd_gather_kernel" in prof:
             alg["bwd_state_kernel"] = 53
+        elif K == 3:
+            # pass A as the tile-local transpose (kernels_local.cuh): the once-per-step schedule build reads offsets,
+            # affinities, confidence, fixed depth and writes the packed record (128 B) + block list (9.3 B) per pixel
+            alg["table_build_kernel"] = 12 * N + 12 + 128 + 10
         fwd_names = ("prologue_fwd_kernel", "iter_fwd_kernel")
         phase_prof = {"forward": sum(prof[k][0] for k in prof if k in fwd_names),
                       "backward": sum(prof[k][0] for k in prof if k not in fwd_names)}
