@@ -120,8 +120,8 @@ inline size_t ws_bytes_local_th(int B, int H, int W, int K, int T)
 //   geo       [nb][tiles][GEOV][256] x 16 B: the packed per-pixel record (LocalGeo::GEOV)
 //   table     [nb][tiles][ROWS] uint16: sorted blocks (block | length << 11), diagonal starts, nnz
 // ======================================================================================
-template <int K, int TH>
-__global__ void __launch_bounds__(LocalGeo<K, TH>::NT)
+template <int K, int TH, int MINB>
+__global__ void __launch_bounds__(LocalGeo<K, TH>::NT, MINB)
 sched_build_kernel(const float *__restrict__ offset, const float *__restrict__ aff, const float *__restrict__ conf,
                    const float *__restrict__ dep, unsigned flags, int H, int W, uint4 *__restrict__ geo,
                    unsigned short *__restrict__ table_g)

@@ -32,7 +32,7 @@ std::atomic<unsigned long long> g_launches{0};
 // -1 = "auto" where a default depends on the shape.
 enum Opt { kOptTiled = 0, kOptPersist, kOptPdl, kOptFwdTH, kOptParamTH, kOptStateTma, kOptStateGather,
            kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint, kOptStateAhead,
-           kOptParamFactored, kOptPersistBwd, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptCount };
+           kOptParamFactored, kOptPersistBwd, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptCount };
 struct OptDef { const char *name; const char *env; int def; };
 const OptDef kOptDefs[kOptCount] = {
     {"tiled", "NLSPN_TILED", 1},
@@ -54,6 +54,7 @@ const OptDef kOptDefs[kOptCount] = {
     {"state_local", "NLSPN_STATE_LOCAL", -1},
     {"local_prefetch", "NLSPN_LOCAL_PREFETCH", 0},
     {"local_minb", "NLSPN_LOCAL_MINB", 1},      // 0 / 1 / 2 = 4 / 5 / 6 CTAs per SM
+    {"sched_minb", "NLSPN_SCHED_MINB", 5},      // CTAs per SM of the schedule build (4: 0.275 ms, 5: 0.249 ms per step)
 };
 std::atomic<int> g_opt[kOptCount];
 const bool g_opt_init = []() {
@@ -1171,7 +1172,10 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             const dim3 lblock(L::TW, L::TH);
             {
                 ProfScope prof__(kProfBwdTable, st);
-                sched_build_kernel<3, TH><<<lgrid, lblock, 0, st>>>(off_g, aff_g, cf, fx, flags, H, W, geo, sched_tab);
+                if (opt(kOptSchedMinB) >= 5)
+                    sched_build_kernel<3, TH, 5><<<lgrid, lblock, 0, st>>>(off_g, aff_g, cf, fx, flags, H, W, geo, sched_tab);
+                else
+                    sched_build_kernel<3, TH, 4><<<lgrid, lblock, 0, st>>>(off_g, aff_g, cf, fx, flags, H, W, geo, sched_tab);
                 NLSPN_CHECK_LAUNCH("sched_build_kernel");
             }
             for (int t = T; t >= 1; --t) {
