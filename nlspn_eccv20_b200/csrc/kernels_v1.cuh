@@ -84,9 +84,17 @@ prologue_fwd_kernel(const float *__restrict__ guidance, const float *__restrict_
     const float g = affinity == kTGASS ? gamma + 1e-8f : gamma;
     const bool sampled = (flags & kConfSampled) != 0;     // upstream conf_prop (parity unpinned)
     const int hh0 = r / W, ww0 = r - hh0 * W;
+    // all loads ahead of the first tanhf (its branches would fence them into small groups)
+    const long q = b * P + r;
+    const bool preserve = (flags & kPreserve) != 0;
+#pragma unroll
+    for (int n = 0; n < G::N; ++n) a[n] = __ldg(gb + (long)(aff_ch0 + n) * P);
+    const float d = preserve ? __ldg(dep + q) : 0.f;
+    float x = __ldg(init + q);
+    float c = (conf && !sampled) ? __ldg(conf + q) : 1.f;
 #pragma unroll
     for (int n = 0; n < G::N; ++n) {
-        float v = __ldg(gb + (long)(aff_ch0 + n) * P);
+        float v = a[n];
         if (use_tanh) v = tanhf(v) / g;
         if (sampled) v *= sample_conf<K>(conf + b * P, gb, n, hh0, ww0, H, W, P, (flags & kLegacy) != 0);
         a[n] = v;
@@ -104,14 +112,9 @@ prologue_fwd_kernel(const float *__restrict__ guidance, const float *__restrict_
     for (int t = 0; t < G::KK; ++t)
         ab[(long)t * P] = t == G::REF ? 1.0f - sum : a[t < G::REF ? t : t - 1];
 
-    const long q = b * P + r;
-    const bool preserve = (flags & kPreserve) != 0;
-    const float d = preserve ? __ldg(dep + q) : 0.f;
-    float x = __ldg(init + q);
     if (preserve) x = blend_fix(x, d);
     if (flags & kAlwaysClip) x = fmaxf(x, 0.f);
     if (conf && !sampled) {
-        float c = __ldg(conf + q);
         if (preserve) {
             const float m = d > 0.f ? 1.f : 0.f;
             c = (1.0f - m) * c + m;
@@ -388,10 +391,21 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         constexpr bool sampled = SAMPLED;   // compile-time: the common (fork) path carries none of this
         const int ph = r / W, pw = r - ph * W;
         float a[G::N], th[G::N], Gh[G::N];
+        // every load of the affinity part is issued before the first tanhf: its branches otherwise fence the loads
+        // into small groups (ncu, round 2: 2.9 TB/s with long-scoreboard 8.9 per issue on the dependent FADDs)
+        float raw[G::N], gav[G::KK];
+#pragma unroll
+        for (int n = 0; n < G::N; ++n) raw[n] = __ldg(gb + (long)(aff_ch0 + n) * P);
+#pragma unroll
+        for (int t = 0; t < G::KK; ++t) gav[t] = __ldg(gab + (long)t * P);
+        if (eab) {
+#pragma unroll
+            for (int t = 0; t < G::KK; ++t) gav[t] += __ldg(eab + (long)t * P);
+        }
         float s0 = 0.f;
 #pragma unroll
         for (int n = 0; n < G::N; ++n) {
-            const float rr = __ldg(gb + (long)(aff_ch0 + n) * P);
+            const float rr = raw[n];
             th[n] = use_tanh ? tanhf(rr) : 0.f;
             a[n] = use_tanh ? th[n] * inv_g : rr;
             if (sampled) a[n] *= sample_conf<K>(conf_raw + b * P, gb, n, ph, pw, H, W, P, (flags & kLegacy) != 0);
@@ -405,14 +419,12 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
             clamped = true;
         }
         const float inv_s = 1.0f / s;
-        float Gref = __ldg(gab + (long)G::REF * P);
-        if (eab) Gref += __ldg(eab + (long)G::REF * P);
+        const float Gref = gav[G::REF];
         float dot = 0.f, gsum = 0.f;
 #pragma unroll
         for (int n = 0; n < G::N; ++n) {
             const int t = n < G::REF ? n : n + 1;
-            float gv = __ldg(gab + (long)t * P);
-            if (eab) gv += __ldg(eab + (long)t * P);
+            const float gv = gav[t];
             Gh[n] = gv - Gref;
             dot += Gh[n] * a[n];
         }
@@ -431,7 +443,7 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
                 float hc, wc;
                 const float cs = sample_conf<K>(conf_raw + b * P, gb, n, ph, pw, H, W, P, (flags & kLegacy) != 0,
                                                 &hc, &wc);
-                const float un = use_tanh ? th[n] * inv_g : __ldg(gb + (long)(aff_ch0 + n) * P);
+                const float un = use_tanh ? th[n] * inv_g : raw[n];
                 const float gcs = da * un;            // d loss / d c_n
                 if (tap_valid(hc, wc, H, W) && gcs != 0.f) {
                     // grad_input of the 1x1 gather: mdmcn_get_gradient_weight, cuh:56-81
