@@ -147,17 +147,32 @@ sched_build_kernel(const float *__restrict__ offset, const float *__restrict__ a
     int blk[L::NTAP];
     unsigned rank[L::NTAP];
     float oh[L::NTAP], ow[L::NTAP];
+    // every global load of the kernel is issued here, ahead of the shared-memory atomics and barriers
+    float av[G::KK];
+    float cf = 1.f, pm = 1.f;
+    const float *ab = aff + b * G::KK * P + r;
+#pragma unroll
+    for (int n = 0; n < L::NTAP; ++n) {
+        const int t = n < G::REF ? n : n + 1;
+        oh[n] = inside ? __ldg(ob + (long)(2 * t) * P) : 0.f;
+        ow[n] = inside ? __ldg(ob + (long)(2 * t + 1) * P) : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < G::KK; ++t) av[t] = inside ? __ldg(ab + (long)t * P) : 0.f;
+    if (inside) {
+        if (conf) cf = __ldg(conf + b * P + r);
+        if (flags & kPreserve) pm = 1.0f - (__ldg(dep + b * P + r) > 0.f ? 1.f : 0.f);   // nlspnmodel.py:357 backwards
+    }
 #pragma unroll
     for (int n = 0; n < L::NTAP; ++n) {
         const int t = n < G::REF ? n : n + 1;
         blk[n] = -1;
         rank[n] = 0u;
-        oh[n] = ow[n] = 0.f;
         if (!inside) continue;
         // the record keeps the sampling COORDINATE (integer part added first, one floating add: cuh:157-158), which
         // is what every iteration would rebuild from the offset
-        const float h_im = (float)(h - G::PAD + t / K) + __ldg(ob + (long)(2 * t) * P);
-        const float w_im = (float)(w - G::PAD + t % K) + __ldg(ob + (long)(2 * t + 1) * P);
+        const float h_im = (float)(h - G::PAD + t / K) + oh[n];
+        const float w_im = (float)(w - G::PAD + t % K) + ow[n];
         oh[n] = h_im;
         ow[n] = w_im;
         if (!tap_valid(h_im, w_im, H, W)) continue;
@@ -221,15 +236,6 @@ sched_build_kernel(const float *__restrict__ offset, const float *__restrict__ a
     }
     const long tile = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     // the packed record (pixels of the tile that lie outside the image: all taps skipped, zeros)
-    float av[G::KK];
-    float cf = 1.f, pm = 1.f;
-    const float *ab = aff + b * G::KK * P + r;
-#pragma unroll
-    for (int t = 0; t < G::KK; ++t) av[t] = inside ? __ldg(ab + (long)t * P) : 0.f;
-    if (inside) {
-        if (conf) cf = __ldg(conf + b * P + r);
-        if (flags & kPreserve) pm = 1.0f - (__ldg(dep + b * P + r) > 0.f ? 1.f : 0.f);   // nlspnmodel.py:357 backwards
-    }
     uint4 *gp = geo + tile * (L::GEOV * L::NT) + tid;
     gp[0] = make_uint4(sl[0] | (sl[1] << 16), sl[2] | (sl[3] << 16), sl[4] | (sl[5] << 16), sl[6] | (sl[7] << 16));
     float4 *gf = reinterpret_cast<float4 *>(gp);
