@@ -85,28 +85,40 @@ table_build_kernel(const float *__restrict__ offset, const float *__restrict__ a
     int *cnt = count + b * table_groups(NB) * 32;          // counters are padded to whole groups
     float4 *ent = entries + b * table_groups(NB) * CAP * 32;
     M mask = 0;
+    // eight neighbours at a time: their 24 loads are issued before the first counter atomic (an atomic with a
+    // return value otherwise serialises load -> atomic -> store per tap)
 #pragma unroll
-    for (int t = 0; t < G::KK; ++t) {
-        if (t == G::REF) continue;
-        const int n = t < G::REF ? t : t - 1;
-        const float h_im = (float)(h - G::PAD + t / K) + __ldg(ob + (long)(2 * t) * P);
-        const float w_im = (float)(w - G::PAD + t % K) + __ldg(ob + (long)(2 * t + 1) * P);
-        if (!tap_valid(h_im, w_im, H, W)) continue;
-        float hf, wf;
-        int hl, wl;
-        floor_small(h_im, hf, hl);
-        floor_small(w_im, wf, wl);
-        const int Y = hl + 1, X = wl + 1;         // padded coordinates of the top-left corner
-        const int sy = Y & 1, sx = X & 1;
-        const int blk = (sy * 2 + sx) * blocks_per_phase + ((Y + sy) >> 1) * sg.Wb + ((X + sx) >> 1);
-        const int slot = atomicAdd(cnt + blk, 1);
-        // top-row and left-column weights of cuh:71-79, (hl+1) - h and (wl+1) - w, formed literally; the
-        // readers take the bottom / right weights as 1 - th and 1 - lw (equal up to one rounding of 2^-25)
-        if (slot < CAP)
-            ent[table_index<CAP>(blk, slot)] = make_float4(__int_as_float((h << 16) | w), __ldg(ab + (long)t * P),
-                                                           (hf + 1.f) - h_im, (wf + 1.f) - w_im);
-        else
-            mask |= (M)1 << n;
+    for (int n0 = 0; n0 < G::N; n0 += 8) {
+        float oh[8], ow[8], av[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int n = n0 + i, t = n < G::REF ? n : n + 1;
+            oh[i] = __ldg(ob + (long)(2 * t) * P);
+            ow[i] = __ldg(ob + (long)(2 * t + 1) * P);
+            av[i] = __ldg(ab + (long)t * P);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int n = n0 + i, t = n < G::REF ? n : n + 1;
+            const float h_im = (float)(h - G::PAD + t / K) + oh[i];
+            const float w_im = (float)(w - G::PAD + t % K) + ow[i];
+            if (!tap_valid(h_im, w_im, H, W)) continue;
+            float hf, wf;
+            int hl, wl;
+            floor_small(h_im, hf, hl);
+            floor_small(w_im, wf, wl);
+            const int Y = hl + 1, X = wl + 1;         // padded coordinates of the top-left corner
+            const int sy = Y & 1, sx = X & 1;
+            const int blk = (sy * 2 + sx) * blocks_per_phase + ((Y + sy) >> 1) * sg.Wb + ((X + sx) >> 1);
+            const int slot = atomicAdd(cnt + blk, 1);
+            // top-row and left-column weights of cuh:71-79, (hl+1) - h and (wl+1) - w, formed literally; the
+            // readers take the bottom / right weights as 1 - th and 1 - lw (equal up to one rounding of 2^-25)
+            if (slot < CAP)
+                ent[table_index<CAP>(blk, slot)] = make_float4(__int_as_float((h << 16) | w), av[i],
+                                                               (hf + 1.f) - h_im, (wf + 1.f) - w_im);
+            else
+                mask |= (M)1 << n;
+        }
     }
     ovf[b * P + r] = mask;
 }
