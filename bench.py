@@ -362,7 +362,7 @@ class GpuRun:
     def e2e(self, steps, warmup, sync_all, d2h="result"):
         torch, dev, mod, train = self.torch, self.dev, self.mod, self.train
         host, names, B, H, W = self.host, self.names, self.B, self.H, self.W
-        auto_chunk = max(1, -(-400000 // (H * W)))   # about one KITTI frame's worth of pixels per upload
+        auto_chunk = max(1, -(-800000 // (H * W)))   # about two KITTI frames' worth of pixels per upload (B200: chunk 1 / 2 / 4 / 8 -> 8.45 / 8.77 / 8.81 / 8.5 Gpix*iter/s; 2 is also the steadiest)
         chunk = max(1, min(B, int(os.environ.get("NLSPN_E2E_CHUNK", str(auto_chunk)))))
         copy_stream = torch.cuda.Stream(device=dev)
         down_stream = torch.cuda.Stream(device=dev)
@@ -383,6 +383,7 @@ class GpuRun:
                 evt.record(copy_stream)
             return inp, evt
 
+        prefetch = os.environ.get("NLSPN_E2E_PREFETCH", "1") != "0"
         nxt = [None]     # chunk 0 of the NEXT step, uploaded while this step's last chunk computes (a pinned
                          # DataLoader's prefetch: the copy engine never idles between steps)
 
@@ -396,7 +397,7 @@ class GpuRun:
                     pending = upload(i + chunk)
                 else:
                     pending = None
-                    if more:
+                    if more and prefetch:
                         nxt[0] = upload(0)
                 main_stream.wait_event(evt)
                 for t_ in inp.values():
@@ -425,7 +426,7 @@ class GpuRun:
             down_stream.synchronize()                      # results are in host memory when the step ends
             return total
 
-        for _ in range(min(2, warmup)):
+        for _ in range(min(3, warmup)):
             mod.aff_scale_const.grad = None
             e2e_step(False)
         sync_all()

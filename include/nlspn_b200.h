@@ -108,7 +108,8 @@ NLSPN_API unsigned long long nlspn_launch_count(void);
 /* Tuning options.  The NLSPN_<NAME> environment variables seed the defaults ONCE, when the
  * library is loaded; nothing on the call path reads the environment.  Names: tiled, persist, pdl, fwd_th,
  * param_th, state_tma, state_gather, gather_compact, state_zero3, state_minb, group_images, stream_hint,
- * state_ahead, param_factored, persist_bwd, dcn_blocked.  value -1 = auto where the default depends on the shape.
+ * param_factored, dcn_blocked, state_local, local_prefetch, local_minb, sched_minb.
+ * value -1 = auto where the default depends on the shape.
  * Options that select the form of the backward (state_gather) change nlspn_backward_workspace_bytes: query
  * after setting them (a too-small workspace is always refused, never overrun). */
 NLSPN_API int nlspn_set_option(const char *name, int value);
@@ -176,8 +177,9 @@ NLSPN_API int nlspn_forward(const float *guidance, const float *confidence, cons
  * The scatter uses fp32 atomics: summation order, hence the last bits, vary run to run,
  * as in the reference (deformconv/test.py:627-631).
  * Workspace: query with the same (B, H, W, K, T) -- and the same environment -- as the call.  The size
- * depends on the form the state-gradient pass takes: RED scatter (K = 3, or T < 8): three sets of blocked
- * planes, ~0.55 GB at KITTI B = 8, K = 3, T = 18; tabulated gather (K >= 5 and T >= 8): a table of
+ * depends on the form the state-gradient pass takes: tile-local transpose (K = 3, W % 4 == 0): two padded planes
+ * and a packed record of 128 B per pixel, ~0.87 GB at KITTI B = 8, K = 3, T = 18; RED scatter (otherwise, or
+ * T < 8 at K >= 5): three sets of blocked planes, ~0.55 GB; tabulated gather (K >= 5 and T >= 8): a table of
  * 16 B x CAP(K) x blocks, ~3.2 GB at K = 5 and ~4.9 GB at K = 7 for the same batch. */
 NLSPN_API size_t nlspn_backward_workspace_bytes(int B, int H, int W, int K, int T);
 /* the same query for a call with `flags` (NLSPN_FLAG_DETERMINISTIC changes the workspace layout) */

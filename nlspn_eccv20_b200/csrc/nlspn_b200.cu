@@ -31,8 +31,8 @@ std::atomic<unsigned long long> g_launches{0};
 // nlspn_set_option changes them (tests, tools).  Nothing on the call path touches getenv.
 // -1 = "auto" where a default depends on the shape.
 enum Opt { kOptTiled = 0, kOptPersist, kOptPdl, kOptFwdTH, kOptParamTH, kOptStateTma, kOptStateGather,
-           kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint, kOptStateAhead,
-           kOptParamFactored, kOptPersistBwd, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptCount };
+           kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint,
+           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptCount };
 struct OptDef { const char *name; const char *env; int def; };
 const OptDef kOptDefs[kOptCount] = {
     {"tiled", "NLSPN_TILED", 1},
@@ -47,9 +47,7 @@ const OptDef kOptDefs[kOptCount] = {
     {"state_minb", "NLSPN_STATE_MINB", 4},
     {"group_images", "NLSPN_GROUP_IMAGES", 0},
     {"stream_hint", "NLSPN_STREAM_HINT", -1},
-    {"state_ahead", "NLSPN_STATE_AHEAD", -1},
     {"param_factored", "NLSPN_PARAM_FACTORED", 1},
-    {"persist_bwd", "NLSPN_PERSIST_BWD", -1},
     {"dcn_blocked", "NLSPN_DCN_BLOCKED", 1},
     {"state_local", "NLSPN_STATE_LOCAL", -1},
     {"local_prefetch", "NLSPN_LOCAL_PREFETCH", 0},

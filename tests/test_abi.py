@@ -78,6 +78,10 @@ def test_validation_errors_are_negative_and_described(lib):
     assert lib.nlspn_backward_workspace_bytes(2, 8, 8, 3, 1) >= 4 * (3 + 9) * 2 * 64
     assert lib.nlspn_backward_workspace_bytes(2, 8, 8, 3, 40) >= 4 * 40 * 2 * 64
     assert lib.nlspn_backward_workspace_bytes(0, 8, 8, 3, 1) == 0
+    # the flags-aware query: flags 0 = the plain query; DETERMINISTIC holds the exact CSR (8 B per corner of every tap)
+    from nlspn_eccv20_b200 import _lib
+    assert lib.nlspn_backward_workspace_bytes_ex(2, 8, 8, 3, 4, 0) == lib.nlspn_backward_workspace_bytes(2, 8, 8, 3, 4)
+    assert lib.nlspn_backward_workspace_bytes_ex(2, 8, 8, 5, 4, _lib.FLAG_DETERMINISTIC) >= 8 * 4 * 24 * 2 * 64
 
 
 def test_product_never_imports_the_oracle():
