@@ -334,11 +334,22 @@ bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
     const uint4 *gp = geo + tile * (L::GEOV * L::NT) + tid;
     const float4 *gf = reinterpret_cast<const float4 *>(gp);
     const uint4 sl4 = STREAM ? __ldcs(gp) : __ldg(gp);
-    float4 o4[4], a4[2], m4;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o4[i] = STREAM ? __ldcs(gf + (1 + i) * L::NT) : __ldg(gf + (1 + i) * L::NT);
+    // SPLIT (6 CTAs per SM, 40 registers): only the first four neighbours' vectors are loaded here; the other three
+    // vectors are pulled into L2 and loaded when the first four have been consumed (32 -> 20 registers of record)
+    constexpr bool SPLIT = MINB >= 6;
+    float4 o4[SPLIT ? 2 : 4], a4[SPLIT ? 1 : 2], m4;
+    o4[0] = STREAM ? __ldcs(gf + 1 * L::NT) : __ldg(gf + 1 * L::NT);
+    o4[1] = STREAM ? __ldcs(gf + 2 * L::NT) : __ldg(gf + 2 * L::NT);
     a4[0] = STREAM ? __ldcs(gf + 5 * L::NT) : __ldg(gf + 5 * L::NT);
-    a4[1] = STREAM ? __ldcs(gf + 6 * L::NT) : __ldg(gf + 6 * L::NT);
+    if constexpr (!SPLIT) {
+        o4[2] = STREAM ? __ldcs(gf + 3 * L::NT) : __ldg(gf + 3 * L::NT);
+        o4[3] = STREAM ? __ldcs(gf + 4 * L::NT) : __ldg(gf + 4 * L::NT);
+        a4[1] = STREAM ? __ldcs(gf + 6 * L::NT) : __ldg(gf + 6 * L::NT);
+    } else if ((tid & 7) == 0) {          // one lane per 128-byte line
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gf + 3 * L::NT));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gf + 4 * L::NT));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gf + 6 * L::NT));
+    }
     m4 = STREAM ? __ldcs(gf + 7 * L::NT) : __ldg(gf + 7 * L::NT);   // (centre affinity, confidence, preserve factor, -)
     const bool need_x = (s_in && has_conf) || (flags & kAlwaysClip);
     float gext = 0.f, xt = 1.f;
@@ -382,33 +393,44 @@ bwd_state_local_kernel(const __grid_constant__ CUtensorMap plane_map, int z_out,
     const unsigned slw[4] = {sl4.x, sl4.y, sl4.z, sl4.w};
     unsigned quads_s = tma::smem_u32(quads);
     asm volatile("" : "+r"(quads_s));            // opaque: computed once, not rebuilt in front of every store
-    const float ohv[8] = {o4[0].x, o4[0].z, o4[1].x, o4[1].z, o4[2].x, o4[2].z, o4[3].x, o4[3].z};
-    const float owv[8] = {o4[0].y, o4[0].w, o4[1].y, o4[1].w, o4[2].y, o4[2].w, o4[3].y, o4[3].w};
-    const float avv[8] = {a4[0].x, a4[0].y, a4[0].z, a4[0].w, a4[1].x, a4[1].y, a4[1].z, a4[1].w};
+    // four neighbours n0 .. n0+3: coordinates (h, w, h, w) of two taps per vector, one vector of affinities
+    auto four_taps = [&](int n0, const float4 &oa, const float4 &ob_, const float4 &aa) {
+        const float ohv[4] = {oa.x, oa.z, ob_.x, ob_.z};
+        const float owv[4] = {oa.y, oa.w, ob_.y, ob_.w};
+        const float avv[4] = {aa.x, aa.y, aa.z, aa.w};
 #pragma unroll
-    for (int n = 0; n < L::NTAP; ++n) {
-        const unsigned slot = (slw[n >> 1] >> (16 * (n & 1))) & 0xFFFFu;
-        if (slot == kSlotSkip) continue;
-        const float top = gy * avv[n];
-        const float h_im = ohv[n], w_im = owv[n];
-        const float hf = floor_small_f(h_im), wf = floor_small_f(w_im);
-        // mdmcn_get_gradient_weight, cuh:71-79 (expressions kept literal; (float)(hl+1) == hf + 1 exactly)
-        const float h1 = hf + 1.f, w1 = wf + 1.f;
-        const float th = h1 - h_im, bh = (h_im + 1.f) - h1;
-        const float lw_ = w1 - w_im, rw = (w_im + 1.f) - w1;
-        const float4 qd = make_float4(th * lw_ * top, th * rw * top, bh * lw_ * top, bh * rw * top);
-        if (slot != kSlotGlobal) {
-            sts128(quads_s + slot * 16u, qd);
-        } else if (gy != 0.f) {
-            // far footprint: guarded scalar REDs (cuh:229-252 with the guards of :37-48) into the padded plane
-            const int hl = (int)hf, wl = (int)wf;
-            float *sp = sob + ((hl + L::R) * pg.PW + (wl + L::R));
-            const bool topv = hl >= 0, botv = hl + 1 <= H - 1, lefv = wl >= 0, rigv = wl + 1 <= W - 1;
-            if (topv && lefv) atomicAdd(sp, qd.x);
-            if (topv && rigv) atomicAdd(sp + 1, qd.y);
-            if (botv && lefv) atomicAdd(sp + pg.PW, qd.z);
-            if (botv && rigv) atomicAdd(sp + pg.PW + 1, qd.w);
+        for (int i = 0; i < 4; ++i) {
+            const int n = n0 + i;
+            const unsigned slot = (slw[n >> 1] >> (16 * (n & 1))) & 0xFFFFu;
+            if (slot == kSlotSkip) continue;
+            const float top = gy * avv[i];
+            const float h_im = ohv[i], w_im = owv[i];
+            const float hf = floor_small_f(h_im), wf = floor_small_f(w_im);
+            // mdmcn_get_gradient_weight, cuh:71-79 (expressions kept literal; (float)(hl+1) == hf + 1 exactly)
+            const float h1 = hf + 1.f, w1 = wf + 1.f;
+            const float th = h1 - h_im, bh = (h_im + 1.f) - h1;
+            const float lw_ = w1 - w_im, rw = (w_im + 1.f) - w1;
+            const float4 qd = make_float4(th * lw_ * top, th * rw * top, bh * lw_ * top, bh * rw * top);
+            if (slot != kSlotGlobal) {
+                sts128(quads_s + slot * 16u, qd);
+            } else if (gy != 0.f) {
+                // far footprint: guarded scalar REDs (cuh:229-252 with the guards of :37-48) into the padded plane
+                const int hl = (int)hf, wl = (int)wf;
+                float *sp = sob + ((hl + L::R) * pg.PW + (wl + L::R));
+                const bool topv = hl >= 0, botv = hl + 1 <= H - 1, lefv = wl >= 0, rigv = wl + 1 <= W - 1;
+                if (topv && lefv) atomicAdd(sp, qd.x);
+                if (topv && rigv) atomicAdd(sp + 1, qd.y);
+                if (botv && lefv) atomicAdd(sp + pg.PW, qd.z);
+                if (botv && rigv) atomicAdd(sp + pg.PW + 1, qd.w);
+            }
         }
+    };
+    four_taps(0, o4[0], o4[1], a4[0]);
+    if constexpr (SPLIT) {
+        const float4 oc = __ldg(gf + 3 * L::NT), od = __ldg(gf + 4 * L::NT), ab_ = __ldg(gf + 6 * L::NT);
+        four_taps(4, oc, od, ab_);
+    } else {
+        four_taps(4, o4[2], o4[3], a4[1]);
     }
     centre[tid] = gy * m4.x;     // the centre tap has a structurally zero offset: lands on the pixel itself
     asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -414,9 +414,25 @@ final_bwd_kernel(const float *__restrict__ guidance, const float *__restrict__ i
         s0 += 1e-4f;
         bool clamped = false;
         float s = s0;
-        if ((affinity == kASS || affinity == kTGASS) && s0 < 1.0f) {
-            s = 1.0f;
-            clamped = true;
+        if (affinity == kASS || affinity == kTGASS) {
+            clamped = s0 < 1.0f;
+            // The clamp `s[s < 1] = 1` (nlspnmodel.py:193-194) is a kink: within a few ulp of 1 the DECISION must be
+            // the forward's, and th * (1/g) above is not bit-identical to the prologue's tanhf(r) / g.  Near the
+            // kink the sum is therefore re-formed with the prologue's exact expressions and order (soak case 121 of
+            // the randomized sweep: one pixel in 170 k with s = 1 - 1 ulp took the other branch).
+            if (fabsf(s0 - 1.0f) < 1e-5f) {
+                float se = 0.f;
+#pragma unroll
+                for (int n = 0; n < G::N; ++n) {
+                    float v = raw[n];
+                    if (use_tanh) v = tanhf(v) / g;
+                    if (sampled) v *= sample_conf<K>(conf_raw + b * P, gb, n, ph, pw, H, W, P, (flags & kLegacy) != 0);
+                    se += fabsf(v);
+                }
+                se += 1e-4f;
+                clamped = se < 1.0f;
+            }
+            if (clamped) s = 1.0f;
         }
         const float inv_s = 1.0f / s;
         const float Gref = gav[G::REF];

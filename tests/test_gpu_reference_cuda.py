@@ -137,14 +137,20 @@ def test_randomized_sweep_against_reference_cuda_kernels(ref):
         H, W = rnd.randint(9, 70), rnd.randint(9, 150)
         if case % 3 == 0:
             W = (W // 4) * 4 + 4                       # TMA-tiled path
+        if os.environ.get("NLSPN_SWEEP_BIG", "0") == "1":
+            # soak variant for the tile-local transpose (kernels_local.cuh): K = 3, many tiles, W % 4 == 0
+            K, T = 3, rnd.randint(1, 6)
+            H, W = rnd.randint(8, 260), 4 * rnd.randint(8, 110)
         affinity = rnd.choice(["TGASS", "TGASS", "ASS", "AS", "TC"])
         use_conf, preserve, clip = rnd.random() < 0.7, rnd.random() < 0.7, rnd.random() < 0.3
         sigma = rnd.choice([0.5, 2.0, 2.0, 6.0])
         d = make_inputs(B, H, W, K, max_depth=10.0, seed=1000 + case, conf_mean=3.0, off_sigma=sigma,
                         num_sample=max(1, H * W // 40), device=dev)
         N = K * K - 1
+        # every fourth case (all of them with NLSPN_SWEEP_DETERMINISTIC=1) takes the deterministic backward
+        det = case % 4 == 3 or os.environ.get("NLSPN_SWEEP_DETERMINISTIC", "0") == "1"
         mod = NLSPN(prop_kernel=K, prop_time=T, affinity=affinity, conf_prop=use_conf,
-                    preserve_input=preserve, always_clip=clip).to(dev)
+                    preserve_input=preserve, always_clip=clip, deterministic=det).to(dev)
         g_out = torch.randn(T, B, 1, H, W, generator=torch.Generator().manual_seed(case)).to(dev)
         leaves = lambda: [d[k].clone().requires_grad_(True) for k in ("feat_init", "guidance", "confidence")]
         fi, gd, cf = leaves()
@@ -155,8 +161,8 @@ def test_randomized_sweep_against_reference_cuda_kernels(ref):
         r = ref.propagate(fi2, gd2, cf2 if use_conf else None, d["feat_fix"] if preserve else None, gam, K, T,
                           affinity=affinity, preserve_input=preserve, always_clip=clip)
         torch.autograd.backward(r["list_feat"], [g_out[t] for t in range(T)])
-        tag = "case %d: K=%d T=%d B=%d %dx%d %s conf=%s preserve=%s clip=%s sigma=%.1f" % (
-            case, K, T, B, H, W, affinity, use_conf, preserve, clip, sigma)
+        tag = "case %d: K=%d T=%d B=%d %dx%d %s conf=%s preserve=%s clip=%s sigma=%.1f det=%s" % (
+            case, K, T, B, H, W, affinity, use_conf, preserve, clip, sigma, det)
         assert torch.equal(out[2], r["offset"]), tag
         lf, lr = torch.stack(out[1]), torch.stack(r["list_feat"])
         scale = float(lr.abs().max().clamp_min(1.0))
@@ -164,10 +170,27 @@ def test_randomized_sweep_against_reference_cuda_kernels(ref):
         assert _rel(fi.grad, fi2.grad) < 1e-4, tag
         if use_conf:
             assert _rel(cf.grad, cf2.grad) < 1e-4, tag
-        assert _rel(gd.grad[:, 2 * N:], gd2.grad[:, 2 * N:]) < 2e-4, tag
+        ga, gb_ = gd.grad[:, 2 * N:], gd2.grad[:, 2 * N:]
+        has_kink = False
+        if affinity in ("ASS", "TGASS"):
+            # `s[s < 1] = 1` (nlspnmodel.py:193-194) is a kink of the normalisation: where the abs-sum lies within an
+            # ulp or two of 1 the branch -- and with it the one-sided derivative -- follows the summation ORDER of the
+            # 8/24/48 terms (ours: sequential; torch's CUDA reduction: its own), while the forward values differ by 1e-7.
+            # Such pixels (soak: 1 in ~3e7) are left out of the affinity-gradient comparison.
+            raw = d["guidance"][:, 2 * N:]
+            a_ = torch.tanh(raw) / (float(mod.aff_scale_const.detach()) + 1e-8) if affinity == "TGASS" else raw
+            kink = ((a_.abs().sum(1, keepdim=True) + 1e-4) - 1.0).abs() < 2e-6
+            ga, gb_ = ga.masked_fill(kink, 0.0), gb_.masked_fill(kink, 0.0)
+            has_kink = bool(kink.any())
+        assert _rel(ga, gb_) < 2e-4, tag
         if affinity == "TGASS":
             rg = float(gam.grad)
-            assert abs(float(mod.aff_scale_const.grad) - rg) <= 2e-4 * max(abs(rg), 1e-6), tag
+            # gamma's gradient is ONE scalar summed over every pixel and neighbour; where the terms cancel (|rg| small)
+            # the fp32 summation order of the reference's autograd decides its last digits (soak case 217: 1.5770e-3 vs
+            # our fp64-accumulated 1.5766e-3), hence the absolute floor ~ eps * sqrt(number of terms)
+            floor = 1e-7 * (B * H * W * N) ** 0.5
+            # (a kink pixel carries its one-sided derivative into gamma's sum as well)
+            assert abs(float(mod.aff_scale_const.grad) - rg) <= (5e-3 if has_kink else 2e-4) * max(abs(rg), 1e-6) + floor, tag
         dd = (gd.grad[:, :2 * N] - gd2.grad[:, :2 * N]).abs()
         s = gd2.grad[:, :2 * N].abs().max().clamp_min(1e-30)
         assert float((dd > 1e-4 * s).float().mean()) < 2e-3, tag
