@@ -53,7 +53,7 @@ L2_MB = 126.0
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--workload", default="kitti", choices=["kitti", "nyu"])
@@ -376,12 +376,29 @@ class GpuRun:
                 out_host["g_" + k] = torch.empty_like(host[k]).pin_memory()
         d2h_bytes = 4 + sum(t.numel() * 4 for t in out_host.values())
 
+        # device-side input ring: three preallocated chunk buffers per tensor, refilled by the copy stream once the
+        # compute stream is done with them (no caching-allocator traffic, no record_stream bookkeeping on the hot
+        # path: with freshly allocated chunk tensors one of the variants would run 20-25 % slow every few runs)
+        ring = 3
+        slots = [{k: torch.empty((chunk,) + tuple(host[k].shape[1:]), device=dev) for k in names} for _ in range(ring)]
+        slot_free = [None] * ring
+        n_up = [0]
+
         def upload(i):
+            slot = n_up[0] % ring
+            n_up[0] += 1
+            n = min(chunk, B - i)
             with torch.cuda.stream(copy_stream):
-                inp = {k: host[k][i:i + chunk].to(dev, non_blocking=True) for k in names}
+                if slot_free[slot] is not None:
+                    copy_stream.wait_event(slot_free[slot])
+                inp = {}
+                for k in names:
+                    dst = slots[slot][k][:n]
+                    dst.copy_(host[k][i:i + n], non_blocking=True)
+                    inp[k] = dst
                 evt = torch.cuda.Event()
                 evt.record(copy_stream)
-            return inp, evt
+            return inp, evt, slot
 
         prefetch = os.environ.get("NLSPN_E2E_PREFETCH", "1") != "0"
         nxt = [None]     # chunk 0 of the NEXT step, uploaded while this step's last chunk computes (a pinned
@@ -392,7 +409,7 @@ class GpuRun:
             pending = nxt[0] if nxt[0] is not None else upload(0)
             nxt[0] = None
             for ci, i in enumerate(range(0, B, chunk)):
-                inp, evt = pending
+                inp, evt, slot = pending
                 if i + chunk < B:
                     pending = upload(i + chunk)
                 else:
@@ -400,17 +417,18 @@ class GpuRun:
                     if more and prefetch:
                         nxt[0] = upload(0)
                 main_stream.wait_event(evt)
-                for t_ in inp.values():
-                    t_.record_stream(main_stream)
                 fi, gd, cf = inp["feat_init"], inp["guidance"], inp["confidence"]
                 if train:
-                    fi, gd, cf = (t_.requires_grad_(True) for t_ in (fi, gd, cf))
+                    fi, gd, cf = (t_.detach().requires_grad_(True) for t_ in (fi, gd, cf))
                 with torch.set_grad_enabled(train):
                     feat_result = mod(fi, gd, cf, inp["feat_fix"])[0]
                     loss = (torch.clamp(feat_result, min=0) - gt_chunks[ci]).abs().sum()
                 if train:
                     loss.backward()
                 losses.append(loss.detach())
+                freed = torch.cuda.Event()
+                freed.record(main_stream)          # the chunk's inputs are consumed: its slot may be refilled
+                slot_free[slot] = freed
                 if out_host:
                     done = torch.cuda.Event()
                     done.record(main_stream)
