@@ -253,6 +253,26 @@ NLSPN_API int nlspn_step_bwd(const float *src_prev, const float *offset, const f
                              float *g_src_prev, float *g_offset, float *g_aff, float *g_conf,
                              void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- the three final head convolutions in front of the propagation (first half) ----------
+ * Replaces, in NLSPNModel.forward (nlspnmodel.py:297,301,313 with the layers of :69-86):
+ *     pred_init  = id_dec0     (cat(id_fd1,      fe1))      3x3 conv 128 -> 1,  ReLU
+ *     off_aff    = off_aff_dec0(cat(off_aff_fd1, fe1))      3x3 conv 128 -> 3N, no activation   ("guidance")
+ *     confidence = cf_dec0     (cat(cf_fd1,      fe1))      3x3 conv 128 -> 1,  Sigmoid
+ * by ONE tcgen05 (kind::tf32, fp32 accumulation in tensor memory) implicit GEMM that reads the four 64-channel
+ * NCHW tensors where they lie (no concatenation).  TF32 is what cuDNN computes these layers in under PyTorch's
+ * default torch.backends.cudnn.allow_tf32 = True.
+ *   nlspn_heads_packed_floats(K)  floats of the packed weight matrix
+ *   nlspn_heads_pack              packs w_id [1,128,3,3], w_oa [3N,128,3,3], w_cf [1,128,3,3] (device pointers;
+ *                                 input channels 0..63 = the head's own branch, 64..127 = fe1, as torch.cat orders
+ *                                 them) into `packed` (device, 16-byte aligned); call again when the weights change
+ *   nlspn_heads_fwd               bias [3N + 2] = (b_id, b_oa[0..3N), b_cf); outputs pred_init [B,1,H,W],
+ *                                 guidance [B,3N,H,W], confidence [B,1,H,W] */
+NLSPN_API size_t nlspn_heads_packed_floats(int K);
+NLSPN_API int nlspn_heads_pack(const float *w_id, const float *w_oa, const float *w_cf, int K, float *packed, void *stream);
+NLSPN_API int nlspn_heads_fwd(const float *id_fd1, const float *oa_fd1, const float *cf_fd1, const float *fe1,
+                              const float *packed, const float *bias, int B, int H, int W, int K,
+                              float *pred_init, float *guidance, float *confidence, void *stream);
+
 /* Double-precision variants of the single-step operator: the reference dispatches this op over
  * float and double (AT_DISPATCH_FLOATING_TYPES, modulated_deform_conv_cuda.cu:93,224) and its
  * tests run gradcheck in double (src/model/deformconv/test.py).  Same domain, argument order and

@@ -19,6 +19,7 @@
 #include "kernels_step.cuh"
 #include "kernels_local.cuh"
 #include "kernels_det.cuh"
+#include "kernels_head.cuh"
 
 using namespace nlspn;
 
@@ -67,11 +68,11 @@ inline int opt(Opt o) { return g_opt[o].load(std::memory_order_relaxed); }
 
 // ---- optional per-kernel-class timing (bench.py's roofline): CUDA events around every launch
 enum ProfClass { kProfPrologue = 0, kProfIterFwd, kProfBwdState, kProfBwdParam, kProfFinalBwd,
-                 kProfIterBwdV1, kProfDcnFwd, kProfDcnBwd, kProfBwdTable, kProfBwdGather, kProfClasses };
+                 kProfIterBwdV1, kProfDcnFwd, kProfDcnBwd, kProfBwdTable, kProfBwdGather, kProfHeads, kProfClasses };
 const char *const kProfNames[kProfClasses] = {"prologue_fwd_kernel", "iter_fwd_kernel", "bwd_state_kernel",
                                               "bwd_param_kernel", "final_bwd_kernel", "iter_bwd_kernel",
                                               "dcn_forward", "dcn_backward", "table_build_kernel",
-                                              "bwd_gather_kernel"};
+                                              "bwd_gather_kernel", "head_fused_kernel"};
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
 std::mutex g_prof_mu;
 std::atomic<int> g_prof_on{0};
@@ -1355,6 +1356,45 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         NLSPN_CHECK_LAUNCH("final_bwd_kernel");
     }
     gamma_reduce.armed = true;
+    return 0;
+}
+
+// ---- the three final head convolutions as one tcgen05 implicit GEMM (kernels_head.cuh) ----
+size_t nlspn_heads_packed_floats(int K)
+{
+    if (K != 3 && K != 5 && K != 7) return 0;
+    return (size_t)head_packed_floats(K);
+}
+
+int nlspn_heads_pack(const float *w_id, const float *w_oa, const float *w_cf, int K, float *packed, void *stream)
+{
+    if (K != 3 && K != 5 && K != 7) return fail(NLSPN_ERR_KERNEL, "prop_kernel must be 3, 5 or 7 (got %d)", K);
+    if (!w_id || !w_oa || !w_cf || !packed) return fail(NLSPN_ERR_NULL, "heads_pack: a required pointer is NULL");
+    head_pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w_id, w_oa, w_cf, 3 * (K * K - 1), head_np(K), packed);
+    NLSPN_CHECK_LAUNCH("head_pack_weights_kernel");
+    return 0;
+}
+
+int nlspn_heads_fwd(const float *id_fd1, const float *oa_fd1, const float *cf_fd1, const float *fe1,
+                    const float *packed, const float *bias, int B, int H, int W, int K,
+                    float *pred_init, float *guidance, float *confidence, void *stream)
+{
+    if (int rc = check_shape(B, H, W, K, 1)) return rc;
+    if (!id_fd1 || !oa_fd1 || !cf_fd1 || !fe1 || !packed || !bias || !pred_init || !guidance || !confidence)
+        return fail(NLSPN_ERR_NULL, "heads_fwd: a required pointer is NULL");
+    if (H > 65535) return fail(NLSPN_ERR_SHAPE, "heads_fwd: H > 65535 is not supported (got %d)", H);
+    if (!aligned16(packed)) return fail(NLSPN_ERR_ALIGN, "heads_fwd: the packed weights must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N3 = 3 * (K * K - 1);
+    ProfScope prof__(kProfHeads, st);
+    cudaError_t e;
+    switch (K) {
+    case 3: e = head_launch<head_np(3)>(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
+    case 5: e = head_launch<head_np(5)>(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
+    default: e = head_launch<head_np(7)>(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "head_fused_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
