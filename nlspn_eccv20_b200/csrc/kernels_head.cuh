@@ -107,6 +107,57 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
     __trap();
 }
 
+// epilogue shared by both kernels: warps 0-3 own TMEM lanes 32 w .. 32 w + 31 = pixels; 32 columns per tcgen05.ld
+template <int NP>
+__device__ __forceinline__ void head_epilogue(uint32_t tmem, int warp, int tid, int x0, int y, long b, long P, int N3, int W,
+                                              const float *__restrict__ bias, float *__restrict__ pred_init,
+                                              float *__restrict__ guidance, float *__restrict__ confidence)
+{
+    if (warp < 4) {
+        const int px = x0 + warp * 32 + (tid & 31);
+        const bool valid = px < W;
+        const long q = b * P + (long)y * W + px;
+        const int NOUT = N3 + 2;
+#pragma unroll
+        for (int cb = 0; cb < NP; cb += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
+            if (NP - cb >= 32) {
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                    "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                      "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                      "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+            } else {     // 16 columns left (NP = 80: 32 + 32 + 16)
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                    "%15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+#pragma unroll
+                for (int i = 16; i < 32; ++i) v[i] = 0u;
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int n = cb + i;
+                    if (n >= NOUT) break;
+                    const float o = __uint_as_float(v[i]) + __ldg(bias + n);
+                    if (n == 0) pred_init[q] = fmaxf(o, 0.f);                                   // nlspnmodel.py:68 (relu)
+                    else if (n <= N3) guidance[(b * N3 + (n - 1)) * P + (long)y * W + px] = o;  // :81 (no activation)
+                    else confidence[q] = 1.f / (1.f + expf(-o));                                // :83-86 (sigmoid)
+                }
+            }
+        }
+    }
+}
+
 // grid = (ceil(W / 128), H, B), block = 256, dynamic shared memory HeadSmem<NP>::bytes
 template <int NP>
 __global__ void __launch_bounds__(kHeadThreads, 2)
@@ -201,50 +252,129 @@ head_fused_kernel(const float *__restrict__ id_fd1, const float *__restrict__ oa
     mbar_wait_bounded(&bars[2], 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: warps 0-3 own TMEM lanes 32 w .. 32 w + 31 = pixels; 32 columns per tcgen05.ld
-    if (warp < 4) {
-        const int px = x0 + warp * 32 + (tid & 31);
-        const bool valid = px < W;
-        const long q = b * P + (long)y * W + px;
-        const int NOUT = N3 + 2;
+    head_epilogue<NP>(tmem, warp, tid, x0, y, b, P, N3, W, bias, pred_init, guidance, confidence);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kCols));
+}
+
+// ======================================================================================
+// The same GEMM with the activations delivered by TMA (W % 4 == 0).  ncu on head_fused_kernel at KITTI B = 8: 9.5 ms,
+// DRAM 5 %, every warp parked on the shared-memory store that waits for its global loads -- one exposed memory round
+// trip per stage and only 16 warps per SM to hide it.  Here one thread keeps a ring of kHeadRing stages in flight:
+// per stage one 4-D TMA box {136 px, 3 rows, 8 channels} of the source tensor (zero fill outside the image = the
+// convolution's padding) and one bulk copy of the stage's packed weights straight into their MMA layout; the 256
+// threads only re-pack the box into the nine K-major tap tiles (shared -> shared) and the tensor core reads the weights
+// from the ring slot.  One mbarrier per ring slot (bytes landed), one for "MMAs of the previous stage retired".
+// grid = (ceil(W / 128), H, B), block = 256, dynamic shared memory HeadSmemTma<NP>::bytes
+// ======================================================================================
+constexpr int kHeadRawW = 136;           // 4 + 128 + 4 pixels: the box must START on a 16-byte boundary (x0 - 4, not x0 - 1)
+                                         // and a box row must be a multiple of 32 bytes
+                                         // (528-byte rows make cp.async.bulk.tensor trap with error 715 on B200, like the
+                                         // 208-byte rows of DESIGN.md decision 6)
+constexpr int kHeadRing = 3;
+
+template <int NP>
+struct HeadSmemTma {
+    static constexpr int kRaw = kHeadChunk * 3 * kHeadRawW;            // floats per stage: [8 ch][3 rows][136 px]
+    static constexpr int kB = 9 * kHeadChunk * NP;
+    static constexpr int kATile = kHeadTM * kHeadChunk;
+    static constexpr int kA = 9 * kATile;
+    static constexpr uint32_t kStageBytes = sizeof(float) * (kRaw + kB);
+    static constexpr size_t bytes = sizeof(float) * (kHeadRing * (kRaw + kB) + kA) + 8 * (kHeadRing + 1) + 128;
+    static_assert((kRaw * 4) % 128 == 0 && (kB * 4) % 128 == 0, "ring slots stay 128-byte aligned");
+};
+
+template <int NP>
+__global__ void __launch_bounds__(kHeadThreads, 2)
+head_fused_tma_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_constant__ CUtensorMap map_oa,
+                      const __grid_constant__ CUtensorMap map_cf, const __grid_constant__ CUtensorMap map_fe,
+                      const float *__restrict__ packed, const float *__restrict__ bias, int N3, int H, int W,
+                      float *__restrict__ pred_init, float *__restrict__ guidance, float *__restrict__ confidence)
+{
+    using S = HeadSmemTma<NP>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *sRaw = reinterpret_cast<float *>(smem_raw);                  // [ring][8][3][136]
+    float *sB = sRaw + kHeadRing * S::kRaw;                             // [ring][9][NP x 8]
+    float *sA = sB + kHeadRing * S::kB;                                 // [9][128 x 8]
+    uint64_t *full = reinterpret_cast<uint64_t *>(sA + S::kA);          // [ring]
+    uint64_t *mma_bar = full + kHeadRing;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int x0 = blockIdx.x * kHeadTM, y = blockIdx.y;
+    const int b = blockIdx.z;
+    const long P = (long)H * W;
+    constexpr uint32_t kCols = NP <= 32 ? 32 : NP <= 64 ? 64 : NP <= 128 ? 128 : 256;
+    if (tid == 0) {
 #pragma unroll
-        for (int cb = 0; cb < NP; cb += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
-            if (NP - cb >= 32) {
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-                    "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
-                      "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-                      "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-            } else {     // 16 columns left (NP = 80: 32 + 32 + 16)
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-                    "%15}, [%16];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(taddr));
+        for (int i = 0; i < kHeadRing; ++i) tma::mbar_init(&full[i], 1);
+        tma::mbar_init(mma_bar, 1);
+        tma::fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma::smem_u32(&tmem_base_s)), "r"(kCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(kHeadTM >> 4) << 24);
+
+    // stage -> (source tensor, first channel); slot = stage % ring
+    auto issue = [&](int stage) {          // thread 0 only
+        const int slot = stage % kHeadRing;
+        const int s = stage / (kHeadCin / kHeadChunk), c0 = (stage % (kHeadCin / kHeadChunk)) * kHeadChunk;
+        const CUtensorMap *mp = s == 0 ? &map_id : s == 1 ? &map_oa : s == 2 ? &map_cf : &map_fe;
+        tma::mbar_arrive_expect_tx(&full[slot], S::kStageBytes);
+        tma::load_4d(sRaw + slot * S::kRaw, mp, &full[slot], x0 - 4, y - 1, c0, b);   // start column: a multiple of 16 bytes
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         tma::smem_u32(sB + slot * S::kB)), "l"(packed + (long)stage * S::kB), "r"((uint32_t)(S::kB * 4)),
+                     "r"(tma::smem_u32(&full[slot])) : "memory");
+    };
+    if (tid == 0) {
 #pragma unroll
-                for (int i = 16; i < 32; ++i) v[i] = 0u;
+        for (int i = 0; i < kHeadRing; ++i) issue(i);
+    }
+    const int m = tid & (kHeadTM - 1), j = tid >> 7;
+
+    for (int stage = 0; stage < kHeadStages; ++stage) {
+        const int slot = stage % kHeadRing;
+        if (stage >= 1) {
+            // the MMAs of the previous stage have retired: the A tiles and that stage's weight slot are free again
+            mbar_wait_bounded(mma_bar, (uint32_t)((stage - 1) & 1));
+            if (tid == 0 && stage - 1 + kHeadRing < kHeadStages) issue(stage - 1 + kHeadRing);
+        }
+        mbar_wait_bounded(&full[slot], (uint32_t)((stage / kHeadRing) & 1));
+        // ---- re-pack: thread (pixel m, k-column j) moves channels 4j .. 4j+3 of nine shifted pixels
+        const float *raw = sRaw + slot * S::kRaw + (4 * j) * 3 * kHeadRawW + m;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const float *p = raw + (tap / 3) * kHeadRawW + (tap % 3) + 3;     // box column 0 = image column x0 - 4
+            const float4 v = make_float4(p[0], p[3 * kHeadRawW], p[6 * kHeadRawW], p[9 * kHeadRawW]);
+            *reinterpret_cast<float4 *>(sA + tap * S::kATile + ((j * (kHeadTM / 8) + (m >> 3)) * 8 + (m & 7)) * 4) = v;
+        }
+        tma::fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a0 = tma::smem_u32(sA), b0 = tma::smem_u32(sB + slot * S::kB);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const uint64_t da = umma_desc_kmajor(a0 + tap * S::kATile * 4, (kHeadTM / 8) * 128, 128);
+                const uint64_t db = umma_desc_kmajor(b0 + tap * kHeadChunk * NP * 4, (NP / 8) * 128, 128);
+                const uint32_t acc = (stage | tap) != 0 ? 1u : 0u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem), "l"(da), "l"(db),
+                             "r"(idesc), "r"(acc) : "memory");
             }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (valid) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int n = cb + i;
-                    if (n >= NOUT) break;
-                    const float o = __uint_as_float(v[i]) + __ldg(bias + n);
-                    if (n == 0) pred_init[q] = fmaxf(o, 0.f);                                   // nlspnmodel.py:68 (relu)
-                    else if (n <= N3) guidance[(b * N3 + (n - 1)) * P + (long)y * W + px] = o;  // :81 (no activation)
-                    else confidence[q] = 1.f / (1.f + expf(-o));                                // :83-86 (sigmoid)
-                }
-            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             tma::smem_u32(mma_bar)) : "memory");
         }
     }
+    mbar_wait_bounded(mma_bar, (uint32_t)((kHeadStages - 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    head_epilogue<NP>(tmem, warp, tid, x0, y, b, P, N3, W, bias, pred_init, guidance, confidence);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kCols));
@@ -266,6 +396,24 @@ inline cudaError_t head_launch(const float *id_fd1, const float *oa_fd1, const f
     const dim3 grid((unsigned)((W + kHeadTM - 1) / kHeadTM), (unsigned)H, (unsigned)B);
     head_fused_kernel<NP><<<grid, kHeadThreads, HeadSmem<NP>::bytes, st>>>(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, N3, H, W,
                                                                            pred_init, guidance, confidence);
+    return cudaGetLastError();
+}
+
+template <int NP>
+inline cudaError_t head_launch_tma(const CUtensorMap &m_id, const CUtensorMap &m_oa, const CUtensorMap &m_cf,
+                                   const CUtensorMap &m_fe, const float *packed, const float *bias, int B, int H, int W,
+                                   int N3, float *pred_init, float *guidance, float *confidence, cudaStream_t st)
+{
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(head_fused_tma_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)HeadSmemTma<NP>::bytes);
+    });
+    if (attr_err != cudaSuccess) return attr_err;
+    const dim3 grid((unsigned)((W + kHeadTM - 1) / kHeadTM), (unsigned)H, (unsigned)B);
+    head_fused_tma_kernel<NP><<<grid, kHeadThreads, HeadSmemTma<NP>::bytes, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, N3, H,
+                                                                                  W, pred_init, guidance, confidence);
     return cudaGetLastError();
 }
 

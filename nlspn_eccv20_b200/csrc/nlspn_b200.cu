@@ -33,7 +33,7 @@ std::atomic<unsigned long long> g_launches{0};
 // -1 = "auto" where a default depends on the shape.
 enum Opt { kOptTiled = 0, kOptPersist, kOptPdl, kOptFwdTH, kOptParamTH, kOptStateTma, kOptStateGather,
            kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint,
-           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptCount };
+           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptHeadsTma, kOptCount };
 struct OptDef { const char *name; const char *env; int def; };
 const OptDef kOptDefs[kOptCount] = {
     {"tiled", "NLSPN_TILED", 1},
@@ -54,6 +54,7 @@ const OptDef kOptDefs[kOptCount] = {
     {"local_prefetch", "NLSPN_LOCAL_PREFETCH", 0},
     {"local_minb", "NLSPN_LOCAL_MINB", 1},      // 0 / 1 / 2 = 4 / 5 / 6 CTAs per SM
     {"sched_minb", "NLSPN_SCHED_MINB", 5},      // CTAs per SM of the schedule build (4: 0.275 ms, 5: 0.249 ms per step)
+    {"heads_tma", "NLSPN_HEADS_TMA", 1},         // head convolutions: activations by TMA ring (0: direct global loads)
 };
 std::atomic<int> g_opt[kOptCount];
 const bool g_opt_init = []() {
@@ -441,6 +442,24 @@ static int make_geometry_map(CUtensorMap *map, const float *base, int B, int C, 
     const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
     const cuuint32_t box[4] = {(cuuint32_t)kTileW, (cuuint32_t)box_h, (cuuint32_t)C, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims,
+                                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NLSPN_ERR_SHAPE, "cuTensorMapEncodeTiled(4d) failed (CUresult %d)", (int)r);
+    map_cache_put(key, *map);
+    return 0;
+}
+
+// [B, C, H, W] fp32 tensor viewed 4-D with an arbitrary box {box_w px, box_h rows, box_c channels, 1 image}
+static int make_nchw_map(CUtensorMap *map, const float *base, int B, int C, int H, int W, int box_w, int box_h, int box_c)
+{
+    const MapKey key{base, C, B, H, W, box_w, box_h, box_c, 4};
+    if (map_cache_get(key, map)) return 0;
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_c, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims,
                                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1388,10 +1407,25 @@ int nlspn_heads_fwd(const float *id_fd1, const float *oa_fd1, const float *cf_fd
     const int N3 = 3 * (K * K - 1);
     ProfScope prof__(kProfHeads, st);
     cudaError_t e;
-    switch (K) {
-    case 3: e = head_launch<head_np(3)>(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
-    case 5: e = head_launch<head_np(5)>(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
-    default: e = head_launch<head_np(7)>(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
+    // activations by TMA when the rows are 16-byte multiples (option heads_tma = 0 keeps the direct-load kernel)
+    const bool use_tma = opt(kOptHeadsTma) != 0 && tiled_ok(id_fd1, W) && aligned16(oa_fd1) && aligned16(cf_fd1) && aligned16(fe1);
+    if (use_tma) {
+        CUtensorMap m_id, m_oa, m_cf, m_fe;
+        if (int rc = make_nchw_map(&m_id, id_fd1, B, kHeadCin, H, W, kHeadRawW, 3, kHeadChunk)) return rc;
+        if (int rc = make_nchw_map(&m_oa, oa_fd1, B, kHeadCin, H, W, kHeadRawW, 3, kHeadChunk)) return rc;
+        if (int rc = make_nchw_map(&m_cf, cf_fd1, B, kHeadCin, H, W, kHeadRawW, 3, kHeadChunk)) return rc;
+        if (int rc = make_nchw_map(&m_fe, fe1, B, kHeadCin, H, W, kHeadRawW, 3, kHeadChunk)) return rc;
+        switch (K) {
+        case 3: e = head_launch_tma<head_np(3)>(m_id, m_oa, m_cf, m_fe, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
+        case 5: e = head_launch_tma<head_np(5)>(m_id, m_oa, m_cf, m_fe, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
+        default: e = head_launch_tma<head_np(7)>(m_id, m_oa, m_cf, m_fe, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
+        }
+    } else {
+        switch (K) {
+        case 3: e = head_launch<head_np(3)>(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
+        case 5: e = head_launch<head_np(5)>(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
+        default: e = head_launch<head_np(7)>(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, N3, pred_init, guidance, confidence, st); break;
+        }
     }
     if (e != cudaSuccess) return cuda_fail(e, "head_fused_kernel");
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -46,4 +46,20 @@ with torch.no_grad():
     xcl = x.contiguous(memory_format=torch.channels_last)
     c_oa_cl = c_oa.to(memory_format=torch.channels_last)
     out["conv_oa_channels_last_ms"] = timed(lambda: c_oa_cl(xcl))
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nlspn_eccv20_b200 import heads, _lib  # noqa: E402
+args = (id1, oa1, cf1, fe1, c_id.weight, c_id.bias, c_oa.weight, c_oa.bias, c_cf.weight, c_cf.bias)
+with torch.no_grad():
+    out["fused_tcgen05_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=3))
+    a = heads.fused_heads(*args, prop_kernel=3)
+    r = heads.reference_heads(*args)
+    out["max_abs_diff_vs_cudnn_tf32"] = [float((x - y).abs().max()) for x, y in zip(a, r)]
+    lib = _lib.load()
+    lib.nlspn_profile_enable(1)
+    for _ in range(5):
+        heads.fused_heads(*args, prop_kernel=3)
+    torch.cuda.synchronize()
+    out["kernel_only_ms"] = {k: v[0] / 5 for k, v in _lib.profile_read().items()}
+    lib.nlspn_profile_enable(0)
 print(json.dumps(out))
