@@ -548,6 +548,45 @@ def dcn_step_leg(torch, run, steps=10, warmup=3):
     return out
 
 
+def heads_leg(torch, dev, B, H, W, K=3, steps=10, warmup=3):
+    """the three final head convolutions (nlspnmodel.py:297,301,313) at the headline shape -- stock
+    torch (three torch.cat + three cuDNN TF32 convolutions, NCHW) vs ours (one tcgen05 implicit GEMM, heads.py)."""
+    from nlspn_eccv20_b200 import heads
+    N3 = 3 * (K * K - 1)
+    g = torch.Generator(device=dev).manual_seed(7240)
+    x = [torch.randn(B, 64, H, W, device=dev, generator=g) for _ in range(4)]
+    s = (128 * 9) ** -0.5
+    w = [s * torch.randn(n, 128, 3, 3, device=dev, generator=g) for n in (1, N3, 1)]
+    b = [0.1 * torch.randn(n, device=dev, generator=g) for n in (1, N3, 1)]
+    args = (x[0], x[1], x[2], x[3], w[0], b[0], w[1], b[1], w[2], b[2])
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    with torch.no_grad():
+        ours = timed(lambda: heads.fused_heads(*args, prop_kernel=K))
+        stock = timed(lambda: heads.reference_heads(*args))
+        o, r = heads.fused_heads(*args, prop_kernel=K), heads.reference_heads(*args)
+        diff = max(float((a - c).abs().max()) for a, c in zip(o, r))
+    flops = 2.0 * B * H * W * (128 * 9) * (N3 + 2)
+    out = {"workload": "head convolutions 128 -> 1 / %d / 1, 3x3, %dx%d B=%d, forward" % (N3, H, W, B),
+           "ours_ms": ours, "stock_torch_ms": stock, "ours_over_stock": stock / ours, "dtype": "tf32 (fp32 accumulate)",
+           "useful_tflops": flops / (ours * 1e-3) / 1e12, "max_abs_diff_vs_cudnn_tf32": diff,
+           "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)}
+    del x, w, b, args, o, r
+    torch.cuda.empty_cache()
+    return out
+
+
 def other_configs(torch, dev, lib, peaks):
     """BASELINE.json configs 1, 2, 3, 5 on this GPU (config 4 is the full model: tests/perf_config4_train_step.py)."""
     out = {}
@@ -742,6 +781,10 @@ def main():
                 line["dcn_step"] = dcn_step_leg(torch, run)
             except Exception as e:
                 line["dcn_step"] = {"error": str(e)[:200]}
+            try:
+                line["heads"] = heads_leg(torch, dev, run.B, run.H, run.W, run.K)
+            except Exception as e:
+                line["heads"] = {"error": str(e)[:200]}
         del run
         torch.cuda.empty_cache()
         if not args.no_other_configs:

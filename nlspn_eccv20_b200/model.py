@@ -145,6 +145,11 @@ class NLSPNModel(NLSPN):
         super().__init__(args, **kw)
         opt = lambda k, d: kw.get(k, getattr(args, k, d) if args is not None else d)
         self.use_GRU, self.use_S2D = bool(opt("use_GRU", False)), bool(opt("use_S2D", False))
+        # The three final head convolutions (:69-86) as ONE tcgen05 implicit GEMM (heads.py, kernels_head.cuh) instead of
+        # three torch.cat + three cuDNN convolutions.  'auto' (default): on CUDA, when the configuration has all three
+        # heads with 3N guidance channels and PyTorch's cuDNN TF32 switch is on (the kernel computes in TF32, which is
+        # what cuDNN does for these layers then); True: whenever the tensors qualify; False: always the stock layers.
+        self.fused_heads = opt("fused_heads", "auto")
         if self.use_GRU and (self.conf_mode != "premul" or self.blend != "post"):
             raise NotImplementedError("use_GRU is a fork feature: fork semantics (conf_mode='premul', blend='post') only")
         network = opt("network", "resnet34")
@@ -200,10 +205,26 @@ class NLSPNModel(NLSPN):
         fd3 = self.dec3(_crop_cat(fd4, fe4))
         fd2 = self.dec2(_crop_cat(fd3, fe3))
         trunk = _crop_cat(fd2, fe2)
+        if self._use_fused_heads(fe1):
+            from . import heads as H_
+            crop = lambda t: t[:, :, :fe1.shape[2], :fe1.shape[3]]
+            return H_.fused_heads(crop(self.id_dec1(trunk)), crop(self.off_aff_dec1(trunk)), crop(self.cf_dec1(trunk)), fe1,
+                                  self.id_dec0[0].weight, self.id_dec0[0].bias, self.off_aff_dec0[0].weight,
+                                  self.off_aff_dec0[0].bias, self.cf_dec0[0].weight, self.cf_dec0[0].bias, self.prop_kernel)
         pred_init = self.id_dec0(_crop_cat(self.id_dec1(trunk), fe1))
         guidance = self.off_aff_dec0(_crop_cat(self.off_aff_dec1(trunk), fe1))
         confidence = self.cf_dec0(_crop_cat(self.cf_dec1(trunk), fe1)) if self.conf_prop else None
         return pred_init, guidance, confidence
+
+    def _use_fused_heads(self, fe1):
+        if self.fused_heads is False or not (self.conf_prop and self.offset):
+            return False
+        ok = fe1.is_cuda and fe1.dtype == torch.float32 and fe1.shape[1] == 64
+        if self.fused_heads == "auto":
+            return ok and torch.backends.cudnn.allow_tf32
+        if not ok:
+            raise RuntimeError("fused_heads=True needs CUDA float32 tensors")
+        return True
 
     # ---- the fork's GRU mode: one native fused step per iteration ---------------------------------------
     def _normalize_affinity(self, raw):

@@ -67,3 +67,32 @@ def test_fused_heads_reject_what_they_do_not_implement():
         heads.fused_heads(x[0][:, :32], x[1], x[2], x[3], w[0], b[0], w[1], b[1], w[2], b[2], 3)
     with pytest.raises(RuntimeError):
         heads.fused_heads(x[0].cpu(), x[1], x[2], x[3], w[0], b[0], w[1], b[1], w[2], b[2], 3)
+
+
+def test_model_with_fused_heads_matches_stock_heads_and_trains():
+    """NLSPNModel(fused_heads=True) against the same weights with fused_heads=False: head outputs within TF32
+    rounding, final prediction close, and a few Adam steps reduce the loss with gradients reaching the head weights."""
+    from nlspn_eccv20_b200.model import NLSPNModel, NLSPNLoss, train_step
+    from nlspn_eccv20_b200.synth import make_inputs
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    a = NLSPNModel(network="resnet18", prop_kernel=3, prop_time=6, max_depth=10.0, fused_heads=True).to(dev).eval()
+    b = NLSPNModel(network="resnet18", prop_kernel=3, prop_time=6, max_depth=10.0, fused_heads=False).to(dev).eval()
+    b.load_state_dict(a.state_dict())
+    d = make_inputs(2, 61, 84, 3, seed=5, device=dev)
+    s = {"rgb": torch.randn(2, 3, 61, 84, device=dev), "dep": d["feat_fix"], "gt": d["gt"]}
+    with torch.no_grad():
+        ha, hb = a.heads(s["rgb"], s["dep"]), b.heads(s["rgb"], s["dep"])
+        for x, y, name in zip(ha, hb, ("pred_init", "guidance", "confidence")):
+            scale = float(y.abs().max().clamp_min(1.0))
+            assert float((x - y).abs().max()) <= 5e-3 * scale, name
+        oa, ob = a(s), b(s)
+    assert float((oa["pred"] - ob["pred"]).abs().max()) <= 5e-2           # metres, after 6 iterations of a random net
+    a.train()
+    opt = torch.optim.Adam(a.param_groups, lr=1e-3)
+    w0 = a.off_aff_dec0[0].weight.detach().clone()
+    l0, _ = train_step(a, NLSPNLoss(10.0), opt, s)
+    for _ in range(5):
+        l1, _ = train_step(a, NLSPNLoss(10.0), opt, s)
+    assert torch.isfinite(l1) and float(l1) < float(l0)
+    assert not torch.equal(w0, a.off_aff_dec0[0].weight.detach())
