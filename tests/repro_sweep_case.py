@@ -1,5 +1,5 @@
 """Re-run ONE case of tests/test_gpu_reference_cuda.py::test_randomized_sweep... and show where the raw-affinity gradient
-differs (tool).  python tools/repro_sweep_case.py CASE [--big]"""
+differs (test infrastructure: it executes oracle/).  python tests/repro_sweep_case.py CASE [--big]"""
 import os
 import random
 import sys
