@@ -572,16 +572,38 @@ def heads_leg(torch, dev, B, H, W, K=3, steps=10, warmup=3):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
+    from nlspn_eccv20_b200 import _lib as L_, functional as F_
+    from nlspn_eccv20_b200.synth import make_inputs
+    fix = make_inputs(B, H, W, K, seed=11, density=0.05, device="cpu")["feat_fix"].to(dev)
+    gamma = torch.tensor([0.5 * (K * K - 1)], device=dev)
     with torch.no_grad():
         ours = timed(lambda: heads.fused_heads(*args, prop_kernel=K))
+        with L_.options(heads_rows=0):
+            ninetap = timed(lambda: heads.fused_heads(*args, prop_kernel=K))
         stock = timed(lambda: heads.reference_heads(*args))
         o, r = heads.fused_heads(*args, prop_kernel=K), heads.reference_heads(*args)
         diff = max(float((a - c).abs().max()) for a, c in zip(o, r))
+        prologue = timed(lambda: F_.prologue_fwd(o[1], o[2], o[0], fix, gamma, K))
+        fused = timed(lambda: heads.fused_heads_prologue(*args, fix, gamma, K)) if heads.prologue_supported(W, K) else None
     flops = 2.0 * B * H * W * (128 * 9) * (N3 + 2)
+    KK = K * K
+    # algorithmic bytes: the four 64-channel inputs once; heads write 3N + 2 planes; fused: 3 KK + 4 planes + feat_fix read
+    bytes_heads = 4.0 * B * H * W * (256 + N3 + 2)
+    bytes_fused = 4.0 * B * H * W * (256 + 1 + 3 * KK + 4)
+    peak = float(measured_peaks()[0].get("hbm_gbs", 0.0))
     out = {"workload": "head convolutions 128 -> 1 / %d / 1, 3x3, %dx%d B=%d, forward" % (N3, H, W, B),
-           "ours_ms": ours, "stock_torch_ms": stock, "ours_over_stock": stock / ours, "dtype": "tf32 (fp32 accumulate)",
-           "useful_tflops": flops / (ours * 1e-3) / 1e12, "max_abs_diff_vs_cudnn_tf32": diff,
-           "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)}
+           "ours_ms": ours, "ours_ninetap_form_ms": ninetap, "stock_torch_ms": stock, "ours_over_stock": stock / ours,
+           "dtype": "tf32 (fp32 accumulate)", "useful_tflops": flops / (ours * 1e-3) / 1e12,
+           "hbm_gbs": bytes_heads / (ours * 1e-3) / 1e9, "alg_bytes": bytes_heads,
+           "max_abs_diff_vs_cudnn_tf32": diff, "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+           "prologue_ms": prologue, "heads_plus_prologue_ms": ours + prologue,
+           "stock_heads_plus_prologue_ms": stock + prologue,
+           "fused_heads_prologue_ms": fused,
+           "fused_hbm_gbs": (bytes_fused / (fused * 1e-3) / 1e9) if fused else None}
+    if peak > 0:
+        out["hbm_frac"] = out["hbm_gbs"] / peak
+        if fused:
+            out["fused_hbm_frac"] = out["fused_hbm_gbs"] / peak
     del x, w, b, args, o, r
     torch.cuda.empty_cache()
     return out

@@ -259,7 +259,8 @@ NLSPN_API int nlspn_step_bwd(const float *src_prev, const float *offset, const f
  *     off_aff    = off_aff_dec0(cat(off_aff_fd1, fe1))      3x3 conv 128 -> 3N, no activation   ("guidance")
  *     confidence = cf_dec0     (cat(cf_fd1,      fe1))      3x3 conv 128 -> 1,  Sigmoid
  * by ONE tcgen05 (kind::tf32, fp32 accumulation in tensor memory) implicit GEMM that reads the four 64-channel
- * NCHW tensors where they lie (no concatenation).  TF32 is what cuDNN computes these layers in under PyTorch's
+ * NCHW tensors where they lie (no concatenation; for K = 3, 5 and W % 4 == 0 as MN-major operands straight from TMA
+ * boxes, kernels_head2.cuh).  TF32 is what cuDNN computes these layers in under PyTorch's
  * default torch.backends.cudnn.allow_tf32 = True.
  *   nlspn_heads_packed_floats(K)  floats of the packed weight matrix
  *   nlspn_heads_pack              packs w_id [1,128,3,3], w_oa [3N,128,3,3], w_cf [1,128,3,3] (device pointers;
@@ -272,6 +273,20 @@ NLSPN_API int nlspn_heads_pack(const float *w_id, const float *w_oa, const float
 NLSPN_API int nlspn_heads_fwd(const float *id_fd1, const float *oa_fd1, const float *cf_fd1, const float *fe1,
                               const float *packed, const float *bias, int B, int H, int W, int K,
                               float *pred_init, float *guidance, float *confidence, void *stream);
+
+/* The same GEMM with the propagation's prologue as its epilogue: `guidance` never reaches HBM (pass NULL), the
+ * kernel writes what nlspn_prologue_fwd would have written from it -- offset [B,2K^2,H,W], aff [B,K^2,H,W],
+ * conf_fixed [B,1,H,W] (NULL = no confidence propagation), src0 [B,1,H,W] -- next to pred_init and confidence
+ * (nlspnmodel.py:297-313 followed by :252-269,179-201,328-351); continue with nlspn_propagate_fwd.  A non-NULL
+ * `guidance` is written as well (a training step needs it for the backward).  flags: PRESERVE_INPUT (needs
+ * feat_fix), ALWAYS_CLIP.  Implemented for K = 3, 5 and W % 4 == 0 (nlspn_heads_prologue_supported); anything else
+ * returns NLSPN_ERR_SHAPE / NLSPN_ERR_DOMAIN and the caller uses nlspn_heads_fwd + nlspn_prologue_fwd. */
+NLSPN_API int nlspn_heads_prologue_supported(int W, int K);
+NLSPN_API int nlspn_heads_prologue_fwd(const float *id_fd1, const float *oa_fd1, const float *cf_fd1, const float *fe1,
+                                       const float *packed, const float *bias, const float *feat_fix, const float *gamma,
+                                       int affinity, unsigned flags, int B, int H, int W, int K,
+                                       float *pred_init, float *confidence, float *guidance,
+                                       float *offset, float *aff, float *conf_fixed, float *src0, void *stream);
 
 /* Double-precision variants of the single-step operator: the reference dispatches this op over
  * float and double (AT_DISPATCH_FLOATING_TYPES, modulated_deform_conv_cuda.cu:93,224) and its

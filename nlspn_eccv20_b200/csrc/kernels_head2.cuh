@@ -1,0 +1,355 @@
+// kernels_head2.cuh -- the three head convolutions as a tcgen05 GEMM WITHOUT any re-packing of the activations, and
+// with the propagation's prologue as its epilogue (first half; sm_100a only).
+//
+// kernels_head.cuh stages nine tap-shifted copies of every activation tile (K-major): ncu showed it bound by
+// shared-memory bandwidth (72 KB of re-pack traffic + 45 KB of operand reads per 128 pixels x 8 channels), 4.6 ms at
+// KITTI B = 8.  Here the activations are used as they lie in NCHW -- pixels contiguous = an MN-major A operand:
+//
+//   * one TMA box {32 px, 8 channels, R + 2 rows} (dims ordered x, channel, row, image; CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+//     IS a column of MMA atoms: tf32 MN-major operands take exactly one shared-memory layout, SWIZZLE_128B_BASE32B
+//     (32 px x 4 channels per atom; LBO = bytes between the four 32-pixel boxes of a tile, SBO = 512 = the second
+//     group of four channels).  Four boxes = 128 pixels = M.  tools/umma_mn_probe.cu pins all of this on the GPU.
+//   * a row shift (dy) is a descriptor start address (+1024 bytes per row).  A column shift (dx) would be a 4-byte
+//     shift, which no descriptor can express -- so it is moved to the OUTPUT side: the weights of the three dx taps
+//     sit side by side in N (accumulator column 3 n + dx), the MMA runs on the unshifted tile, and the epilogue forms
+//     D[px][n] = E[px - 1][3n] + E[px][3n + 1] + E[px + 1][3n + 2] with two warp shuffles.  A tile therefore loads
+//     128 pixels and produces the 120 in the middle (x tiles step by 120, a multiple of four pixels because TMA box
+//     starts must be 16-byte aligned); zero fill outside the image is the convolution's padding.
+//   * per output pixel the tensor core reads 3 KB of activations (three dy) instead of 9 KB, nothing is re-packed,
+//     and the block sparsity of the weights is used: the 64-channel branches of the init / confidence heads only feed
+//     one output each, so their MMAs are N = 16 instead of N = NW.
+//   * R output rows per CTA (R accumulators side by side in TMEM, R * NW <= 256 columns, two CTAs per SM) share
+//     R + 2 input rows; one thread runs the whole pipeline (TMA ring of three stages -> MMAs -> commit), the other
+//     127 sleep at the CTA barrier until the accumulators are complete.
+//   * epilogue: bias, relu / sigmoid, and -- when the caller passes the prologue's outputs -- _off_insert,
+//     _affinity_normalization, _aff_insert, the confidence fix-up and the first blend + pre-multiply
+//     (nlspnmodel.py:252-269,179-201,328-351; same expressions as prologue_fwd_kernel), so that `guidance` never
+//     reaches HBM (it is still written when the caller asks for it: training needs it for the backward).
+#pragma once
+#include "kernels_head.cuh"
+#include "kernels_v1.cuh"      // flag / affinity constants, blend_fix
+
+namespace nlspn {
+
+template <int K>
+struct HeadRows {
+    static constexpr int KK = K * K, N = KK - 1, N3 = 3 * N, NOUT = N3 + 2, REF = N / 2;
+    static constexpr int NW = (3 * NOUT + 15) / 16 * 16;          // accumulator columns per output row
+    static constexpr int R = 256 / NW >= 3 ? 3 : 256 / NW;        // output rows per CTA (K = 3: 3, K = 5: 1)
+    static constexpr int ROWS = R + 2;
+    static constexpr int CF_BASE = (3 * (NOUT - 1)) / 16 * 16;    // first column of the confidence head's narrow MMA
+    static constexpr int A_BOX = ROWS * 1024, A_BYTES = 4 * A_BOX;
+    static constexpr int B_WIDE = 3 * NW * 32, B_NARROW = 3 * 16 * 32;     // bytes per stage: [dy][N x 8 tf32]
+    static constexpr int B_SLOT = (B_WIDE + 1023) / 1024 * 1024;
+    static constexpr int SLOT = A_BYTES + B_SLOT;
+    static constexpr int RING = 3;
+    static constexpr int TILE_OUT = 120;
+    static constexpr int STAGES = 32, WIDE_STAGES = 16;           // (fe1, oa) x 8 chunks wide, (id, cf) x 8 chunks narrow
+    static constexpr size_t smem = (size_t)RING * SLOT + 1024;
+    static constexpr long packed_floats = (long)WIDE_STAGES * (B_WIDE + B_NARROW) / 4;
+    static_assert(R >= 1 && R * NW <= 256 && NW <= 256, "accumulators must fit 256 TMEM columns");
+    static_assert(3 * (NOUT - 1) + 2 < CF_BASE + 16, "the confidence columns must fit one N = 16 MMA");
+    static_assert(2 * smem <= 225 * 1024, "two CTAs per SM");
+};
+
+// stage -> source tensor: 0..7 fe1 (shared, feeds every output), 8..15 off_aff branch, 16..23 init branch, 24..31
+// confidence branch.  The first stage must be a wide one (it initialises all accumulator columns).
+__host__ __device__ constexpr int head_rows_source(int stage) { return stage < 8 ? 3 : stage < 16 ? 1 : stage < 24 ? 0 : 2; }
+
+// Packs w_id [1,128,3,3], w_oa [3N,128,3,3], w_cf [1,128,3,3] into the per-stage B blocks: [dy][k-column 2][Ns / 8][8][4]
+// (K-major un-swizzled core matrices, as kernels_head.cuh), column 3 n + dx of output n (0 = init, 1..3N = off_aff,
+// 3N + 1 = confidence); channels 0..63 of a head = its own branch, 64..127 = fe1 (torch.cat((x_fd1, fe1), 1)).
+template <int K>
+__global__ void head_rows_pack_kernel(const float *__restrict__ w_id, const float *__restrict__ w_oa,
+                                      const float *__restrict__ w_cf, float *__restrict__ packed)
+{
+    using C = HeadRows<K>;
+    constexpr long kWideFloats = (long)C::WIDE_STAGES * C::B_WIDE / 4;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < C::packed_floats; i += (long)gridDim.x * blockDim.x) {
+        const bool wide = i < kWideFloats;
+        const long li = wide ? i : i - kWideFloats;
+        const int ns = wide ? C::NW : 16;
+        const int per_stage = 3 * ns * 8;
+        const int stage = (int)(li / per_stage) + (wide ? 0 : C::WIDE_STAGES);
+        int t = (int)(li % per_stage);
+        const int kk = t % 4; t /= 4;
+        const int nr = t % 8; t /= 8;
+        const int ng = t % (ns / 8); t /= (ns / 8);
+        const int j = t % 2; t /= 2;
+        const int dy = t;
+        const int s = head_rows_source(stage);
+        const int col = ng * 8 + nr + (wide ? 0 : (s == 2 ? C::CF_BASE : 0));
+        const int n = col / 3, dx = col % 3;
+        const int c = (stage % 8) * 8 + j * 4 + kk;
+        const int cin = s == 3 ? kHeadCin + c : c;
+        const int tap = dy * 3 + dx;
+        float v = 0.f;
+        if (n == 0) {
+            if (s == 0 || s == 3) v = w_id[(long)cin * 9 + tap];
+        } else if (n <= C::N3) {
+            if (s == 1 || s == 3) v = w_oa[((long)(n - 1) * 2 * kHeadCin + cin) * 9 + tap];
+        } else if (n == C::N3 + 1) {
+            if (s == 2 || s == 3) v = w_cf[(long)cin * 9 + tap];
+        }
+        packed[i] = v;
+    }
+}
+
+// MN-major tf32 operand: layout type 1 = SWIZZLE_128B_BASE32B
+__device__ __forceinline__ uint64_t umma_desc_mn_tf32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return umma_desc_kmajor(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)1 << 61);
+}
+
+struct HeadRowsOut {
+    float *pred_init, *confidence, *guidance;        // head outputs; guidance may be NULL when the prologue is fused
+    // fused prologue (all NULL = heads only)
+    const float *feat_fix, *gamma;
+    float *offset, *aff, *conf_fixed, *src0;
+    int affinity;
+    unsigned flags;
+};
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_load_cols(uint32_t taddr, uint32_t (&v)[48])
+{
+#pragma unroll
+    for (int c = 0; c < NCOLS; c += 16)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(v[c + 0]), "=r"(v[c + 1]), "=r"(v[c + 2]), "=r"(v[c + 3]), "=r"(v[c + 4]), "=r"(v[c + 5]),
+                       "=r"(v[c + 6]), "=r"(v[c + 7]), "=r"(v[c + 8]), "=r"(v[c + 9]), "=r"(v[c + 10]), "=r"(v[c + 11]),
+                       "=r"(v[c + 12]), "=r"(v[c + 13]), "=r"(v[c + 14]), "=r"(v[c + 15])
+                     : "r"(taddr + (uint32_t)c));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// grid = (ceil(W / 120), ceil(H / R), B), block = 128, dynamic shared memory HeadRows<K>::smem
+template <int K>
+__global__ void __launch_bounds__(128, 2)
+head_rows_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_constant__ CUtensorMap map_oa,
+                 const __grid_constant__ CUtensorMap map_cf, const __grid_constant__ CUtensorMap map_fe,
+                 const float *__restrict__ packed, const float *__restrict__ bias, int H, int W, HeadRowsOut o)
+{
+    using C = HeadRows<K>;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[C::RING], empty[C::RING];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float xch[2][4][C::R][C::NOUT];      // [0]: column 3n of lane 31, [1]: column 3n + 2 of lane 0, per warp
+    const uint32_t ring = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int x0 = blockIdx.x * C::TILE_OUT - 4, y0 = blockIdx.y * C::R;
+    const int b = blockIdx.z;
+    const long P = (long)H * W;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < C::RING; ++i) {
+            tma::mbar_init(&full[i], 1);
+            tma::mbar_init(&empty[i], 1);
+        }
+        tma::fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma::smem_u32(&tmem_base_s)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+
+    if (tid == 0) {
+        // D fp32, A = B = TF32, A MN-major (bit 15), B K-major, N >> 3 at bit 17, M >> 4 at bit 24
+        constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t kIdescWide = kIdescBase | ((uint32_t)(C::NW >> 3) << 17);
+        constexpr uint32_t kIdescNarrow = kIdescBase | ((uint32_t)(16 >> 3) << 17);
+        auto issue = [&](int st) {
+            const int slot = st % C::RING;
+            const int s = head_rows_source(st), c0 = (st & 7) * 8;
+            const CUtensorMap *mp = s == 0 ? &map_id : s == 1 ? &map_oa : s == 2 ? &map_cf : &map_fe;
+            const bool wide = st < C::WIDE_STAGES;
+            const uint32_t sa = ring + slot * C::SLOT, sb = sa + C::A_BYTES;
+            const uint32_t bbytes = wide ? C::B_WIDE : C::B_NARROW;
+            const float *wsrc = packed + (wide ? (long)st * (C::B_WIDE / 4)
+                                               : (long)C::WIDE_STAGES * (C::B_WIDE / 4) + (long)(st - C::WIDE_STAGES) * (C::B_NARROW / 4));
+            tma::mbar_arrive_expect_tx(&full[slot], C::A_BYTES + bbytes);
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                    ::"r"(sa + w * C::A_BOX), "l"(reinterpret_cast<uint64_t>(mp)), "r"(tma::smem_u32(&full[slot])),
+                    "r"(x0 + 32 * w), "r"(c0), "r"(y0 - 1), "r"(b) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb),
+                         "l"(wsrc), "r"(bbytes), "r"(tma::smem_u32(&full[slot])) : "memory");
+        };
+#pragma unroll
+        for (int i = 0; i < C::RING; ++i) issue(i);
+        for (int st = 0; st < C::STAGES; ++st) {
+            const int slot = st % C::RING;
+            mbar_wait_bounded(&full[slot], (uint32_t)((st / C::RING) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool wide = st < C::WIDE_STAGES;
+            const uint32_t ns = wide ? C::NW : 16;
+            const uint32_t idesc = wide ? kIdescWide : kIdescNarrow;
+            const uint32_t dcol = wide ? 0u : (head_rows_source(st) == 2 ? (uint32_t)C::CF_BASE : 0u);
+            const uint32_t sa = ring + slot * C::SLOT, sb = sa + C::A_BYTES;
+#pragma unroll
+            for (int r = 0; r < C::R; ++r) {
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const uint64_t da = umma_desc_mn_tf32(sa + (r + dy) * 1024, C::A_BOX, 512);
+                    const uint64_t db = umma_desc_kmajor(sb + dy * ns * 32, (ns / 8) * 128, 128);
+                    const uint32_t acc = (st | dy) != 0 ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem + r * C::NW + dcol),
+                                 "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                }
+            }
+            // the barrier completes when every MMA issued so far has retired (also with its shared-memory reads)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             tma::smem_u32(&empty[slot])) : "memory");
+            // refill the slot of the PREVIOUS stage: its MMAs retire while this stage's are queued behind them
+            if (st >= 1 && st - 1 + C::RING < C::STAGES) {
+                mbar_wait_bounded(&empty[(st - 1) % C::RING], (uint32_t)(((st - 1) / C::RING) & 1));
+                issue(st - 1 + C::RING);
+            }
+        }
+        mbar_wait_bounded(&empty[(C::STAGES - 1) % C::RING], (uint32_t)(((C::STAGES - 1) / C::RING) & 1));
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---------------- epilogue: lane = pixel x0 + tid; TMEM lane = tid
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    constexpr int kChunks = (C::NW + 47) / 48;
+    // pass 1: the columns the neighbouring warps need from this warp's edge lanes
+#pragma unroll
+    for (int r = 0; r < C::R; ++r) {
+#pragma unroll
+        for (int q = 0; q < kChunks; ++q) {
+            uint32_t e[48];
+            constexpr int kTail = C::NW - 48 * (kChunks - 1);
+            if (q + 1 < kChunks) tmem_load_cols<48>(tlane + r * C::NW + q * 48, e);
+            else tmem_load_cols<kTail>(tlane + r * C::NW + q * 48, e);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int n = q * 16 + i;
+                if (n < C::NOUT) {
+                    if (lane == 31) xch[0][warp][r][n] = __uint_as_float(e[3 * i]);
+                    if (lane == 0) xch[1][warp][r][n] = __uint_as_float(e[3 * i + 2]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int px = x0 + tid;
+    const bool lane_out = tid >= 4 && tid < 4 + C::TILE_OUT && px < W;
+    const bool fused = o.aff != nullptr;
+    const bool preserve = fused && (o.flags & kPreserve) != 0;
+    const float gamma = fused ? __ldg(o.gamma) : 1.f;
+#pragma unroll 1
+    for (int r = 0; r < C::R; ++r) {
+        const int y = y0 + r;
+        float d[C::NOUT];
+#pragma unroll
+        for (int q = 0; q < kChunks; ++q) {
+            uint32_t e[48];
+            constexpr int kTail = C::NW - 48 * (kChunks - 1);
+            if (q + 1 < kChunks) tmem_load_cols<48>(tlane + r * C::NW + q * 48, e);
+            else tmem_load_cols<kTail>(tlane + r * C::NW + q * 48, e);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int n = q * 16 + i;
+                if (n < C::NOUT) {
+                    float left = __shfl_up_sync(0xffffffffu, __uint_as_float(e[3 * i]), 1);
+                    float right = __shfl_down_sync(0xffffffffu, __uint_as_float(e[3 * i + 2]), 1);
+                    if (lane == 0) left = warp > 0 ? xch[0][warp - 1][r][n] : 0.f;
+                    if (lane == 31) right = warp < 3 ? xch[1][warp + 1][r][n] : 0.f;
+                    d[n] = ((__uint_as_float(e[3 * i + 1]) + left) + right) + __ldg(bias + n);
+                }
+            }
+        }
+        if (!lane_out || y >= H) continue;
+        const long q = (long)b * P + (long)y * W + px;
+        const float init = fmaxf(d[0], 0.f);                                   // nlspnmodel.py:68 (relu)
+        const float conf = 1.f / (1.f + expf(-d[C::N3 + 1]));                  // :83-86 (sigmoid)
+        o.pred_init[q] = init;
+        o.confidence[q] = conf;
+        if (o.guidance) {
+            float *gp = o.guidance + (long)b * C::N3 * P + (long)y * W + px;   // :81 (no activation)
+#pragma unroll
+            for (int n = 0; n < C::N3; ++n) gp[(long)n * P] = d[1 + n];
+        }
+        if (!fused) continue;
+        // ---- the propagation's prologue (same expressions as prologue_fwd_kernel, kernels_v1.cuh)
+        const float dep = preserve ? __ldg(o.feat_fix + q) : 0.f;
+        float *ob = o.offset + (long)b * 2 * C::KK * P + (long)y * W + px;
+        float *ab = o.aff + (long)b * C::KK * P + (long)y * W + px;
+#pragma unroll
+        for (int t = 0; t < C::KK; ++t) {
+            if (t == C::REF) {
+                ob[(long)(2 * t) * P] = 0.f;
+                ob[(long)(2 * t + 1) * P] = 0.f;
+            } else {
+                const int n = t < C::REF ? t : t - 1;
+                ob[(long)(2 * t) * P] = d[1 + 2 * n];
+                ob[(long)(2 * t + 1) * P] = d[1 + 2 * n + 1];
+            }
+        }
+        float a[C::N];
+        float abs_sum = 0.f;
+        const bool use_tanh = o.affinity == kTC || o.affinity == kTGASS;
+        const float g = o.affinity == kTGASS ? gamma + 1e-8f : gamma;
+#pragma unroll
+        for (int n = 0; n < C::N; ++n) {
+            float v = d[1 + 2 * C::N + n];
+            if (use_tanh) v = tanhf(v) / g;
+            a[n] = v;
+            abs_sum += fabsf(v);
+        }
+        abs_sum += 1e-4f;
+        if ((o.affinity == kASS || o.affinity == kTGASS) && abs_sum < 1.0f) abs_sum = 1.0f;
+        float sum = 0.f;
+#pragma unroll
+        for (int n = 0; n < C::N; ++n) {
+            if (o.affinity != kTC) a[n] = a[n] / abs_sum;
+            sum += a[n];
+        }
+#pragma unroll
+        for (int t = 0; t < C::KK; ++t) ab[(long)t * P] = t == C::REF ? 1.0f - sum : a[t < C::REF ? t : t - 1];
+        float x = init, c = conf;
+        if (preserve) x = blend_fix(x, dep);
+        if (o.flags & kAlwaysClip) x = fmaxf(x, 0.f);
+        if (o.conf_fixed) {
+            if (preserve) {
+                const float m = dep > 0.f ? 1.f : 0.f;
+                c = (1.0f - m) * c + m;
+            }
+            o.conf_fixed[q] = c;
+            x = x * c;
+        }
+        o.src0[q] = x;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
+}
+
+template <int K>
+inline cudaError_t head_rows_launch(const CUtensorMap &m_id, const CUtensorMap &m_oa, const CUtensorMap &m_cf,
+                                    const CUtensorMap &m_fe, const float *packed, const float *bias, int B, int H, int W,
+                                    const HeadRowsOut &o, cudaStream_t st)
+{
+    using C = HeadRows<K>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(head_rows_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem);
+    });
+    if (attr_err != cudaSuccess) return attr_err;
+    const dim3 grid((unsigned)((W + C::TILE_OUT - 1) / C::TILE_OUT), (unsigned)((H + C::R - 1) / C::R), (unsigned)B);
+    head_rows_kernel<K><<<grid, 128, C::smem, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, H, W, o);
+    return cudaGetLastError();
+}
+
+} // namespace nlspn

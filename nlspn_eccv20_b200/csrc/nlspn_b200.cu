@@ -20,6 +20,7 @@
 #include "kernels_local.cuh"
 #include "kernels_det.cuh"
 #include "kernels_head.cuh"
+#include "kernels_head2.cuh"
 
 using namespace nlspn;
 
@@ -33,7 +34,7 @@ std::atomic<unsigned long long> g_launches{0};
 // -1 = "auto" where a default depends on the shape.
 enum Opt { kOptTiled = 0, kOptPersist, kOptPdl, kOptFwdTH, kOptParamTH, kOptStateTma, kOptStateGather,
            kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint,
-           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptHeadsTma, kOptCount };
+           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptHeadsTma, kOptHeadsRows, kOptCount };
 struct OptDef { const char *name; const char *env; int def; };
 const OptDef kOptDefs[kOptCount] = {
     {"tiled", "NLSPN_TILED", 1},
@@ -55,6 +56,7 @@ const OptDef kOptDefs[kOptCount] = {
     {"local_minb", "NLSPN_LOCAL_MINB", 1},      // 0 / 1 / 2 = 4 / 5 / 6 CTAs per SM
     {"sched_minb", "NLSPN_SCHED_MINB", 5},      // CTAs per SM of the schedule build (4: 0.275 ms, 5: 0.249 ms per step)
     {"heads_tma", "NLSPN_HEADS_TMA", 1},         // head convolutions: activations by TMA ring (0: direct global loads)
+    {"heads_rows", "NLSPN_HEADS_ROWS", 1},       // head convolutions: MN-major operand form (kernels_head2.cuh; K = 3, 5, W % 4 == 0)
 };
 std::atomic<int> g_opt[kOptCount];
 const bool g_opt_init = []() {
@@ -466,6 +468,25 @@ static int make_nchw_map(CUtensorMap *map, const float *base, int B, int C, int 
                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(NLSPN_ERR_SHAPE, "cuTensorMapEncodeTiled(4d) failed (CUresult %d)", (int)r);
+    map_cache_put(key, *map);
+    return 0;
+}
+
+// [B, 64, H, W] fp32 tensor with the dims ordered (x, channel, row, image) and a box {32 px, 8 channels, rows, 1}
+// in the 128-byte swizzle with 32-byte atoms: the box is a column of MN-major tf32 MMA atoms (kernels_head2.cuh)
+static int make_head_rows_map(CUtensorMap *map, const float *base, int B, int H, int W, int rows)
+{
+    const MapKey key{base, kHeadCin, B, H, W, 32, rows, 8, 14};
+    if (map_cache_get(key, map)) return 0;
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)kHeadCin, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)H * W * 4, (cuuint64_t)W * 4, (cuuint64_t)kHeadCin * H * W * 4};
+    const cuuint32_t box[4] = {32, 8, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims,
+                                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NLSPN_ERR_SHAPE, "cuTensorMapEncodeTiled(head rows) failed (CUresult %d)", (int)r);
     map_cache_put(key, *map);
     return 0;
 }
@@ -1378,11 +1399,14 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
     return 0;
 }
 
-// ---- the three final head convolutions as one tcgen05 implicit GEMM (kernels_head.cuh) ----
+// ---- the three final head convolutions as one tcgen05 implicit GEMM (kernels_head.cuh, kernels_head2.cuh) ----
+// `packed` = [K-major nine-tap blocks of kernels_head.cuh | per-stage blocks of kernels_head2.cuh (K = 3, 5)]
+static long head_rows_packed_floats(int K) { return K == 3 ? HeadRows<3>::packed_floats : K == 5 ? HeadRows<5>::packed_floats : 0; }
+
 size_t nlspn_heads_packed_floats(int K)
 {
     if (K != 3 && K != 5 && K != 7) return 0;
-    return (size_t)head_packed_floats(K);
+    return (size_t)(head_packed_floats(K) + head_rows_packed_floats(K));
 }
 
 int nlspn_heads_pack(const float *w_id, const float *w_oa, const float *w_cf, int K, float *packed, void *stream)
@@ -1391,6 +1415,35 @@ int nlspn_heads_pack(const float *w_id, const float *w_oa, const float *w_cf, in
     if (!w_id || !w_oa || !w_cf || !packed) return fail(NLSPN_ERR_NULL, "heads_pack: a required pointer is NULL");
     head_pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w_id, w_oa, w_cf, 3 * (K * K - 1), head_np(K), packed);
     NLSPN_CHECK_LAUNCH("head_pack_weights_kernel");
+    float *rows = packed + head_packed_floats(K);
+    if (K == 3) head_rows_pack_kernel<3><<<64, 256, 0, (cudaStream_t)stream>>>(w_id, w_oa, w_cf, rows);
+    else if (K == 5) head_rows_pack_kernel<5><<<64, 256, 0, (cudaStream_t)stream>>>(w_id, w_oa, w_cf, rows);
+    NLSPN_CHECK_LAUNCH("head_rows_pack_kernel");
+    return 0;
+}
+
+// the MN-major operand form applies: K = 3 or 5, rows that are 16-byte multiples, 16-byte aligned tensors
+static bool head_rows_ok(const float *id_fd1, const float *oa_fd1, const float *cf_fd1, const float *fe1, int W, int K)
+{
+    return opt(kOptHeadsRows) != 0 && (K == 3 || K == 5) && tiled_ok(id_fd1, W) && aligned16(oa_fd1) && aligned16(cf_fd1) &&
+           aligned16(fe1);
+}
+
+static int launch_head_rows(const float *id_fd1, const float *oa_fd1, const float *cf_fd1, const float *fe1,
+                            const float *packed, const float *bias, int B, int H, int W, int K, const HeadRowsOut &o,
+                            cudaStream_t st)
+{
+    const int rows = (K == 3 ? HeadRows<3>::ROWS : HeadRows<5>::ROWS);
+    CUtensorMap m_id, m_oa, m_cf, m_fe;
+    if (int rc = make_head_rows_map(&m_id, id_fd1, B, H, W, rows)) return rc;
+    if (int rc = make_head_rows_map(&m_oa, oa_fd1, B, H, W, rows)) return rc;
+    if (int rc = make_head_rows_map(&m_cf, cf_fd1, B, H, W, rows)) return rc;
+    if (int rc = make_head_rows_map(&m_fe, fe1, B, H, W, rows)) return rc;
+    const float *rows_packed = packed + head_packed_floats(K);
+    const cudaError_t e = K == 3 ? head_rows_launch<3>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, o, st)
+                                 : head_rows_launch<5>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, o, st);
+    if (e != cudaSuccess) return cuda_fail(e, "head_rows_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
@@ -1406,6 +1459,10 @@ int nlspn_heads_fwd(const float *id_fd1, const float *oa_fd1, const float *cf_fd
     cudaStream_t st = (cudaStream_t)stream;
     const int N3 = 3 * (K * K - 1);
     ProfScope prof__(kProfHeads, st);
+    if (head_rows_ok(id_fd1, oa_fd1, cf_fd1, fe1, W, K)) {
+        HeadRowsOut o{pred_init, confidence, guidance, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0u};
+        return launch_head_rows(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, K, o, st);
+    }
     cudaError_t e;
     // activations by TMA when the rows are 16-byte multiples (option heads_tma = 0 keeps the direct-load kernel)
     const bool use_tma = opt(kOptHeadsTma) != 0 && tiled_ok(id_fd1, W) && aligned16(oa_fd1) && aligned16(cf_fd1) && aligned16(fe1);
@@ -1430,6 +1487,36 @@ int nlspn_heads_fwd(const float *id_fd1, const float *oa_fd1, const float *cf_fd
     if (e != cudaSuccess) return cuda_fail(e, "head_fused_kernel");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
+}
+
+int nlspn_heads_prologue_supported(int W, int K)
+{
+    return opt(kOptHeadsRows) != 0 && (K == 3 || K == 5) && W % 4 == 0 && tiled_enabled() ? 1 : 0;
+}
+
+int nlspn_heads_prologue_fwd(const float *id_fd1, const float *oa_fd1, const float *cf_fd1, const float *fe1,
+                             const float *packed, const float *bias, const float *feat_fix, const float *gamma,
+                             int affinity, unsigned flags, int B, int H, int W, int K,
+                             float *pred_init, float *confidence, float *guidance,
+                             float *offset, float *aff, float *conf_fixed, float *src0, void *stream)
+{
+    if (int rc = check_shape(B, H, W, K, 1)) return rc;
+    if (!id_fd1 || !oa_fd1 || !cf_fd1 || !fe1 || !packed || !bias || !gamma || !pred_init || !confidence || !offset || !aff || !src0)
+        return fail(NLSPN_ERR_NULL, "heads_prologue_fwd: a required pointer is NULL");
+    if (affinity < 0 || affinity > 3) return fail(NLSPN_ERR_AFFINITY, "heads_prologue_fwd: unknown affinity mode %d", affinity);
+    if (flags & ~(unsigned)(NLSPN_FLAG_PRESERVE_INPUT | NLSPN_FLAG_ALWAYS_CLIP))
+        return fail(NLSPN_ERR_DOMAIN, "heads_prologue_fwd: only PRESERVE_INPUT and ALWAYS_CLIP are implemented in the fused epilogue (flags 0x%x)", flags);
+    if ((flags & NLSPN_FLAG_PRESERVE_INPUT) && !feat_fix)
+        return fail(NLSPN_ERR_NULL, "heads_prologue_fwd: PRESERVE_INPUT needs feat_fix");
+    if (H > 65535) return fail(NLSPN_ERR_SHAPE, "heads_prologue_fwd: H > 65535 is not supported (got %d)", H);
+    if (!aligned16(packed)) return fail(NLSPN_ERR_ALIGN, "heads_prologue_fwd: the packed weights must be 16-byte aligned");
+    if (!head_rows_ok(id_fd1, oa_fd1, cf_fd1, fe1, W, K))
+        return fail(NLSPN_ERR_SHAPE, "heads_prologue_fwd: needs prop_kernel 3 or 5, W %% 4 == 0 and 16-byte aligned tensors "
+                                     "(got K = %d, W = %d): call nlspn_heads_fwd + nlspn_prologue_fwd instead", K, W);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof__(kProfHeads, st);
+    HeadRowsOut o{pred_init, confidence, guidance, feat_fix, gamma, offset, aff, conf_fixed, src0, affinity, flags};
+    return launch_head_rows(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, K, o, st);
 }
 
 static int check_dcn_domain(int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h,

@@ -20,7 +20,7 @@ from torch.nn import functional as TF
 
 from . import _lib
 
-__all__ = ["fused_heads", "FusedHeadsFunction", "supported"]
+__all__ = ["fused_heads", "fused_heads_prologue", "prologue_supported", "FusedHeadsFunction", "supported"]
 
 CIN = 64       # channels of each of the four tensors (64 + 64 = the reference's 128-channel concatenations)
 
@@ -35,9 +35,9 @@ def supported(id_fd1, oa_fd1, cf_fd1, fe1, K) -> bool:
         and all(t.shape == fe1.shape for t in ts) and K in (3, 5, 7)
 
 
-def _forward(id_fd1, oa_fd1, cf_fd1, fe1, w_id, b_id, w_oa, b_oa, w_cf, b_cf, K):
+def _prepare(id_fd1, oa_fd1, cf_fd1, fe1, w_id, b_id, w_oa, b_oa, w_cf, b_cf, K):
+    """Validation + the packed weight matrix and the bias vector of one call (on the current stream)."""
     lib = _lib.load()
-    B, C, H, W = fe1.shape
     N3 = 3 * (K * K - 1)
     if not supported(id_fd1, oa_fd1, cf_fd1, fe1, K):
         raise RuntimeError("fused_heads: four CUDA float32 [B,64,H,W] tensors and prop_kernel in (3, 5, 7) are required")
@@ -47,13 +47,66 @@ def _forward(id_fd1, oa_fd1, cf_fd1, fe1, w_id, b_id, w_oa, b_oa, w_cf, b_cf, K)
     ins = [t.contiguous() for t in (id_fd1, oa_fd1, cf_fd1, fe1)]
     packed = torch.empty((lib.nlspn_heads_packed_floats(K),), device=dev, dtype=torch.float32)
     bias = torch.cat([b_id.reshape(1), b_oa.reshape(-1), b_cf.reshape(1)]).to(dev, torch.float32).contiguous()
-    pred_init = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
-    guidance = torch.empty((B, N3, H, W), device=dev, dtype=torch.float32)
-    confidence = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
     st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     with torch.cuda.device(dev):
         _lib.check(lib.nlspn_heads_pack(_ptr(w_id.contiguous()), _ptr(w_oa.contiguous()), _ptr(w_cf.contiguous()), K,
                                         _ptr(packed), st), "nlspn_heads_pack")
+    return lib, ins, packed, bias, st
+
+
+def prologue_supported(W, K) -> bool:
+    """Can the head GEMM run the propagation's prologue as its epilogue for this width / prop_kernel?"""
+    return bool(_lib.load().nlspn_heads_prologue_supported(int(W), int(K)))
+
+
+def fused_heads_prologue(id_fd1, oa_fd1, cf_fd1, fe1, w_id, b_id, w_oa, b_oa, w_cf, b_cf, feat_fix, gamma, prop_kernel=3,
+                         affinity="TGASS", preserve_input=True, always_clip=False, conf_prop=True, src0=None,
+                         want_guidance=False):
+    """Heads + prologue in ONE kernel (nlspn_heads_prologue_fwd; inference -- no autograd): the 3N-channel `guidance`
+    tensor never reaches HBM unless ``want_guidance``.  Replaces nlspnmodel.py:297-313 followed by :252-269, :179-201,
+    :328-351.  -> dict(pred_init, confidence, guidance|None, offset, aff, conf_fixed|None, src0); continue with
+    ``functional.propagate_fwd``.  ``src0``: optional [B,1,H,W] view to write the first gather source into (plane 0
+    of the propagation's ``src`` buffer)."""
+    K = int(prop_kernel)
+    lib, ins, packed, bias, st = _prepare(id_fd1.detach(), oa_fd1.detach(), cf_fd1.detach(), fe1.detach(), w_id.detach(),
+                                          b_id.detach(), w_oa.detach(), b_oa.detach(), w_cf.detach(), b_cf.detach(), K)
+    B, C, H, W = fe1.shape
+    N3 = 3 * (K * K - 1)
+    dev = fe1.device
+    opt = dict(device=dev, dtype=torch.float32)
+    preserve = bool(preserve_input and feat_fix is not None)
+    if feat_fix is not None:
+        if not (feat_fix.is_cuda and feat_fix.dtype == torch.float32 and tuple(feat_fix.shape) == (B, 1, H, W)):
+            raise RuntimeError("fused_heads_prologue: feat_fix must be a CUDA float32 [B,1,H,W] tensor")
+        feat_fix = feat_fix.detach().contiguous()
+    gam = gamma.detach().reshape(-1)[:1].to(device=dev, dtype=torch.float32).contiguous() if torch.is_tensor(gamma) \
+        else torch.full((1,), float(gamma), **opt)
+    out = dict(pred_init=torch.empty((B, 1, H, W), **opt), confidence=torch.empty((B, 1, H, W), **opt),
+               guidance=torch.empty((B, N3, H, W), **opt) if want_guidance else None,
+               offset=torch.empty((B, 2 * K * K, H, W), **opt), aff=torch.empty((B, K * K, H, W), **opt),
+               conf_fixed=torch.empty((B, 1, H, W), **opt) if conf_prop else None,
+               src0=torch.empty((B, 1, H, W), **opt) if src0 is None else src0)
+    if not (out["src0"].is_cuda and out["src0"].is_contiguous() and tuple(out["src0"].shape) == (B, 1, H, W)):
+        raise RuntimeError("fused_heads_prologue: src0 must be a contiguous CUDA [B,1,H,W] tensor")
+    flags = (_lib.FLAG_PRESERVE_INPUT if preserve else 0) | (_lib.FLAG_ALWAYS_CLIP if always_clip else 0)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nlspn_heads_prologue_fwd(_ptr(ins[0]), _ptr(ins[1]), _ptr(ins[2]), _ptr(ins[3]), _ptr(packed), _ptr(bias),
+                                                _ptr(feat_fix if preserve else None), _ptr(gam), _lib.AFFINITY[affinity], flags,
+                                                B, H, W, K, _ptr(out["pred_init"]), _ptr(out["confidence"]), _ptr(out["guidance"]),
+                                                _ptr(out["offset"]), _ptr(out["aff"]), _ptr(out["conf_fixed"]), _ptr(out["src0"]), st),
+                   "nlspn_heads_prologue_fwd")
+    return out
+
+
+def _forward(id_fd1, oa_fd1, cf_fd1, fe1, w_id, b_id, w_oa, b_oa, w_cf, b_cf, K):
+    lib, ins, packed, bias, st = _prepare(id_fd1, oa_fd1, cf_fd1, fe1, w_id, b_id, w_oa, b_oa, w_cf, b_cf, K)
+    B, C, H, W = fe1.shape
+    N3 = 3 * (K * K - 1)
+    dev = fe1.device
+    pred_init = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+    guidance = torch.empty((B, N3, H, W), device=dev, dtype=torch.float32)
+    confidence = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
         _lib.check(lib.nlspn_heads_fwd(_ptr(ins[0]), _ptr(ins[1]), _ptr(ins[2]), _ptr(ins[3]), _ptr(packed), _ptr(bias),
                                        B, H, W, K, _ptr(pred_init), _ptr(guidance), _ptr(confidence), st),
                    "nlspn_heads_fwd")

@@ -150,6 +150,9 @@ class NLSPNModel(NLSPN):
         # heads with 3N guidance channels and PyTorch's cuDNN TF32 switch is on (the kernel computes in TF32, which is
         # what cuDNN does for these layers then); True: whenever the tensors qualify; False: always the stock layers.
         self.fused_heads = opt("fused_heads", "auto")
+        # ... and, when no backward can follow (torch.no_grad / eval inference), with the propagation's prologue as that
+        # GEMM's epilogue: the 3N-channel guidance tensor is never written (heads.fused_heads_prologue).  False: never.
+        self.fused_prologue = opt("fused_prologue", "auto")
         if self.use_GRU and (self.conf_mode != "premul" or self.blend != "post"):
             raise NotImplementedError("use_GRU is a fork feature: fork semantics (conf_mode='premul', blend='post') only")
         network = opt("network", "resnet34")
@@ -194,9 +197,11 @@ class NLSPNModel(NLSPN):
         self.param_groups = [{"params": [p for p in self.parameters() if p.requires_grad],
                               "lr": float(opt("lr", 1e-3))}]
 
-    def heads(self, rgb, dep):
+    def heads(self, rgb, dep, _defer_heads=False):
         """Encoder-decoder up to the three head outputs (nlspnmodel.py:271-315):
-        -> (pred_init [B,1,H,W], guidance [B,3N,H,W] (or [B,N,H,W] without offsets), confidence|None)."""
+        -> (pred_init [B,1,H,W], guidance [B,3N,H,W] (or [B,N,H,W] without offsets), confidence|None).
+        ``_defer_heads``: return the head GEMM's arguments instead of running it (forward() fuses it with the
+        propagation's prologue), or None when the fused heads do not apply."""
         fe1 = torch.cat((self.conv1_rgb(rgb), self.S2D(dep) if self.use_S2D else self.conv1_dep(dep)), 1)
         fe2 = self.conv2(fe1)
         fe3 = self.conv3(fe2)
@@ -208,9 +213,14 @@ class NLSPNModel(NLSPN):
         if self._use_fused_heads(fe1):
             from . import heads as H_
             crop = lambda t: t[:, :, :fe1.shape[2], :fe1.shape[3]]
-            return H_.fused_heads(crop(self.id_dec1(trunk)), crop(self.off_aff_dec1(trunk)), crop(self.cf_dec1(trunk)), fe1,
-                                  self.id_dec0[0].weight, self.id_dec0[0].bias, self.off_aff_dec0[0].weight,
-                                  self.off_aff_dec0[0].bias, self.cf_dec0[0].weight, self.cf_dec0[0].bias, self.prop_kernel)
+            head_in = (crop(self.id_dec1(trunk)), crop(self.off_aff_dec1(trunk)), crop(self.cf_dec1(trunk)), fe1,
+                       self.id_dec0[0].weight, self.id_dec0[0].bias, self.off_aff_dec0[0].weight,
+                       self.off_aff_dec0[0].bias, self.cf_dec0[0].weight, self.cf_dec0[0].bias)
+            if _defer_heads:
+                return head_in
+            return H_.fused_heads(*head_in, self.prop_kernel)
+        if _defer_heads:
+            return None
         pred_init = self.id_dec0(_crop_cat(self.id_dec1(trunk), fe1))
         guidance = self.off_aff_dec0(_crop_cat(self.off_aff_dec1(trunk), fe1))
         confidence = self.cf_dec0(_crop_cat(self.cf_dec1(trunk), fe1)) if self.conf_prop else None
@@ -225,6 +235,40 @@ class NLSPNModel(NLSPN):
         if not ok:
             raise RuntimeError("fused_heads=True needs CUDA float32 tensors")
         return True
+
+    # ---- inference: heads + prologue in one kernel, `guidance` never materialised ------------------------
+    def _use_fused_prologue(self, rgb):
+        """The head GEMM can run the prologue as its epilogue when no backward will follow (the backward re-derives the
+        normalisation from `guidance`), in the fork's default semantics, for K = 3, 5 and W % 4 == 0."""
+        if self.fused_prologue is False or self.fused_heads is False or self.use_GRU or torch.is_grad_enabled():
+            return False
+        if not (self.conf_prop and self.offset and self.conf_mode == "premul" and self.blend == "post"):
+            return False
+        if not (rgb.is_cuda and rgb.dtype == torch.float32):
+            return False
+        if self.fused_heads == "auto" and not torch.backends.cudnn.allow_tf32:
+            return False
+        from . import heads as H_
+        return H_.prologue_supported(rgb.shape[3], self.prop_kernel)
+
+    def _forward_fused_prologue(self, rgb, dep):
+        from . import heads as H_, functional as F_
+        head_in = self.heads(rgb, dep, _defer_heads=True)
+        if head_in is None:
+            return None
+        B, _, H, W = head_in[3].shape
+        T, K = self.prop_time, self.prop_kernel
+        fix = dep if self.preserve_input else None
+        src = torch.empty((min(T, 2), B, 1, H, W), device=rgb.device, dtype=torch.float32)
+        list_feat = torch.empty((T, B, 1, H, W), device=rgb.device, dtype=torch.float32)
+        o = H_.fused_heads_prologue(*head_in, fix, self.aff_scale_const, K, self.affinity, self.preserve_input,
+                                    self.always_clip, conf_prop=True, src0=src[0])
+        F_.propagate_fwd(o["offset"], o["aff"], o["conf_fixed"], fix, src, list_feat, K, T, self.preserve_input, self.always_clip)
+        list_feat = [list_feat[t] for t in range(T)]
+        feat_result = list_feat[-1]
+        pred = feat_result if self.always_clip else torch.clamp(feat_result, min=0)      # :375-377
+        return {"pred": pred, "pred_init": o["pred_init"], "pred_inter": list_feat, "offset": o["offset"], "aff": o["aff"],
+                "gamma": self.aff_scale_const.data, "confidence": o["conf_fixed"]}
 
     # ---- the fork's GRU mode: one native fused step per iteration ---------------------------------------
     def _normalize_affinity(self, raw):
@@ -304,6 +348,10 @@ class NLSPNModel(NLSPN):
 
     def forward(self, sample):
         rgb, dep = sample["rgb"], sample["dep"]
+        if self._use_fused_prologue(rgb):
+            out = self._forward_fused_prologue(rgb, dep)
+            if out is not None:
+                return out
         pred_init, guidance, confidence = self.heads(rgb, dep)
         if self.use_GRU:
             return self._forward_gru(pred_init, guidance, confidence, dep)

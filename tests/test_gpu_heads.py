@@ -96,3 +96,94 @@ def test_model_with_fused_heads_matches_stock_heads_and_trains():
         l1, _ = train_step(a, NLSPNLoss(10.0), opt, s)
     assert torch.isfinite(l1) and float(l1) < float(l0)
     assert not torch.equal(w0, a.off_aff_dec0[0].weight.detach())
+
+
+@pytest.mark.parametrize("B,H,W,K", [(1, 7, 1216, 3), (2, 10, 120, 3), (1, 5, 124, 3), (1, 8, 244, 3), (2, 3, 4, 3),
+                                     (1, 6, 360, 5), (1, 4, 128, 5)])
+def test_rows_form_matches_the_ninetap_form(B, H, W, K):
+    """kernels_head2.cuh (MN-major operands straight from TMA boxes, dx taps on the output side, 120-pixel tiles) against
+    kernels_head.cuh (nine re-packed tap tiles) and the fp32 layers: tile seams (W = 120, 124, 244), the last partial
+    tile, rows that are not a multiple of the row group, the KITTI width."""
+    from nlspn_eccv20_b200 import heads, _lib
+    dev = torch.device("cuda:0")
+    x, w, b = _case(B, H, W, K, 300 + W, dev)
+    args = (x[0], x[1], x[2], x[3], w[0], b[0], w[1], b[1], w[2], b[2], K)
+    assert _lib.get_option("heads_rows") == 1
+    rows = heads.fused_heads(*args)
+    with _lib.options(heads_rows=0):
+        nine = heads.fused_heads(*args)
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        ref32 = heads.reference_heads(*args[:-1])
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    for o, n, r, name in zip(rows, nine, ref32, ("pred_init", "guidance", "confidence")):
+        scale = float(r.abs().max().clamp_min(1.0))
+        assert float((o - r).abs().max()) <= 4e-3 * scale, name
+        assert float((o - n).abs().max()) <= 2e-3 * scale, name       # same TF32 products, another summation order
+
+
+@pytest.mark.parametrize("affinity,preserve,clip,conf", [("TGASS", True, False, True), ("AS", False, True, True),
+                                                         ("TC", True, True, False), ("ASS", True, False, True)])
+@pytest.mark.parametrize("B,H,W,K", [(2, 37, 132, 3), (1, 20, 300, 5)])
+def test_fused_prologue_equals_heads_then_prologue(affinity, preserve, clip, conf, B, H, W, K):
+    """nlspn_heads_prologue_fwd (the prologue as the GEMM's epilogue) against the same GEMM followed by
+    nlspn_prologue_fwd on the materialised guidance: offsets bit-identical, the rest to the last bit or two (the same
+    expressions compiled into another kernel); with and without writing guidance."""
+    from nlspn_eccv20_b200 import heads, functional as F_
+    from nlspn_eccv20_b200.synth import make_inputs
+    dev = torch.device("cuda:0")
+    x, w, b = _case(B, H, W, K, 500 + K, dev)
+    fix = make_inputs(B, H, W, K, seed=9, device=dev)["feat_fix"]
+    gamma = torch.tensor([0.5 * (K * K - 1)], device=dev)
+    args = (x[0], x[1], x[2], x[3], w[0], b[0], w[1], b[1], w[2], b[2])
+    p, g, c = heads.fused_heads(*args, K)
+    off, aff, cfix, src0 = F_.prologue_fwd(g, c if conf else None, p, fix if preserve else None, gamma, K, affinity, preserve, clip)
+    for want in (True, False):
+        o = heads.fused_heads_prologue(*args, fix if preserve else None, gamma, K, affinity, preserve, clip, conf_prop=conf,
+                                       want_guidance=want)
+        assert torch.equal(o["pred_init"], p) and torch.equal(o["confidence"], c)
+        assert (o["guidance"] is None) != want
+        if want:
+            assert torch.equal(o["guidance"], g)
+        assert torch.equal(o["offset"], off)
+        assert float((o["aff"] - aff).abs().max()) <= 2e-7
+        assert float((o["src0"] - src0).abs().max()) <= 1e-6 * float(src0.abs().max().clamp_min(1.0))
+        if conf:
+            assert float((o["conf_fixed"] - cfix).abs().max()) <= 2e-7
+        else:
+            assert o["conf_fixed"] is None and cfix is None
+
+
+def test_fused_prologue_rejects_what_it_does_not_implement():
+    from nlspn_eccv20_b200 import heads
+    dev = torch.device("cuda:0")
+    x, w, b = _case(1, 8, 18, 3, 1, dev)           # W % 4 != 0
+    assert not heads.prologue_supported(18, 3) and not heads.prologue_supported(16, 7) and heads.prologue_supported(16, 3)
+    with pytest.raises(RuntimeError):
+        heads.fused_heads_prologue(x[0], x[1], x[2], x[3], w[0], b[0], w[1], b[1], w[2], b[2], None, 4.0, 3)
+
+
+def test_model_inference_with_the_prologue_fused_into_the_heads():
+    """NLSPNModel under torch.no_grad(): heads + prologue as one kernel (fused_prologue='auto') against the same model
+    with fused_prologue=False (heads kernel, then the propagation's own prologue)."""
+    from nlspn_eccv20_b200.model import NLSPNModel
+    from nlspn_eccv20_b200.synth import make_inputs
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    a = NLSPNModel(network="resnet18", prop_kernel=3, prop_time=6, max_depth=10.0, fused_heads=True).to(dev).eval()
+    d = make_inputs(2, 60, 84, 3, seed=6, device=dev)
+    s = {"rgb": torch.randn(2, 3, 60, 84, device=dev), "dep": d["feat_fix"]}
+    with torch.no_grad():
+        assert a._use_fused_prologue(s["rgb"])
+        oa = a(s)
+        a.fused_prologue = False
+        assert not a._use_fused_prologue(s["rgb"])
+        ob = a(s)
+    for k in ("pred", "pred_init", "offset", "aff", "confidence"):
+        assert oa[k].shape == ob[k].shape, k
+        assert float((oa[k] - ob[k]).abs().max()) <= 1e-5 * float(ob[k].abs().max().clamp_min(1.0)), k
+    assert len(oa["pred_inter"]) == len(ob["pred_inter"]) == 6
+    a.fused_prologue = "auto"
+    assert not a._use_fused_prologue(s["rgb"])            # grad mode: a backward may follow, guidance is needed
