@@ -19,8 +19,8 @@
 //     and the block sparsity of the weights is used: the 64-channel branches of the init / confidence heads only feed
 //     one output each, so their MMAs are N = 16 instead of N = NW.
 //   * R output rows per CTA (R accumulators side by side in TMEM, R * NW <= 256 columns, two CTAs per SM) share
-//     R + 2 input rows; one thread runs the whole pipeline (TMA ring of three stages -> MMAs -> commit), the other
-//     127 sleep at the CTA barrier until the accumulators are complete.
+//     R + 2 input rows; warp 0 feeds a ring of TMA stages, warp 1 issues the MMAs (one elected lane each, the warps
+//     stay converged), the other two sleep at the CTA barrier until the accumulators are complete.
 //   * epilogue: bias, relu / sigmoid, and -- when the caller passes the prologue's outputs -- _off_insert,
 //     _affinity_normalization, _aff_insert, the confidence fix-up and the first blend + pre-multiply
 //     (nlspnmodel.py:252-269,179-201,328-351; same expressions as prologue_fwd_kernel), so that `guidance` never
@@ -31,7 +31,7 @@
 
 namespace nlspn {
 
-template <int K>
+template <int K, int RING_ = 0>
 struct HeadRows {
     static constexpr int KK = K * K, N = KK - 1, N3 = 3 * N, NOUT = N3 + 2, REF = N / 2;
     static constexpr int NW = (3 * NOUT + 15) / 16 * 16;          // accumulator columns per output row
@@ -40,16 +40,18 @@ struct HeadRows {
     static constexpr int CF_BASE = (3 * (NOUT - 1)) / 16 * 16;    // first column of the confidence head's narrow MMA
     static constexpr int A_BOX = ROWS * 1024, A_BYTES = 4 * A_BOX;
     static constexpr int B_WIDE = 3 * NW * 32, B_NARROW = 3 * 16 * 32;     // bytes per stage: [dy][N x 8 tf32]
-    static constexpr int B_SLOT = (B_WIDE + 1023) / 1024 * 1024;
-    static constexpr int SLOT = A_BYTES + B_SLOT;
-    static constexpr int RING = 3;
+    static constexpr int B_SLOT = B_WIDE;                         // multiple of 128 bytes
+    // ring depth: the kernel is bound by bytes in flight (ncu: DRAM 32 %, L2 42 %, tensor pipe 39 %, no unit busy), so
+    // take the deepest ring that still lets two CTAs share an SM (228 KB minus 1 KB reserved per CTA)
+    static constexpr int RING = RING_ > 0 ? RING_ : ((4 * (A_BYTES + B_SLOT) + 1024 + 1024 + 256) * 2 <= 228 * 1024 ? 4 : 3);
     static constexpr int TILE_OUT = 120;
     static constexpr int STAGES = 32, WIDE_STAGES = 16;           // (fe1, oa) x 8 chunks wide, (id, cf) x 8 chunks narrow
-    static constexpr size_t smem = (size_t)RING * SLOT + 1024;
+    static constexpr size_t smem = (size_t)RING * (A_BYTES + B_SLOT) + 1024;      // [RING A slots][RING B slots] + alignment slack
     static constexpr long packed_floats = (long)WIDE_STAGES * (B_WIDE + B_NARROW) / 4;
     static_assert(R >= 1 && R * NW <= 256 && NW <= 256, "accumulators must fit 256 TMEM columns");
     static_assert(3 * (NOUT - 1) + 2 < CF_BASE + 16, "the confidence columns must fit one N = 16 MMA");
-    static_assert(2 * smem <= 225 * 1024, "two CTAs per SM");
+    static_assert(2 * (smem + 1024 + 256) <= 228 * 1024, "two CTAs per SM");
+    static_assert(B_SLOT % 128 == 0 && (size_t)2 * 4 * R * NOUT * 4 <= (size_t)RING * A_BYTES, "exchange buffer aliases the ring");
 };
 
 // stage -> source tensor: 0..7 fe1 (shared, feeds every output), 8..15 off_aff branch, 16..23 init branch, 24..31
@@ -101,6 +103,14 @@ __device__ __forceinline__ uint64_t umma_desc_mn_tf32(uint32_t saddr, uint32_t l
     return umma_desc_kmajor(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)1 << 61);
 }
 
+// one lane of a converged warp (cute::elect_one_sync)
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 struct HeadRowsOut {
     float *pred_init, *confidence, *guidance;        // head outputs; guidance may be NULL when the prologue is fused
     // fused prologue (all NULL = heads only)
@@ -124,18 +134,20 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, uint32_t (&v)[48]
 }
 
 // grid = (ceil(W / 120), ceil(H / R), B), block = 128, dynamic shared memory HeadRows<K>::smem
-template <int K>
+template <int K, int RING_>
 __global__ void __launch_bounds__(128, 2)
 head_rows_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_constant__ CUtensorMap map_oa,
                  const __grid_constant__ CUtensorMap map_cf, const __grid_constant__ CUtensorMap map_fe,
                  const float *__restrict__ packed, const float *__restrict__ bias, int H, int W, HeadRowsOut o)
 {
-    using C = HeadRows<K>;
+    using C = HeadRows<K, RING_>;
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[C::RING], empty[C::RING];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float xch[2][4][C::R][C::NOUT];      // [0]: column 3n of lane 31, [1]: column 3n + 2 of lane 0, per warp
-    const uint32_t ring = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;       // [RING][A_BYTES] then [RING][B_SLOT]
+    // the epilogue's exchange buffer aliases the ring (free once the last MMA has retired):
+    // [0]: column 3n of lane 31, [1]: column 3n + 2 of lane 0, per warp
+    float (*xch)[4][C::R][C::NOUT] = reinterpret_cast<float (*)[4][C::R][C::NOUT]>(smem_raw + (ring - tma::smem_u32(smem_raw)));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int x0 = blockIdx.x * C::TILE_OUT - 4, y0 = blockIdx.y * C::R;
     const int b = blockIdx.z;
@@ -157,32 +169,39 @@ head_rows_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    if (tid == 0) {
+    // Warp-specialised main loop.  Warp 0 = TMA producer, warp 1 = MMA issuer; both run CONVERGED (all 32 lanes carry the
+    // same loop state, one elected lane issues): a loop inside `if (tid == 0)` is a divergent region in which every
+    // tcgen05 / TMA instruction gets a uniform-register waterfall (ELECT / PLOP3 / BRA.U.ANY per instruction; ncu: the
+    // issuing thread spent 90 % of the main loop in those sequences, 1.43 ms per call at KITTI B = 8).
+    if (warp == 0) {
+        for (int st = 0; st < C::STAGES; ++st) {
+            const int slot = st % C::RING;
+            if (st >= C::RING) mbar_wait_bounded(&empty[slot], (uint32_t)((st / C::RING - 1) & 1));   // its MMAs have retired
+            const int s = head_rows_source(st), c0 = (st & 7) * 8;
+            const CUtensorMap *mp = s == 0 ? &map_id : s == 1 ? &map_oa : s == 2 ? &map_cf : &map_fe;
+            const bool wide = st < C::WIDE_STAGES;
+            const uint32_t sa = ring + slot * C::A_BYTES, sb = ring + C::RING * C::A_BYTES + slot * C::B_SLOT;
+            const uint32_t bbytes = wide ? C::B_WIDE : C::B_NARROW;
+            const float *wsrc = packed + (wide ? (long)st * (C::B_WIDE / 4)
+                                               : (long)C::WIDE_STAGES * (C::B_WIDE / 4) + (long)(st - C::WIDE_STAGES) * (C::B_NARROW / 4));
+            if (elect_one_sync()) {
+                tma::mbar_arrive_expect_tx(&full[slot], C::A_BYTES + bbytes);
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    asm volatile(
+                        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                        ::"r"(sa + w * C::A_BOX), "l"(reinterpret_cast<uint64_t>(mp)), "r"(tma::smem_u32(&full[slot])),
+                        "r"(x0 + 32 * w), "r"(c0), "r"(y0 - 1), "r"(b) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb),
+                             "l"(wsrc), "r"(bbytes), "r"(tma::smem_u32(&full[slot])) : "memory");
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
         // D fp32, A = B = TF32, A MN-major (bit 15), B K-major, N >> 3 at bit 17, M >> 4 at bit 24
         constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(128 >> 4) << 24);
         constexpr uint32_t kIdescWide = kIdescBase | ((uint32_t)(C::NW >> 3) << 17);
         constexpr uint32_t kIdescNarrow = kIdescBase | ((uint32_t)(16 >> 3) << 17);
-        auto issue = [&](int st) {
-            const int slot = st % C::RING;
-            const int s = head_rows_source(st), c0 = (st & 7) * 8;
-            const CUtensorMap *mp = s == 0 ? &map_id : s == 1 ? &map_oa : s == 2 ? &map_cf : &map_fe;
-            const bool wide = st < C::WIDE_STAGES;
-            const uint32_t sa = ring + slot * C::SLOT, sb = sa + C::A_BYTES;
-            const uint32_t bbytes = wide ? C::B_WIDE : C::B_NARROW;
-            const float *wsrc = packed + (wide ? (long)st * (C::B_WIDE / 4)
-                                               : (long)C::WIDE_STAGES * (C::B_WIDE / 4) + (long)(st - C::WIDE_STAGES) * (C::B_NARROW / 4));
-            tma::mbar_arrive_expect_tx(&full[slot], C::A_BYTES + bbytes);
-#pragma unroll
-            for (int w = 0; w < 4; ++w)
-                asm volatile(
-                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                    ::"r"(sa + w * C::A_BOX), "l"(reinterpret_cast<uint64_t>(mp)), "r"(tma::smem_u32(&full[slot])),
-                    "r"(x0 + 32 * w), "r"(c0), "r"(y0 - 1), "r"(b) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb),
-                         "l"(wsrc), "r"(bbytes), "r"(tma::smem_u32(&full[slot])) : "memory");
-        };
-#pragma unroll
-        for (int i = 0; i < C::RING; ++i) issue(i);
         for (int st = 0; st < C::STAGES; ++st) {
             const int slot = st % C::RING;
             mbar_wait_bounded(&full[slot], (uint32_t)((st / C::RING) & 1));
@@ -191,27 +210,25 @@ head_rows_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_consta
             const uint32_t ns = wide ? C::NW : 16;
             const uint32_t idesc = wide ? kIdescWide : kIdescNarrow;
             const uint32_t dcol = wide ? 0u : (head_rows_source(st) == 2 ? (uint32_t)C::CF_BASE : 0u);
-            const uint32_t sa = ring + slot * C::SLOT, sb = sa + C::A_BYTES;
+            const uint32_t sa = ring + slot * C::A_BYTES, sb = ring + C::RING * C::A_BYTES + slot * C::B_SLOT;
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int r = 0; r < C::R; ++r) {
+                for (int r = 0; r < C::R; ++r) {
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    const uint64_t da = umma_desc_mn_tf32(sa + (r + dy) * 1024, C::A_BOX, 512);
-                    const uint64_t db = umma_desc_kmajor(sb + dy * ns * 32, (ns / 8) * 128, 128);
-                    const uint32_t acc = (st | dy) != 0 ? 1u : 0u;
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem + r * C::NW + dcol),
-                                 "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint64_t da = umma_desc_mn_tf32(sa + (r + dy) * 1024, C::A_BOX, 512);
+                        const uint64_t db = umma_desc_kmajor(sb + dy * ns * 32, (ns / 8) * 128, 128);
+                        const uint32_t acc = (st | dy) != 0 ? 1u : 0u;
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem + r * C::NW + dcol),
+                                     "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                    }
                 }
+                // the barrier completes when every MMA issued so far has retired (also with its shared-memory reads)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 tma::smem_u32(&empty[slot])) : "memory");
             }
-            // the barrier completes when every MMA issued so far has retired (also with its shared-memory reads)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                             tma::smem_u32(&empty[slot])) : "memory");
-            // refill the slot of the PREVIOUS stage: its MMAs retire while this stage's are queued behind them
-            if (st >= 1 && st - 1 + C::RING < C::STAGES) {
-                mbar_wait_bounded(&empty[(st - 1) % C::RING], (uint32_t)(((st - 1) / C::RING) & 1));
-                issue(st - 1 + C::RING);
-            }
+            __syncwarp();
         }
         mbar_wait_bounded(&empty[(C::STAGES - 1) % C::RING], (uint32_t)(((C::STAGES - 1) / C::RING) & 1));
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -335,20 +352,20 @@ head_rows_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_consta
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
 }
 
-template <int K>
+template <int K, int RING_ = 0>
 inline cudaError_t head_rows_launch(const CUtensorMap &m_id, const CUtensorMap &m_oa, const CUtensorMap &m_cf,
                                     const CUtensorMap &m_fe, const float *packed, const float *bias, int B, int H, int W,
                                     const HeadRowsOut &o, cudaStream_t st)
 {
-    using C = HeadRows<K>;
+    using C = HeadRows<K, RING_>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(head_rows_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem);
+        attr_err = cudaFuncSetAttribute(head_rows_kernel<K, RING_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem);
     });
     if (attr_err != cudaSuccess) return attr_err;
     const dim3 grid((unsigned)((W + C::TILE_OUT - 1) / C::TILE_OUT), (unsigned)((H + C::R - 1) / C::R), (unsigned)B);
-    head_rows_kernel<K><<<grid, 128, C::smem, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, H, W, o);
+    head_rows_kernel<K, RING_><<<grid, 128, C::smem, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, H, W, o);
     return cudaGetLastError();
 }
 
