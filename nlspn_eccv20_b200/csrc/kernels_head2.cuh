@@ -133,6 +133,128 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, uint32_t (&v)[48]
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+struct HeadRowsPixel { int x0, y0, b, H, W; long P; };
+
+// Epilogue, part 1: what the neighbouring warps need from this warp's edge lanes.  `tq` = TMEM address of the
+// accumulator set with this warp's lane quarter `quarter`; xch[0][quarter][r][n] = column 3n of lane 31,
+// xch[1][quarter][r][n] = column 3n + 2 of lane 0.
+template <class C>
+__device__ __forceinline__ void head_rows_edge_columns(uint32_t tq, int quarter, int lane, int r,
+                                                       float (*xch)[4][C::R][C::NOUT])
+{
+    constexpr int kChunks = (C::NW + 47) / 48;
+    constexpr int kTail = C::NW - 48 * (kChunks - 1);
+#pragma unroll
+    for (int q = 0; q < kChunks; ++q) {
+        uint32_t e[48];
+        if (q + 1 < kChunks) tmem_load_cols<48>(tq + r * C::NW + q * 48, e);
+        else tmem_load_cols<kTail>(tq + r * C::NW + q * 48, e);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int n = q * 16 + i;
+            if (n < C::NOUT) {
+                if (lane == 31) xch[0][quarter][r][n] = __uint_as_float(e[3 * i]);
+                if (lane == 0) xch[1][quarter][r][n] = __uint_as_float(e[3 * i + 2]);
+            }
+        }
+    }
+}
+
+// Epilogue, part 2: output row r of the tile.  D[px][n] = E[px - 1][3n] + E[px][3n + 1] + E[px + 1][3n + 2] + bias, the
+// activations, and (fused) the propagation's prologue for that pixel.
+template <class C>
+__device__ __forceinline__ void head_rows_finish_row(uint32_t tq, int quarter, int lane, int r,
+                                                     float (*xch)[4][C::R][C::NOUT], const HeadRowsPixel &t,
+                                                     const float *__restrict__ bias, const HeadRowsOut &o, float gamma)
+{
+    constexpr int kChunks = (C::NW + 47) / 48;
+    constexpr int kTail = C::NW - 48 * (kChunks - 1);
+    const int tl = quarter * 32 + lane;                 // lane of the 128-pixel tile
+    const int px = t.x0 + tl, y = t.y0 + r;
+    const int W = t.W;
+    const long P = t.P;
+    const bool fused = o.aff != nullptr;
+    const bool preserve = fused && (o.flags & kPreserve) != 0;
+    float d[C::NOUT];
+#pragma unroll
+    for (int q = 0; q < kChunks; ++q) {
+        uint32_t e[48];
+        if (q + 1 < kChunks) tmem_load_cols<48>(tq + r * C::NW + q * 48, e);
+        else tmem_load_cols<kTail>(tq + r * C::NW + q * 48, e);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int n = q * 16 + i;
+            if (n < C::NOUT) {
+                float left = __shfl_up_sync(0xffffffffu, __uint_as_float(e[3 * i]), 1);
+                float right = __shfl_down_sync(0xffffffffu, __uint_as_float(e[3 * i + 2]), 1);
+                if (lane == 0) left = quarter > 0 ? xch[0][quarter - 1][r][n] : 0.f;
+                if (lane == 31) right = quarter < 3 ? xch[1][quarter + 1][r][n] : 0.f;
+                d[n] = ((__uint_as_float(e[3 * i + 1]) + left) + right) + __ldg(bias + n);
+            }
+        }
+    }
+    if (!(tl >= 4 && tl < 4 + C::TILE_OUT && px < W) || y >= t.H) return;
+    const long q = (long)t.b * P + (long)y * W + px;
+    const float init = fmaxf(d[0], 0.f);                                   // nlspnmodel.py:68 (relu)
+    const float conf = 1.f / (1.f + expf(-d[C::N3 + 1]));                  // :83-86 (sigmoid)
+    o.pred_init[q] = init;
+    o.confidence[q] = conf;
+    if (o.guidance) {
+        float *gp = o.guidance + (long)t.b * C::N3 * P + (long)y * W + px;   // :81 (no activation)
+#pragma unroll
+        for (int n = 0; n < C::N3; ++n) gp[(long)n * P] = d[1 + n];
+    }
+    if (!fused) return;
+    // ---- the propagation's prologue (same expressions as prologue_fwd_kernel, kernels_v1.cuh)
+    const float dep = preserve ? __ldg(o.feat_fix + q) : 0.f;
+    float *ob = o.offset + (long)t.b * 2 * C::KK * P + (long)y * W + px;
+    float *ab = o.aff + (long)t.b * C::KK * P + (long)y * W + px;
+#pragma unroll
+    for (int tp = 0; tp < C::KK; ++tp) {
+        if (tp == C::REF) {
+            ob[(long)(2 * tp) * P] = 0.f;
+            ob[(long)(2 * tp + 1) * P] = 0.f;
+        } else {
+            const int n = tp < C::REF ? tp : tp - 1;
+            ob[(long)(2 * tp) * P] = d[1 + 2 * n];
+            ob[(long)(2 * tp + 1) * P] = d[1 + 2 * n + 1];
+        }
+    }
+    float a[C::N];
+    float abs_sum = 0.f;
+    const bool use_tanh = o.affinity == kTC || o.affinity == kTGASS;
+    const float g = o.affinity == kTGASS ? gamma + 1e-8f : gamma;
+#pragma unroll
+    for (int n = 0; n < C::N; ++n) {
+        float v = d[1 + 2 * C::N + n];
+        if (use_tanh) v = tanhf(v) / g;
+        a[n] = v;
+        abs_sum += fabsf(v);
+    }
+    abs_sum += 1e-4f;
+    if ((o.affinity == kASS || o.affinity == kTGASS) && abs_sum < 1.0f) abs_sum = 1.0f;
+    float sum = 0.f;
+#pragma unroll
+    for (int n = 0; n < C::N; ++n) {
+        if (o.affinity != kTC) a[n] = a[n] / abs_sum;
+        sum += a[n];
+    }
+#pragma unroll
+    for (int tp = 0; tp < C::KK; ++tp) ab[(long)tp * P] = tp == C::REF ? 1.0f - sum : a[tp < C::REF ? tp : tp - 1];
+    float x = init, c = conf;
+    if (preserve) x = blend_fix(x, dep);
+    if (o.flags & kAlwaysClip) x = fmaxf(x, 0.f);
+    if (o.conf_fixed) {
+        if (preserve) {
+            const float m = dep > 0.f ? 1.f : 0.f;
+            c = (1.0f - m) * c + m;
+        }
+        o.conf_fixed[q] = c;
+        x = x * c;
+    }
+    o.src0[q] = x;
+}
+
 // grid = (ceil(W / 120), ceil(H / R), B), block = 128, dynamic shared memory HeadRows<K>::smem
 template <int K, int RING_>
 __global__ void __launch_bounds__(128, 2)
@@ -238,115 +360,13 @@ head_rows_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_consta
 
     // ---------------- epilogue: lane = pixel x0 + tid; TMEM lane = tid
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-    constexpr int kChunks = (C::NW + 47) / 48;
-    // pass 1: the columns the neighbouring warps need from this warp's edge lanes
 #pragma unroll
-    for (int r = 0; r < C::R; ++r) {
-#pragma unroll
-        for (int q = 0; q < kChunks; ++q) {
-            uint32_t e[48];
-            constexpr int kTail = C::NW - 48 * (kChunks - 1);
-            if (q + 1 < kChunks) tmem_load_cols<48>(tlane + r * C::NW + q * 48, e);
-            else tmem_load_cols<kTail>(tlane + r * C::NW + q * 48, e);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int n = q * 16 + i;
-                if (n < C::NOUT) {
-                    if (lane == 31) xch[0][warp][r][n] = __uint_as_float(e[3 * i]);
-                    if (lane == 0) xch[1][warp][r][n] = __uint_as_float(e[3 * i + 2]);
-                }
-            }
-        }
-    }
+    for (int r = 0; r < C::R; ++r) head_rows_edge_columns<C>(tlane, warp, lane, r, xch);
     __syncthreads();
-    const int px = x0 + tid;
-    const bool lane_out = tid >= 4 && tid < 4 + C::TILE_OUT && px < W;
-    const bool fused = o.aff != nullptr;
-    const bool preserve = fused && (o.flags & kPreserve) != 0;
-    const float gamma = fused ? __ldg(o.gamma) : 1.f;
+    const HeadRowsPixel px{x0, y0, b, H, W, P};
+    const float gamma = o.aff != nullptr ? __ldg(o.gamma) : 1.f;
 #pragma unroll 1
-    for (int r = 0; r < C::R; ++r) {
-        const int y = y0 + r;
-        float d[C::NOUT];
-#pragma unroll
-        for (int q = 0; q < kChunks; ++q) {
-            uint32_t e[48];
-            constexpr int kTail = C::NW - 48 * (kChunks - 1);
-            if (q + 1 < kChunks) tmem_load_cols<48>(tlane + r * C::NW + q * 48, e);
-            else tmem_load_cols<kTail>(tlane + r * C::NW + q * 48, e);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int n = q * 16 + i;
-                if (n < C::NOUT) {
-                    float left = __shfl_up_sync(0xffffffffu, __uint_as_float(e[3 * i]), 1);
-                    float right = __shfl_down_sync(0xffffffffu, __uint_as_float(e[3 * i + 2]), 1);
-                    if (lane == 0) left = warp > 0 ? xch[0][warp - 1][r][n] : 0.f;
-                    if (lane == 31) right = warp < 3 ? xch[1][warp + 1][r][n] : 0.f;
-                    d[n] = ((__uint_as_float(e[3 * i + 1]) + left) + right) + __ldg(bias + n);
-                }
-            }
-        }
-        if (!lane_out || y >= H) continue;
-        const long q = (long)b * P + (long)y * W + px;
-        const float init = fmaxf(d[0], 0.f);                                   // nlspnmodel.py:68 (relu)
-        const float conf = 1.f / (1.f + expf(-d[C::N3 + 1]));                  // :83-86 (sigmoid)
-        o.pred_init[q] = init;
-        o.confidence[q] = conf;
-        if (o.guidance) {
-            float *gp = o.guidance + (long)b * C::N3 * P + (long)y * W + px;   // :81 (no activation)
-#pragma unroll
-            for (int n = 0; n < C::N3; ++n) gp[(long)n * P] = d[1 + n];
-        }
-        if (!fused) continue;
-        // ---- the propagation's prologue (same expressions as prologue_fwd_kernel, kernels_v1.cuh)
-        const float dep = preserve ? __ldg(o.feat_fix + q) : 0.f;
-        float *ob = o.offset + (long)b * 2 * C::KK * P + (long)y * W + px;
-        float *ab = o.aff + (long)b * C::KK * P + (long)y * W + px;
-#pragma unroll
-        for (int t = 0; t < C::KK; ++t) {
-            if (t == C::REF) {
-                ob[(long)(2 * t) * P] = 0.f;
-                ob[(long)(2 * t + 1) * P] = 0.f;
-            } else {
-                const int n = t < C::REF ? t : t - 1;
-                ob[(long)(2 * t) * P] = d[1 + 2 * n];
-                ob[(long)(2 * t + 1) * P] = d[1 + 2 * n + 1];
-            }
-        }
-        float a[C::N];
-        float abs_sum = 0.f;
-        const bool use_tanh = o.affinity == kTC || o.affinity == kTGASS;
-        const float g = o.affinity == kTGASS ? gamma + 1e-8f : gamma;
-#pragma unroll
-        for (int n = 0; n < C::N; ++n) {
-            float v = d[1 + 2 * C::N + n];
-            if (use_tanh) v = tanhf(v) / g;
-            a[n] = v;
-            abs_sum += fabsf(v);
-        }
-        abs_sum += 1e-4f;
-        if ((o.affinity == kASS || o.affinity == kTGASS) && abs_sum < 1.0f) abs_sum = 1.0f;
-        float sum = 0.f;
-#pragma unroll
-        for (int n = 0; n < C::N; ++n) {
-            if (o.affinity != kTC) a[n] = a[n] / abs_sum;
-            sum += a[n];
-        }
-#pragma unroll
-        for (int t = 0; t < C::KK; ++t) ab[(long)t * P] = t == C::REF ? 1.0f - sum : a[t < C::REF ? t : t - 1];
-        float x = init, c = conf;
-        if (preserve) x = blend_fix(x, dep);
-        if (o.flags & kAlwaysClip) x = fmaxf(x, 0.f);
-        if (o.conf_fixed) {
-            if (preserve) {
-                const float m = dep > 0.f ? 1.f : 0.f;
-                c = (1.0f - m) * c + m;
-            }
-            o.conf_fixed[q] = c;
-            x = x * c;
-        }
-        o.src0[q] = x;
-    }
+    for (int r = 0; r < C::R; ++r) head_rows_finish_row<C>(tlane, warp, lane, r, xch, px, bias, o, gamma);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
@@ -366,6 +386,189 @@ inline cudaError_t head_rows_launch(const CUtensorMap &m_id, const CUtensorMap &
     if (attr_err != cudaSuccess) return attr_err;
     const dim3 grid((unsigned)((W + C::TILE_OUT - 1) / C::TILE_OUT), (unsigned)((H + C::R - 1) / C::R), (unsigned)B);
     head_rows_kernel<K, RING_><<<grid, 128, C::smem, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, H, W, o);
+    return cudaGetLastError();
+}
+
+// ======================================================================================
+// The same GEMM as ONE persistent CTA per SM.  ncu on head_rows_kernel (two CTAs per SM): a CTA's life is ~60 % main
+// loop and ~40 % epilogue, and the two CTAs of an SM run in lockstep, so the tensor core and the TMA ring idle during
+// every epilogue.  Here the roles never stop: warp 0 streams TMA stages of tile after tile through one deep ring, warp 1
+// issues the MMAs into one of TWO accumulator sets in tensor memory (2 x 256 columns), and NG groups of four epilogue
+// warps drain the set the MMA warp finished last while it fills the other one (mbarriers acc_full / acc_empty).  With
+// NG = 2 the rows of a tile are dealt to the two groups alternately, so that every scheduler holds two epilogue warps.
+// grid = min(tiles, SMs), block = 64 + 128 NG, dynamic shared memory HeadPersist<K>::smem
+// ======================================================================================
+template <int K>
+struct HeadPersist : HeadRows<K, 3> {
+    using Base = HeadRows<K, 3>;
+    static constexpr int NG = Base::R >= 2 ? 2 : 1;
+    static constexpr int THREADS = 64 + 128 * NG;
+    static constexpr int XCH_BYTES = 2 * 4 * Base::R * Base::NOUT * 4;              // per group
+    static constexpr int SLOT_BYTES = Base::A_BYTES + Base::B_SLOT;
+    static constexpr int RING_MAX = (227 * 1024 - 1024 - NG * XCH_BYTES - 1024) / SLOT_BYTES;
+    static constexpr int PRING = RING_MAX > 7 ? 7 : RING_MAX;
+    static constexpr size_t smem = (size_t)PRING * SLOT_BYTES + NG * XCH_BYTES + 1024;
+    static_assert(PRING >= 3, "ring too shallow");
+};
+
+template <int K>
+__global__ void __launch_bounds__(HeadPersist<K>::THREADS, 1)
+head_persist_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_constant__ CUtensorMap map_oa,
+                    const __grid_constant__ CUtensorMap map_cf, const __grid_constant__ CUtensorMap map_fe,
+                    const float *__restrict__ packed, const float *__restrict__ bias, int H, int W, int tiles_x,
+                    int tiles_y, int ntiles, HeadRowsOut o)
+{
+    using C = HeadPersist<K>;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[C::PRING], empty[C::PRING], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t ring = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;       // [PRING][A_BYTES], [PRING][B_SLOT], [NG] exchange
+    unsigned char *ring_p = smem_raw + (ring - tma::smem_u32(smem_raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long P = (long)H * W;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < C::PRING; ++i) {
+            tma::mbar_init(&full[i], 1);
+            tma::mbar_init(&empty[i], 1);
+        }
+        tma::mbar_init(&acc_full[0], 1);
+        tma::mbar_init(&acc_full[1], 1);
+        tma::mbar_init(&acc_empty[0], 128 * C::NG);
+        tma::mbar_init(&acc_empty[1], 128 * C::NG);
+        tma::fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma::smem_u32(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 0) {
+        // ---- TMA producer: stage g of the CTA's whole tile sequence goes to ring slot g % PRING
+        uint32_t g = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+            const int x0 = tx * C::TILE_OUT - 4, y0 = ty * C::R;
+            for (int st = 0; st < C::STAGES; ++st, ++g) {
+                const uint32_t slot = g % C::PRING;
+                mbar_wait_bounded(&empty[slot], ((g / C::PRING) & 1u) ^ 1u);          // passes at once on the first lap
+                const int s = head_rows_source(st), c0 = (st & 7) * 8;
+                const CUtensorMap *mp = s == 0 ? &map_id : s == 1 ? &map_oa : s == 2 ? &map_cf : &map_fe;
+                const bool wide = st < C::WIDE_STAGES;
+                const uint32_t sa = ring + slot * C::A_BYTES, sb = ring + C::PRING * C::A_BYTES + slot * C::B_SLOT;
+                const uint32_t bbytes = wide ? C::B_WIDE : C::B_NARROW;
+                const float *wsrc = packed + (wide ? (long)st * (C::B_WIDE / 4)
+                                                   : (long)C::WIDE_STAGES * (C::B_WIDE / 4) + (long)(st - C::WIDE_STAGES) * (C::B_NARROW / 4));
+                if (elect_one_sync()) {
+                    tma::mbar_arrive_expect_tx(&full[slot], C::A_BYTES + bbytes);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                        asm volatile(
+                            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                            ::"r"(sa + w * C::A_BOX), "l"(reinterpret_cast<uint64_t>(mp)), "r"(tma::smem_u32(&full[slot])),
+                            "r"(x0 + 32 * w), "r"(c0), "r"(y0 - 1), "r"(b) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb),
+                                 "l"(wsrc), "r"(bbytes), "r"(tma::smem_u32(&full[slot])) : "memory");
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t kIdescWide = kIdescBase | ((uint32_t)(C::NW >> 3) << 17);
+        constexpr uint32_t kIdescNarrow = kIdescBase | ((uint32_t)(16 >> 3) << 17);
+        uint32_t g = 0, i = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+            const uint32_t buf = i & 1u;
+            mbar_wait_bounded(&acc_empty[buf], ((i >> 1) & 1u) ^ 1u);                 // the epilogue has drained this set
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tacc = tmem + buf * 256u;
+            for (int st = 0; st < C::STAGES; ++st, ++g) {
+                const uint32_t slot = g % C::PRING;
+                mbar_wait_bounded(&full[slot], (g / C::PRING) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const bool wide = st < C::WIDE_STAGES;
+                const uint32_t ns = wide ? C::NW : 16;
+                const uint32_t idesc = wide ? kIdescWide : kIdescNarrow;
+                const uint32_t dcol = wide ? 0u : (head_rows_source(st) == 2 ? (uint32_t)C::CF_BASE : 0u);
+                const uint32_t sa = ring + slot * C::A_BYTES, sb = ring + C::PRING * C::A_BYTES + slot * C::B_SLOT;
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int r = 0; r < C::R; ++r) {
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint64_t da = umma_desc_mn_tf32(sa + (r + dy) * 1024, C::A_BOX, 512);
+                            const uint64_t db = umma_desc_kmajor(sb + dy * ns * 32, (ns / 8) * 128, 128);
+                            const uint32_t acc = (st | dy) != 0 ? 1u : 0u;
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tacc + r * C::NW + dcol),
+                                         "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                        }
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                     tma::smem_u32(&empty[slot])) : "memory");
+                    if (st == C::STAGES - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                         tma::smem_u32(&acc_full[buf])) : "memory");
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---- epilogue groups
+        const int grp = (warp - 2) >> 2, quarter = warp & 3;          // TMEM lane quarter of a warp = warp id % 4
+        float (*xch)[4][C::R][C::NOUT] =
+            reinterpret_cast<float (*)[4][C::R][C::NOUT]>(ring_p + (size_t)C::PRING * C::SLOT_BYTES + (size_t)grp * C::XCH_BYTES);
+        const float gamma = o.aff != nullptr ? __ldg(o.gamma) : 1.f;
+        uint32_t i = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+            const HeadRowsPixel px{tx * C::TILE_OUT - 4, ty * C::R, b, H, W, P};
+            const uint32_t buf = i & 1u;
+            mbar_wait_bounded(&acc_full[buf], (i >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tq = tmem + buf * 256u + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+            for (int r = 0; r < C::R; ++r)
+                if ((int)((r + i) % C::NG) == grp) head_rows_edge_columns<C>(tq, quarter, lane, r, xch);
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+#pragma unroll 1
+            for (int r = 0; r < C::R; ++r)
+                if ((int)((r + i) % C::NG) == grp) head_rows_finish_row<C>(tq, quarter, lane, r, xch, px, bias, o, gamma);
+            // this thread's reads of the accumulator set are complete (tcgen05.wait::ld inside the loads)
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(&acc_empty[buf])) : "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");           // the exchange buffer is free again
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
+template <int K>
+inline cudaError_t head_persist_launch(const CUtensorMap &m_id, const CUtensorMap &m_oa, const CUtensorMap &m_cf,
+                                       const CUtensorMap &m_fe, const float *packed, const float *bias, int B, int H, int W,
+                                       int sm_count, const HeadRowsOut &o, cudaStream_t st)
+{
+    using C = HeadPersist<K>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(head_persist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem);
+    });
+    if (attr_err != cudaSuccess) return attr_err;
+    const int tiles_x = (W + C::TILE_OUT - 1) / C::TILE_OUT, tiles_y = (H + C::R - 1) / C::R;
+    const long ntiles = (long)tiles_x * tiles_y * B;
+    if (ntiles > 0x7fffffffL) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
+    head_persist_kernel<K><<<grid, C::THREADS, C::smem, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, H, W, tiles_x, tiles_y,
+                                                               (int)ntiles, o);
     return cudaGetLastError();
 }
 

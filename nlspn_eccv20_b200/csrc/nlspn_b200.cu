@@ -34,7 +34,7 @@ std::atomic<unsigned long long> g_launches{0};
 // -1 = "auto" where a default depends on the shape.
 enum Opt { kOptTiled = 0, kOptPersist, kOptPdl, kOptFwdTH, kOptParamTH, kOptStateTma, kOptStateGather,
            kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint,
-           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptHeadsTma, kOptHeadsRows, kOptHeadsRing, kOptCount };
+           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptHeadsTma, kOptHeadsRows, kOptHeadsRing, kOptHeadsPersist, kOptCount };
 struct OptDef { const char *name; const char *env; int def; };
 const OptDef kOptDefs[kOptCount] = {
     {"tiled", "NLSPN_TILED", 1},
@@ -57,7 +57,8 @@ const OptDef kOptDefs[kOptCount] = {
     {"sched_minb", "NLSPN_SCHED_MINB", 5},      // CTAs per SM of the schedule build (4: 0.275 ms, 5: 0.249 ms per step)
     {"heads_tma", "NLSPN_HEADS_TMA", 1},         // head convolutions: activations by TMA ring (0: direct global loads)
     {"heads_rows", "NLSPN_HEADS_ROWS", 1},       // head convolutions: MN-major operand form (kernels_head2.cuh; K = 3, 5, W % 4 == 0)
-    {"heads_ring", "NLSPN_HEADS_RING", 0},       // its TMA ring depth for K = 3 (0 = deepest that keeps two CTAs per SM = 4; 3)
+    {"heads_ring", "NLSPN_HEADS_RING", 0},       // ring depth of the one-CTA-per-tile form for K = 3 (0 = deepest that keeps two CTAs per SM = 4; 3)
+    {"heads_persist", "NLSPN_HEADS_PERSIST", 1}, // MN-major form as one persistent warp-specialised CTA per SM (0: one CTA per tile, two per SM)
 };
 std::atomic<int> g_opt[kOptCount];
 const bool g_opt_init = []() {
@@ -1441,6 +1442,15 @@ static int launch_head_rows(const float *id_fd1, const float *oa_fd1, const floa
     if (int rc = make_head_rows_map(&m_cf, cf_fd1, B, H, W, rows)) return rc;
     if (int rc = make_head_rows_map(&m_fe, fe1, B, H, W, rows)) return rc;
     const float *rows_packed = packed + head_packed_floats(K);
+    if (opt(kOptHeadsPersist) != 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, &sms, nullptr) != 0 || sms <= 0) sms = 148;
+        const cudaError_t pe = K == 3 ? head_persist_launch<3>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, o, st)
+                                      : head_persist_launch<5>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, o, st);
+        if (pe != cudaSuccess) return cuda_fail(pe, "head_persist_kernel");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     const cudaError_t e = K == 3 ? (opt(kOptHeadsRing) == 3 ? head_rows_launch<3, 3>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, o, st)
                                                             : head_rows_launch<3>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, o, st))
                                  : head_rows_launch<5>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, o, st);
