@@ -5,7 +5,11 @@ import json
 import sys
 import torch
 
-B, H, W, N = int(sys.argv[1]) if len(sys.argv) > 1 else 8, 352, 1216, 8
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 352
+W = int(sys.argv[3]) if len(sys.argv) > 3 else 1216
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+N = K * K - 1
 dev = torch.device("cuda:0")
 fe1, id1, oa1, cf1 = (torch.randn(B, 64, H, W, device=dev) for _ in range(4))
 c_id = torch.nn.Conv2d(128, 1, 3, 1, 1).to(dev)
@@ -33,7 +37,7 @@ def timed(fn, n=10):
     return e0.elapsed_time(e1) / n
 
 
-out = {}
+out = {"shape": [B, H, W, K]}
 with torch.no_grad():
     for tf32 in (True, False):
         torch.backends.cudnn.allow_tf32 = tf32
@@ -51,21 +55,23 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nlspn_eccv20_b200 import heads, _lib  # noqa: E402
 args = (id1, oa1, cf1, fe1, c_id.weight, c_id.bias, c_oa.weight, c_oa.bias, c_cf.weight, c_cf.bias)
 with torch.no_grad():
-    out["fused_tcgen05_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=3))
+    out["fused_tcgen05_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=K))
+    with _lib.options(heads_strip=0):
+        out["fused_tcgen05_persistent_tiles_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=K))
     with _lib.options(heads_persist=0):
-        out["fused_tcgen05_cta_per_tile_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=3))
+        out["fused_tcgen05_cta_per_tile_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=K))
     with _lib.options(heads_rows=0):
-        out["fused_tcgen05_ninetap_form_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=3))
+        out["fused_tcgen05_ninetap_form_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=K))
     fix = (torch.rand(B, 1, H, W, device=dev) < 0.05).float() * 5.0
-    gam = torch.tensor([4.0], device=dev)
-    out["fused_heads_prologue_ms"] = timed(lambda: heads.fused_heads_prologue(*args, fix, gam, 3))
-    a = heads.fused_heads(*args, prop_kernel=3)
+    gam = torch.tensor([0.5 * N], device=dev)
+    out["fused_heads_prologue_ms"] = timed(lambda: heads.fused_heads_prologue(*args, fix, gam, K))
+    a = heads.fused_heads(*args, prop_kernel=K)
     r = heads.reference_heads(*args)
     out["max_abs_diff_vs_cudnn_tf32"] = [float((x - y).abs().max()) for x, y in zip(a, r)]
     lib = _lib.load()
     lib.nlspn_profile_enable(1)
     for _ in range(5):
-        heads.fused_heads(*args, prop_kernel=3)
+        heads.fused_heads(*args, prop_kernel=K)
     torch.cuda.synchronize()
     out["kernel_only_ms"] = {k: v[0] / 5 for k, v in _lib.profile_read().items()}
     lib.nlspn_profile_enable(0)
