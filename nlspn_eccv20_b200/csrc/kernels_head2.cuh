@@ -585,263 +585,4 @@ inline cudaError_t head_persist_launch(const CUtensorMap &m_id, const CUtensorMa
     return cudaGetLastError();
 }
 
-// Epilogue of head_strip_kernel for ONE accumulator row (TMEM address trow incl. the lane quarter): all NW columns are
-// read once, the accumulator is handed back to the MMA warp at once (acc_empty), the edge columns go through `xch`
-// ([side][quarter][n], double-buffered by the caller), one named barrier of the row's four warps, then the pixel.
-__device__ __forceinline__ void head_strip_finish_row(uint32_t trow, int quarter, int lane, int grp, int k, float *xch,
-                                                      const HeadRowsPixel &t, const float *__restrict__ bias,
-                                                      const HeadRowsOut &o, float gamma, uint64_t *acc_empty)
-{
-    using C = HeadRows<3, 3>;
-    static_assert(C::NW == 80, "five 16-column loads");
-    uint32_t e[C::NW];
-#pragma unroll
-    for (int c = 0; c < C::NW; c += 16)
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                     : "=r"(e[c + 0]), "=r"(e[c + 1]), "=r"(e[c + 2]), "=r"(e[c + 3]), "=r"(e[c + 4]), "=r"(e[c + 5]),
-                       "=r"(e[c + 6]), "=r"(e[c + 7]), "=r"(e[c + 8]), "=r"(e[c + 9]), "=r"(e[c + 10]), "=r"(e[c + 11]),
-                       "=r"(e[c + 12]), "=r"(e[c + 13]), "=r"(e[c + 14]), "=r"(e[c + 15])
-                     : "r"(trow + (uint32_t)c));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(acc_empty)) : "memory");
-    if (lane == 31) {
-#pragma unroll
-        for (int n = 0; n < C::NOUT; ++n) xch[(0 * 4 + quarter) * C::NOUT + n] = __uint_as_float(e[3 * n]);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int n = 0; n < C::NOUT; ++n) xch[(1 * 4 + quarter) * C::NOUT + n] = __uint_as_float(e[3 * n + 2]);
-    }
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-    float d[C::NOUT];
-#pragma unroll
-    for (int n = 0; n < C::NOUT; ++n) {
-        float left = __shfl_up_sync(0xffffffffu, __uint_as_float(e[3 * n]), 1);
-        float right = __shfl_down_sync(0xffffffffu, __uint_as_float(e[3 * n + 2]), 1);
-        if (lane == 0) left = quarter > 0 ? xch[(0 * 4 + quarter - 1) * C::NOUT + n] : 0.f;
-        if (lane == 31) right = quarter < 3 ? xch[(1 * 4 + quarter + 1) * C::NOUT + n] : 0.f;
-        d[n] = ((__uint_as_float(e[3 * n + 1]) + left) + right) + __ldg(bias + n);
-    }
-    head_rows_emit<C>(d, quarter * 32 + lane, t.y0 + k, t, o, gamma);
-}
-
-// ======================================================================================
-// K = 3: the persistent GEMM with a ROLLING window of accumulators -- no halo re-reads.
-// head_persist_kernel moves 9.9 GB from L2 to the SMs for 3.5 GB of activations (5 input rows per 3 output rows, times the
-// tile overlap, plus the weights) and that path is at its cap (ncu: 10.4 TB/s, lts 63 %).  Here a CTA walks DOWN a column
-// strip of 120 pixels: input rows arrive in groups of two (all 256 channels of the group = 32 stages), every input row i
-// feeds the three output rows it touches (i + 1 - dy, weights dy), and an output row is complete once input row y + 1 has
-// been through.  Six accumulators (6 x 80 = 480 TMEM columns) = three PAIRS of output rows: while group j adds to pairs
-// j - 1 and j, the epilogue drains pair j - 2 (barriers acc_full / acc_empty per pair slot).  An input row is loaded
-// exactly once per strip segment (+2 rows per segment of SEG rows); the weights are re-streamed per group.
-// Epilogue group g (four warps) owns row g of every pair; it reads the whole accumulator row once (80 registers), passes
-// the edge columns through a double-buffered exchange and needs one named barrier per row.
-// grid = min(items, SMs), block = 320, dynamic shared memory HeadStrip::smem
-// ======================================================================================
-struct HeadStrip : HeadRows<3, 3> {
-    using Base = HeadRows<3, 3>;
-    static constexpr int G = 2;                                   // input rows per group = output rows per pair
-    static constexpr int SA_BOX = G * 1024, SA_BYTES = 4 * SA_BOX;      // one stage of activations: 4 boxes {32 px, 8 ch, 2 rows}
-    static constexpr int SSLOT = SA_BYTES + Base::B_SLOT;
-    static constexpr int XCH_FLOATS = 2 * 4 * Base::NOUT;         // one row: [side][quarter][n]
-    static constexpr int XCH_BYTES = 2 * 2 * XCH_FLOATS * 4;      // [group][parity]
-    static constexpr int SRING = 12;
-    static constexpr int THREADS = 64 + 256;
-    static constexpr size_t smem = (size_t)SRING * SSLOT + XCH_BYTES + 1024;
-    static_assert(smem <= 227 * 1024 && 6 * Base::NW <= 512, "one CTA per SM");
-};
-
-__global__ void __launch_bounds__(HeadStrip::THREADS, 1)
-head_strip_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_constant__ CUtensorMap map_oa,
-                  const __grid_constant__ CUtensorMap map_cf, const __grid_constant__ CUtensorMap map_fe,
-                  const float *__restrict__ packed, const float *__restrict__ bias, int H, int W, int tiles_x, int nseg,
-                  int seg_rows, int nitems, HeadRowsOut o)
-{
-    using C = HeadStrip;
-    extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full[C::SRING], empty[C::SRING], acc_full[3], acc_empty[3];
-    __shared__ uint32_t tmem_base_s;
-    const uint32_t ring = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;       // [SRING][SA_BYTES], [SRING][B_SLOT], exchange
-    float *xch_all = reinterpret_cast<float *>(smem_raw + (ring - tma::smem_u32(smem_raw)) + (size_t)C::SRING * C::SSLOT);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long P = (long)H * W;
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < C::SRING; ++i) {
-            tma::mbar_init(&full[i], 1);
-            tma::mbar_init(&empty[i], 1);
-        }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            tma::mbar_init(&acc_full[i], 1);
-            tma::mbar_init(&acc_empty[i], 256);
-        }
-        tma::fence_barrier_init();
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma::smem_u32(&tmem_base_s)), "r"(512u));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmem_base_s;
-
-    // item -> (strip column tx, segment, image): tx fastest so that concurrently running CTAs are neighbours
-    auto item_rows = [&](int it, int &tx, int &ys, int &b) {
-        tx = it % tiles_x;
-        const int sg = (it / tiles_x) % nseg;
-        b = it / (tiles_x * nseg);
-        ys = sg * seg_rows;
-        const int rem = H - ys;
-        return rem < seg_rows ? rem : seg_rows;                    // output rows of this item (>= 1)
-    };
-
-    if (warp == 0) {
-        // ---- TMA producer
-        uint32_t g = 0;
-        for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-            int tx, ys, b;
-            const int nrows = item_rows(it, tx, ys, b);
-            const int x0 = tx * C::TILE_OUT - 4;
-            const int groups = (nrows + 1) / 2 + 1;               // input rows ys - 1 .. ys + 2 * pairs, two at a time
-            for (int j = 0; j < groups; ++j) {
-                for (int st = 0; st < C::STAGES; ++st, ++g) {
-                    const uint32_t slot = g % C::SRING;
-                    mbar_wait_bounded(&empty[slot], ((g / C::SRING) & 1u) ^ 1u);
-                    const int s = head_rows_source(st), c0 = (st & 7) * 8;
-                    const CUtensorMap *mp = s == 0 ? &map_id : s == 1 ? &map_oa : s == 2 ? &map_cf : &map_fe;
-                    const bool wide = st < C::WIDE_STAGES;
-                    const uint32_t sa = ring + slot * C::SA_BYTES, sb = ring + C::SRING * C::SA_BYTES + slot * C::B_SLOT;
-                    const uint32_t bbytes = wide ? C::B_WIDE : C::B_NARROW;
-                    const float *wsrc = packed + (wide ? (long)st * (C::B_WIDE / 4)
-                                                       : (long)C::WIDE_STAGES * (C::B_WIDE / 4) + (long)(st - C::WIDE_STAGES) * (C::B_NARROW / 4));
-                    if (elect_one_sync()) {
-                        tma::mbar_arrive_expect_tx(&full[slot], C::SA_BYTES + bbytes);
-#pragma unroll
-                        for (int w = 0; w < 4; ++w)
-                            asm volatile(
-                                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                                ::"r"(sa + w * C::SA_BOX), "l"(reinterpret_cast<uint64_t>(mp)), "r"(tma::smem_u32(&full[slot])),
-                                "r"(x0 + 32 * w), "r"(c0), "r"(ys - 1 + 2 * j), "r"(b) : "memory");
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb),
-                                     "l"(wsrc), "r"(bbytes), "r"(tma::smem_u32(&full[slot])) : "memory");
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ---- MMA issuer.  q0 = pairs of all earlier items: pair p of this item lives in pair slot (q0 + p) % 3.
-        constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t kIdescWide = kIdescBase | ((uint32_t)(C::NW >> 3) << 17);
-        constexpr uint32_t kIdescNarrow = kIdescBase | ((uint32_t)(16 >> 3) << 17);
-        uint32_t g = 0, q0 = 0;
-        for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-            int tx, ys, b;
-            const int nrows = item_rows(it, tx, ys, b);
-            const int pairs = (nrows + 1) / 2, groups = pairs + 1;
-            for (int j = 0; j < groups; ++j) {
-                if (j < pairs) {                                   // pair j receives its first MMAs in this group
-                    const uint32_t q = q0 + j;
-                    mbar_wait_bounded(&acc_empty[q % 3u], ((q / 3u) & 1u) ^ 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                for (int st = 0; st < C::STAGES; ++st, ++g) {
-                    const uint32_t slot = g % C::SRING;
-                    mbar_wait_bounded(&full[slot], (g / C::SRING) & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const bool wide = st < C::WIDE_STAGES;
-                    const uint32_t ns = wide ? C::NW : 16;
-                    const uint32_t idesc = wide ? kIdescWide : kIdescNarrow;
-                    const uint32_t dcol = wide ? 0u : (head_rows_source(st) == 2 ? (uint32_t)C::CF_BASE : 0u);
-                    const uint32_t sa = ring + slot * C::SA_BYTES, sb = ring + C::SRING * C::SA_BYTES + slot * C::B_SLOT;
-                    if (elect_one_sync()) {
-#pragma unroll
-                        for (int a = 0; a < C::G; ++a) {
-#pragma unroll
-                            for (int dy = 0; dy < 3; ++dy) {
-                                const int k = 2 * j + a - dy;          // output row (relative to ys) fed by input row 2j + a - 1
-                                if (k < 0 || k >= 2 * pairs) continue;
-                                const uint32_t q = q0 + (uint32_t)(k >> 1);
-                                const uint32_t col = ((q % 3u) * 2u + (uint32_t)(k & 1)) * (uint32_t)C::NW + dcol;
-                                const uint64_t da = umma_desc_mn_tf32(sa + a * 1024, C::SA_BOX, 512);
-                                const uint64_t db = umma_desc_kmajor(sb + dy * ns * 32, (ns / 8) * 128, 128);
-                                const uint32_t acc = (st | dy) != 0 ? 1u : 0u;      // dy = 0 of stage 0 is a row's first MMA
-                                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem + col),
-                                             "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-                            }
-                        }
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                         tma::smem_u32(&empty[slot])) : "memory");
-                        if (st == C::STAGES - 1 && j >= 1)             // pair j - 1 has seen its last input row
-                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                             tma::smem_u32(&acc_full[(q0 + (uint32_t)j - 1u) % 3u])) : "memory");
-                    }
-                    __syncwarp();
-                }
-            }
-            q0 += (uint32_t)pairs;
-        }
-    } else {
-        // ---- epilogue: group grp owns row grp of every pair
-        const int grp = (warp - 2) >> 2, quarter = warp & 3;
-        const float gamma = o.aff != nullptr ? __ldg(o.gamma) : 1.f;
-        uint32_t q0 = 0, rowctr = 0;
-        for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-            int tx, ys, b;
-            const int nrows = item_rows(it, tx, ys, b);
-            const int pairs = (nrows + 1) / 2;
-            const HeadRowsPixel px{tx * C::TILE_OUT - 4, ys, b, H, W, P};
-            for (int p = 0; p < pairs; ++p, ++rowctr) {
-                const uint32_t q = q0 + (uint32_t)p;
-                mbar_wait_bounded(&acc_full[q % 3u], (q / 3u) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t trow = tmem + ((q % 3u) * 2u + (uint32_t)grp) * (uint32_t)C::NW + ((uint32_t)(quarter * 32) << 16);
-                float *xch = xch_all + ((size_t)grp * 2 + (rowctr & 1u)) * C::XCH_FLOATS;
-                head_strip_finish_row(trow, quarter, lane, grp, 2 * p + grp, xch, px, bias, o, gamma, &acc_empty[q % 3u]);
-            }
-            q0 += (uint32_t)pairs;
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
-}
-
-inline cudaError_t head_strip_launch(const CUtensorMap &m_id, const CUtensorMap &m_oa, const CUtensorMap &m_cf,
-                                     const CUtensorMap &m_fe, const float *packed, const float *bias, int B, int H, int W,
-                                     int sm_count, const HeadRowsOut &o, cudaStream_t st)
-{
-    using C = HeadStrip;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(head_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem);
-    });
-    if (attr_err != cudaSuccess) return attr_err;
-    const int tiles_x = (W + C::TILE_OUT - 1) / C::TILE_OUT;
-    // segment height: even; minimise (items per CTA, rounded up) x (input rows per item incl. the 2 halo rows)
-    int best_seg = 2;
-    double best_cost = 1e30;
-    for (int seg = 2; seg <= 128; seg += 2) {
-        const long nseg = (H + seg - 1) / seg, items = nseg * tiles_x * B;
-        const long per_cta = (items + sm_count - 1) / sm_count;
-        const double cost = (double)per_cta * (seg + 2);
-        if (cost < best_cost - 1e-9) {
-            best_cost = cost;
-            best_seg = seg;
-        }
-    }
-    const int nseg = (H + best_seg - 1) / best_seg;
-    const long nitems = (long)nseg * tiles_x * B;
-    if (nitems > 0x7fffffffL) return cudaErrorInvalidValue;
-    const unsigned grid = (unsigned)(nitems < sm_count ? nitems : sm_count);
-    head_strip_kernel<<<grid, C::THREADS, C::smem, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, H, W, tiles_x, nseg, best_seg,
-                                                        (int)nitems, o);
-    return cudaGetLastError();
-}
-
 } // namespace nlspn
