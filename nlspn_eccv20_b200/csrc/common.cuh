@@ -9,6 +9,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 namespace nlspn {
 
 constexpr int kBlock = 256;
@@ -129,6 +133,23 @@ __device__ __forceinline__ long scatter_cell(const ScatterGeo &g, int sy, int sx
     const int by = (Y + sy) >> 1, ly = (Y + sy) & 1;
     const int bx = (X + sx) >> 1, lx = (X + sx) & 1;
     return (long)(sy * 2 + sx) * g.plane + ((long)by * g.Wb + bx) * 4 + ly * 2 + lx;
+}
+
+// Host: opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is per DEVICE (per context), so it
+// is remembered per (kernel, device): a process that drives several GPUs (nn.DataParallel threads) must set it on each.
+inline cudaError_t ensure_dynamic_smem(const void *kernel, int bytes)
+{
+    static std::mutex mu;
+    static std::vector<std::pair<const void *, int>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto &d : done)
+        if (d.first == kernel && d.second == dev) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.emplace_back(kernel, dev);
+    return e;
 }
 
 } // namespace nlspn

@@ -102,7 +102,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 // bounded: a tensor-core fault must surface as an error, not as a hung GPU
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity)
 {
-    for (long spin = 0; spin < (1L << 22); ++spin)
+    for (long spin = 0; spin < (1L << 26); ++spin)      // seconds: longer than any legitimate wait (persistent kernels included)
         if (mbar_try_wait(bar, parity)) return;
     __trap();
 }
@@ -386,13 +386,7 @@ inline cudaError_t head_launch(const float *id_fd1, const float *oa_fd1, const f
                                const float *packed, const float *bias, int B, int H, int W, int N3, float *pred_init,
                                float *guidance, float *confidence, cudaStream_t st)
 {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(head_fused_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)HeadSmem<NP>::bytes);
-    });
-    if (attr_err != cudaSuccess) return attr_err;
+    if (const cudaError_t ae = ensure_dynamic_smem(reinterpret_cast<const void *>(&head_fused_kernel<NP>), (int)HeadSmem<NP>::bytes)) return ae;
     const dim3 grid((unsigned)((W + kHeadTM - 1) / kHeadTM), (unsigned)H, (unsigned)B);
     head_fused_kernel<NP><<<grid, kHeadThreads, HeadSmem<NP>::bytes, st>>>(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, N3, H, W,
                                                                            pred_init, guidance, confidence);
@@ -404,13 +398,7 @@ inline cudaError_t head_launch_tma(const CUtensorMap &m_id, const CUtensorMap &m
                                    const CUtensorMap &m_fe, const float *packed, const float *bias, int B, int H, int W,
                                    int N3, float *pred_init, float *guidance, float *confidence, cudaStream_t st)
 {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(head_fused_tma_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)HeadSmemTma<NP>::bytes);
-    });
-    if (attr_err != cudaSuccess) return attr_err;
+    if (const cudaError_t ae = ensure_dynamic_smem(reinterpret_cast<const void *>(&head_fused_tma_kernel<NP>), (int)HeadSmemTma<NP>::bytes)) return ae;
     const dim3 grid((unsigned)((W + kHeadTM - 1) / kHeadTM), (unsigned)H, (unsigned)B);
     head_fused_tma_kernel<NP><<<grid, kHeadThreads, HeadSmemTma<NP>::bytes, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, N3, H,
                                                                                   W, pred_init, guidance, confidence);

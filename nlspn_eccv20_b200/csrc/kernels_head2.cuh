@@ -391,12 +391,7 @@ inline cudaError_t head_rows_launch(const CUtensorMap &m_id, const CUtensorMap &
                                     const HeadRowsOut &o, cudaStream_t st)
 {
     using C = HeadRows<K, RING_>;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(head_rows_kernel<K, RING_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem);
-    });
-    if (attr_err != cudaSuccess) return attr_err;
+    if (const cudaError_t ae = ensure_dynamic_smem(reinterpret_cast<const void *>(&head_rows_kernel<K, RING_>), (int)C::smem)) return ae;
     const dim3 grid((unsigned)((W + C::TILE_OUT - 1) / C::TILE_OUT), (unsigned)((H + C::R - 1) / C::R), (unsigned)B);
     head_rows_kernel<K, RING_><<<grid, 128, C::smem, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, H, W, o);
     return cudaGetLastError();
@@ -570,12 +565,7 @@ inline cudaError_t head_persist_launch(const CUtensorMap &m_id, const CUtensorMa
                                        int sm_count, const HeadRowsOut &o, cudaStream_t st)
 {
     using C = HeadPersist<K>;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(head_persist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem);
-    });
-    if (attr_err != cudaSuccess) return attr_err;
+    if (const cudaError_t ae = ensure_dynamic_smem(reinterpret_cast<const void *>(&head_persist_kernel<K>), (int)C::smem)) return ae;
     const int tiles_x = (W + C::TILE_OUT - 1) / C::TILE_OUT, tiles_y = (H + C::R - 1) / C::R;
     const long ntiles = (long)tiles_x * tiles_y * B;
     if (ntiles > 0x7fffffffL) return cudaErrorInvalidValue;

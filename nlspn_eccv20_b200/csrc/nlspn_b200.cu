@@ -1175,12 +1175,10 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
         unsigned short *sched_tab = reinterpret_cast<unsigned short *>(geo + (size_t)G * tiles * L::GEOV * L::NT);
         CUtensorMap plane_map;
         if (int rc = make_plane_map(&plane_map, planes, 2L * G, pg.PH, pg.PW, L::RW, L::RH)) return rc;
-        static std::once_flag smem_once;
-        static cudaError_t smem_err = cudaSuccess;
-        std::call_once(smem_once, [] {
-            auto set = [](auto kernel) {
-                const cudaError_t e1 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                            (int)LocalSmem<3, TH>::bytes);
+        cudaError_t smem_err = cudaSuccess;
+        {
+            auto set = [&smem_err](auto kernel) {
+                const cudaError_t e1 = ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), (int)LocalSmem<3, TH>::bytes);
                 if (e1 != cudaSuccess && smem_err == cudaSuccess) smem_err = e1;
             };
             set(bwd_state_local_kernel<3, TH, true, MB_LO>);
@@ -1189,7 +1187,7 @@ int nlspn_backward(const float *guidance, const float *feat_init, const float *f
             set(bwd_state_local_kernel<3, TH, false, MB_MID>);
             set(bwd_state_local_kernel<3, TH, true, MB_HI>);
             set(bwd_state_local_kernel<3, TH, false, MB_HI>);
-        });
+        }
         if (smem_err != cudaSuccess) return cuda_fail(smem_err, "cudaFuncSetAttribute(bwd_state_local_kernel)");
         const int local_minb = opt(kOptLocalMinB);
         // L2 prefetch distance (in tiles) of the packed records; -1 = one wave of resident CTAs.  Measured on B200
