@@ -111,6 +111,56 @@ __device__ __forceinline__ bool elect_one_sync()
     return pred != 0;
 }
 
+// tcgen05.mma kind::tf32 with the A-operand collector hint: consecutive MMAs on the SAME A tile keep it in the tensor
+// core's collector buffer instead of re-reading 4 KB from shared memory (SASS: UTCHMMA ... .A_KEEP / .A_REUSE).
+// MODE 0 = discard (default), 1 = fill (first of a run), 2 = use (middle), 3 = lastuse (last).
+template <int MODE>
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    if (MODE == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da), "l"(db),
+                     "r"(idesc), "r"(accumulate) : "memory");
+    else if (MODE == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32.collector::a::use [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da), "l"(db),
+                     "r"(idesc), "r"(accumulate) : "memory");
+    else if (MODE == 3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da), "l"(db),
+                     "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc),
+                     "r"(accumulate) : "memory");
+}
+
+// All MMAs of one stage, grouped by input row so that a row's A tile is read once: input row i feeds output rows
+// r = i - dy (0 <= r < R, 0 <= dy < 3).  Per accumulator the order stays dy = 0, 1, 2.
+template <class C, bool REUSE>
+__device__ __forceinline__ void head_stage_mmas(uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t ns, uint32_t idesc, uint32_t dcol,
+                                                int st)
+{
+#pragma unroll
+    for (int i = 0; i < C::ROWS; ++i) {
+        const uint64_t da = umma_desc_mn_tf32(sa + i * 1024, C::A_BOX, 512);
+        constexpr int R = C::R;
+        const int dy_lo = i - (R - 1) > 0 ? i - (R - 1) : 0, dy_hi = i < 2 ? i : 2;      // dy range with 0 <= i - dy < R
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            if (dy < dy_lo || dy > dy_hi) continue;
+            const int r = i - dy;
+            const uint64_t db = umma_desc_kmajor(sb + dy * ns * 32, (ns / 8) * 128, 128);
+            const uint32_t acc = (st | dy) != 0 ? 1u : 0u;
+            const uint32_t d = tacc + r * C::NW + dcol;
+            if (!REUSE || dy_lo == dy_hi) umma_tf32<0>(d, da, db, idesc, acc);
+            else if (dy == dy_lo) umma_tf32<1>(d, da, db, idesc, acc);
+            else if (dy == dy_hi) umma_tf32<3>(d, da, db, idesc, acc);
+            else umma_tf32<2>(d, da, db, idesc, acc);
+        }
+    }
+}
+
 struct HeadRowsOut {
     float *pred_init, *confidence, *guidance;        // head outputs; guidance may be NULL when the prologue is fused
     // fused prologue (all NULL = heads only)
@@ -347,18 +397,7 @@ head_rows_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_consta
             const uint32_t dcol = wide ? 0u : (head_rows_source(st) == 2 ? (uint32_t)C::CF_BASE : 0u);
             const uint32_t sa = ring + slot * C::A_BYTES, sb = ring + C::RING * C::A_BYTES + slot * C::B_SLOT;
             if (elect_one_sync()) {
-#pragma unroll
-                for (int r = 0; r < C::R; ++r) {
-#pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        const uint64_t da = umma_desc_mn_tf32(sa + (r + dy) * 1024, C::A_BOX, 512);
-                        const uint64_t db = umma_desc_kmajor(sb + dy * ns * 32, (ns / 8) * 128, 128);
-                        const uint32_t acc = (st | dy) != 0 ? 1u : 0u;
-                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem + r * C::NW + dcol),
-                                     "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-                    }
-                }
+                head_stage_mmas<C, true>(tmem, sa, sb, ns, idesc, dcol, st);
                 // the barrier completes when every MMA issued so far has retired (also with its shared-memory reads)
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                  tma::smem_u32(&empty[slot])) : "memory");
@@ -424,7 +463,7 @@ __global__ void __launch_bounds__(HeadPersist<K>::THREADS, 1)
 head_persist_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_constant__ CUtensorMap map_oa,
                     const __grid_constant__ CUtensorMap map_cf, const __grid_constant__ CUtensorMap map_fe,
                     const float *__restrict__ packed, const float *__restrict__ bias, int H, int W, int tiles_x,
-                    int tiles_y, int ntiles, HeadRowsOut o)
+                    int tiles_y, int ntiles, int reuse, HeadRowsOut o)
 {
     using C = HeadPersist<K>;
     extern __shared__ unsigned char smem_raw[];
@@ -506,18 +545,8 @@ head_persist_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_con
                 const uint32_t dcol = wide ? 0u : (head_rows_source(st) == 2 ? (uint32_t)C::CF_BASE : 0u);
                 const uint32_t sa = ring + slot * C::A_BYTES, sb = ring + C::PRING * C::A_BYTES + slot * C::B_SLOT;
                 if (elect_one_sync()) {
-#pragma unroll
-                    for (int r = 0; r < C::R; ++r) {
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
-                            const uint64_t da = umma_desc_mn_tf32(sa + (r + dy) * 1024, C::A_BOX, 512);
-                            const uint64_t db = umma_desc_kmajor(sb + dy * ns * 32, (ns / 8) * 128, 128);
-                            const uint32_t acc = (st | dy) != 0 ? 1u : 0u;
-                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tacc + r * C::NW + dcol),
-                                         "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-                        }
-                    }
+                    if (reuse) head_stage_mmas<C, true>(tacc, sa, sb, ns, idesc, dcol, st);
+                    else head_stage_mmas<C, false>(tacc, sa, sb, ns, idesc, dcol, st);
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                      tma::smem_u32(&empty[slot])) : "memory");
                     if (st == C::STAGES - 1)
@@ -562,7 +591,7 @@ head_persist_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_con
 template <int K>
 inline cudaError_t head_persist_launch(const CUtensorMap &m_id, const CUtensorMap &m_oa, const CUtensorMap &m_cf,
                                        const CUtensorMap &m_fe, const float *packed, const float *bias, int B, int H, int W,
-                                       int sm_count, const HeadRowsOut &o, cudaStream_t st)
+                                       int sm_count, bool reuse, const HeadRowsOut &o, cudaStream_t st)
 {
     using C = HeadPersist<K>;
     if (const cudaError_t ae = ensure_dynamic_smem(reinterpret_cast<const void *>(&head_persist_kernel<K>), (int)C::smem)) return ae;
@@ -571,7 +600,7 @@ inline cudaError_t head_persist_launch(const CUtensorMap &m_id, const CUtensorMa
     if (ntiles > 0x7fffffffL) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
     head_persist_kernel<K><<<grid, C::THREADS, C::smem, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, H, W, tiles_x, tiles_y,
-                                                               (int)ntiles, o);
+                                                               (int)ntiles, reuse ? 1 : 0, o);
     return cudaGetLastError();
 }
 

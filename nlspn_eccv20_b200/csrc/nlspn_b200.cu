@@ -34,7 +34,7 @@ std::atomic<unsigned long long> g_launches{0};
 // -1 = "auto" where a default depends on the shape.
 enum Opt { kOptTiled = 0, kOptPersist, kOptPdl, kOptFwdTH, kOptParamTH, kOptStateTma, kOptStateGather,
            kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint,
-           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptHeadsTma, kOptHeadsRows, kOptHeadsRing, kOptHeadsPersist, kOptCount };
+           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptHeadsTma, kOptHeadsRows, kOptHeadsRing, kOptHeadsPersist, kOptHeadsReuse, kOptCount };
 struct OptDef { const char *name; const char *env; int def; };
 const OptDef kOptDefs[kOptCount] = {
     {"tiled", "NLSPN_TILED", 1},
@@ -59,6 +59,7 @@ const OptDef kOptDefs[kOptCount] = {
     {"heads_rows", "NLSPN_HEADS_ROWS", 1},       // head convolutions: MN-major operand form (kernels_head2.cuh; K = 3, 5, W % 4 == 0)
     {"heads_ring", "NLSPN_HEADS_RING", 0},       // ring depth of the one-CTA-per-tile form for K = 3 (0 = deepest that keeps two CTAs per SM = 4; 3)
     {"heads_persist", "NLSPN_HEADS_PERSIST", 1}, // MN-major form as one persistent warp-specialised CTA per SM (0: one CTA per tile, two per SM)
+    {"heads_reuse", "NLSPN_HEADS_REUSE", 1},     // persistent form: keep an input row's A tile in the tensor core's collector across its dy MMAs
 };
 std::atomic<int> g_opt[kOptCount];
 const bool g_opt_init = []() {
@@ -1443,8 +1444,8 @@ static int launch_head_rows(const float *id_fd1, const float *oa_fd1, const floa
     if (opt(kOptHeadsPersist) != 0) {
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, &sms, nullptr) != 0 || sms <= 0) sms = 148;
-        const cudaError_t pe = K == 3 ? head_persist_launch<3>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, o, st)
-                                      : head_persist_launch<5>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, o, st);
+        const cudaError_t pe = K == 3 ? head_persist_launch<3>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, opt(kOptHeadsReuse) != 0, o, st)
+                                      : head_persist_launch<5>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, opt(kOptHeadsReuse) != 0, o, st);
         if (pe != cudaSuccess) return cuda_fail(pe, "head_persist_kernel");
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return 0;
