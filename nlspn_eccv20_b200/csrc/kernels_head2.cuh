@@ -139,11 +139,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t
 // r = i - dy (0 <= r < R, 0 <= dy < 3).  Per accumulator the order stays dy = 0, 1, 2.
 template <class C, bool REUSE>
 __device__ __forceinline__ void head_stage_mmas(uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t ns, uint32_t idesc, uint32_t dcol,
-                                                int st)
+                                                int st, uint32_t row_bytes = 1024, uint32_t box_bytes = C::A_BOX)
 {
 #pragma unroll
     for (int i = 0; i < C::ROWS; ++i) {
-        const uint64_t da = umma_desc_mn_tf32(sa + i * 1024, C::A_BOX, 512);
+        const uint64_t da = umma_desc_mn_tf32(sa + i * row_bytes, box_bytes, 512);
         constexpr int R = C::R;
         const int dy_lo = i - (R - 1) > 0 ? i - (R - 1) : 0, dy_hi = i < 2 ? i : 2;      // dy range with 0 <= i - dy < R
 #pragma unroll
@@ -397,7 +397,7 @@ head_rows_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_consta
             const uint32_t dcol = wide ? 0u : (head_rows_source(st) == 2 ? (uint32_t)C::CF_BASE : 0u);
             const uint32_t sa = ring + slot * C::A_BYTES, sb = ring + C::RING * C::A_BYTES + slot * C::B_SLOT;
             if (elect_one_sync()) {
-                head_stage_mmas<C, true>(tmem, sa, sb, ns, idesc, dcol, st);
+                head_stage_mmas<C, false>(tmem, sa, sb, ns, idesc, dcol, st);     // (with two CTAs per SM the collector hints cost 10 %)
                 // the barrier completes when every MMA issued so far has retired (also with its shared-memory reads)
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                  tma::smem_u32(&empty[slot])) : "memory");
@@ -445,27 +445,31 @@ inline cudaError_t head_rows_launch(const CUtensorMap &m_id, const CUtensorMap &
 // NG = 2 the rows of a tile are dealt to the two groups alternately, so that every scheduler holds two epilogue warps.
 // grid = min(tiles, SMs), block = 64 + 128 NG, dynamic shared memory HeadPersist<K>::smem
 // ======================================================================================
-template <int K>
+template <int K, int KS = 1>                                       // KS 8-channel K-steps per TMA stage
 struct HeadPersist : HeadRows<K, 3> {
     using Base = HeadRows<K, 3>;
     static constexpr int NG = Base::R >= 2 ? 2 : 1;
     static constexpr int THREADS = 64 + 128 * NG;
     static constexpr int XCH_BYTES = 2 * 4 * Base::R * Base::NOUT * 4;              // per group
-    static constexpr int SLOT_BYTES = Base::A_BYTES + Base::B_SLOT;
+    static constexpr int PA_ROW = KS * 1024;                                        // one input row of one 32-pixel box: [8 KS ch][32 px]
+    static constexpr int PA_BOX = Base::ROWS * PA_ROW, PA_BYTES = 4 * PA_BOX;
+    static constexpr int PB_BYTES = KS * Base::B_SLOT;
+    static constexpr int SLOT_BYTES = PA_BYTES + PB_BYTES;
+    static constexpr int PSTAGES = Base::STAGES / KS, PWIDE = Base::WIDE_STAGES / KS;
     static constexpr int RING_MAX = (227 * 1024 - 1024 - NG * XCH_BYTES - 1024) / SLOT_BYTES;
     static constexpr int PRING = RING_MAX > 7 ? 7 : RING_MAX;
     static constexpr size_t smem = (size_t)PRING * SLOT_BYTES + NG * XCH_BYTES + 1024;
-    static_assert(PRING >= 3, "ring too shallow");
+    static_assert(PRING >= 3 && 8 % KS == 0, "ring too shallow");
 };
 
-template <int K>
-__global__ void __launch_bounds__(HeadPersist<K>::THREADS, 1)
+template <int K, int KS>
+__global__ void __launch_bounds__(HeadPersist<K, KS>::THREADS, 1)
 head_persist_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_constant__ CUtensorMap map_oa,
                     const __grid_constant__ CUtensorMap map_cf, const __grid_constant__ CUtensorMap map_fe,
                     const float *__restrict__ packed, const float *__restrict__ bias, int H, int W, int tiles_x,
                     int tiles_y, int ntiles, int reuse, HeadRowsOut o)
 {
-    using C = HeadPersist<K>;
+    using C = HeadPersist<K, KS>;
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[C::PRING], empty[C::PRING], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
@@ -500,23 +504,24 @@ head_persist_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_con
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
             const int x0 = tx * C::TILE_OUT - 4, y0 = ty * C::R;
-            for (int st = 0; st < C::STAGES; ++st, ++g) {
+            for (int st = 0; st < C::PSTAGES; ++st, ++g) {
                 const uint32_t slot = g % C::PRING;
                 mbar_wait_bounded(&empty[slot], ((g / C::PRING) & 1u) ^ 1u);          // passes at once on the first lap
-                const int s = head_rows_source(st), c0 = (st & 7) * 8;
+                const int st8 = st * KS;                                              // first 8-channel block of the stage
+                const int s = head_rows_source(st8), c0 = (st8 & 7) * 8;
                 const CUtensorMap *mp = s == 0 ? &map_id : s == 1 ? &map_oa : s == 2 ? &map_cf : &map_fe;
-                const bool wide = st < C::WIDE_STAGES;
-                const uint32_t sa = ring + slot * C::A_BYTES, sb = ring + C::PRING * C::A_BYTES + slot * C::B_SLOT;
-                const uint32_t bbytes = wide ? C::B_WIDE : C::B_NARROW;
-                const float *wsrc = packed + (wide ? (long)st * (C::B_WIDE / 4)
-                                                   : (long)C::WIDE_STAGES * (C::B_WIDE / 4) + (long)(st - C::WIDE_STAGES) * (C::B_NARROW / 4));
+                const bool wide = st < C::PWIDE;
+                const uint32_t sa = ring + slot * C::PA_BYTES, sb = ring + C::PRING * C::PA_BYTES + slot * C::PB_BYTES;
+                const uint32_t bbytes = KS * (wide ? C::B_WIDE : C::B_NARROW);
+                const float *wsrc = packed + (wide ? (long)st8 * (C::B_WIDE / 4)
+                                                   : (long)C::WIDE_STAGES * (C::B_WIDE / 4) + (long)(st8 - C::WIDE_STAGES) * (C::B_NARROW / 4));
                 if (elect_one_sync()) {
-                    tma::mbar_arrive_expect_tx(&full[slot], C::A_BYTES + bbytes);
+                    tma::mbar_arrive_expect_tx(&full[slot], C::PA_BYTES + bbytes);
 #pragma unroll
                     for (int w = 0; w < 4; ++w)
                         asm volatile(
                             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                            ::"r"(sa + w * C::A_BOX), "l"(reinterpret_cast<uint64_t>(mp)), "r"(tma::smem_u32(&full[slot])),
+                            ::"r"(sa + w * C::PA_BOX), "l"(reinterpret_cast<uint64_t>(mp)), "r"(tma::smem_u32(&full[slot])),
                             "r"(x0 + 32 * w), "r"(c0), "r"(y0 - 1), "r"(b) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb),
                                  "l"(wsrc), "r"(bbytes), "r"(tma::smem_u32(&full[slot])) : "memory");
@@ -535,21 +540,25 @@ head_persist_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_con
             mbar_wait_bounded(&acc_empty[buf], ((i >> 1) & 1u) ^ 1u);                 // the epilogue has drained this set
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem + buf * 256u;
-            for (int st = 0; st < C::STAGES; ++st, ++g) {
+            for (int st = 0; st < C::PSTAGES; ++st, ++g) {
                 const uint32_t slot = g % C::PRING;
                 mbar_wait_bounded(&full[slot], (g / C::PRING) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const bool wide = st < C::WIDE_STAGES;
+                const bool wide = st < C::PWIDE;
                 const uint32_t ns = wide ? C::NW : 16;
                 const uint32_t idesc = wide ? kIdescWide : kIdescNarrow;
-                const uint32_t dcol = wide ? 0u : (head_rows_source(st) == 2 ? (uint32_t)C::CF_BASE : 0u);
-                const uint32_t sa = ring + slot * C::A_BYTES, sb = ring + C::PRING * C::A_BYTES + slot * C::B_SLOT;
+                const uint32_t dcol = wide ? 0u : (head_rows_source(st * KS) == 2 ? (uint32_t)C::CF_BASE : 0u);
+                const uint32_t sa = ring + slot * C::PA_BYTES, sb = ring + C::PRING * C::PA_BYTES + slot * C::PB_BYTES;
                 if (elect_one_sync()) {
-                    if (reuse) head_stage_mmas<C, true>(tacc, sa, sb, ns, idesc, dcol, st);
-                    else head_stage_mmas<C, false>(tacc, sa, sb, ns, idesc, dcol, st);
+#pragma unroll
+                    for (int kk = 0; kk < KS; ++kk) {
+                        // K-step kk: channels 8 kk .. 8 kk + 7 of every row of the box, its own block of weights
+                        if (reuse) head_stage_mmas<C, true>(tacc, sa + kk * 1024, sb + kk * (3 * ns * 32), ns, idesc, dcol, st * KS + kk, C::PA_ROW, C::PA_BOX);
+                        else head_stage_mmas<C, false>(tacc, sa + kk * 1024, sb + kk * (3 * ns * 32), ns, idesc, dcol, st * KS + kk, C::PA_ROW, C::PA_BOX);
+                    }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                      tma::smem_u32(&empty[slot])) : "memory");
-                    if (st == C::STAGES - 1)
+                    if (st == C::PSTAGES - 1)
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                          tma::smem_u32(&acc_full[buf])) : "memory");
                 }
@@ -588,18 +597,18 @@ head_persist_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_con
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }
 
-template <int K>
+template <int K, int KS = 1>
 inline cudaError_t head_persist_launch(const CUtensorMap &m_id, const CUtensorMap &m_oa, const CUtensorMap &m_cf,
                                        const CUtensorMap &m_fe, const float *packed, const float *bias, int B, int H, int W,
                                        int sm_count, bool reuse, const HeadRowsOut &o, cudaStream_t st)
 {
-    using C = HeadPersist<K>;
-    if (const cudaError_t ae = ensure_dynamic_smem(reinterpret_cast<const void *>(&head_persist_kernel<K>), (int)C::smem)) return ae;
+    using C = HeadPersist<K, KS>;
+    if (const cudaError_t ae = ensure_dynamic_smem(reinterpret_cast<const void *>(&head_persist_kernel<K, KS>), (int)C::smem)) return ae;
     const int tiles_x = (W + C::TILE_OUT - 1) / C::TILE_OUT, tiles_y = (H + C::R - 1) / C::R;
     const long ntiles = (long)tiles_x * tiles_y * B;
     if (ntiles > 0x7fffffffL) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
-    head_persist_kernel<K><<<grid, C::THREADS, C::smem, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, H, W, tiles_x, tiles_y,
+    head_persist_kernel<K, KS><<<grid, C::THREADS, C::smem, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, H, W, tiles_x, tiles_y,
                                                                (int)ntiles, reuse ? 1 : 0, o);
     return cudaGetLastError();
 }

@@ -34,7 +34,7 @@ std::atomic<unsigned long long> g_launches{0};
 // -1 = "auto" where a default depends on the shape.
 enum Opt { kOptTiled = 0, kOptPersist, kOptPdl, kOptFwdTH, kOptParamTH, kOptStateTma, kOptStateGather,
            kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint,
-           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptHeadsTma, kOptHeadsRows, kOptHeadsRing, kOptHeadsPersist, kOptHeadsReuse, kOptCount };
+           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptHeadsTma, kOptHeadsRows, kOptHeadsRing, kOptHeadsPersist, kOptHeadsReuse, kOptHeadsKs, kOptCount };
 struct OptDef { const char *name; const char *env; int def; };
 const OptDef kOptDefs[kOptCount] = {
     {"tiled", "NLSPN_TILED", 1},
@@ -60,6 +60,7 @@ const OptDef kOptDefs[kOptCount] = {
     {"heads_ring", "NLSPN_HEADS_RING", 0},       // ring depth of the one-CTA-per-tile form for K = 3 (0 = deepest that keeps two CTAs per SM = 4; 3)
     {"heads_persist", "NLSPN_HEADS_PERSIST", 1}, // MN-major form as one persistent warp-specialised CTA per SM (0: one CTA per tile, two per SM)
     {"heads_reuse", "NLSPN_HEADS_REUSE", 1},     // persistent form: keep an input row's A tile in the tensor core's collector across its dy MMAs
+    {"heads_ks", "NLSPN_HEADS_KS", 2},           // persistent form, K = 3: channels per TMA stage / 8 (1 or 2: fewer, larger TMA operations)
 };
 std::atomic<int> g_opt[kOptCount];
 const bool g_opt_init = []() {
@@ -477,13 +478,13 @@ static int make_nchw_map(CUtensorMap *map, const float *base, int B, int C, int 
 
 // [B, 64, H, W] fp32 tensor with the dims ordered (x, channel, row, image) and a box {32 px, 8 channels, rows, 1}
 // in the 128-byte swizzle with 32-byte atoms: the box is a column of MN-major tf32 MMA atoms (kernels_head2.cuh)
-static int make_head_rows_map(CUtensorMap *map, const float *base, int B, int H, int W, int rows)
+static int make_head_rows_map(CUtensorMap *map, const float *base, int B, int H, int W, int rows, int chans = 8)
 {
-    const MapKey key{base, kHeadCin, B, H, W, 32, rows, 8, 14};
+    const MapKey key{base, kHeadCin, B, H, W, 32, rows, chans, 14};
     if (map_cache_get(key, map)) return 0;
     const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)kHeadCin, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)H * W * 4, (cuuint64_t)W * 4, (cuuint64_t)kHeadCin * H * W * 4};
-    const cuuint32_t box[4] = {32, 8, (cuuint32_t)rows, 1};
+    const cuuint32_t box[4] = {32, (cuuint32_t)chans, (cuuint32_t)rows, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims,
                                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1436,15 +1437,18 @@ static int launch_head_rows(const float *id_fd1, const float *oa_fd1, const floa
 {
     const int rows = (K == 3 ? HeadRows<3>::ROWS : HeadRows<5>::ROWS);
     CUtensorMap m_id, m_oa, m_cf, m_fe;
-    if (int rc = make_head_rows_map(&m_id, id_fd1, B, H, W, rows)) return rc;
-    if (int rc = make_head_rows_map(&m_oa, oa_fd1, B, H, W, rows)) return rc;
-    if (int rc = make_head_rows_map(&m_cf, cf_fd1, B, H, W, rows)) return rc;
-    if (int rc = make_head_rows_map(&m_fe, fe1, B, H, W, rows)) return rc;
+    const bool tiles_ks2 = K == 3 && opt(kOptHeadsPersist) != 0 && opt(kOptHeadsKs) == 2;
+    const int chans = tiles_ks2 ? 16 : 8;
+    if (int rc = make_head_rows_map(&m_id, id_fd1, B, H, W, rows, chans)) return rc;
+    if (int rc = make_head_rows_map(&m_oa, oa_fd1, B, H, W, rows, chans)) return rc;
+    if (int rc = make_head_rows_map(&m_cf, cf_fd1, B, H, W, rows, chans)) return rc;
+    if (int rc = make_head_rows_map(&m_fe, fe1, B, H, W, rows, chans)) return rc;
     const float *rows_packed = packed + head_packed_floats(K);
     if (opt(kOptHeadsPersist) != 0) {
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, &sms, nullptr) != 0 || sms <= 0) sms = 148;
-        const cudaError_t pe = K == 3 ? head_persist_launch<3>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, opt(kOptHeadsReuse) != 0, o, st)
+        const cudaError_t pe = tiles_ks2 ? head_persist_launch<3, 2>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, opt(kOptHeadsReuse) != 0, o, st)
+                             : K == 3 ? head_persist_launch<3>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, opt(kOptHeadsReuse) != 0, o, st)
                                       : head_persist_launch<5>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, opt(kOptHeadsReuse) != 0, o, st);
         if (pe != cudaSuccess) return cuda_fail(pe, "head_persist_kernel");
         g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -112,8 +112,10 @@ def test_rows_form_matches_the_ninetap_form(B, H, W, K):
     rows = heads.fused_heads(*args)
     with _lib.options(heads_persist=0):
         per_tile = heads.fused_heads(*args)
-    for o, t in zip(rows, per_tile):           # persistent and one-CTA-per-tile forms: the same arithmetic
-        assert torch.equal(o, t)
+    with _lib.options(heads_ks=1, heads_reuse=0):
+        plain = heads.fused_heads(*args)
+    for o, t, q in zip(rows, per_tile, plain):     # persistent / one-CTA-per-tile forms, 16- / 8-channel stages, with / without
+        assert torch.equal(o, t) and torch.equal(o, q)     # the A-collector hints: the same arithmetic
     with _lib.options(heads_rows=0):
         nine = heads.fused_heads(*args)
     old = torch.backends.cudnn.allow_tf32

@@ -56,7 +56,9 @@ from nlspn_eccv20_b200 import heads, _lib  # noqa: E402
 args = (id1, oa1, cf1, fe1, c_id.weight, c_id.bias, c_oa.weight, c_oa.bias, c_cf.weight, c_cf.bias)
 with torch.no_grad():
     out["fused_tcgen05_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=K))
-    with _lib.options(heads_reuse=0):
+    with _lib.options(heads_ks=1):
+        out["fused_tcgen05_8ch_stages_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=K))
+    with _lib.options(heads_ks=1, heads_reuse=0):
         out["fused_tcgen05_no_collector_reuse_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=K))
     with _lib.options(heads_persist=0):
         out["fused_tcgen05_cta_per_tile_ms"] = timed(lambda: heads.fused_heads(*args, prop_kernel=K))
