@@ -13,8 +13,8 @@
 //     shift, which no descriptor can express -- so it is moved to the OUTPUT side: the weights of the three dx taps
 //     sit side by side in N (accumulator column 3 n + dx), the MMA runs on the unshifted tile, and the epilogue forms
 //     D[px][n] = E[px - 1][3n] + E[px][3n + 1] + E[px + 1][3n + 2] with two warp shuffles.  A tile therefore loads
-//     128 pixels and produces the 120 in the middle (x tiles step by 120, a multiple of four pixels because TMA box
-//     starts must be 16-byte aligned); zero fill outside the image is the convolution's padding.
+//     128 pixels and produces 124 of them (lanes 1 .. 124; x tiles step by 124, a multiple of four pixels because TMA
+//     box starts must be 16-byte aligned); zero fill outside the image is the convolution's padding.
 //   * per output pixel the tensor core reads 3 KB of activations (three dy) instead of 9 KB, nothing is re-packed,
 //     and the block sparsity of the weights is used: the 64-channel branches of the init / confidence heads only feed
 //     one output each, so their MMAs are N = 16 instead of N = NW.
@@ -44,7 +44,7 @@ struct HeadRows {
     // ring depth: the kernel is bound by bytes in flight (ncu: DRAM 32 %, L2 42 %, tensor pipe 39 %, no unit busy), so
     // take the deepest ring that still lets two CTAs share an SM (228 KB minus 1 KB reserved per CTA)
     static constexpr int RING = RING_ > 0 ? RING_ : ((4 * (A_BYTES + B_SLOT) + 1024 + 1024 + 256) * 2 <= 228 * 1024 ? 4 : 3);
-    static constexpr int TILE_OUT = 120;
+    static constexpr int TILE_OUT = 124;                          // lanes 1 .. 124 of a 128-pixel tile are outputs (see head_tiles_x)
     static constexpr int STAGES = 32, WIDE_STAGES = 16;           // (fe1, oa) x 8 chunks wide, (id, cf) x 8 chunks narrow
     static constexpr size_t smem = (size_t)RING * (A_BYTES + B_SLOT) + 1024;      // [RING A slots][RING B slots] + alignment slack
     static constexpr long packed_floats = (long)WIDE_STAGES * (B_WIDE + B_NARROW) / 4;
@@ -53,6 +53,11 @@ struct HeadRows {
     static_assert(2 * (smem + 1024 + 256) <= 228 * 1024, "two CTAs per SM");
     static_assert(B_SLOT % 128 == 0 && (size_t)2 * 4 * R * NOUT * 4 <= (size_t)RING * A_BYTES, "exchange buffer aliases the ring");
 };
+
+// Tile tx loads pixels 124 tx - 4 .. 124 tx + 123 (a 16-byte aligned start) and produces lanes 1 .. 124 = pixels
+// 124 tx - 3 .. 124 tx + 120: every output lane has both neighbours in the tile, consecutive tiles abut, and the first
+// tile's lanes 1 .. 3 fall left of the image.  (With outputs on lanes 4 .. 123 KITTI's 1216 columns took 11 tiles; now 10.)
+__host__ __device__ constexpr int head_tiles_x(int W, int tile_out) { return (W + 3 + tile_out - 1) / tile_out; }
 
 // stage -> source tensor: 0..7 fe1 (shared, feeds every output), 8..15 off_aff branch, 16..23 init branch, 24..31
 // confidence branch.  The first stage must be a wide one (it initialises all accumulator columns).
@@ -256,7 +261,7 @@ __device__ __forceinline__ void head_rows_emit(const float (&d)[C::NOUT], int tl
     const long P = t.P;
     const bool fused = o.aff != nullptr;
     const bool preserve = fused && (o.flags & kPreserve) != 0;
-    if (!(tl >= 4 && tl < 4 + C::TILE_OUT && px < W) || y >= t.H) return;
+    if (!(tl >= 1 && tl <= C::TILE_OUT && px >= 0 && px < W) || y >= t.H) return;
     const long q = (long)t.b * P + (long)y * W + px;
     const float init = fmaxf(d[0], 0.f);                                   // nlspnmodel.py:68 (relu)
     const float conf = 1.f / (1.f + expf(-d[C::N3 + 1]));                  // :83-86 (sigmoid)
@@ -318,7 +323,7 @@ __device__ __forceinline__ void head_rows_emit(const float (&d)[C::NOUT], int tl
     o.src0[q] = x;
 }
 
-// grid = (ceil(W / 120), ceil(H / R), B), block = 128, dynamic shared memory HeadRows<K>::smem
+// grid = (head_tiles_x(W), ceil(H / R), B), block = 128, dynamic shared memory HeadRows<K>::smem
 template <int K, int RING_>
 __global__ void __launch_bounds__(128, 2)
 head_rows_kernel(const __grid_constant__ CUtensorMap map_id, const __grid_constant__ CUtensorMap map_oa,
@@ -431,7 +436,7 @@ inline cudaError_t head_rows_launch(const CUtensorMap &m_id, const CUtensorMap &
 {
     using C = HeadRows<K, RING_>;
     if (const cudaError_t ae = ensure_dynamic_smem(reinterpret_cast<const void *>(&head_rows_kernel<K, RING_>), (int)C::smem)) return ae;
-    const dim3 grid((unsigned)((W + C::TILE_OUT - 1) / C::TILE_OUT), (unsigned)((H + C::R - 1) / C::R), (unsigned)B);
+    const dim3 grid((unsigned)head_tiles_x(W, C::TILE_OUT), (unsigned)((H + C::R - 1) / C::R), (unsigned)B);
     head_rows_kernel<K, RING_><<<grid, 128, C::smem, st>>>(m_id, m_oa, m_cf, m_fe, packed, bias, H, W, o);
     return cudaGetLastError();
 }
@@ -604,7 +609,7 @@ inline cudaError_t head_persist_launch(const CUtensorMap &m_id, const CUtensorMa
 {
     using C = HeadPersist<K, KS>;
     if (const cudaError_t ae = ensure_dynamic_smem(reinterpret_cast<const void *>(&head_persist_kernel<K, KS>), (int)C::smem)) return ae;
-    const int tiles_x = (W + C::TILE_OUT - 1) / C::TILE_OUT, tiles_y = (H + C::R - 1) / C::R;
+    const int tiles_x = head_tiles_x(W, C::TILE_OUT), tiles_y = (H + C::R - 1) / C::R;
     const long ntiles = (long)tiles_x * tiles_y * B;
     if (ntiles > 0x7fffffffL) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
