@@ -60,7 +60,7 @@ const OptDef kOptDefs[kOptCount] = {
     {"heads_ring", "NLSPN_HEADS_RING", 0},       // ring depth of the one-CTA-per-tile form for K = 3 (0 = deepest that keeps two CTAs per SM = 4; 3)
     {"heads_persist", "NLSPN_HEADS_PERSIST", 1}, // MN-major form as one persistent warp-specialised CTA per SM (0: one CTA per tile, two per SM)
     {"heads_reuse", "NLSPN_HEADS_REUSE", 1},     // persistent form: keep an input row's A tile in the tensor core's collector across its dy MMAs
-    {"heads_ks", "NLSPN_HEADS_KS", 2},           // persistent form, K = 3: channels per TMA stage / 8 (1 or 2: fewer, larger TMA operations)
+    {"heads_ks", "NLSPN_HEADS_KS", 2},           // persistent form: channels per TMA stage / 8 (1 or 2: fewer, larger TMA operations)
 };
 std::atomic<int> g_opt[kOptCount];
 const bool g_opt_init = []() {
@@ -1437,7 +1437,7 @@ static int launch_head_rows(const float *id_fd1, const float *oa_fd1, const floa
 {
     const int rows = (K == 3 ? HeadRows<3>::ROWS : HeadRows<5>::ROWS);
     CUtensorMap m_id, m_oa, m_cf, m_fe;
-    const bool tiles_ks2 = K == 3 && opt(kOptHeadsPersist) != 0 && opt(kOptHeadsKs) == 2;
+    const bool tiles_ks2 = opt(kOptHeadsPersist) != 0 && opt(kOptHeadsKs) == 2;
     const int chans = tiles_ks2 ? 16 : 8;
     if (int rc = make_head_rows_map(&m_id, id_fd1, B, H, W, rows, chans)) return rc;
     if (int rc = make_head_rows_map(&m_oa, oa_fd1, B, H, W, rows, chans)) return rc;
@@ -1447,7 +1447,8 @@ static int launch_head_rows(const float *id_fd1, const float *oa_fd1, const floa
     if (opt(kOptHeadsPersist) != 0) {
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, &sms, nullptr) != 0 || sms <= 0) sms = 148;
-        const cudaError_t pe = tiles_ks2 ? head_persist_launch<3, 2>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, opt(kOptHeadsReuse) != 0, o, st)
+        const cudaError_t pe = tiles_ks2 && K == 5 ? head_persist_launch<5, 2>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, opt(kOptHeadsReuse) != 0, o, st)
+                             : tiles_ks2 ? head_persist_launch<3, 2>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, opt(kOptHeadsReuse) != 0, o, st)
                              : K == 3 ? head_persist_launch<3>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, opt(kOptHeadsReuse) != 0, o, st)
                                       : head_persist_launch<5>(m_id, m_oa, m_cf, m_fe, rows_packed, bias, B, H, W, sms, opt(kOptHeadsReuse) != 0, o, st);
         if (pe != cudaSuccess) return cuda_fail(pe, "head_persist_kernel");
