@@ -128,3 +128,44 @@ def test_only_test_infrastructure_touches_the_oracle():
                 if "import oracle" in txt or "from oracle" in txt or "liboracle" in txt or "oracle/_ref" in txt:
                     bad.append(os.path.relpath(p, ROOT))
     assert not bad, bad
+
+
+def test_heads_entries_validate_before_touching_cuda(lib):
+    """The head GEMM's C entries: sizes, the supported-domain query and the argument checks are
+    host-only; the tcgen05 kernel itself is covered by tests/test_gpu_heads.py."""
+    from nlspn_eccv20_b200 import _lib
+    P = ctypes.c_void_p
+    one = P(16)
+    assert lib.nlspn_heads_packed_floats(4) == 0                       # prop_kernel must be 3, 5 or 7
+    f3, f5, f7 = (lib.nlspn_heads_packed_floats(k) for k in (3, 5, 7))
+    assert 0 < f3 < f5 and f7 > 0 and f3 % 4 == 0 and f5 % 4 == 0       # 16-byte granules
+    assert lib.nlspn_heads_prologue_supported(1216, 3) == 1 and lib.nlspn_heads_prologue_supported(304, 5) == 1
+    assert lib.nlspn_heads_prologue_supported(1218, 3) == 0            # W % 4 != 0: nine-tap form, no fused prologue
+    assert lib.nlspn_heads_prologue_supported(1216, 7) == 0            # N = 448 accumulator columns do not fit one MMA
+    with _lib.options(heads_rows=0):
+        assert lib.nlspn_heads_prologue_supported(1216, 3) == 0
+    # NULL output / NULL gamma
+    rc = lib.nlspn_heads_prologue_fwd(one, one, one, one, one, one, None, None, 3, 0, 1, 8, 16, 3,
+                                      one, one, None, one, one, None, one, None)
+    assert rc == -1 and b"NULL" in lib.nlspn_last_error()
+    # PRESERVE_INPUT without feat_fix
+    rc = lib.nlspn_heads_prologue_fwd(one, one, one, one, one, one, None, one, 3, _lib.FLAG_PRESERVE_INPUT, 1, 8, 16, 3,
+                                      one, one, None, one, one, None, one, None)
+    assert rc == -1 and b"feat_fix" in lib.nlspn_last_error()
+    # a flag the fused epilogue does not implement
+    rc = lib.nlspn_heads_prologue_fwd(one, one, one, one, one, one, None, one, 3, _lib.FLAG_CONF_SAMPLED, 1, 8, 16, 3,
+                                      one, one, None, one, one, None, one, None)
+    assert rc == -4 and b"PRESERVE_INPUT and ALWAYS_CLIP" in lib.nlspn_last_error()
+    # unknown affinity mode, bad kernel size
+    rc = lib.nlspn_heads_prologue_fwd(one, one, one, one, one, one, None, one, 9, 0, 1, 8, 16, 3,
+                                      one, one, None, one, one, None, one, None)
+    assert rc == -6
+    rc = lib.nlspn_heads_prologue_fwd(one, one, one, one, one, one, None, one, 3, 0, 1, 8, 16, 4,
+                                      one, one, None, one, one, None, one, None)
+    assert rc == -3
+    # a width the fused form does not take: refused with a pointer to the two-call path
+    rc = lib.nlspn_heads_prologue_fwd(one, one, one, one, one, one, None, one, 3, 0, 1, 8, 18, 3,
+                                      one, one, None, one, one, None, one, None)
+    assert rc == -2 and b"nlspn_heads_fwd + nlspn_prologue_fwd" in lib.nlspn_last_error()
+    rc = lib.nlspn_heads_fwd(one, one, one, None, one, one, 1, 8, 16, 3, one, one, one, None)
+    assert rc == -1
