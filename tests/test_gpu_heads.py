@@ -193,3 +193,37 @@ def test_model_inference_with_the_prologue_fused_into_the_heads():
     assert len(oa["pred_inter"]) == len(ob["pred_inter"]) == 6
     a.fused_prologue = "auto"
     assert not a._use_fused_prologue(s["rgb"])            # grad mode: a backward may follow, guidance is needed
+
+
+def test_heads_random_shapes_against_fp32_layers():
+    """Randomized sweep over tile geometry: widths around the 124-pixel tile seams, heights around the 3-row groups,
+    batches; K = 3 (three rows per tile) and K = 5 (one row per tile); heads alone and with the fused prologue
+    (offsets must be the guidance channels bit for bit)."""
+    import random
+    from nlspn_eccv20_b200 import heads
+    dev = torch.device("cuda:0")
+    rnd = random.Random(20261019)
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        for case in range(24):
+            K = 3 if case % 3 else 5
+            B = rnd.choice((1, 1, 2, 3))
+            H = rnd.choice((1, 2, 3, 4, 5, 7, 8, 17, 31, 40))
+            W = 4 * rnd.choice((1, 2, 29, 30, 31, 32, 33, 61, 62, 63, 93, 94, 100))
+            x, w, b = _case(B, H, W, K, 1000 + case, dev)
+            args = (x[0], x[1], x[2], x[3], w[0], b[0], w[1], b[1], w[2], b[2])
+            ours = heads.fused_heads(*args, K)
+            torch.backends.cudnn.allow_tf32 = False
+            ref32 = heads.reference_heads(*args)
+            torch.backends.cudnn.allow_tf32 = old
+            for o, r, name in zip(ours, ref32, ("pred_init", "guidance", "confidence")):
+                scale = float(r.abs().max().clamp_min(1.0))
+                assert float((o - r).abs().max()) <= 4e-3 * scale, (case, K, B, H, W, name)
+            fz = heads.fused_heads_prologue(*args, None, 0.5 * (K * K - 1), K, preserve_input=False)
+            N = K * K - 1
+            g = ours[1]
+            ref_off = torch.cat((g[:, :N], torch.zeros_like(g[:, :2]), g[:, N:2 * N]), 1)      # zero pair at the centre tap
+            assert torch.equal(fz["offset"], ref_off), (case, K, B, H, W)
+            assert float((fz["aff"].sum(1) - 1.0).abs().max()) <= 2e-6, (case, K, B, H, W)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
