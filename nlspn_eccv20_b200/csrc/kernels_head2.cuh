@@ -453,7 +453,8 @@ inline cudaError_t head_rows_launch(const CUtensorMap &m_id, const CUtensorMap &
 template <int K, int KS = 1>                                       // KS 8-channel K-steps per TMA stage
 struct HeadPersist : HeadRows<K, 3> {
     using Base = HeadRows<K, 3>;
-    static constexpr int NG = Base::R >= 2 ? 2 : 1;
+    static constexpr int NG = 2;    // epilogue groups of four warps: the rows of a tile are dealt alternately (K = 3); with R = 1 (K = 5)
+                                    // they take alternate tiles (one group: 2.74 ms at KITTI B = 8, two: 2.18; three for K = 3: no gain)
     static constexpr int THREADS = 64 + 128 * NG;
     static constexpr int XCH_BYTES = 2 * 4 * Base::R * Base::NOUT * 4;              // per group
     static constexpr int PA_ROW = KS * 1024;                                        // one input row of one 32-pixel box: [8 KS ch][32 px]
