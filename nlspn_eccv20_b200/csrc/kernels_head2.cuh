@@ -18,9 +18,11 @@
 //   * per output pixel the tensor core reads 3 KB of activations (three dy) instead of 9 KB, nothing is re-packed,
 //     and the block sparsity of the weights is used: the 64-channel branches of the init / confidence heads only feed
 //     one output each, so their MMAs are N = 16 instead of N = NW.
-//   * R output rows per CTA (R accumulators side by side in TMEM, R * NW <= 256 columns, two CTAs per SM) share
-//     R + 2 input rows; warp 0 feeds a ring of TMA stages, warp 1 issues the MMAs (one elected lane each, the warps
-//     stay converged), the other two sleep at the CTA barrier until the accumulators are complete.
+//   * R output rows per tile (R accumulators side by side in TMEM, R * NW <= 256 columns) share R + 2 input rows.
+//   * two kernels run this GEMM: head_rows_kernel (one CTA per tile, two per SM: warp 0 feeds a ring of TMA stages,
+//     warp 1 issues the MMAs -- one elected lane each, the warps stay converged -- and all four warps run the epilogue)
+//     and, the default, head_persist_kernel (one persistent CTA per SM: TMA warp, MMA warp, two groups of four
+//     epilogue warps, two accumulator sets so that the epilogue of a tile overlaps the main loop of the next).
 //   * epilogue: bias, relu / sigmoid, and -- when the caller passes the prologue's outputs -- _off_insert,
 //     _affinity_normalization, _aff_insert, the confidence fix-up and the first blend + pre-multiply
 //     (nlspnmodel.py:252-269,179-201,328-351; same expressions as prologue_fwd_kernel), so that `guidance` never
@@ -41,8 +43,7 @@ struct HeadRows {
     static constexpr int A_BOX = ROWS * 1024, A_BYTES = 4 * A_BOX;
     static constexpr int B_WIDE = 3 * NW * 32, B_NARROW = 3 * 16 * 32;     // bytes per stage: [dy][N x 8 tf32]
     static constexpr int B_SLOT = B_WIDE;                         // multiple of 128 bytes
-    // ring depth: the kernel is bound by bytes in flight (ncu: DRAM 32 %, L2 42 %, tensor pipe 39 %, no unit busy), so
-    // take the deepest ring that still lets two CTAs share an SM (228 KB minus 1 KB reserved per CTA)
+    // ring depth of head_rows_kernel: the deepest that still lets two CTAs share an SM (228 KB minus 1 KB reserved per CTA)
     static constexpr int RING = RING_ > 0 ? RING_ : ((4 * (A_BYTES + B_SLOT) + 1024 + 1024 + 256) * 2 <= 228 * 1024 ? 4 : 3);
     static constexpr int TILE_OUT = 124;                          // lanes 1 .. 124 of a 128-pixel tile are outputs (see head_tiles_x)
     static constexpr int STAGES = 32, WIDE_STAGES = 16;           // (fe1, oa) x 8 chunks wide, (id, cf) x 8 chunks narrow
