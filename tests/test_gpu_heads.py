@@ -50,13 +50,18 @@ def test_fused_heads_backward_is_the_stock_layers_backward():
     leaves = [t.clone().requires_grad_(True) for t in x + w + b]
     o = heads.fused_heads(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], leaves[7], leaves[5], leaves[8], leaves[6], leaves[9], K)
     g = [torch.randn_like(t) for t in o]
+    # pixels whose init pre-activation lies within TF32 rounding of the ReLU kink may take the other branch in the two
+    # implementations: no upstream gradient there, so that both backward passes see the same mask
+    with torch.no_grad():
+        z_init = torch.nn.functional.conv2d(torch.cat((x[0], x[3]), 1), w[0], b[0], 1, 1)
+        g[0] = g[0] * (z_init.abs() > 2e-2).to(g[0].dtype)
     torch.autograd.backward(o, g)
     leaves2 = [t.clone().requires_grad_(True) for t in x + w + b]
     r = heads.reference_heads(leaves2[0], leaves2[1], leaves2[2], leaves2[3], leaves2[4], leaves2[7], leaves2[5], leaves2[8], leaves2[6], leaves2[9])
     torch.autograd.backward(r, g)
     for a, c in zip(leaves, leaves2):
         s = float(c.grad.abs().max().clamp_min(1e-6))
-        assert float((a.grad - c.grad).abs().max()) <= 2e-2 * s
+        assert float((a.grad - c.grad).abs().max()) <= 5e-3 * s
 
 
 def test_fused_heads_reject_what_they_do_not_implement():
