@@ -288,6 +288,27 @@ NLSPN_API int nlspn_heads_prologue_fwd(const float *id_fd1, const float *oa_fd1,
                                        float *pred_init, float *confidence, float *guidance,
                                        float *offset, float *aff, float *conf_fixed, float *src0, void *stream);
 
+/* Weight (and bias) gradients of the same three layers on tcgen05 (training; kernels_head_wgrad.cuh).  Replaces what
+ * autograd runs for nlspnmodel.py:69-86,297,301,313 in the reference -- the ReLU / Sigmoid backward, three
+ * cudnn_convolution_backward_weight calls on the 128-channel concatenations and three bias sums -- by
+ *   nlspn_heads_grad_prep   g_init / g_guidance / g_confidence (upstream gradients of pred_init [B,1,H,W], guidance
+ *                           [B,3N,H,W], confidence [B,1,H,W]; NULL = zero) -> g_shift [3][B][3N+2][H][W]: the activation
+ *                           derivatives applied (pred_init, confidence = the forward outputs), channels concatenated
+ *                           (0 = init, 1..3N = guidance, 3N+1 = confidence), and the whole written three times, shifted
+ *                           by +1 / 0 / -1 pixels along x (copy 1, g_shift + B (3N+2) H W, is the plain concatenation: the
+ *                           input of the data gradients); g_bias [3N+2] (NULL = skip) = (db_id, db_oa[0..3N), db_cf)
+ *   nlspn_heads_wgrad       dw_all [3N+2,128,3,3] (overwritten): rows 0 = dw_id, 1..3N = dw_oa, 3N+1 = dw_cf, input
+ *                           channels 0..63 = the head's own branch, 64..127 = fe1.  A NULL branch tensor (id_fd1 /
+ *                           oa_fd1 / cf_fd1) leaves its 64-channel block zero.  TF32 products, fp32 accumulation over the
+ *                           pixels in tensor memory, split-K partials added with fp32 atomics.
+ * W % 4 == 0 and 16-byte aligned tensors (nlspn_heads_wgrad_supported); otherwise NLSPN_ERR_SHAPE / NLSPN_ERR_ALIGN. */
+NLSPN_API int nlspn_heads_wgrad_supported(int W, int K);
+NLSPN_API int nlspn_heads_grad_prep(const float *g_init, const float *pred_init, const float *g_guidance,
+                                    const float *g_confidence, const float *confidence, int B, int H, int W, int K,
+                                    float *g_shift, float *g_bias, void *stream);
+NLSPN_API int nlspn_heads_wgrad(const float *id_fd1, const float *oa_fd1, const float *cf_fd1, const float *fe1,
+                                const float *g_shift, int B, int H, int W, int K, float *dw_all, void *stream);
+
 /* Double-precision variants of the single-step operator: the reference dispatches this op over
  * float and double (AT_DISPATCH_FLOATING_TYPES, modulated_deform_conv_cuda.cu:93,224) and its
  * tests run gradcheck in double (src/model/deformconv/test.py).  Same domain, argument order and

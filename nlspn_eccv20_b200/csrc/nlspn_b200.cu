@@ -21,6 +21,7 @@
 #include "kernels_det.cuh"
 #include "kernels_head.cuh"
 #include "kernels_head2.cuh"
+#include "kernels_head_wgrad.cuh"
 
 using namespace nlspn;
 
@@ -75,11 +76,11 @@ inline int opt(Opt o) { return g_opt[o].load(std::memory_order_relaxed); }
 
 // ---- optional per-kernel-class timing (bench.py's roofline): CUDA events around every launch
 enum ProfClass { kProfPrologue = 0, kProfIterFwd, kProfBwdState, kProfBwdParam, kProfFinalBwd,
-                 kProfIterBwdV1, kProfDcnFwd, kProfDcnBwd, kProfBwdTable, kProfBwdGather, kProfHeads, kProfClasses };
+                 kProfIterBwdV1, kProfDcnFwd, kProfDcnBwd, kProfBwdTable, kProfBwdGather, kProfHeads, kProfHeadsGrad, kProfClasses };
 const char *const kProfNames[kProfClasses] = {"prologue_fwd_kernel", "iter_fwd_kernel", "bwd_state_kernel",
                                               "bwd_param_kernel", "final_bwd_kernel", "iter_bwd_kernel",
                                               "dcn_forward", "dcn_backward", "table_build_kernel",
-                                              "bwd_gather_kernel", "head_fused_kernel"};
+                                              "bwd_gather_kernel", "head_fused_kernel", "head_wgrad_kernel"};
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
 std::mutex g_prof_mu;
 std::atomic<int> g_prof_on{0};
@@ -1533,6 +1534,112 @@ int nlspn_heads_prologue_fwd(const float *id_fd1, const float *oa_fd1, const flo
     ProfScope prof__(kProfHeads, st);
     HeadRowsOut o{pred_init, confidence, guidance, feat_fix, gamma, offset, aff, conf_fixed, src0, affinity, flags};
     return launch_head_rows(id_fd1, oa_fd1, cf_fd1, fe1, packed, bias, B, H, W, K, o, st);
+}
+
+// ---- weight gradient of the head convolutions on tcgen05 (kernels_head_wgrad.cuh) ----
+// [imgs, chans, H, W] fp32 tensor with the dims ordered (x, channel, row, image) and a box {32 px, box_c channels, box_r rows, 1}
+// in the 128-byte swizzle: box row = one K-major tf32 operand row (32 pixels)
+static int make_wgrad_map(CUtensorMap *map, const float *base, int imgs, int chans, int H, int W, int box_c, int box_r)
+{
+    const MapKey key{base, chans, imgs, H, W, 32, box_r, box_c, 15};
+    if (map_cache_get(key, map)) return 0;
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)chans, (cuuint64_t)H, (cuuint64_t)imgs};
+    const cuuint64_t strides[3] = {(cuuint64_t)H * W * 4, (cuuint64_t)W * 4, (cuuint64_t)chans * H * W * 4};
+    const cuuint32_t box[4] = {32, (cuuint32_t)box_c, (cuuint32_t)box_r, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims,
+                                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NLSPN_ERR_SHAPE, "cuTensorMapEncodeTiled(head wgrad) failed (CUresult %d)", (int)r);
+    map_cache_put(key, *map);
+    return 0;
+}
+
+int nlspn_heads_wgrad_supported(int W, int K)
+{
+    return (K == 3 || K == 5 || K == 7) && W > 0 && W % 4 == 0 && tiled_enabled() && encode_tiled_fn() != nullptr ? 1 : 0;
+}
+
+static int check_heads_grad(const char *who, int B, int H, int W, int K)
+{
+    if (int rc = check_shape(B, H, W, K, 1)) return rc;
+    if (!nlspn_heads_wgrad_supported(W, K))
+        return fail(NLSPN_ERR_SHAPE, "%s: needs W %% 4 == 0 and the TMA path (got W = %d): use the framework's own "
+                                     "convolution gradients instead", who, W);
+    if (H > 65535 || 3L * B > 0x7fffffffL) return fail(NLSPN_ERR_SHAPE, "%s: H > 65535 is not supported (got %d)", who, H);
+    return 0;
+}
+
+int nlspn_heads_grad_prep(const float *g_init, const float *pred_init, const float *g_guidance, const float *g_confidence,
+                          const float *confidence, int B, int H, int W, int K, float *g_shift, float *g_bias, void *stream)
+{
+    if (int rc = check_heads_grad("heads_grad_prep", B, H, W, K)) return rc;
+    if (!pred_init || !confidence || !g_shift) return fail(NLSPN_ERR_NULL, "heads_grad_prep: a required pointer is NULL");
+    if (!aligned16(g_shift) || !aligned16(pred_init) || !aligned16(confidence) || !aligned16(g_init) || !aligned16(g_guidance) ||
+        !aligned16(g_confidence))
+        return fail(NLSPN_ERR_ALIGN, "heads_grad_prep: tensors must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NT = 3 * (K * K - 1) + 2;
+    if (g_bias) {
+        const cudaError_t e = cudaMemsetAsync(g_bias, 0, sizeof(float) * NT, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(g_bias)");
+    }
+    const long quads = (long)H * (W / 4);
+    dim3 grid((unsigned)((quads + kGradPrepQuads - 1) / kGradPrepQuads), (unsigned)NT, (unsigned)B);
+    ProfScope prof__(kProfHeadsGrad, st);
+    head_grad_prep_kernel<<<grid, kGradPrepThreads, 0, st>>>(g_init, pred_init, g_guidance, g_confidence, confidence, B, NT, H, W,
+                                                             g_shift, g_bias);
+    NLSPN_CHECK_LAUNCH("head_grad_prep_kernel");
+    return 0;
+}
+
+int nlspn_heads_wgrad(const float *id_fd1, const float *oa_fd1, const float *cf_fd1, const float *fe1, const float *g_shift,
+                      int B, int H, int W, int K, float *dw_all, void *stream)
+{
+    if (int rc = check_heads_grad("heads_wgrad", B, H, W, K)) return rc;
+    if (!fe1 || !g_shift || !dw_all) return fail(NLSPN_ERR_NULL, "heads_wgrad: a required pointer is NULL");
+    if (!aligned16(id_fd1) || !aligned16(oa_fd1) || !aligned16(cf_fd1) || !aligned16(fe1) || !aligned16(g_shift))
+        return fail(NLSPN_ERR_ALIGN, "heads_wgrad: tensors must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N3 = 3 * (K * K - 1), NT = N3 + 2, ldw = 2 * kHeadCin * 9;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, &sms, nullptr) != 0 || sms <= 0) sms = 148;
+    cudaError_t e = cudaMemsetAsync(dw_all, 0, sizeof(float) * (size_t)NT * ldw, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(dw_all)");
+    CUtensorMap mg32, mg8, mx;
+    if (int rc = make_wgrad_map(&mg32, g_shift, 3 * B, NT, H, W, 32, 3)) return rc;
+    if (int rc = make_wgrad_map(&mg8, g_shift, 3 * B, NT, H, W, 8, 3)) return rc;
+    ProfScope prof__(kProfHeadsGrad, st);
+    // the shared fe1 (input channels 64..127 of every head) against all 3N + 2 gradient channels, 32 at a time
+    if (int rc = make_wgrad_map(&mx, fe1, B, kHeadCin, H, W, kHeadCin, 1)) return rc;
+    for (int n0 = 0; n0 < NT; n0 += 32) {
+        e = head_wgrad_launch<32>(mx, mg32, B, H, W, n0, NT - n0 < 32 ? NT - n0 : 32, ldw, dw_all + kHeadCin * 9, sms, st);
+        if (e != cudaSuccess) return cuda_fail(e, "head_wgrad_kernel<32>(fe1)");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    // each head's own branch (input channels 0..63) against its own gradient channels; NULL = that branch needs no gradient
+    if (oa_fd1) {
+        if (int rc = make_wgrad_map(&mx, oa_fd1, B, kHeadCin, H, W, kHeadCin, 1)) return rc;
+        for (int n0 = 1; n0 < 1 + N3; n0 += 32) {
+            e = head_wgrad_launch<32>(mx, mg32, B, H, W, n0, 1 + N3 - n0 < 32 ? 1 + N3 - n0 : 32, ldw, dw_all, sms, st);
+            if (e != cudaSuccess) return cuda_fail(e, "head_wgrad_kernel<32>(off_aff)");
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+    }
+    if (id_fd1) {
+        if (int rc = make_wgrad_map(&mx, id_fd1, B, kHeadCin, H, W, kHeadCin, 1)) return rc;
+        e = head_wgrad_launch<8>(mx, mg8, B, H, W, 0, 1, ldw, dw_all, sms, st);
+        if (e != cudaSuccess) return cuda_fail(e, "head_wgrad_kernel<8>(init)");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    if (cf_fd1) {
+        if (int rc = make_wgrad_map(&mx, cf_fd1, B, kHeadCin, H, W, kHeadCin, 1)) return rc;
+        e = head_wgrad_launch<8>(mx, mg8, B, H, W, NT - 1, 1, ldw, dw_all, sms, st);
+        if (e != cudaSuccess) return cuda_fail(e, "head_wgrad_kernel<8>(confidence)");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return 0;
 }
 
 static int check_dcn_domain(int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h,

@@ -8,8 +8,9 @@ Replaces, in the reference's ``NLSPNModel.forward`` (nlspnmodel.py:297,301,313; 
     confidence = cf_dec0(cat(cf_fd1, fe1))            # conv3x3 128 -> 1,  Sigmoid
 
 without the three concatenations.  Arithmetic: TF32 products, fp32 accumulation -- what cuDNN uses for these layers
-under PyTorch's default ``torch.backends.cudnn.allow_tf32 = True``.  The backward (data and weight gradients of the
-same layers) is stock torch (cuDNN), from the saved inputs.  There is no fallback in here: callers that cannot use it
+under PyTorch's default ``torch.backends.cudnn.allow_tf32 = True``.  Backward: the weight and bias gradients are tcgen05
+too (nlspn_heads_grad_prep / nlspn_heads_wgrad, csrc/kernels_head_wgrad.cuh; W % 4 == 0), the data gradients stock torch
+(cuDNN), all from the saved inputs.  There is no fallback in here: callers that cannot use it
 (CPU tensors, other channel counts) keep their stock layers -- see ``model.NLSPNModel``."""
 from __future__ import annotations
 
@@ -20,7 +21,7 @@ from torch.nn import functional as TF
 
 from . import _lib
 
-__all__ = ["fused_heads", "fused_heads_prologue", "prologue_supported", "FusedHeadsFunction", "supported"]
+__all__ = ["fused_heads", "fused_heads_prologue", "prologue_supported", "wgrad_supported", "grad_prep", "weight_grads", "FusedHeadsFunction", "supported"]
 
 CIN = 64       # channels of each of the four tensors (64 + 64 = the reference's 128-channel concatenations)
 
@@ -119,22 +120,27 @@ class FusedHeadsFunction(torch.autograd.Function):
         outs = _forward(id_fd1.detach(), oa_fd1.detach(), cf_fd1.detach(), fe1.detach(), w_id.detach(), b_id.detach(),
                         w_oa.detach(), b_oa.detach(), w_cf.detach(), b_cf.detach(), K)
         ctx.save_for_backward(id_fd1, oa_fd1, cf_fd1, fe1, w_id, w_oa, w_cf, outs[0], outs[2])
+        ctx.K = int(K)
         return outs
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_init, g_guid, g_conf):
-        """Stock cuDNN data / weight gradients of the same three layers, WITHOUT re-building the three 128-channel
+        """W % 4 == 0: `_backward_native` (weight gradients on tcgen05).  Otherwise:
+        stock cuDNN data / weight gradients of the same three layers, WITHOUT re-building the three 128-channel
         concatenations: a convolution is linear in its input channels, so each head's own 64-channel branch gets its own
         (64-channel) gradient calls, and the shared fe1 gets ONE call pair with all 3N + 2 output channels at once
         (instead of three 128-channel calls whose fe1 halves are then added).  KITTI B = 8: 16.5 -> see DESIGN 12."""
         id_fd1, oa_fd1, cf_fd1, fe1, w_id, w_oa, w_cf, pred_init, confidence = ctx.saved_tensors
+        need_in, need_w = ctx.needs_input_grad[:4], (ctx.needs_input_grad[4], ctx.needs_input_grad[6], ctx.needs_input_grad[8])
+        if wgrad_supported(fe1.shape[3], ctx.K) and all(t.is_contiguous() and t.data_ptr() % 16 == 0 for t in (id_fd1, oa_fd1, cf_fd1, fe1)):
+            return _backward_native(ctx.K, need_in, need_w, id_fd1, oa_fd1, cf_fd1, fe1, w_id, w_oa, w_cf, pred_init, confidence,
+                                    g_init, g_guid, g_conf)
         z = torch.zeros_like
         g_init = z(pred_init) if g_init is None else g_init * (pred_init > 0).to(g_init.dtype)        # ReLU
         g_conf = z(confidence) if g_conf is None else g_conf * confidence * (1.0 - confidence)         # Sigmoid
         g_guid = torch.zeros((fe1.shape[0], w_oa.shape[0]) + tuple(fe1.shape[2:]), device=fe1.device) if g_guid is None else g_guid
         gs = [g_init.contiguous(), g_guid.contiguous(), g_conf.contiguous()]
-        need_in, need_w = ctx.needs_input_grad[:4], (ctx.needs_input_grad[4], ctx.needs_input_grad[6], ctx.needs_input_grad[8])
         grads_in, g_w_own = [None, None, None, None], [None, None, None]
         for k, (x, w, g) in enumerate(((id_fd1, w_id, gs[0]), (oa_fd1, w_oa, gs[1]), (cf_fd1, w_cf, gs[2]))):
             w_own = w[:, :CIN].contiguous()
@@ -154,6 +160,71 @@ class FusedHeadsFunction(torch.autograd.Function):
             g_w = [torch.cat((g_w_own[k], parts[k]), 1) if need_w[k] else None for k in range(3)]
         g_b = [g.sum(dim=(0, 2, 3)) for g in gs]
         return grads_in[0], grads_in[1], grads_in[2], grads_in[3], g_w[0], g_b[0], g_w[1], g_b[1], g_w[2], g_b[2], None
+
+
+def wgrad_supported(W, K) -> bool:
+    """Do the tcgen05 weight-gradient kernels (nlspn_heads_grad_prep / nlspn_heads_wgrad) cover this width / prop_kernel?"""
+    return bool(_lib.load().nlspn_heads_wgrad_supported(int(W), int(K)))
+
+
+def grad_prep(pred_init, confidence, g_init, g_guid, g_conf, K):
+    """nlspn_heads_grad_prep: -> (g_shift [3,B,3N+2,H,W], g_bias [3N+2]); a None gradient is a zero gradient.  g_shift[1] is
+    the concatenated gradient with the ReLU / Sigmoid derivatives applied, g_shift[0] / g_shift[2] the same shifted by one
+    pixel (g[.., x + 1] / g[.., x - 1], zero outside the row)."""
+    lib = _lib.load()
+    B, _, H, W = pred_init.shape
+    NT = 3 * (K * K - 1) + 2
+    dev = pred_init.device
+    gin = [None if g is None else g.to(torch.float32).contiguous() for g in (g_init, g_guid, g_conf)]
+    g_shift = torch.empty((3, B, NT, H, W), device=dev, dtype=torch.float32)
+    g_bias = torch.empty((NT,), device=dev, dtype=torch.float32)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nlspn_heads_grad_prep(_ptr(gin[0]), _ptr(pred_init.contiguous()), _ptr(gin[1]), _ptr(gin[2]),
+                                             _ptr(confidence.contiguous()), B, H, W, K, _ptr(g_shift), _ptr(g_bias), st),
+                   "nlspn_heads_grad_prep")
+    return g_shift, g_bias
+
+
+def weight_grads(id_fd1, oa_fd1, cf_fd1, fe1, g_shift, K):
+    """nlspn_heads_wgrad: -> dw_all [3N+2,128,3,3] (row 0 = dw_id, 1..3N = dw_oa, 3N+1 = dw_cf); a None branch tensor leaves
+    its 64 input channels zero."""
+    lib = _lib.load()
+    B, _, H, W = fe1.shape
+    dev = fe1.device
+    dw_all = torch.empty((3 * (K * K - 1) + 2, 2 * CIN, 3, 3), device=dev, dtype=torch.float32)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nlspn_heads_wgrad(_ptr(id_fd1), _ptr(oa_fd1), _ptr(cf_fd1), _ptr(fe1), _ptr(g_shift), B, H, W, K,
+                                         _ptr(dw_all), st), "nlspn_heads_wgrad")
+    return dw_all
+
+
+def _backward_native(K, need_in, need_w, id_fd1, oa_fd1, cf_fd1, fe1, w_id, w_oa, w_cf, pred_init, confidence, g_init, g_guid, g_conf):
+    """Activation derivatives + concatenation + bias sums in one kernel (nlspn_heads_grad_prep), every weight gradient on
+    tcgen05 (nlspn_heads_wgrad, csrc/kernels_head_wgrad.cuh); the four data gradients stay with cuDNN, fed from the
+    concatenated gradient the first kernel wrote."""
+    N3 = 3 * (K * K - 1)
+    NT = N3 + 2
+    g_shift, g_bias = grad_prep(pred_init, confidence, g_init, g_guid, g_conf, K)
+    g_all = g_shift[1]                                                            # [B, 3N + 2, H, W]
+    grads_in = [None, None, None, None]
+    own = ((id_fd1, w_id, slice(0, 1)), (oa_fd1, w_oa, slice(1, 1 + N3)), (cf_fd1, w_cf, slice(NT - 1, NT)))
+    for k, (x, w, sl) in enumerate(own):
+        if need_in[k]:
+            # the guidance head has no activation: its upstream gradient is usable as it came
+            g = g_guid if (k == 1 and g_guid is not None and g_guid.is_contiguous()) else g_all[:, sl].contiguous()
+            grads_in[k] = torch.nn.grad.conv2d_input(x.shape, w[:, :CIN].contiguous(), g, stride=1, padding=1)
+    if need_in[3]:
+        w_fe = torch.cat((w_id[:, CIN:], w_oa[:, CIN:], w_cf[:, CIN:]), 0).contiguous()      # [3N + 2, 64, 3, 3]
+        grads_in[3] = torch.nn.grad.conv2d_input(fe1.shape, w_fe, g_all, stride=1, padding=1)
+    g_w = [None, None, None]
+    if any(need_w):
+        dw_all = weight_grads(id_fd1 if need_w[0] else None, oa_fd1 if need_w[1] else None, cf_fd1 if need_w[2] else None,
+                              fe1, g_shift, K)
+        g_w = [dw_all[sl] if need_w[k] else None for k, (_, _, sl) in enumerate(own)]
+    g_b = [g_bias[sl] for _, _, sl in own]
+    return grads_in[0], grads_in[1], grads_in[2], grads_in[3], g_w[0], g_b[0], g_w[1], g_b[1], g_w[2], g_b[2], None
 
 
 def fused_heads(id_fd1, oa_fd1, cf_fd1, fe1, w_id, b_id, w_oa, b_oa, w_cf, b_cf, prop_kernel=3):

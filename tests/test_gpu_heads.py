@@ -232,3 +232,63 @@ def test_heads_random_shapes_against_fp32_layers():
             assert float((fz["aff"].sum(1) - 1.0).abs().max()) <= 2e-6, (case, K, B, H, W)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("B,H,W,K", [(2, 7, 44, 3), (1, 9, 128, 3), (2, 37, 132, 3), (1, 5, 1216, 3), (1, 20, 300, 5),
+                                     (1, 11, 132, 7), (3, 1, 4, 3)])
+def test_heads_weight_gradients_on_tcgen05_match_fp32(B, H, W, K):
+    """nlspn_heads_grad_prep + nlspn_heads_wgrad (csrc/kernels_head_wgrad.cuh) against what autograd runs for the reference's
+    three head layers (nlspnmodel.py:69-86,297,301,313): activation derivatives, concatenation, the shifted copies
+    (exact), bias sums and the fp32 weight gradients of the 128-channel layers (TF32 products: <= 3e-3 of the scale)."""
+    from nlspn_eccv20_b200 import heads
+    dev = torch.device("cuda:0")
+    assert heads.wgrad_supported(W, K)
+    x, w, b = _case(B, H, W, K, 11, dev)
+    g = torch.Generator().manual_seed(12)
+    N3 = 3 * (K * K - 1)
+    pred_init = torch.relu(torch.randn(B, 1, H, W, generator=g)).to(dev)
+    confidence = torch.sigmoid(torch.randn(B, 1, H, W, generator=g)).to(dev)
+    gi, gg, gc = (torch.randn(B, n, H, W, generator=g).to(dev) for n in (1, N3, 1))
+    g_shift, g_bias = heads.grad_prep(pred_init, confidence, gi, gg, gc, K)
+    g_all = torch.cat((gi * (pred_init > 0), gg, gc * confidence * (1.0 - confidence)), 1)
+    assert float((g_shift[1] - g_all).abs().max()) <= 1e-6
+    z = torch.zeros_like(g_all[..., :1])
+    assert torch.equal(g_shift[0], torch.cat((g_shift[1][..., 1:], z), -1))          # g[.., x + 1]
+    assert torch.equal(g_shift[2], torch.cat((z, g_shift[1][..., :-1]), -1))         # g[.., x - 1]
+    bias_ref = g_all.double().sum(dim=(0, 2, 3))
+    assert float((g_bias.double() - bias_ref).abs().max()) <= 1e-4 * float(bias_ref.abs().max().clamp_min(1.0))
+    dw = heads.weight_grads(x[0], x[1], x[2], x[3], g_shift, K)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        own = (slice(0, 1), slice(1, 1 + N3), slice(N3 + 1, N3 + 2))
+        ref = torch.empty_like(dw)
+        for k, sl in enumerate(own):
+            ref[sl] = torch.nn.grad.conv2d_weight(torch.cat((x[k], x[3]), 1), (sl.stop - sl.start, 128, 3, 3),
+                                                  g_all[:, sl].contiguous(), stride=1, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    scale = float(ref.abs().max().clamp_min(1e-6))
+    assert float((dw - ref).abs().max()) <= 3e-3 * scale
+    # a NULL branch leaves its block zero and the others unchanged; a NULL gradient is a zero gradient
+    dw2 = heads.weight_grads(None, x[1], None, x[3], g_shift, K)
+    assert float(dw2[0, :64].abs().max()) == 0.0 and float(dw2[-1, :64].abs().max()) == 0.0
+    assert float((dw2[1:-1] - dw[1:-1]).abs().max()) <= 1e-4 * scale
+    s0, b0 = heads.grad_prep(pred_init, confidence, None, gg, None, K)
+    assert float(s0[:, :, 0].abs().max()) == 0.0 and float(s0[:, :, -1].abs().max()) == 0.0 and torch.equal(s0[1][:, 1:-1], gg)
+    assert float(b0[0]) == 0.0 and float(b0[-1]) == 0.0
+
+
+def test_heads_weight_gradients_reject_what_they_do_not_implement():
+    from nlspn_eccv20_b200 import heads
+    dev = torch.device("cuda:0")
+    assert not heads.wgrad_supported(131, 3)
+    x, w, b = _case(1, 6, 18, 3, 2, dev)
+    a = torch.rand(1, 1, 6, 18, device=dev)
+    with pytest.raises(RuntimeError):
+        heads.grad_prep(a, a, None, None, None, 3)
+    # ... and the autograd Function keeps the stock gradients there
+    leaves = [t.clone().requires_grad_(True) for t in x + w + b]
+    o = heads.fused_heads(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], leaves[7], leaves[5], leaves[8], leaves[6], leaves[9], 3)
+    torch.autograd.backward(o, [torch.ones_like(t) for t in o])
+    assert all(t.grad is not None and bool(torch.isfinite(t.grad).all()) for t in leaves)
