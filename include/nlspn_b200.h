@@ -294,10 +294,10 @@ NLSPN_API int nlspn_heads_prologue_fwd(const float *id_fd1, const float *oa_fd1,
  *   nlspn_heads_grad_prep   g_init / g_guidance / g_confidence (upstream gradients of pred_init [B,1,H,W], guidance
  *                           [B,3N,H,W], confidence [B,1,H,W]; NULL = zero) -> g_shift [3][B][3N+2][H][W]: the activation
  *                           derivatives applied (pred_init, confidence = the forward outputs), channels concatenated
- *                           (0 = init, 1..3N = guidance, 3N+1 = confidence), and the whole written three times, shifted
+ *                           (0 = init, 1 = confidence, 2..3N+1 = guidance), and the whole written three times, shifted
  *                           by +1 / 0 / -1 pixels along x (copy 1, g_shift + B (3N+2) H W, is the plain concatenation: the
- *                           input of the data gradients); g_bias [3N+2] (NULL = skip) = (db_id, db_oa[0..3N), db_cf)
- *   nlspn_heads_wgrad       dw_all [3N+2,128,3,3] (overwritten): rows 0 = dw_id, 1..3N = dw_oa, 3N+1 = dw_cf, input
+ *                           input of the data gradients); g_bias [3N+2] (NULL = skip) = (db_id, db_cf, db_oa[0..3N))
+ *   nlspn_heads_wgrad       dw_all [3N+2,128,3,3] (overwritten): rows 0 = dw_id, 1 = dw_cf, 2..3N+1 = dw_oa, input
  *                           channels 0..63 = the head's own branch, 64..127 = fe1.  A NULL branch tensor (id_fd1 /
  *                           oa_fd1 / cf_fd1) leaves its 64-channel block zero.  TF32 products, fp32 accumulation over the
  *                           pixels in tensor memory, split-K partials added with fp32 atomics.

@@ -43,8 +43,9 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr)
            ((uint64_t)2 << 61);
 }
 
-// Upstream gradients of the three heads -> g_shift [3][B][NT][H][W], NT = 3N + 2 (channel 0 = init, 1 .. 3N = guidance,
-// NT - 1 = confidence): copy d holds g[.., x - d + 1] (zero outside the row).  Init: g * (pred_init > 0) (ReLU, nlspnmodel.py
+// Upstream gradients of the three heads -> g_shift [3][B][NT][H][W], NT = 3N + 2 (channel 0 = init, 1 = confidence,
+// 2 .. 3N + 1 = guidance -- the two one-channel heads side by side, so that one 8-channel box serves both):
+// copy d holds g[.., x - d + 1] (zero outside the row).  Init: g * (pred_init > 0) (ReLU, nlspnmodel.py
 // :69-72); confidence: g * c (1 - c) (Sigmoid, :83-86).  A NULL gradient is a zero gradient.  g_bias[n] += sum of channel n.
 // grid (plane chunks, NT, B), one thread per four pixels; W % 4 == 0.
 constexpr int kGradPrepThreads = 256;
@@ -68,8 +69,8 @@ head_grad_prep_kernel(const float *__restrict__ g_init, const float *__restrict_
     const float *g, *act = nullptr;
     int mode = 0;
     if (n == 0) { g = g_init ? g_init + (long)b * P : nullptr; act = pred_init + (long)b * P; mode = 1; }
-    else if (n == NT - 1) { g = g_conf ? g_conf + (long)b * P : nullptr; act = confidence + (long)b * P; mode = 2; }
-    else g = g_guid ? g_guid + ((long)b * (NT - 2) + (n - 1)) * P : nullptr;
+    else if (n == 1) { g = g_conf ? g_conf + (long)b * P : nullptr; act = confidence + (long)b * P; mode = 2; }
+    else g = g_guid ? g_guid + ((long)b * (NT - 2) + (n - 2)) * P : nullptr;
     const long copy = (long)B * NT * P;
     float *out = g_shift + ((long)b * NT + n) * P;
     float sum = 0.f;
@@ -232,6 +233,184 @@ inline cudaError_t head_wgrad_launch(const CUtensorMap &map_x, const CUtensorMap
     const long items = (long)B * H * ((W + 31) / 32);
     const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
     head_wgrad_kernel<NP><<<grid, C::THREADS, C::smem, st>>>(map_x, map_g, B, H, W, n0, n_cnt, ldw, dW);
+    return cudaGetLastError();
+}
+
+// ---- rolling form: a CTA walks DOWN a 32-pixel column strip, so that a gradient row is loaded once for the three input rows
+// it meets (instead of three times), and NX input tensors share it (N = 64 NX columns per MMA).  Stage j of the ring holds
+// {X tiles of input row y, the three shifted copies of gradient row y + 1}; the MMAs of row y read the gradient rows of stages
+// j (dy = 0), j - 1 (dy = 1), j - 2 (dy = 2), one accumulator per dy.  Roles swapped against the per-chunk form: M = 128 rows =
+// the input channels (A = X, shared by the three dy MMAs of a K-step: read once into the collector), N = 3 NP columns =
+// (copy d = dx, gradient channel) -- tf32 MMAs with K = 8 read 32 bytes per operand row and are bound by shared-memory
+// reads, not by the tensor core (measured: 110 cycles per M128 N128 K8 without the sharing).  Per step: 8 NX KB of X +
+// 3 NP x 128 B of gradient instead of 8 KB + 9 NP x 128 B, and the ring is 7-11 stages deep instead of 3.
+// Items = (image, strip, segment of SEG rows); an item starts with two gradient-only steps (rows y0 - 1 and y0).
+struct HeadWgradX { int n_lo[2], n_hi[2], c_off[2]; };       // per input tensor: valid gradient channels, first dW input channel
+
+template <int NP, int NX>
+struct HeadWgradRoll {
+    static constexpr int XT = kHeadCin * 128 * NX;               // bytes of the X tiles of a stage: [64 NX channels][32 px]
+    static constexpr int GT = NP * 128;                          // one shifted copy of a gradient row [NP channels][32 px]
+    static constexpr int STAGE = XT + 3 * GT;
+    static constexpr int NCOL = NP == 32 ? 96 : 32;              // MMA N: the 3 NP (copy, gradient channel) rows, rounded up to 16
+    // the last stage's MMAs read 128 A rows from its X base (NX = 1: 64 of them are whatever follows) and NCOL B rows from its
+    // gradient base: what of that lies beyond the stage must still be shared memory
+    static constexpr int PAD = (STAGE < 128 * 128 ? 128 * 128 - STAGE : 0) + (NCOL * 128 - 3 * GT);
+    static constexpr int RING = (232448 - 3072 - PAD) / STAGE < 12 ? (232448 - 3072 - PAD) / STAGE : 12;   // 227 KB - alignment, static
+    static constexpr int THREADS = 192;
+    static constexpr uint32_t TMEM_COLS = NP == 32 ? 512u : 128u; // 3 accumulators x NCOL columns, a power of two
+    static constexpr size_t smem = (size_t)RING * STAGE + PAD + 1024;
+    static_assert(RING >= 4, "three stages are in use by the MMAs of one step");
+};
+
+__host__ __device__ constexpr int head_wgrad_seg_rows(int H) { return H <= 32 ? H : (H + (H + 31) / 32 - 1) / ((H + 31) / 32); }
+
+// map_x*: dims (x, channel, row, image), box {32, 64, 1, 1}; map_g: dims (x, channel, copy, row, image), box {32, NP, 3, 1, 1}
+template <int NP, int NX>
+__global__ void __launch_bounds__(HeadWgradRoll<NP, NX>::THREADS, 1)
+head_wgrad_roll_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
+                       const __grid_constant__ CUtensorMap map_g, int B, int H, int W, int seg, int n0, HeadWgradX xs, int ldw,
+                       float *__restrict__ dW)
+{
+    using C = HeadWgradRoll<NP, NX>;
+    extern __shared__ unsigned char wgrad_smem_raw[];
+    __shared__ __align__(8) uint64_t full[C::RING], empty[C::RING], done_bar;
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t ring = (tma::smem_u32(wgrad_smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunks = (W + 31) / 32, nseg = (H + seg - 1) / seg;
+    const long items = (long)B * nseg * chunks;
+    if (tid == 0) {
+        for (int i = 0; i < C::RING; ++i) {
+            tma::mbar_init(&full[i], 1);
+            tma::mbar_init(&empty[i], 1);
+        }
+        tma::mbar_init(&done_bar, 1);
+        tma::fence_barrier_init();
+        tma::prefetch_descriptor(&map_x0);
+        if (NX == 2) tma::prefetch_descriptor(&map_x1);
+        tma::prefetch_descriptor(&map_g);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma::smem_u32(&tmem_base_s)), "r"(C::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 0) {
+        uint32_t j = 0;
+        for (long it = blockIdx.x; it < items; it += gridDim.x) {
+            const int xc = (int)(it % chunks), sg = (int)((it / chunks) % nseg), b = (int)(it / ((long)chunks * nseg));
+            const int y0 = sg * seg, rows = min(seg, H - y0);
+            for (int k = 0; k < rows + 2; ++k, ++j) {
+                const uint32_t slot = j % C::RING;
+                mbar_wait_bounded(&empty[slot], ((j / C::RING) & 1u) ^ 1u);
+                const uint32_t sx = ring + slot * C::STAGE;
+                if (elect_one_sync()) {
+                    tma::mbar_arrive_expect_tx(&full[slot], (k >= 2 ? C::XT : 0) + 3 * C::GT);
+                    if (k >= 2) {
+                        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                                     ::"r"(sx), "l"(reinterpret_cast<uint64_t>(&map_x0)), "r"(tma::smem_u32(&full[slot])), "r"(xc * 32), "r"(0),
+                                     "r"(y0 + k - 2), "r"(b) : "memory");
+                        if (NX == 2)
+                            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                                         ::"r"(sx + kHeadCin * 128), "l"(reinterpret_cast<uint64_t>(&map_x1)), "r"(tma::smem_u32(&full[slot])),
+                                         "r"(xc * 32), "r"(0), "r"(y0 + k - 2), "r"(b) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                                 ::"r"(sx + C::XT), "l"(reinterpret_cast<uint64_t>(&map_g)), "r"(tma::smem_u32(&full[slot])), "r"(xc * 32), "r"(n0),
+                                 "r"(0), "r"(y0 - 1 + k), "r"(b) : "memory");
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // D fp32, A = X tiles [128 input channels][32 px], B = gradient tiles [NCOL (copy, channel) rows][32 px], both tf32 K-major.
+        // The three MMAs of a K-step share A: it stays in the tensor core's collector (fill / use / lastuse), so a K-step reads
+        // 4 KB + 3 x NCOL x 32 B of shared memory instead of three times both operands.
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C::NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        uint32_t j = 0, started = 0;
+        for (long it = blockIdx.x; it < items; it += gridDim.x) {
+            const int sg = (int)((it / chunks) % nseg);
+            const int rows = min(seg, H - sg * seg);
+            for (int k = 0; k < rows + 2; ++k, ++j) {
+                const uint32_t slot = j % C::RING;
+                mbar_wait_bounded(&full[slot], (j / C::RING) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one_sync()) {
+                    if (k >= 2) {
+                        const uint32_t sx = ring + slot * C::STAGE;
+                        const uint32_t sb0 = sx + C::XT, sb1 = ring + ((j + C::RING - 1) % C::RING) * C::STAGE + C::XT,
+                                       sb2 = ring + ((j + C::RING - 2) % C::RING) * C::STAGE + C::XT;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t da = umma_desc_k_sw128(sx + kk * 32);
+                            const uint32_t acc = (started | (uint32_t)kk) != 0 ? 1u : 0u;
+                            umma_tf32<1>(tmem + 0 * C::NCOL, da, umma_desc_k_sw128(sb0 + kk * 32), idesc, acc);
+                            umma_tf32<2>(tmem + 1 * C::NCOL, da, umma_desc_k_sw128(sb1 + kk * 32), idesc, acc);
+                            umma_tf32<3>(tmem + 2 * C::NCOL, da, umma_desc_k_sw128(sb2 + kk * 32), idesc, acc);
+                        }
+                    }
+                    // stage j - 2 (its gradient row was this step's dy = 2 operand) is free once these MMAs have read it
+                    if (j >= 2)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                     ::"r"(tma::smem_u32(&empty[(j - 2) % C::RING])) : "memory");
+                }
+                __syncwarp();
+                if (k >= 2) started = 1;
+            }
+        }
+        if (elect_one_sync())
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tma::smem_u32(&done_bar)) : "memory");
+        __syncwarp();
+    } else {
+        // accumulator dy: lane = input channel (tensor t = lane / 64), column = copy d (= dx) x NP + gradient channel
+        mbar_wait_bounded(&done_bar, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3;                           // the TMEM lane quarter this warp may read
+        const int t = quarter >> 1, c = (quarter & 1) * 32 + lane;
+        if (t < NX) {
+            float *out = dW + (xs.c_off[t] + c) * 9;
+            const int lo = xs.n_lo[t], hi = xs.n_hi[t];
+            for (int dy = 0; dy < 3; ++dy)
+                for (int cb = 0; cb < 3 * NP; cb += (NP == 32 ? 16 : 8)) {
+                    uint32_t v[16];
+                    const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(dy * C::NCOL + cb);
+                    if (NP == 32)
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                     : "r"(taddr));
+                    else
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                                     : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const int d = cb / NP, nb = n0 + cb % NP;
+#pragma unroll
+                    for (int i = 0; i < (NP == 32 ? 16 : 8); ++i)
+                        if (nb + i >= lo && nb + i < hi) atomicAdd(out + (long)(nb + i) * ldw + dy * 3 + d, __uint_as_float(v[i]));
+                }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS));
+}
+
+template <int NP, int NX>
+inline cudaError_t head_wgrad_roll_launch(const CUtensorMap &map_x0, const CUtensorMap &map_x1, const CUtensorMap &map_g, int B, int H,
+                                          int W, int n0, const HeadWgradX &xs, int ldw, float *dW, int sm_count, cudaStream_t st)
+{
+    using C = HeadWgradRoll<NP, NX>;
+    if (const cudaError_t ae = ensure_dynamic_smem(reinterpret_cast<const void *>(&head_wgrad_roll_kernel<NP, NX>), (int)C::smem)) return ae;
+    const int seg = head_wgrad_seg_rows(H);
+    const long items = (long)B * ((H + seg - 1) / seg) * ((W + 31) / 32);
+    const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
+    head_wgrad_roll_kernel<NP, NX><<<grid, C::THREADS, C::smem, st>>>(map_x0, map_x1, map_g, B, H, W, seg, n0, xs, ldw, dW);
     return cudaGetLastError();
 }
 

@@ -35,7 +35,7 @@ std::atomic<unsigned long long> g_launches{0};
 // -1 = "auto" where a default depends on the shape.
 enum Opt { kOptTiled = 0, kOptPersist, kOptPdl, kOptFwdTH, kOptParamTH, kOptStateTma, kOptStateGather,
            kOptGatherCompact, kOptStateZero3, kOptStateMinB, kOptGroupImages, kOptStreamHint,
-           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptHeadsTma, kOptHeadsRows, kOptHeadsRing, kOptHeadsPersist, kOptHeadsReuse, kOptHeadsKs, kOptCount };
+           kOptParamFactored, kOptDcnBlocked, kOptStateLocal, kOptLocalPrefetch, kOptLocalMinB, kOptSchedMinB, kOptHeadsTma, kOptHeadsRows, kOptHeadsRing, kOptHeadsPersist, kOptHeadsReuse, kOptHeadsKs, kOptHeadsWgradRoll, kOptCount };
 struct OptDef { const char *name; const char *env; int def; };
 const OptDef kOptDefs[kOptCount] = {
     {"tiled", "NLSPN_TILED", 1},
@@ -62,6 +62,7 @@ const OptDef kOptDefs[kOptCount] = {
     {"heads_persist", "NLSPN_HEADS_PERSIST", 1}, // MN-major form as one persistent warp-specialised CTA per SM (0: one CTA per tile, two per SM)
     {"heads_reuse", "NLSPN_HEADS_REUSE", 1},     // persistent form: keep an input row's A tile in the tensor core's collector across its dy MMAs
     {"heads_ks", "NLSPN_HEADS_KS", 2},           // persistent form: channels per TMA stage / 8 (1 or 2: fewer, larger TMA operations)
+    {"heads_wgrad_roll", "NLSPN_HEADS_WGRAD_ROLL", 1},   // head weight gradients: rolling column-strip form (0: one 32-pixel chunk per stage)
 };
 std::atomic<int> g_opt[kOptCount];
 const bool g_opt_init = []() {
@@ -1594,6 +1595,45 @@ int nlspn_heads_grad_prep(const float *g_init, const float *pred_init, const flo
     return 0;
 }
 
+// gradient copies [3][B][NT][H][W] with the dims ordered (x, channel, copy, row, image), box {32, box_c, 3, 1, 1}, 128-byte swizzle
+static int make_wgrad_g5_map(CUtensorMap *map, const float *base, int B, int NT, int H, int W, int box_c)
+{
+    const MapKey key{base, NT, B, H, W, 32, 3, box_c, 16};
+    if (map_cache_get(key, map)) return 0;
+    const cuuint64_t P4 = (cuuint64_t)H * W * 4;
+    const cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)NT, 3, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {P4, (cuuint64_t)B * NT * P4, (cuuint64_t)W * 4, (cuuint64_t)NT * P4};
+    const cuuint32_t box[5] = {32, (cuuint32_t)box_c, 3, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(base), dims,
+                                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NLSPN_ERR_SHAPE, "cuTensorMapEncodeTiled(head wgrad, 5d) failed (CUresult %d)", (int)r);
+    map_cache_put(key, *map);
+    return 0;
+}
+
+// one rolling launch: input tensors x0 (and x1), gradient channels n0 .. n0 + np - 1 (np = 32 or 8)
+static int launch_wgrad_roll(int np, const float *x0, const float *x1, const CUtensorMap &mg, int B, int H, int W, int n0, HeadWgradX xs,
+                             int ldw, float *dw_all, int sms, cudaStream_t st)
+{
+    CUtensorMap m0, m1;
+    if (int rc = make_wgrad_map(&m0, x0, B, kHeadCin, H, W, kHeadCin, 1)) return rc;
+    cudaError_t e;
+    if (x1) {
+        if (int rc = make_wgrad_map(&m1, x1, B, kHeadCin, H, W, kHeadCin, 1)) return rc;
+        e = np == 32 ? head_wgrad_roll_launch<32, 2>(m0, m1, mg, B, H, W, n0, xs, ldw, dw_all, sms, st)
+                     : head_wgrad_roll_launch<8, 2>(m0, m1, mg, B, H, W, n0, xs, ldw, dw_all, sms, st);
+    } else {
+        e = np == 32 ? head_wgrad_roll_launch<32, 1>(m0, m0, mg, B, H, W, n0, xs, ldw, dw_all, sms, st)
+                     : head_wgrad_roll_launch<8, 1>(m0, m0, mg, B, H, W, n0, xs, ldw, dw_all, sms, st);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "head_wgrad_roll_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 int nlspn_heads_wgrad(const float *id_fd1, const float *oa_fd1, const float *cf_fd1, const float *fe1, const float *g_shift,
                       int B, int H, int W, int K, float *dw_all, void *stream)
 {
@@ -1607,22 +1647,42 @@ int nlspn_heads_wgrad(const float *id_fd1, const float *oa_fd1, const float *cf_
     if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, &sms, nullptr) != 0 || sms <= 0) sms = 148;
     cudaError_t e = cudaMemsetAsync(dw_all, 0, sizeof(float) * (size_t)NT * ldw, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(dw_all)");
+    ProfScope prof__(kProfHeadsGrad, st);
+    if (opt(kOptHeadsWgradRoll) != 0) {
+        CUtensorMap mg32, mg8;
+        if (int rc = make_wgrad_g5_map(&mg32, g_shift, B, NT, H, W, 32)) return rc;
+        if (int rc = make_wgrad_g5_map(&mg8, g_shift, B, NT, H, W, 8)) return rc;
+        // the shared fe1 (dW input channels 64..127, every gradient channel) and the guidance branch (input channels 0..63,
+        // gradient channels 2..NT-1) side by side as one N = 128 operand, 32 gradient channels per launch
+        for (int n0 = 0; n0 < NT; n0 += 32) {
+            const HeadWgradX xs{{0, 2}, {NT, NT}, {kHeadCin, 0}};
+            if (int rc = launch_wgrad_roll(32, fe1, oa_fd1, mg32, B, H, W, n0, xs, ldw, dw_all, sms, st)) return rc;
+        }
+        // the two one-channel heads: init (gradient channel 0) and confidence (channel 1), input channels 0..63 each
+        if (id_fd1 && cf_fd1) {
+            const HeadWgradX xs{{0, 1}, {1, 2}, {0, 0}};
+            if (int rc = launch_wgrad_roll(8, id_fd1, cf_fd1, mg8, B, H, W, 0, xs, ldw, dw_all, sms, st)) return rc;
+        } else if (id_fd1 || cf_fd1) {
+            const int n = id_fd1 ? 0 : 1;
+            const HeadWgradX xs{{n, 0}, {n + 1, 0}, {0, 0}};
+            if (int rc = launch_wgrad_roll(8, id_fd1 ? id_fd1 : cf_fd1, nullptr, mg8, B, H, W, 0, xs, ldw, dw_all, sms, st)) return rc;
+        }
+        return 0;
+    }
+    // per-chunk form (option heads_wgrad_roll = 0): one launch per input tensor and block of gradient channels
     CUtensorMap mg32, mg8, mx;
     if (int rc = make_wgrad_map(&mg32, g_shift, 3 * B, NT, H, W, 32, 3)) return rc;
     if (int rc = make_wgrad_map(&mg8, g_shift, 3 * B, NT, H, W, 8, 3)) return rc;
-    ProfScope prof__(kProfHeadsGrad, st);
-    // the shared fe1 (input channels 64..127 of every head) against all 3N + 2 gradient channels, 32 at a time
     if (int rc = make_wgrad_map(&mx, fe1, B, kHeadCin, H, W, kHeadCin, 1)) return rc;
     for (int n0 = 0; n0 < NT; n0 += 32) {
         e = head_wgrad_launch<32>(mx, mg32, B, H, W, n0, NT - n0 < 32 ? NT - n0 : 32, ldw, dw_all + kHeadCin * 9, sms, st);
         if (e != cudaSuccess) return cuda_fail(e, "head_wgrad_kernel<32>(fe1)");
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
-    // each head's own branch (input channels 0..63) against its own gradient channels; NULL = that branch needs no gradient
     if (oa_fd1) {
         if (int rc = make_wgrad_map(&mx, oa_fd1, B, kHeadCin, H, W, kHeadCin, 1)) return rc;
-        for (int n0 = 1; n0 < 1 + N3; n0 += 32) {
-            e = head_wgrad_launch<32>(mx, mg32, B, H, W, n0, 1 + N3 - n0 < 32 ? 1 + N3 - n0 : 32, ldw, dw_all, sms, st);
+        for (int n0 = 2; n0 < NT; n0 += 32) {
+            e = head_wgrad_launch<32>(mx, mg32, B, H, W, n0, NT - n0 < 32 ? NT - n0 : 32, ldw, dw_all, sms, st);
             if (e != cudaSuccess) return cuda_fail(e, "head_wgrad_kernel<32>(off_aff)");
             g_launches.fetch_add(1, std::memory_order_relaxed);
         }
@@ -1635,7 +1695,7 @@ int nlspn_heads_wgrad(const float *id_fd1, const float *oa_fd1, const float *cf_
     }
     if (cf_fd1) {
         if (int rc = make_wgrad_map(&mx, cf_fd1, B, kHeadCin, H, W, kHeadCin, 1)) return rc;
-        e = head_wgrad_launch<8>(mx, mg8, B, H, W, NT - 1, 1, ldw, dw_all, sms, st);
+        e = head_wgrad_launch<8>(mx, mg8, B, H, W, 1, 1, ldw, dw_all, sms, st);
         if (e != cudaSuccess) return cuda_fail(e, "head_wgrad_kernel<8>(confidence)");
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }

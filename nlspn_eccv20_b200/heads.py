@@ -169,8 +169,8 @@ def wgrad_supported(W, K) -> bool:
 
 def grad_prep(pred_init, confidence, g_init, g_guid, g_conf, K):
     """nlspn_heads_grad_prep: -> (g_shift [3,B,3N+2,H,W], g_bias [3N+2]); a None gradient is a zero gradient.  g_shift[1] is
-    the concatenated gradient with the ReLU / Sigmoid derivatives applied, g_shift[0] / g_shift[2] the same shifted by one
-    pixel (g[.., x + 1] / g[.., x - 1], zero outside the row)."""
+    the concatenated gradient (channel 0 = init, 1 = confidence, 2.. = guidance) with the ReLU / Sigmoid derivatives applied,
+    g_shift[0] / g_shift[2] the same shifted by one pixel (g[.., x + 1] / g[.., x - 1], zero outside the row)."""
     lib = _lib.load()
     B, _, H, W = pred_init.shape
     NT = 3 * (K * K - 1) + 2
@@ -187,7 +187,7 @@ def grad_prep(pred_init, confidence, g_init, g_guid, g_conf, K):
 
 
 def weight_grads(id_fd1, oa_fd1, cf_fd1, fe1, g_shift, K):
-    """nlspn_heads_wgrad: -> dw_all [3N+2,128,3,3] (row 0 = dw_id, 1..3N = dw_oa, 3N+1 = dw_cf); a None branch tensor leaves
+    """nlspn_heads_wgrad: -> dw_all [3N+2,128,3,3] (row 0 = dw_id, 1 = dw_cf, 2.. = dw_oa); a None branch tensor leaves
     its 64 input channels zero."""
     lib = _lib.load()
     B, _, H, W = fe1.shape
@@ -209,14 +209,14 @@ def _backward_native(K, need_in, need_w, id_fd1, oa_fd1, cf_fd1, fe1, w_id, w_oa
     g_shift, g_bias = grad_prep(pred_init, confidence, g_init, g_guid, g_conf, K)
     g_all = g_shift[1]                                                            # [B, 3N + 2, H, W]
     grads_in = [None, None, None, None]
-    own = ((id_fd1, w_id, slice(0, 1)), (oa_fd1, w_oa, slice(1, 1 + N3)), (cf_fd1, w_cf, slice(NT - 1, NT)))
+    own = ((id_fd1, w_id, slice(0, 1)), (oa_fd1, w_oa, slice(2, NT)), (cf_fd1, w_cf, slice(1, 2)))      # channel order: init, confidence, guidance
     for k, (x, w, sl) in enumerate(own):
         if need_in[k]:
             # the guidance head has no activation: its upstream gradient is usable as it came
             g = g_guid if (k == 1 and g_guid is not None and g_guid.is_contiguous()) else g_all[:, sl].contiguous()
             grads_in[k] = torch.nn.grad.conv2d_input(x.shape, w[:, :CIN].contiguous(), g, stride=1, padding=1)
     if need_in[3]:
-        w_fe = torch.cat((w_id[:, CIN:], w_oa[:, CIN:], w_cf[:, CIN:]), 0).contiguous()      # [3N + 2, 64, 3, 3]
+        w_fe = torch.cat((w_id[:, CIN:], w_cf[:, CIN:], w_oa[:, CIN:]), 0).contiguous()      # [3N + 2, 64, 3, 3], g_all's order
         grads_in[3] = torch.nn.grad.conv2d_input(fe1.shape, w_fe, g_all, stride=1, padding=1)
     g_w = [None, None, None]
     if any(need_w):

@@ -240,7 +240,7 @@ def test_heads_weight_gradients_on_tcgen05_match_fp32(B, H, W, K):
     """nlspn_heads_grad_prep + nlspn_heads_wgrad (csrc/kernels_head_wgrad.cuh) against what autograd runs for the reference's
     three head layers (nlspnmodel.py:69-86,297,301,313): activation derivatives, concatenation, the shifted copies
     (exact), bias sums and the fp32 weight gradients of the 128-channel layers (TF32 products: <= 3e-3 of the scale)."""
-    from nlspn_eccv20_b200 import heads
+    from nlspn_eccv20_b200 import heads, _lib
     dev = torch.device("cuda:0")
     assert heads.wgrad_supported(W, K)
     x, w, b = _case(B, H, W, K, 11, dev)
@@ -250,7 +250,7 @@ def test_heads_weight_gradients_on_tcgen05_match_fp32(B, H, W, K):
     confidence = torch.sigmoid(torch.randn(B, 1, H, W, generator=g)).to(dev)
     gi, gg, gc = (torch.randn(B, n, H, W, generator=g).to(dev) for n in (1, N3, 1))
     g_shift, g_bias = heads.grad_prep(pred_init, confidence, gi, gg, gc, K)
-    g_all = torch.cat((gi * (pred_init > 0), gg, gc * confidence * (1.0 - confidence)), 1)
+    g_all = torch.cat((gi * (pred_init > 0), gc * confidence * (1.0 - confidence), gg), 1)      # init, confidence, guidance
     assert float((g_shift[1] - g_all).abs().max()) <= 1e-6
     z = torch.zeros_like(g_all[..., :1])
     assert torch.equal(g_shift[0], torch.cat((g_shift[1][..., 1:], z), -1))          # g[.., x + 1]
@@ -261,7 +261,7 @@ def test_heads_weight_gradients_on_tcgen05_match_fp32(B, H, W, K):
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
-        own = (slice(0, 1), slice(1, 1 + N3), slice(N3 + 1, N3 + 2))
+        own = (slice(0, 1), slice(2, N3 + 2), slice(1, 2))
         ref = torch.empty_like(dw)
         for k, sl in enumerate(own):
             ref[sl] = torch.nn.grad.conv2d_weight(torch.cat((x[k], x[3]), 1), (sl.stop - sl.start, 128, 3, 3),
@@ -272,11 +272,16 @@ def test_heads_weight_gradients_on_tcgen05_match_fp32(B, H, W, K):
     assert float((dw - ref).abs().max()) <= 3e-3 * scale
     # a NULL branch leaves its block zero and the others unchanged; a NULL gradient is a zero gradient
     dw2 = heads.weight_grads(None, x[1], None, x[3], g_shift, K)
-    assert float(dw2[0, :64].abs().max()) == 0.0 and float(dw2[-1, :64].abs().max()) == 0.0
-    assert float((dw2[1:-1] - dw[1:-1]).abs().max()) <= 1e-4 * scale
+    assert float(dw2[:2, :64].abs().max()) == 0.0
+    assert float((dw2[2:] - dw[2:]).abs().max()) <= 1e-4 * scale and float((dw2[:2, 64:] - dw[:2, 64:]).abs().max()) <= 1e-4 * scale
+    dw3 = heads.weight_grads(x[0], None, None, x[3], g_shift, K)
+    assert float(dw3[1:, :64].abs().max()) == 0.0 and float((dw3[0] - dw[0]).abs().max()) <= 1e-4 * scale
+    with _lib.options(heads_wgrad_roll=0):           # the per-chunk form
+        dw4 = heads.weight_grads(x[0], x[1], x[2], x[3], g_shift, K)
+    assert float((dw4 - dw).abs().max()) <= 1e-4 * scale
     s0, b0 = heads.grad_prep(pred_init, confidence, None, gg, None, K)
-    assert float(s0[:, :, 0].abs().max()) == 0.0 and float(s0[:, :, -1].abs().max()) == 0.0 and torch.equal(s0[1][:, 1:-1], gg)
-    assert float(b0[0]) == 0.0 and float(b0[-1]) == 0.0
+    assert float(s0[:, :, :2].abs().max()) == 0.0 and torch.equal(s0[1][:, 2:], gg)
+    assert float(b0[:2].abs().max()) == 0.0
 
 
 def test_heads_weight_gradients_reject_what_they_do_not_implement():
