@@ -301,6 +301,10 @@ NLSPN_API int nlspn_heads_prologue_fwd(const float *id_fd1, const float *oa_fd1,
  *                           channels 0..63 = the head's own branch, 64..127 = fe1.  A NULL branch tensor (id_fd1 /
  *                           oa_fd1 / cf_fd1) leaves its 64-channel block zero.  TF32 products, fp32 accumulation over the
  *                           pixels in tensor memory, split-K partials added with fp32 atomics.
+ *   nlspn_heads_dgrad_one   data gradients of the two one-channel heads with respect to their own branches: d_id_fd1,
+ *                           d_cf_fd1 [B,64,H,W] (NULL = skip) from g_all = copy 1 of g_shift and the heads' [1,128,3,3]
+ *                           weights (input channels 0..63): an fp32 nine-tap stencil at the rate of its store
+ *                           (cudnn_convolution_backward_input in the reference)
  * W % 4 == 0 and 16-byte aligned tensors (nlspn_heads_wgrad_supported); otherwise NLSPN_ERR_SHAPE / NLSPN_ERR_ALIGN. */
 NLSPN_API int nlspn_heads_wgrad_supported(int W, int K);
 NLSPN_API int nlspn_heads_grad_prep(const float *g_init, const float *pred_init, const float *g_guidance,
@@ -308,6 +312,8 @@ NLSPN_API int nlspn_heads_grad_prep(const float *g_init, const float *pred_init,
                                     float *g_shift, float *g_bias, void *stream);
 NLSPN_API int nlspn_heads_wgrad(const float *id_fd1, const float *oa_fd1, const float *cf_fd1, const float *fe1,
                                 const float *g_shift, int B, int H, int W, int K, float *dw_all, void *stream);
+NLSPN_API int nlspn_heads_dgrad_one(const float *g_all, const float *w_id, const float *w_cf, int B, int H, int W, int K,
+                                    float *d_id_fd1, float *d_cf_fd1, void *stream);
 
 /* Double-precision variants of the single-step operator: the reference dispatches this op over
  * float and double (AT_DISPATCH_FLOATING_TYPES, modulated_deform_conv_cuda.cu:93,224) and its

@@ -111,6 +111,66 @@ head_grad_prep_kernel(const float *__restrict__ g_init, const float *__restrict_
     }
 }
 
+// Data gradient of the two ONE-channel heads (init, confidence) with respect to their own 64-channel branches:
+//     dX[b, c, y, x] = sum over (dy, dx) of  g[b, y - dy + 1, x - dx + 1] * w[c, dy, dx]       (g zero-padded)
+// 9 multiply-adds per output from one gradient channel: a plain fp32 stencil that is bound by its 64-channel store (what
+// cuDNN spends 0.7-0.8 ms on per head at KITTI B = 8 streams out at the HBM rate).  g_all = the centre copy of
+// head_grad_prep_kernel (channel 0 = init, 1 = confidence); w = the head's [1,128,3,3] weight, input channels 0..63.
+// grid (quads of four pixels / 256, 2 heads), one thread per four pixels; W % 4 == 0.
+constexpr int kDgradOneThreads = 256;
+
+__global__ void __launch_bounds__(kDgradOneThreads)
+head_dgrad_one_kernel(const float *__restrict__ g_all, const float *__restrict__ w_id, const float *__restrict__ w_cf, int B, int NT,
+                      int H, int W, float *__restrict__ d_id, float *__restrict__ d_cf)
+{
+    const int head = blockIdx.y;
+    float *__restrict__ out = head == 0 ? d_id : d_cf;
+    if (!out) return;
+    __shared__ float ws[kHeadCin * 9];
+    const float *w = head == 0 ? w_id : w_cf;
+    for (int i = threadIdx.x; i < kHeadCin * 9; i += kDgradOneThreads) ws[i] = __ldg(w + i);     // [c][dy][dx], c < 64
+    __syncthreads();
+    const int W4 = W >> 2;
+    const long P = (long)H * W, quads = (long)B * H * W4;
+    const long q = (long)blockIdx.x * kDgradOneThreads + threadIdx.x;
+    if (q >= quads) return;
+    const int x0 = (int)(q % W4) * 4, y = (int)((q / W4) % H), b = (int)(q / ((long)W4 * H));
+    const float *g = g_all + ((long)b * NT + head) * P;
+    // v[r][i] = g[y - 1 + r][x0 - 1 + i], r = 0..2, i = 0..5
+    float v[3][6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int yy = y - 1 + r;
+        if (yy >= 0 && yy < H) {
+            const float *row = g + (long)yy * W + x0;
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(row));
+            v[r][0] = x0 > 0 ? __ldg(row - 1) : 0.f;
+            v[r][1] = c.x; v[r][2] = c.y; v[r][3] = c.z; v[r][4] = c.w;
+            v[r][5] = x0 + 4 < W ? __ldg(row + 4) : 0.f;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) v[r][i] = 0.f;
+        }
+    }
+    float *o = out + (long)b * kHeadCin * P + (long)y * W + x0;
+#pragma unroll 4
+    for (int c = 0; c < kHeadCin; ++c) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const float wv = ws[c * 9 + dy * 3 + dx];
+                // output pixel x0 + i reads g[y - dy + 1][x0 + i - dx + 1] = v[2 - dy][i - dx + 2]
+                acc.x = fmaf(v[2 - dy][2 - dx], wv, acc.x);
+                acc.y = fmaf(v[2 - dy][3 - dx], wv, acc.y);
+                acc.z = fmaf(v[2 - dy][4 - dx], wv, acc.z);
+                acc.w = fmaf(v[2 - dy][5 - dx], wv, acc.w);
+            }
+        __stcs(reinterpret_cast<float4 *>(o + (long)c * P), acc);
+    }
+}
+
 // One input tensor X [B, 64, H, W] against gradient channels n0 .. n0 + n_cnt - 1 (n_cnt <= NP) of g_shift:
 //     dW[(n0 + n) * ldw + c * 9 + dy * 3 + dx] += ...      (dW already offset to X's channel block; ldw = 128 * 9)
 // map_x: dims (x, channel, row, image), box {32, 64, 1, 1}; map_g: dims (x, channel, row, copy * B + image), box {32, NP, 3, 1};

@@ -1595,6 +1595,23 @@ int nlspn_heads_grad_prep(const float *g_init, const float *pred_init, const flo
     return 0;
 }
 
+int nlspn_heads_dgrad_one(const float *g_all, const float *w_id, const float *w_cf, int B, int H, int W, int K,
+                          float *d_id_fd1, float *d_cf_fd1, void *stream)
+{
+    if (int rc = check_heads_grad("heads_dgrad_one", B, H, W, K)) return rc;
+    if (!g_all || (d_id_fd1 && !w_id) || (d_cf_fd1 && !w_cf)) return fail(NLSPN_ERR_NULL, "heads_dgrad_one: a required pointer is NULL");
+    if (!aligned16(g_all) || !aligned16(d_id_fd1) || !aligned16(d_cf_fd1))
+        return fail(NLSPN_ERR_ALIGN, "heads_dgrad_one: tensors must be 16-byte aligned");
+    if (!d_id_fd1 && !d_cf_fd1) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long quads = (long)B * H * (W / 4);
+    dim3 grid((unsigned)((quads + kDgradOneThreads - 1) / kDgradOneThreads), 2u);
+    ProfScope prof__(kProfHeadsGrad, st);
+    head_dgrad_one_kernel<<<grid, kDgradOneThreads, 0, st>>>(g_all, w_id, w_cf, B, 3 * (K * K - 1) + 2, H, W, d_id_fd1, d_cf_fd1);
+    NLSPN_CHECK_LAUNCH("head_dgrad_one_kernel");
+    return 0;
+}
+
 // gradient copies [3][B][NT][H][W] with the dims ordered (x, channel, copy, row, image), box {32, box_c, 3, 1, 1}, 128-byte swizzle
 static int make_wgrad_g5_map(CUtensorMap *map, const float *base, int B, int NT, int H, int W, int box_c)
 {

@@ -21,7 +21,7 @@ from torch.nn import functional as TF
 
 from . import _lib
 
-__all__ = ["fused_heads", "fused_heads_prologue", "prologue_supported", "wgrad_supported", "grad_prep", "weight_grads", "FusedHeadsFunction", "supported"]
+__all__ = ["fused_heads", "fused_heads_prologue", "prologue_supported", "wgrad_supported", "grad_prep", "weight_grads", "dgrad_one", "FusedHeadsFunction", "supported"]
 
 CIN = 64       # channels of each of the four tensors (64 + 64 = the reference's 128-channel concatenations)
 
@@ -200,9 +200,24 @@ def weight_grads(id_fd1, oa_fd1, cf_fd1, fe1, g_shift, K):
     return dw_all
 
 
+def dgrad_one(g_all, w_id, w_cf, K):
+    """nlspn_heads_dgrad_one: -> (d_id_fd1, d_cf_fd1) [B,64,H,W] from g_all = grad_prep(..)[0][1]; a None weight skips that head."""
+    lib = _lib.load()
+    B, _, H, W = g_all.shape
+    dev = g_all.device
+    outs = [None if w is None else torch.empty((B, CIN, H, W), device=dev, dtype=torch.float32) for w in (w_id, w_cf)]
+    ws = [None if w is None else w.detach().to(torch.float32).contiguous() for w in (w_id, w_cf)]
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nlspn_heads_dgrad_one(_ptr(g_all), _ptr(ws[0]), _ptr(ws[1]), B, H, W, K, _ptr(outs[0]), _ptr(outs[1]), st),
+                   "nlspn_heads_dgrad_one")
+    return outs[0], outs[1]
+
+
 def _backward_native(K, need_in, need_w, id_fd1, oa_fd1, cf_fd1, fe1, w_id, w_oa, w_cf, pred_init, confidence, g_init, g_guid, g_conf):
     """Activation derivatives + concatenation + bias sums in one kernel (nlspn_heads_grad_prep), every weight gradient on
-    tcgen05 (nlspn_heads_wgrad, csrc/kernels_head_wgrad.cuh); the four data gradients stay with cuDNN, fed from the
+    tcgen05 (nlspn_heads_wgrad, csrc/kernels_head_wgrad.cuh); the data gradients of the two one-channel heads as an fp32
+    stencil (nlspn_heads_dgrad_one); the two wide data gradients (guidance branch, fe1) stay with cuDNN, fed from the
     concatenated gradient the first kernel wrote."""
     N3 = 3 * (K * K - 1)
     NT = N3 + 2
@@ -210,11 +225,13 @@ def _backward_native(K, need_in, need_w, id_fd1, oa_fd1, cf_fd1, fe1, w_id, w_oa
     g_all = g_shift[1]                                                            # [B, 3N + 2, H, W]
     grads_in = [None, None, None, None]
     own = ((id_fd1, w_id, slice(0, 1)), (oa_fd1, w_oa, slice(2, NT)), (cf_fd1, w_cf, slice(1, 2)))      # channel order: init, confidence, guidance
-    for k, (x, w, sl) in enumerate(own):
-        if need_in[k]:
-            # the guidance head has no activation: its upstream gradient is usable as it came
-            g = g_guid if (k == 1 and g_guid is not None and g_guid.is_contiguous()) else g_all[:, sl].contiguous()
-            grads_in[k] = torch.nn.grad.conv2d_input(x.shape, w[:, :CIN].contiguous(), g, stride=1, padding=1)
+    if need_in[0] or need_in[2]:
+        # the one-channel heads: an fp32 nine-tap stencil at the rate of its 64-channel store (nlspn_heads_dgrad_one)
+        grads_in[0], grads_in[2] = dgrad_one(g_all, w_id if need_in[0] else None, w_cf if need_in[2] else None, K)
+    if need_in[1]:
+        # the guidance head has no activation: its upstream gradient is usable as it came
+        g = g_guid if (g_guid is not None and g_guid.is_contiguous()) else g_all[:, 2:].contiguous()
+        grads_in[1] = torch.nn.grad.conv2d_input(oa_fd1.shape, w_oa[:, :CIN].contiguous(), g, stride=1, padding=1)
     if need_in[3]:
         w_fe = torch.cat((w_id[:, CIN:], w_cf[:, CIN:], w_oa[:, CIN:]), 0).contiguous()      # [3N + 2, 64, 3, 3], g_all's order
         grads_in[3] = torch.nn.grad.conv2d_input(fe1.shape, w_fe, g_all, stride=1, padding=1)

@@ -297,3 +297,27 @@ def test_heads_weight_gradients_reject_what_they_do_not_implement():
     o = heads.fused_heads(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], leaves[7], leaves[5], leaves[8], leaves[6], leaves[9], 3)
     torch.autograd.backward(o, [torch.ones_like(t) for t in o])
     assert all(t.grad is not None and bool(torch.isfinite(t.grad).all()) for t in leaves)
+
+
+@pytest.mark.parametrize("B,H,W,K", [(2, 7, 44, 3), (1, 1, 4, 3), (1, 33, 1216, 3), (2, 19, 132, 5)])
+def test_heads_one_channel_data_gradients_match_fp32(B, H, W, K):
+    """nlspn_heads_dgrad_one (fp32 nine-tap stencil) against conv2d_input of the init / confidence layers' own 64-channel
+    branches (nlspnmodel.py:69-72,83-86) in fp32."""
+    from nlspn_eccv20_b200 import heads
+    dev = torch.device("cuda:0")
+    x, w, b = _case(B, H, W, K, 21, dev)
+    g = torch.Generator().manual_seed(22)
+    N3 = 3 * (K * K - 1)
+    g_all = torch.randn(B, N3 + 2, H, W, generator=g).to(dev)
+    d_id, d_cf = heads.dgrad_one(g_all, w[0], w[2], K)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        r_id = torch.nn.grad.conv2d_input((B, 64, H, W), w[0][:, :64].contiguous(), g_all[:, 0:1].contiguous(), stride=1, padding=1)
+        r_cf = torch.nn.grad.conv2d_input((B, 64, H, W), w[2][:, :64].contiguous(), g_all[:, 1:2].contiguous(), stride=1, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    for a, r in ((d_id, r_id), (d_cf, r_cf)):
+        assert float((a - r).abs().max()) <= 1e-5 * float(r.abs().max().clamp_min(1e-6))
+    only_cf = heads.dgrad_one(g_all, None, w[2], K)
+    assert only_cf[0] is None and torch.equal(only_cf[1], d_cf)

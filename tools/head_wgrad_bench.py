@@ -59,6 +59,9 @@ out["grad_prep_ms"] = timed(prep)
 out["wgrad_ms"] = timed(wgrad)
 for name, args in (("fe1", (None, None, None, x[3])), ("fe1+oa", (None, x[1], None, x[3])), ("fe1+id", (x[0], None, None, x[3]))):
     out["wgrad_%s_ms" % name] = timed(lambda: heads.weight_grads(*args, state["g"][0], K))
+w1 = [torch.randn(1, 128, 3, 3, device=dev) for _ in range(2)]
+out["dgrad_one_ms"] = timed(lambda: heads.dgrad_one(state["g"][0][1], w1[0], w1[1], K))
+out["cudnn_dgrad_one_ms"] = timed(lambda: [torch.nn.grad.conv2d_input((B, 64, H, W), w[:, :64].contiguous(), gg[:, :1].contiguous(), stride=1, padding=1) for w in w1])
 ref, _ = stock()
 dw = state["dw"]
 out["rel_diff_fe1"] = float((dw[:, 64:] - ref[3]).abs().max() / ref[3].abs().max())
