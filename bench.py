@@ -604,7 +604,35 @@ def heads_leg(torch, dev, B, H, W, K=3, steps=10, warmup=3):
         out["hbm_frac"] = out["hbm_gbs"] / peak
         if fused:
             out["fused_hbm_frac"] = out["fused_hbm_gbs"] / peak
-    del x, w, b, args, o, r
+    # training: forward + backward of the same layers (every input, weight and bias gradient), stock autograd / cuDNN vs
+    # heads.fused_heads (GEMM forward; weight + bias gradients on tcgen05, one-channel data gradients as a stencil,
+    # the two wide data gradients in cuDNN); and the weight-gradient kernels alone against the bytes they must read
+    leaves = [t.detach().clone().requires_grad_(True) for t in args]
+    gout = [torch.randn(B, n, H, W, device=dev, generator=g) for n in (1, N3, 1)]
+
+    def train(fn):
+        for t in leaves:
+            t.grad = None
+        torch.autograd.backward(fn(), gout)
+    train_ours = timed(lambda: train(lambda: heads.fused_heads(*leaves, prop_kernel=K)))
+    train_stock = timed(lambda: train(lambda: heads.reference_heads(*leaves)))
+    out["train"] = {"workload": "forward + backward (all gradients) of the same layers", "ours_ms": train_ours,
+                    "stock_torch_ms": train_stock, "ours_over_stock": train_stock / train_ours}
+    if heads.wgrad_supported(W, K):
+        with torch.no_grad():
+            gs, _ = heads.grad_prep(o[0], o[2], gout[0], gout[1], gout[2], K)
+            prep = timed(lambda: heads.grad_prep(o[0], o[2], gout[0], gout[1], gout[2], K))
+            wgrad = timed(lambda: heads.weight_grads(x[0], x[1], x[2], x[3], gs, K))
+        # what nlspn_heads_wgrad must read: the four inputs once, the three gradient copies once for the wide launches and
+        # eight channels of them for the one-channel heads (K = 3: one block of gradient channels)
+        blocks = (N3 + 2 + 31) // 32
+        bytes_wgrad = 4.0 * B * H * W * (blocks * 128 + 128 + 3 * (N3 + 2) + 3 * 8)
+        out["train"].update({"grad_prep_ms": prep, "wgrad_ms": wgrad, "wgrad_alg_bytes": bytes_wgrad,
+                             "wgrad_hbm_gbs": bytes_wgrad / (wgrad * 1e-3) / 1e9})
+        if peak > 0:
+            out["train"]["wgrad_hbm_frac"] = out["train"]["wgrad_hbm_gbs"] / peak
+        del gs
+    del x, w, b, args, o, r, leaves, gout
     torch.cuda.empty_cache()
     return out
 
