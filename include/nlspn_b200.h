@@ -305,6 +305,11 @@ NLSPN_API int nlspn_heads_prologue_fwd(const float *id_fd1, const float *oa_fd1,
  *                           d_cf_fd1 [B,64,H,W] (NULL = skip) from g_all = copy 1 of g_shift and the heads' [1,128,3,3]
  *                           weights (input channels 0..63): an fp32 nine-tap stencil at the rate of its store
  *                           (cudnn_convolution_backward_input in the reference)
+ *   nlspn_heads_dgrad_pack  (prop_kernel 3) packs the three weight tensors for the wide data gradients into `packed`
+ *                           (nlspn_heads_dgrad_packed_floats(K) floats, 16-byte aligned); call again when the weights change
+ *   nlspn_heads_dgrad_wide  (prop_kernel 3, nlspn_heads_dgrad_supported) the two wide data gradients as one tcgen05 implicit
+ *                           GEMM over the three shifted copies: d_oa_fd1 [B,64,H,W] (NULL = skip; the guidance head's own
+ *                           branch) and d_fe1 [B,64,H,W] (the shared fe1: all three heads); TF32 products, fp32 accumulation
  * W % 4 == 0 and 16-byte aligned tensors (nlspn_heads_wgrad_supported); otherwise NLSPN_ERR_SHAPE / NLSPN_ERR_ALIGN. */
 NLSPN_API int nlspn_heads_wgrad_supported(int W, int K);
 NLSPN_API int nlspn_heads_grad_prep(const float *g_init, const float *pred_init, const float *g_guidance,
@@ -314,6 +319,11 @@ NLSPN_API int nlspn_heads_wgrad(const float *id_fd1, const float *oa_fd1, const 
                                 const float *g_shift, int B, int H, int W, int K, float *dw_all, void *stream);
 NLSPN_API int nlspn_heads_dgrad_one(const float *g_all, const float *w_id, const float *w_cf, int B, int H, int W, int K,
                                     float *d_id_fd1, float *d_cf_fd1, void *stream);
+NLSPN_API size_t nlspn_heads_dgrad_packed_floats(int K);
+NLSPN_API int nlspn_heads_dgrad_supported(int W, int K);
+NLSPN_API int nlspn_heads_dgrad_pack(const float *w_id, const float *w_oa, const float *w_cf, int K, float *packed, void *stream);
+NLSPN_API int nlspn_heads_dgrad_wide(const float *g_shift, const float *packed, int B, int H, int W, int K,
+                                     float *d_oa_fd1, float *d_fe1, void *stream);
 
 /* Double-precision variants of the single-step operator: the reference dispatches this op over
  * float and double (AT_DISPATCH_FLOATING_TYPES, modulated_deform_conv_cuda.cu:93,224) and its

@@ -49,6 +49,10 @@ SIGNATURES = {
     "nlspn_heads_grad_prep": (_c.c_int, [_c.c_void_p] * 5 + [_c.c_int] * 4 + [_c.c_void_p] * 3),
     "nlspn_heads_wgrad": (_c.c_int, [_c.c_void_p] * 5 + [_c.c_int] * 4 + [_c.c_void_p] * 2),
     "nlspn_heads_dgrad_one": (_c.c_int, [_c.c_void_p] * 3 + [_c.c_int] * 4 + [_c.c_void_p] * 3),
+    "nlspn_heads_dgrad_packed_floats": (_c.c_size_t, [_c.c_int]),
+    "nlspn_heads_dgrad_supported": (_c.c_int, [_c.c_int, _c.c_int]),
+    "nlspn_heads_dgrad_pack": (_c.c_int, [_c.c_void_p] * 3 + [_c.c_int, _c.c_void_p, _c.c_void_p]),
+    "nlspn_heads_dgrad_wide": (_c.c_int, [_c.c_void_p] * 2 + [_c.c_int] * 4 + [_c.c_void_p] * 3),
     "nlspn_heads_prologue_fwd": (_c.c_int, [_c.c_void_p] * 8 + [_c.c_int, _c.c_uint] + [_c.c_int] * 4 + [_c.c_void_p] * 8),
     "nlspn_backward": (_c.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _c.c_int, _fp,
                                   _c.POINTER(_c.c_void_p), _fp, _fp, _fp, _c.c_int, _c.c_uint,

@@ -22,6 +22,7 @@
 #include "kernels_head.cuh"
 #include "kernels_head2.cuh"
 #include "kernels_head_wgrad.cuh"
+#include "kernels_head_dgrad.cuh"
 
 using namespace nlspn;
 
@@ -1609,6 +1610,56 @@ int nlspn_heads_dgrad_one(const float *g_all, const float *w_id, const float *w_
     ProfScope prof__(kProfHeadsGrad, st);
     head_dgrad_one_kernel<<<grid, kDgradOneThreads, 0, st>>>(g_all, w_id, w_cf, B, 3 * (K * K - 1) + 2, H, W, d_id_fd1, d_cf_fd1);
     NLSPN_CHECK_LAUNCH("head_dgrad_one_kernel");
+    return 0;
+}
+
+// ---- the two wide data gradients of the head convolutions as one tcgen05 GEMM (kernels_head_dgrad.cuh; prop_kernel 3) ----
+size_t nlspn_heads_dgrad_packed_floats(int K) { return K == 3 ? (size_t)HeadDgrad::packed_floats : 0; }
+
+int nlspn_heads_dgrad_supported(int W, int K) { return K == 3 && nlspn_heads_wgrad_supported(W, K) ? 1 : 0; }
+
+int nlspn_heads_dgrad_pack(const float *w_id, const float *w_oa, const float *w_cf, int K, float *packed, void *stream)
+{
+    if (K != 3) return fail(NLSPN_ERR_KERNEL, "heads_dgrad_pack: implemented for prop_kernel 3 (got %d)", K);
+    if (!w_id || !w_oa || !w_cf || !packed) return fail(NLSPN_ERR_NULL, "heads_dgrad_pack: a required pointer is NULL");
+    head_dgrad_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w_id, w_oa, w_cf, 3 * (K * K - 1) + 2, packed);
+    NLSPN_CHECK_LAUNCH("head_dgrad_pack_kernel");
+    return 0;
+}
+
+int nlspn_heads_dgrad_wide(const float *g_shift, const float *packed, int B, int H, int W, int K, float *d_oa_fd1, float *d_fe1,
+                           void *stream)
+{
+    if (int rc = check_heads_grad("heads_dgrad_wide", B, H, W, K)) return rc;
+    if (K != 3) return fail(NLSPN_ERR_KERNEL, "heads_dgrad_wide: implemented for prop_kernel 3 (got %d): use the framework's "
+                                              "convolution backward", K);
+    if (!g_shift || !packed || !d_fe1) return fail(NLSPN_ERR_NULL, "heads_dgrad_wide: a required pointer is NULL");
+    if (!aligned16(g_shift) || !aligned16(packed) || !aligned16(d_oa_fd1) || !aligned16(d_fe1))
+        return fail(NLSPN_ERR_ALIGN, "heads_dgrad_wide: tensors must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NT = 3 * (K * K - 1) + 2;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, &sms, nullptr) != 0 || sms <= 0) sms = 148;
+    // g_shift as [3 B images][NT channels][H][W]: dims (x, channel, row, image), box {32 px, 8 channels, 3 rows}, 32-byte-atom swizzle
+    CUtensorMap mg;
+    {
+        const MapKey key{g_shift, NT, 3 * B, H, W, 32, 3, 8, 17};
+        if (!map_cache_get(key, &mg)) {
+            const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)NT, (cuuint64_t)H, (cuuint64_t)(3 * B)};
+            const cuuint64_t strides[3] = {(cuuint64_t)H * W * 4, (cuuint64_t)W * 4, (cuuint64_t)NT * H * W * 4};
+            const cuuint32_t box[4] = {32, 8, 3, 1};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            const CUresult r = encode_tiled_fn()(&mg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(g_shift), dims, strides,
+                                                 box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(NLSPN_ERR_SHAPE, "cuTensorMapEncodeTiled(head dgrad) failed (CUresult %d)", (int)r);
+            map_cache_put(key, mg);
+        }
+    }
+    ProfScope prof__(kProfHeadsGrad, st);
+    const cudaError_t e = head_dgrad_wide_launch(mg, packed, B, H, W, d_oa_fd1, d_fe1, sms, st);
+    if (e != cudaSuccess) return cuda_fail(e, "head_dgrad_wide_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 

@@ -21,7 +21,7 @@ from torch.nn import functional as TF
 
 from . import _lib
 
-__all__ = ["fused_heads", "fused_heads_prologue", "prologue_supported", "wgrad_supported", "grad_prep", "weight_grads", "dgrad_one", "FusedHeadsFunction", "supported"]
+__all__ = ["fused_heads", "fused_heads_prologue", "prologue_supported", "wgrad_supported", "grad_prep", "weight_grads", "dgrad_one", "dgrad_wide", "dgrad_supported", "FusedHeadsFunction", "supported"]
 
 CIN = 64       # channels of each of the four tensors (64 + 64 = the reference's 128-channel concatenations)
 
@@ -214,11 +214,34 @@ def dgrad_one(g_all, w_id, w_cf, K):
     return outs[0], outs[1]
 
 
+def dgrad_supported(W, K) -> bool:
+    """Does nlspn_heads_dgrad_wide (the wide data gradients as a tcgen05 GEMM) cover this width / prop_kernel?"""
+    return bool(_lib.load().nlspn_heads_dgrad_supported(int(W), int(K)))
+
+
+def dgrad_wide(g_shift, w_id, w_oa, w_cf, K, want_oa=True):
+    """nlspn_heads_dgrad_pack + nlspn_heads_dgrad_wide: -> (d_oa_fd1 | None, d_fe1) [B,64,H,W] from g_shift = grad_prep(..)[0]."""
+    lib = _lib.load()
+    _, B, _, H, W = g_shift.shape
+    dev = g_shift.device
+    opt = dict(device=dev, dtype=torch.float32)
+    packed = torch.empty((lib.nlspn_heads_dgrad_packed_floats(K),), **opt)
+    d_oa = torch.empty((B, CIN, H, W), **opt) if want_oa else None
+    d_fe = torch.empty((B, CIN, H, W), **opt)
+    ws = [w.detach().to(torch.float32).contiguous() for w in (w_id, w_oa, w_cf)]
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nlspn_heads_dgrad_pack(_ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]), K, _ptr(packed), st), "nlspn_heads_dgrad_pack")
+        _lib.check(lib.nlspn_heads_dgrad_wide(_ptr(g_shift), _ptr(packed), B, H, W, K, _ptr(d_oa), _ptr(d_fe), st),
+                   "nlspn_heads_dgrad_wide")
+    return d_oa, d_fe
+
+
 def _backward_native(K, need_in, need_w, id_fd1, oa_fd1, cf_fd1, fe1, w_id, w_oa, w_cf, pred_init, confidence, g_init, g_guid, g_conf):
     """Activation derivatives + concatenation + bias sums in one kernel (nlspn_heads_grad_prep), every weight gradient on
     tcgen05 (nlspn_heads_wgrad, csrc/kernels_head_wgrad.cuh); the data gradients of the two one-channel heads as an fp32
-    stencil (nlspn_heads_dgrad_one); the two wide data gradients (guidance branch, fe1) stay with cuDNN, fed from the
-    concatenated gradient the first kernel wrote."""
+    stencil (nlspn_heads_dgrad_one); the two wide data gradients (guidance branch, fe1) as one tcgen05 GEMM over the shifted
+    copies (nlspn_heads_dgrad_wide; prop_kernel 3 -- otherwise cuDNN, fed from the concatenated gradient)."""
     N3 = 3 * (K * K - 1)
     NT = N3 + 2
     g_shift, g_bias = grad_prep(pred_init, confidence, g_init, g_guid, g_conf, K)
@@ -228,13 +251,17 @@ def _backward_native(K, need_in, need_w, id_fd1, oa_fd1, cf_fd1, fe1, w_id, w_oa
     if need_in[0] or need_in[2]:
         # the one-channel heads: an fp32 nine-tap stencil at the rate of its 64-channel store (nlspn_heads_dgrad_one)
         grads_in[0], grads_in[2] = dgrad_one(g_all, w_id if need_in[0] else None, w_cf if need_in[2] else None, K)
-    if need_in[1]:
-        # the guidance head has no activation: its upstream gradient is usable as it came
-        g = g_guid if (g_guid is not None and g_guid.is_contiguous()) else g_all[:, 2:].contiguous()
-        grads_in[1] = torch.nn.grad.conv2d_input(oa_fd1.shape, w_oa[:, :CIN].contiguous(), g, stride=1, padding=1)
-    if need_in[3]:
-        w_fe = torch.cat((w_id[:, CIN:], w_cf[:, CIN:], w_oa[:, CIN:]), 0).contiguous()      # [3N + 2, 64, 3, 3], g_all's order
-        grads_in[3] = torch.nn.grad.conv2d_input(fe1.shape, w_fe, g_all, stride=1, padding=1)
+    if need_in[3] and dgrad_supported(fe1.shape[3], K):
+        # the two wide ones as one tcgen05 GEMM over the shifted copies (nlspn_heads_dgrad_wide)
+        grads_in[1], grads_in[3] = dgrad_wide(g_shift, w_id, w_oa, w_cf, K, want_oa=need_in[1])
+    else:
+        if need_in[1]:
+            # the guidance head has no activation: its upstream gradient is usable as it came
+            g = g_guid if (g_guid is not None and g_guid.is_contiguous()) else g_all[:, 2:].contiguous()
+            grads_in[1] = torch.nn.grad.conv2d_input(oa_fd1.shape, w_oa[:, :CIN].contiguous(), g, stride=1, padding=1)
+        if need_in[3]:
+            w_fe = torch.cat((w_id[:, CIN:], w_cf[:, CIN:], w_oa[:, CIN:]), 0).contiguous()      # [3N + 2, 64, 3, 3], g_all's order
+            grads_in[3] = torch.nn.grad.conv2d_input(fe1.shape, w_fe, g_all, stride=1, padding=1)
     g_w = [None, None, None]
     if any(need_w):
         dw_all = weight_grads(id_fd1 if need_w[0] else None, oa_fd1 if need_w[1] else None, cf_fd1 if need_w[2] else None,

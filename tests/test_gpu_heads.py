@@ -321,3 +321,33 @@ def test_heads_one_channel_data_gradients_match_fp32(B, H, W, K):
         assert float((a - r).abs().max()) <= 1e-5 * float(r.abs().max().clamp_min(1e-6))
     only_cf = heads.dgrad_one(g_all, None, w[2], K)
     assert only_cf[0] is None and torch.equal(only_cf[1], d_cf)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 7, 44), (1, 1, 4), (1, 9, 128), (1, 5, 1216), (2, 37, 132), (1, 3, 260)])
+def test_heads_wide_data_gradients_on_tcgen05_match_fp32(B, H, W):
+    """nlspn_heads_dgrad_wide (csrc/kernels_head_dgrad.cuh) against conv2d_input of the guidance layer's own branch and of
+    the fe1 halves of all three layers (nlspnmodel.py:69-86) in fp32: TF32 products over 9 x 26 terms, <= 3e-3 of the scale."""
+    from nlspn_eccv20_b200 import heads
+    dev = torch.device("cuda:0")
+    K, N3 = 3, 24
+    assert heads.dgrad_supported(W, K) and not heads.dgrad_supported(W, 5)
+    x, w, b = _case(B, H, W, K, 31, dev)
+    g = torch.Generator().manual_seed(32)
+    pred_init = torch.relu(torch.randn(B, 1, H, W, generator=g)).to(dev)
+    confidence = torch.sigmoid(torch.randn(B, 1, H, W, generator=g)).to(dev)
+    gi, gg, gc = (torch.randn(B, n, H, W, generator=g).to(dev) for n in (1, N3, 1))
+    g_shift, _ = heads.grad_prep(pred_init, confidence, gi, gg, gc, K)
+    d_oa, d_fe = heads.dgrad_wide(g_shift, w[0], w[1], w[2], K)
+    g_all = g_shift[1]
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        r_oa = torch.nn.grad.conv2d_input((B, 64, H, W), w[1][:, :64].contiguous(), g_all[:, 2:].contiguous(), stride=1, padding=1)
+        w_fe = torch.cat((w[0][:, 64:], w[2][:, 64:], w[1][:, 64:]), 0).contiguous()
+        r_fe = torch.nn.grad.conv2d_input((B, 64, H, W), w_fe, g_all.contiguous(), stride=1, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    for a, r, name in ((d_oa, r_oa, "oa"), (d_fe, r_fe, "fe1")):
+        assert float((a - r).abs().max()) <= 3e-3 * float(r.abs().max().clamp_min(1e-6)), name
+    only_fe = heads.dgrad_wide(g_shift, w[0], w[1], w[2], K, want_oa=False)
+    assert only_fe[0] is None and torch.equal(only_fe[1], d_fe)

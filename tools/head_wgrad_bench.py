@@ -62,6 +62,13 @@ for name, args in (("fe1", (None, None, None, x[3])), ("fe1+oa", (None, x[1], No
 w1 = [torch.randn(1, 128, 3, 3, device=dev) for _ in range(2)]
 out["dgrad_one_ms"] = timed(lambda: heads.dgrad_one(state["g"][0][1], w1[0], w1[1], K))
 out["cudnn_dgrad_one_ms"] = timed(lambda: [torch.nn.grad.conv2d_input((B, 64, H, W), w[:, :64].contiguous(), gg[:, :1].contiguous(), stride=1, padding=1) for w in w1])
+if heads.dgrad_supported(W, K):
+    w3 = [torch.randn(n, 128, 3, 3, device=dev) for n in (1, N3, 1)]
+    out["dgrad_wide_ms"] = timed(lambda: heads.dgrad_wide(state["g"][0], w3[0], w3[1], w3[2], K))
+    wfe = torch.cat((w3[0][:, 64:], w3[2][:, 64:], w3[1][:, 64:]), 0).contiguous()
+    woa = w3[1][:, :64].contiguous()
+    out["cudnn_dgrad_wide_ms"] = timed(lambda: (torch.nn.grad.conv2d_input((B, 64, H, W), woa, gg, stride=1, padding=1),
+                                                torch.nn.grad.conv2d_input((B, 64, H, W), wfe, state["g"][0][1], stride=1, padding=1)))
 ref, _ = stock()
 dw = state["dw"]
 out["rel_diff_fe1"] = float((dw[:, 64:] - ref[3]).abs().max() / ref[3].abs().max())
