@@ -351,3 +351,41 @@ def test_heads_wide_data_gradients_on_tcgen05_match_fp32(B, H, W):
         assert float((a - r).abs().max()) <= 3e-3 * float(r.abs().max().clamp_min(1e-6)), name
     only_fe = heads.dgrad_wide(g_shift, w[0], w[1], w[2], K, want_oa=False)
     assert only_fe[0] is None and torch.equal(only_fe[1], d_fe)
+
+
+def test_heads_gradient_kernels_random_shapes_against_fp32_autograd():
+    """Randomized sweep of the whole native backward (grad_prep, wgrad, dgrad_one, dgrad_wide through FusedHeadsFunction)
+    against fp32 autograd through the stock layers: widths around the 32-pixel strip and 128-pixel tile seams, heights around
+    the rolling form's row segments (<= 32 rows, two lead-in rows), batches.  The activation masks come from OUR forward
+    values in both passes (no upstream gradient within TF32 rounding of the ReLU kink)."""
+    import random
+    from nlspn_eccv20_b200 import heads
+    dev = torch.device("cuda:0")
+    rnd = random.Random(20261020)
+    old = torch.backends.cudnn.allow_tf32
+    names = ["id_fd1", "oa_fd1", "cf_fd1", "fe1", "w_id", "w_oa", "w_cf", "b_id", "b_oa", "b_cf"]
+    try:
+        for case in range(16):
+            K = 3 if case % 4 else 5
+            B = rnd.choice((1, 1, 2, 3))
+            H = rnd.choice((1, 2, 3, 5, 31, 32, 33, 34, 63, 65, 70))
+            W = 4 * rnd.choice((1, 2, 7, 8, 9, 31, 32, 33, 63, 64, 65, 97))
+            x, w, b = _case(B, H, W, K, 2000 + case, dev)
+            order = (0, 1, 2, 3, 4, 7, 5, 8, 6, 9)                     # (x.., w_id, b_id, w_oa, b_oa, w_cf, b_cf)
+            leaves = [t.clone().requires_grad_(True) for t in x + w + b]
+            o = heads.fused_heads(*[leaves[i] for i in order], K)
+            g = [torch.randn_like(t) for t in o]
+            with torch.no_grad():
+                z = torch.nn.functional.conv2d(torch.cat((x[0], x[3]), 1), w[0], b[0], 1, 1)
+                g[0] = g[0] * (z.abs() > 2e-2).to(g[0].dtype)
+            torch.autograd.backward(o, g)
+            torch.backends.cudnn.allow_tf32 = False
+            ref = [t.clone().requires_grad_(True) for t in x + w + b]
+            r = heads.reference_heads(*[ref[i] for i in order])
+            torch.autograd.backward(r, g)
+            torch.backends.cudnn.allow_tf32 = old
+            for a, c, name in zip(leaves, ref, names):
+                s = float(c.grad.abs().max().clamp_min(1e-6))
+                assert float((a.grad - c.grad).abs().max()) <= 4e-3 * s + 1e-6, (case, K, B, H, W, name)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
