@@ -16,6 +16,13 @@ def _case(B, H, W, K, seed, dev):
     return x, w, b
 
 
+def _bias_scale(k, g):
+    """Scale for comparing the bias gradient of head k (0 init, 1 guidance, 2 confidence): a sum over all pixels of signed
+    terms, so rounding differences of the activations (TF32 forward vs fp32 forward) enter relative to the sum of the
+    terms' magnitudes, not to the (cancelling) sum itself."""
+    return (1.0, 1.0, 0.25)[k] * float(g[k].abs().sum(dim=(0, 2, 3)).max())
+
+
 @pytest.mark.parametrize("B,H,W,K", [(1, 9, 40, 3), (2, 37, 131, 3), (1, 20, 300, 5), (1, 11, 130, 7), (2, 64, 256, 3)])
 def test_fused_heads_match_fp32_and_tf32_convolutions(B, H, W, K):
     """Values: within TF32 rounding of the fp32 layers (|d| <= 4e-3 of the output scale; K = 1152 products of 10-bit
@@ -49,7 +56,8 @@ def test_fused_heads_backward_is_the_stock_layers_backward():
     x, w, b = _case(2, 24, 72, K, 7, dev)
     leaves = [t.clone().requires_grad_(True) for t in x + w + b]
     o = heads.fused_heads(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], leaves[7], leaves[5], leaves[8], leaves[6], leaves[9], K)
-    g = [torch.randn_like(t) for t in o]
+    gen = torch.Generator().manual_seed(8)
+    g = [torch.randn(t.shape, generator=gen).to(dev) for t in o]
     # pixels whose init pre-activation lies within TF32 rounding of the ReLU kink may take the other branch in the two
     # implementations: no upstream gradient there, so that both backward passes see the same mask
     with torch.no_grad():
@@ -59,8 +67,10 @@ def test_fused_heads_backward_is_the_stock_layers_backward():
     leaves2 = [t.clone().requires_grad_(True) for t in x + w + b]
     r = heads.reference_heads(leaves2[0], leaves2[1], leaves2[2], leaves2[3], leaves2[4], leaves2[7], leaves2[5], leaves2[8], leaves2[6], leaves2[9])
     torch.autograd.backward(r, g)
-    for a, c in zip(leaves, leaves2):
+    for i, (a, c) in enumerate(zip(leaves, leaves2)):
         s = float(c.grad.abs().max().clamp_min(1e-6))
+        if i >= 7:                                   # b_id, b_oa, b_cf
+            s = max(s, _bias_scale(i - 7, g))
         assert float((a.grad - c.grad).abs().max()) <= 5e-3 * s
 
 
@@ -374,7 +384,8 @@ def test_heads_gradient_kernels_random_shapes_against_fp32_autograd():
             order = (0, 1, 2, 3, 4, 7, 5, 8, 6, 9)                     # (x.., w_id, b_id, w_oa, b_oa, w_cf, b_cf)
             leaves = [t.clone().requires_grad_(True) for t in x + w + b]
             o = heads.fused_heads(*[leaves[i] for i in order], K)
-            g = [torch.randn_like(t) for t in o]
+            gen = torch.Generator().manual_seed(3000 + case)
+            g = [torch.randn(t.shape, generator=gen).to(dev) for t in o]
             with torch.no_grad():
                 z = torch.nn.functional.conv2d(torch.cat((x[0], x[3]), 1), w[0], b[0], 1, 1)
                 g[0] = g[0] * (z.abs() > 2e-2).to(g[0].dtype)
@@ -384,8 +395,10 @@ def test_heads_gradient_kernels_random_shapes_against_fp32_autograd():
             r = heads.reference_heads(*[ref[i] for i in order])
             torch.autograd.backward(r, g)
             torch.backends.cudnn.allow_tf32 = old
-            for a, c, name in zip(leaves, ref, names):
+            for i, (a, c, name) in enumerate(zip(leaves, ref, names)):
                 s = float(c.grad.abs().max().clamp_min(1e-6))
+                if i >= 7:
+                    s = max(s, _bias_scale(i - 7, g))
                 assert float((a.grad - c.grad).abs().max()) <= 4e-3 * s + 1e-6, (case, K, B, H, W, name)
     finally:
         torch.backends.cudnn.allow_tf32 = old
