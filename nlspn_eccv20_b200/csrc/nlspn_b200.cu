@@ -1560,7 +1560,7 @@ static int make_wgrad_map(CUtensorMap *map, const float *base, int imgs, int cha
 
 int nlspn_heads_wgrad_supported(int W, int K)
 {
-    return (K == 3 || K == 5 || K == 7) && W > 0 && W % 4 == 0 && tiled_enabled() && encode_tiled_fn() != nullptr ? 1 : 0;
+    return (K == 3 || K == 5 || K == 7) && W > 0 && W % 4 == 0 && tiled_enabled() ? 1 : 0;
 }
 
 static int check_heads_grad(const char *who, int B, int H, int W, int K)
@@ -1571,6 +1571,12 @@ static int check_heads_grad(const char *who, int B, int H, int W, int K)
                                      "convolution gradients instead", who, W);
     if (H > 65535 || 3L * B > 0x7fffffffL) return fail(NLSPN_ERR_SHAPE, "%s: H > 65535 is not supported (got %d)", who, H);
     return 0;
+}
+
+// the tensor maps need the driver's cuTensorMapEncodeTiled: absent = no CUDA driver in this process
+static int need_tma_driver(const char *who)
+{
+    return encode_tiled_fn() != nullptr ? 0 : fail(NLSPN_ERR_DOMAIN, "%s: cuTensorMapEncodeTiled is not available (no CUDA driver?)", who);
 }
 
 int nlspn_heads_grad_prep(const float *g_init, const float *pred_init, const float *g_guidance, const float *g_confidence,
@@ -1636,6 +1642,7 @@ int nlspn_heads_dgrad_wide(const float *g_shift, const float *packed, int B, int
     if (!g_shift || !packed || !d_fe1) return fail(NLSPN_ERR_NULL, "heads_dgrad_wide: a required pointer is NULL");
     if (!aligned16(g_shift) || !aligned16(packed) || !aligned16(d_oa_fd1) || !aligned16(d_fe1))
         return fail(NLSPN_ERR_ALIGN, "heads_dgrad_wide: tensors must be 16-byte aligned");
+    if (int rc = need_tma_driver("heads_dgrad_wide")) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int NT = 3 * (K * K - 1) + 2;
     int dev = 0, sms = 0;
@@ -1709,6 +1716,7 @@ int nlspn_heads_wgrad(const float *id_fd1, const float *oa_fd1, const float *cf_
     if (!fe1 || !g_shift || !dw_all) return fail(NLSPN_ERR_NULL, "heads_wgrad: a required pointer is NULL");
     if (!aligned16(id_fd1) || !aligned16(oa_fd1) || !aligned16(cf_fd1) || !aligned16(fe1) || !aligned16(g_shift))
         return fail(NLSPN_ERR_ALIGN, "heads_wgrad: tensors must be 16-byte aligned");
+    if (int rc = need_tma_driver("heads_wgrad")) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int N3 = 3 * (K * K - 1), NT = N3 + 2, ldw = 2 * kHeadCin * 9;
     int dev = 0, sms = 0;

@@ -169,3 +169,30 @@ def test_heads_entries_validate_before_touching_cuda(lib):
     assert rc == -2 and b"nlspn_heads_fwd + nlspn_prologue_fwd" in lib.nlspn_last_error()
     rc = lib.nlspn_heads_fwd(one, one, one, None, one, one, 1, 8, 16, 3, one, one, one, None)
     assert rc == -1
+
+
+def test_heads_gradient_entries_validate_before_touching_cuda(lib):
+    """The heads' backward entries (nlspn_heads_grad_prep / _wgrad / _dgrad_one / _dgrad_pack / _dgrad_wide): sizes, the
+    supported-domain queries and the argument checks are host-only; the kernels are covered by tests/test_gpu_heads.py."""
+    P = ctypes.c_void_p
+    one = P(16)
+    assert lib.nlspn_heads_wgrad_supported(1216, 3) == 1 and lib.nlspn_heads_wgrad_supported(304, 5) == 1
+    assert lib.nlspn_heads_wgrad_supported(1218, 3) == 0 and lib.nlspn_heads_wgrad_supported(1216, 4) == 0
+    assert lib.nlspn_heads_dgrad_supported(1216, 3) == 1 and lib.nlspn_heads_dgrad_supported(1216, 5) == 0
+    assert lib.nlspn_heads_dgrad_packed_floats(3) == 9 * 4 * 128 * 8 and lib.nlspn_heads_dgrad_packed_floats(5) == 0
+    # widths the TMA path does not take; bad prop_kernel; NULL and misaligned pointers
+    assert lib.nlspn_heads_grad_prep(one, one, one, one, one, 1, 8, 18, 3, one, one, None) == -2
+    assert b"W % 4" in lib.nlspn_last_error()
+    assert lib.nlspn_heads_grad_prep(one, one, one, one, one, 1, 8, 16, 4, one, one, None) == -3
+    assert lib.nlspn_heads_grad_prep(None, None, None, None, one, 1, 8, 16, 3, one, None, None) == -1
+    assert lib.nlspn_heads_grad_prep(None, one, None, None, one, 1, 8, 16, 3, P(20), None, None) == -7
+    assert lib.nlspn_heads_wgrad(one, one, one, None, one, 1, 8, 16, 3, one, None) == -1
+    assert lib.nlspn_heads_wgrad(one, P(24), one, one, one, 1, 8, 16, 3, one, None) == -7
+    assert lib.nlspn_heads_dgrad_one(None, one, one, 1, 8, 16, 3, one, one, None) == -1
+    assert lib.nlspn_heads_dgrad_one(one, None, one, 1, 8, 16, 3, one, None, None) == -1          # d_id_fd1 wanted without w_id
+    assert lib.nlspn_heads_dgrad_one(one, None, None, 1, 8, 16, 3, None, None, None) == 0         # nothing to do
+    assert lib.nlspn_heads_dgrad_pack(one, one, one, 5, one, None) == -3
+    assert lib.nlspn_heads_dgrad_pack(one, None, one, 3, one, None) == -1
+    assert lib.nlspn_heads_dgrad_wide(one, one, 1, 8, 16, 5, one, one, None) == -3
+    assert lib.nlspn_heads_dgrad_wide(one, one, 1, 8, 16, 3, None, None, None) == -1              # d_fe1 is required
+    assert lib.nlspn_heads_dgrad_wide(one, one, 1, 8, 20, 3, None, P(40), None) == -7
