@@ -20,10 +20,11 @@ namespace nlspn {
 struct HeadDgrad {
     static constexpr int NCH = 32, GROUPS = NCH / 8;             // gradient channels (padded), 8-channel K-steps
     static constexpr int NCOL = 2 * kHeadCin;                    // output channels: oa branch | fe1
-    static constexpr int A_BOX = 3 * 1024, A_STAGE = 4 * A_BOX;  // box = [3 rows][8 ch][32 px]; four boxes = 128 pixels
+    static constexpr int R = 2, ROWS = R + 2;                    // output rows per tile, gradient rows they read
+    static constexpr int A_BOX = ROWS * 1024, A_STAGE = 4 * A_BOX;   // box = [ROWS rows][8 ch][32 px]; four boxes = 128 pixels
     static constexpr int W_BLOCK = NCOL * 8 * 4;                 // weights of one (tap, channel group): [2][NCOL / 8][8][4] floats
     static constexpr int W_BYTES = 9 * GROUPS * W_BLOCK;         // 147456
-    static constexpr int RING = 6, STAGES = GROUPS * 3;          // stages per tile: (channel group, copy)
+    static constexpr int RING = 5, STAGES = GROUPS * 3;          // stages per tile: (channel group, copy)
     static constexpr int THREADS = 192;                          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
     static constexpr size_t smem = (size_t)W_BYTES + (size_t)RING * A_STAGE + 1024;
     static constexpr long packed_floats = W_BYTES / 4;
@@ -54,11 +55,13 @@ __global__ void head_dgrad_pack_kernel(const float *__restrict__ w_id, const flo
     }
 }
 
-// map_g: g_shift [3 B images][NT channels][H][W] with dims (x, channel, row, image), box {32, 8, 3, 1}, SWIZZLE_128B_ATOM_32B.
+// map_g: g_shift [3 B images][NT channels][H][W] with dims (x, channel, row, image), box {32, 8, ROWS, 1}, SWIZZLE_128B_ATOM_32B.
+// A tile = 128 pixels x R = 2 output rows: the ROWS = 4 gradient rows of a stage feed 2 R + 2 = 6 MMAs, and the two inner
+// rows are read ONCE for their two MMAs (A-operand collector: fill / lastuse).
 // grid = min(tiles, SMs); d_oa may be NULL (that branch needs no gradient).
 __global__ void __launch_bounds__(HeadDgrad::THREADS, 1)
 head_dgrad_wide_kernel(const __grid_constant__ CUtensorMap map_g, const float *__restrict__ packed, int B, int H, int W, int tiles_x,
-                       int ntiles, float *__restrict__ d_oa, float *__restrict__ d_fe)
+                       int tiles_y, int ntiles, float *__restrict__ d_oa, float *__restrict__ d_fe)
 {
     using C = HeadDgrad;
     extern __shared__ unsigned char dgrad_smem_raw[];
@@ -83,7 +86,7 @@ head_dgrad_wide_kernel(const __grid_constant__ CUtensorMap map_g, const float *_
         tma::prefetch_descriptor(&map_g);
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma::smem_u32(&tmem_base_s)), "r"(256u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma::smem_u32(&tmem_base_s)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -103,7 +106,7 @@ head_dgrad_wide_kernel(const __grid_constant__ CUtensorMap map_g, const float *_
         __syncwarp();
         uint32_t g = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const int tx = t % tiles_x, y = (t / tiles_x) % H, b = t / (tiles_x * H);
+            const int tx = t % tiles_x, y = ((t / tiles_x) % tiles_y) * C::R, b = t / (tiles_x * tiles_y);
             for (int st = 0; st < C::STAGES; ++st, ++g) {
                 const uint32_t slot = g % C::RING;
                 mbar_wait_bounded(&empty[slot], ((g / C::RING) & 1u) ^ 1u);
@@ -130,7 +133,7 @@ head_dgrad_wide_kernel(const __grid_constant__ CUtensorMap map_g, const float *_
             const uint32_t buf = i & 1u;
             mbar_wait_bounded(&acc_empty[buf], ((i >> 1) & 1u) ^ 1u);                 // the epilogue has drained this set
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tacc = tmem + buf * (uint32_t)C::NCOL;
+            const uint32_t tacc = tmem + buf * (uint32_t)(C::R * C::NCOL);
             for (int st = 0; st < C::STAGES; ++st, ++g) {
                 const uint32_t slot = g % C::RING;
                 mbar_wait_bounded(&full[slot], (g / C::RING) & 1u);
@@ -138,14 +141,19 @@ head_dgrad_wide_kernel(const __grid_constant__ CUtensorMap map_g, const float *_
                 const int q = st / 3, d = st % 3;
                 const uint32_t sa = ring + slot * C::A_STAGE;
                 if (elect_one_sync()) {
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        // box row r = gradient row y - 1 + r = y - dy + 1  ->  dy = 2 - r; copy d = dx
-                        const int tap = (2 - r) * 3 + d;
-                        const uint64_t da = umma_desc_mn_tf32(sa + r * 1024, C::A_BOX, 512);
-                        const uint64_t db = umma_desc_kmajor(wsm + (tap * C::GROUPS + q) * C::W_BLOCK, (C::NCOL / 8) * 128, 128);
-                        umma_tf32<0>(tacc, da, db, idesc, (st | r) != 0 ? 1u : 0u);
-                    }
+                    // box row i = gradient row y0 - 1 + i feeds output row r with the tap dy = r + 2 - i (0 <= dy <= 2); copy d = dx
+                    const uint32_t wq = wsm + q * C::W_BLOCK;
+                    const uint32_t first = st != 0 ? 1u : 0u;
+#define DGRAD_MMA(MODE, i, r, accum)                                                                                         \
+    umma_tf32<MODE>(tacc + (r) * C::NCOL, umma_desc_mn_tf32(sa + (i) * 1024, C::A_BOX, 512),                                  \
+                    umma_desc_kmajor(wq + (((r) + 2 - (i)) * 3 + d) * C::GROUPS * C::W_BLOCK, (C::NCOL / 8) * 128, 128), idesc, accum)
+                    DGRAD_MMA(0, 0, 0, first);       // row 0: dy = 2 of output row 0 (its first MMA of the tile when st == 0)
+                    DGRAD_MMA(1, 1, 0, 1u);          // row 1: dy = 1 of output row 0 ...
+                    DGRAD_MMA(3, 1, 1, first);       //        ... and dy = 2 of output row 1 (its first MMA), same A
+                    DGRAD_MMA(1, 2, 0, 1u);          // row 2: dy = 0 of output row 0 ...
+                    DGRAD_MMA(3, 2, 1, 1u);          //        ... and dy = 1 of output row 1
+                    DGRAD_MMA(0, 3, 1, 1u);          // row 3: dy = 0 of output row 1
+#undef DGRAD_MMA
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                      tma::smem_u32(&empty[slot])) : "memory");
                     if (st == C::STAGES - 1)
@@ -160,14 +168,16 @@ head_dgrad_wide_kernel(const __grid_constant__ CUtensorMap map_g, const float *_
         const int quarter = warp & 3;
         uint32_t i = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
-            const int tx = t % tiles_x, y = (t / tiles_x) % H, b = t / (tiles_x * H);
+            const int tx = t % tiles_x, y0 = ((t / tiles_x) % tiles_y) * C::R, b = t / (tiles_x * tiles_y);
             const int x = tx * 128 + quarter * 32 + lane;
             const uint32_t buf = i & 1u;
             mbar_wait_bounded(&acc_full[buf], (i >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tq = tmem + buf * (uint32_t)C::NCOL + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t tq = tmem + buf * (uint32_t)(C::R * C::NCOL) + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-            for (int cb = 0; cb < C::NCOL; cb += 32) {
+            for (int cb = 0; cb < C::R * C::NCOL; cb += 32) {
+                const int y = y0 + cb / C::NCOL, col = cb % C::NCOL;
+                if (y >= H) break;                                   // warp-uniform: the second row of the last tile of an odd H
                 uint32_t v[32];
 #pragma unroll
                 for (int c = 0; c < 32; c += 16)
@@ -177,9 +187,9 @@ head_dgrad_wide_kernel(const __grid_constant__ CUtensorMap map_g, const float *_
                                    "=r"(v[c + 12]), "=r"(v[c + 13]), "=r"(v[c + 14]), "=r"(v[c + 15])
                                  : "r"(tq + (uint32_t)(cb + c)));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float *out = cb < kHeadCin ? d_oa : d_fe;
+                float *out = col < kHeadCin ? d_oa : d_fe;
                 if (out && x < W) {
-                    out += ((long)b * kHeadCin + (cb & (kHeadCin - 1))) * P + (long)y * W + x;
+                    out += ((long)b * kHeadCin + (col & (kHeadCin - 1))) * P + (long)y * W + x;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) __stcs(out + (long)c * P, __uint_as_float(v[c]));
                 }
@@ -190,7 +200,7 @@ head_dgrad_wide_kernel(const __grid_constant__ CUtensorMap map_g, const float *_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }
 
 inline cudaError_t head_dgrad_wide_launch(const CUtensorMap &map_g, const float *packed, int B, int H, int W, float *d_oa, float *d_fe,
@@ -198,11 +208,11 @@ inline cudaError_t head_dgrad_wide_launch(const CUtensorMap &map_g, const float 
 {
     using C = HeadDgrad;
     if (const cudaError_t ae = ensure_dynamic_smem(reinterpret_cast<const void *>(&head_dgrad_wide_kernel), (int)C::smem)) return ae;
-    const int tiles_x = (W + 127) / 128;
-    const long ntiles = (long)tiles_x * H * B;
+    const int tiles_x = (W + 127) / 128, tiles_y = (H + C::R - 1) / C::R;
+    const long ntiles = (long)tiles_x * tiles_y * B;
     if (ntiles > 0x7fffffffL) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
-    head_dgrad_wide_kernel<<<grid, C::THREADS, C::smem, st>>>(map_g, packed, B, H, W, tiles_x, (int)ntiles, d_oa, d_fe);
+    head_dgrad_wide_kernel<<<grid, C::THREADS, C::smem, st>>>(map_g, packed, B, H, W, tiles_x, tiles_y, (int)ntiles, d_oa, d_fe);
     return cudaGetLastError();
 }
 

@@ -1647,14 +1647,14 @@ int nlspn_heads_dgrad_wide(const float *g_shift, const float *packed, int B, int
     const int NT = 3 * (K * K - 1) + 2;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || nlspn_device_info(dev, &sms, nullptr) != 0 || sms <= 0) sms = 148;
-    // g_shift as [3 B images][NT channels][H][W]: dims (x, channel, row, image), box {32 px, 8 channels, 3 rows}, 32-byte-atom swizzle
+    // g_shift as [3 B images][NT channels][H][W]: dims (x, channel, row, image), box {32 px, 8 channels, R + 2 rows}, 32-byte-atom swizzle
     CUtensorMap mg;
     {
-        const MapKey key{g_shift, NT, 3 * B, H, W, 32, 3, 8, 17};
+        const MapKey key{g_shift, NT, 3 * B, H, W, 32, HeadDgrad::ROWS, 8, 17};
         if (!map_cache_get(key, &mg)) {
             const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)NT, (cuuint64_t)H, (cuuint64_t)(3 * B)};
             const cuuint64_t strides[3] = {(cuuint64_t)H * W * 4, (cuuint64_t)W * 4, (cuuint64_t)NT * H * W * 4};
-            const cuuint32_t box[4] = {32, 8, 3, 1};
+            const cuuint32_t box[4] = {32, 8, (cuuint32_t)HeadDgrad::ROWS, 1};
             const cuuint32_t estr[4] = {1, 1, 1, 1};
             const CUresult r = encode_tiled_fn()(&mg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(g_shift), dims, strides,
                                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
