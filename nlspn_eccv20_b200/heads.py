@@ -133,7 +133,10 @@ class FusedHeadsFunction(torch.autograd.Function):
         (instead of three 128-channel calls whose fe1 halves are then added).  KITTI B = 8: 16.5 -> see DESIGN 12."""
         id_fd1, oa_fd1, cf_fd1, fe1, w_id, w_oa, w_cf, pred_init, confidence = ctx.saved_tensors
         need_in, need_w = ctx.needs_input_grad[:4], (ctx.needs_input_grad[4], ctx.needs_input_grad[6], ctx.needs_input_grad[8])
-        if wgrad_supported(fe1.shape[3], ctx.K) and all(t.is_contiguous() and t.data_ptr() % 16 == 0 for t in (id_fd1, oa_fd1, cf_fd1, fe1)):
+        # (the split-K partials of the native weight / bias gradients are added with fp32 atomics: under
+        #  torch.use_deterministic_algorithms(True) the stock path below, which torch makes deterministic, is taken)
+        if wgrad_supported(fe1.shape[3], ctx.K) and not torch.are_deterministic_algorithms_enabled() \
+                and all(t.is_contiguous() and t.data_ptr() % 16 == 0 for t in (id_fd1, oa_fd1, cf_fd1, fe1)):
             return _backward_native(ctx.K, need_in, need_w, id_fd1, oa_fd1, cf_fd1, fe1, w_id, w_oa, w_cf, pred_init, confidence,
                                     g_init, g_guid, g_conf)
         z = torch.zeros_like

@@ -402,3 +402,36 @@ def test_heads_gradient_kernels_random_shapes_against_fp32_autograd():
                 assert float((a.grad - c.grad).abs().max()) <= 4e-3 * s + 1e-6, (case, K, B, H, W, name)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_heads_backward_under_deterministic_algorithms_repeats_exactly():
+    """The native weight / bias gradients add split-K partials with fp32 atomics; under
+    torch.use_deterministic_algorithms(True) FusedHeadsFunction takes the stock (deterministic) gradient path instead:
+    two backward passes are bit-identical, and equal the native path within TF32 rounding."""
+    from nlspn_eccv20_b200 import heads
+    dev = torch.device("cuda:0")
+    K = 3
+    x, w, b = _case(2, 40, 96, K, 41, dev)
+    order = (0, 1, 2, 3, 4, 7, 5, 8, 6, 9)
+    gen = torch.Generator().manual_seed(42)
+    gu = None
+
+    def run():
+        nonlocal gu
+        leaves = [t.clone().requires_grad_(True) for t in x + w + b]
+        o = heads.fused_heads(*[leaves[i] for i in order], K)
+        if gu is None:
+            gu = [torch.randn(t.shape, generator=gen).to(dev) for t in o]
+        torch.autograd.backward(o, gu)
+        return [t.grad for t in leaves]
+
+    native = run()
+    old = torch.are_deterministic_algorithms_enabled()
+    torch.use_deterministic_algorithms(True)
+    try:
+        a, c = run(), run()
+    finally:
+        torch.use_deterministic_algorithms(old)
+    for p, q, n in zip(a, c, native):
+        assert torch.equal(p, q)
+        assert float((p - n).abs().max()) <= 5e-3 * float(p.abs().max().clamp_min(1e-6)) + 1e-5
