@@ -7,3 +7,7 @@ timeout 100 python tools/head_baseline.py 12 228 304 3 > /tmp/b.json; python - <
 import json
 d=json.load(open('/tmp/b.json')); print({k:(round(v,3) if isinstance(v,float) else v) for k,v in d.items() if k.startswith("fused") or k.startswith("heads_ms")})
 P
+# training path: gradient kernels alone, then forward + backward against the stock layers
+timeout 100 python tools/head_wgrad_bench.py 8
+timeout 100 python tools/head_train_baseline.py 8
+timeout 100 python tools/head_train_baseline.py 12 228 304
